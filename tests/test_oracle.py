@@ -1,0 +1,83 @@
+"""Pins oracle/local_icp_oracle.py to the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_segments, load_golden
+from oracle import local_icp_oracle as O
+
+CASES = ["tiny", "c1_small", "c2_small", "c3_small", "c5_small"]
+
+
+def _check_direction(xt, xs, lt, ls, T_ref, R_ref, t_ref, it_ref, v_ref, nn, loop, exact_map):
+    det = {}
+    T = O.segment_map(xt, xs, lt, ls, nn=nn, loop=loop, details=det)
+    assert T.dtype == np.int64 and T.shape == (len(xs),)
+    np.testing.assert_array_equal(det["valid"], v_ref)
+    np.testing.assert_array_equal(det["iters"][v_ref], it_ref[v_ref])
+    np.testing.assert_allclose(det["R"][v_ref], R_ref[v_ref], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(det["t"][v_ref], t_ref[v_ref], rtol=0, atol=1e-10)
+    if exact_map:
+        np.testing.assert_array_equal(T, T_ref)
+    else:
+        # exact fp64 ties may resolve differently between KD-tree traversal order and lowest index
+        bad = np.nonzero(T != T_ref)[0]
+        x2t = det["x2t"]
+        for i in bad:
+            da = np.linalg.norm(x2t[i] - xt[T[i]])
+            db = np.linalg.norm(x2t[i] - xt[T_ref[i]])
+            assert abs(da - db) <= 1e-6 * max(da, db)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("nn,loop", [("kdtree", True), ("kdtree", False), ("brute", False)])
+def test_segment_map_matches_reference(case, nn, loop):
+    g = load_golden(case)
+    if loop and case in ("c2_small", "c3_small"):
+        pytest.skip("per-point loop variant is checked on the smaller cases")
+    for s, x1, x2, l1, l2 in golden_segments(g):
+        a, b = g["off1"][s], g["off1"][s + 1]
+        c, d = g["off2"][s], g["off2"][s + 1]
+        e, f = g["lm_off"][s], g["lm_off"][s + 1]
+        _check_direction(x1, x2, l1, l2, g["T21"][c:d], g["R21"][e:f], g["t21"][e:f], g["it21"][e:f],
+                         g["v21"][e:f], nn, loop, exact_map=(nn == "kdtree"))
+        _check_direction(x2, x1, l2, l1, g["T12"][a:b], g["R12"][e:f], g["t12"][e:f], g["it12"][e:f],
+                         g["v12"][e:f], nn, loop, exact_map=(nn == "kdtree"))
+
+
+def test_unit_vectors():
+    u = load_golden("unit")
+    for nn in ("kdtree", "brute"):
+        T, R, t = O.icp(u["icp_src"], u["icp_tgt"], nn=nn)
+        np.testing.assert_allclose(R, u["icp_R"], atol=1e-12)
+        np.testing.assert_allclose(t, u["icp_t"], atol=1e-10)
+        np.testing.assert_allclose(T, u["icp_T"], atol=1e-10)
+        assert t.shape == (3, 1)
+        d, i = O.nn_in_target(u["icp_src"], u["icp_tgt"], nn=nn)
+        assert d.shape == (len(u["icp_src"]), 1) and i.shape == (len(u["icp_src"]),)
+        np.testing.assert_array_equal(i, u["nn_i"])
+        np.testing.assert_allclose(d, u["nn_d"], rtol=1e-15)
+    T, R, t = O.best_fit_transform(u["kab_A"], u["kab_B"])
+    np.testing.assert_allclose(R, u["kab_R"], atol=1e-14)
+    np.testing.assert_allclose(t, u["kab_t"], atol=1e-13)
+    np.testing.assert_allclose(T, u["kab_T"], atol=1e-13)
+    assert t.shape == (3,)
+    T, R, t = O.best_fit_transform(u["kab3_A"], u["kab3_B"])
+    np.testing.assert_allclose(R, u["kab3_R"], atol=1e-14)
+    assert np.linalg.det(R) > 0
+    for (a, b, c), ang in zip(u["tri_in"], u["tri_out"]):
+        np.testing.assert_allclose(O.triangle_angles(a, b, c), ang, rtol=1e-15)
+
+
+def test_fill_order():
+    """p2p_matching_seg_icp.py:422-437: i-1 first (cascading forward), then i+1, then identity/mean shift."""
+    I2 = 2 * np.eye(3)
+    R = [None, None, I2, None, None]
+    t = [None, None, np.ones((3, 1)), None, None]
+    x1, x2 = np.ones((4, 3)) * 5, np.ones((3, 3))
+    R, t = O.fill_missing(R, t, x1, x2)
+    np.testing.assert_array_equal(R[0], np.eye(3))          # 0: no i-1, i+1 missing -> identity
+    np.testing.assert_array_equal(t[0].reshape(3), [4, 4, 4])
+    np.testing.assert_array_equal(R[1], np.eye(3))          # 1: takes the already filled 0
+    np.testing.assert_array_equal(R[3], I2)
+    np.testing.assert_array_equal(R[4], I2)
