@@ -1,0 +1,262 @@
+"""ctypes binding of liblocalicp.so (C ABI declared in include/local_icp.h).
+
+There is no CPU path behind these calls: if the shared library has not been built, or no sm_100
+device is present, every entry point raises.  ``build()`` compiles the library in-tree with nvcc for
+sm_100a (no GPU needed to compile).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "liblocalicp.so")
+SOURCES = ["local_icp.cu", "lip_kernels.cuh", "lip_device.cuh"]
+HEADER = os.path.join(ROOT, "include", "local_icp.h")
+
+DIR_T21, DIR_T12, DIR_BOTH = 1, 2, 3
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-shared", "-Xcompiler", "-fPIC", "-DLIP_ARCH=100"]
+
+# name -> (restype, argtypes); must list every symbol include/local_icp.h declares
+_D, _I64, _I32 = POINTER(c_double), POINTER(c_int64), POINTER(c_int32)
+SIGNATURES = {
+    "lip_default_params": (None, [c_void_p]),
+    "lip_create": (c_int, [POINTER(c_void_p), c_int]),
+    "lip_destroy": (None, [c_void_p]),
+    "lip_last_error": (c_char_p, [c_void_p]),
+    "lip_set_params": (c_int, [c_void_p, c_void_p]),
+    "lip_host_alloc": (c_int, [POINTER(c_void_p), c_uint64]),
+    "lip_host_free": (c_int, [c_void_p]),
+    "lip_batch_plan": (c_int, [c_void_p, c_int64, _I64, _I64, _I64, c_int]),
+    "lip_batch_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lip_batch_run_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lip_batch_get_transforms": (c_int, [c_void_p, c_int, _D, _D, _I32, _I32, _D, _D, _I32, _I32]),
+    "lip_batch_get_landmark_nn": (c_int, [c_void_p, c_int, _I32, _D]),
+    "lip_batch_get_counters": (c_int, [c_void_p, _I64]),
+    "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
+    "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
+    "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
+    "lip_triangle_angles_host": (c_int, [c_void_p, _D, c_int64, _D]),
+    "lip_version": (c_int, []),
+    "lip_compiled_arch": (c_int, []),
+}
+
+
+class LipParams(ctypes.Structure):
+    """mirror of struct lip_params"""
+    _fields_ = [("max_iter", c_int32), ("cost_rise_tol", c_double), ("cost_flat_tol", c_double),
+                ("obtuse_eps", c_double), ("cos_den_eps", c_double), ("reject_dist", c_double)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile liblocalicp.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "local_icp.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise NativeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen the library and declare the prototypes.  Never builds implicitly on a box without nvcc
+    sources changed: a missing library is an error, not a reason to fall back."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+        return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(POINTER(ctype)) if a is not None else None
+
+
+def _f64(a, shape_last=3):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None:
+        a = a.reshape(-1, shape_last)
+    return a
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Context:
+    """One lip_ctx: a CUDA stream plus grow-only device workspace on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = c_void_p()
+        rc = self.lib.lip_create(byref(h), int(device))
+        if rc != 0:
+            msg = self.lib.lip_last_error(None)
+            raise NativeError(f"lip_create(device={device}) failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+        self.device = int(device)
+        self._plan_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lip_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.lip_last_error(self.h)
+            err = f"liblocalicp error {rc}: {msg.decode() if msg else ''}"
+            raise ValueError(err) if rc == -2 else NativeError(err)
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def default_params(self) -> LipParams:
+        p = LipParams()
+        self.lib.lip_default_params(byref(p))
+        return p
+
+    def set_params(self, **kw):
+        p = self.default_params()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._check(self.lib.lip_set_params(self.h, byref(p)))
+
+    # ---- batch --------------------------------------------------------------------------------
+    def plan(self, off1, off2, lm_off, directions=DIR_BOTH):
+        off1, off2, lm_off = _i64(off1), _i64(off2), _i64(lm_off)
+        S = len(off1) - 1
+        if len(off2) != S + 1 or len(lm_off) != S + 1:
+            raise ValueError("off1, off2 and lm_off must have the same length")
+        self._check(self.lib.lip_batch_plan(self.h, S, _ptr(off1, c_int64), _ptr(off2, c_int64), _ptr(lm_off, c_int64),
+                                            int(directions)))
+        self.S, self.n1, self.n2, self.sumK, self.directions = S, int(off1[-1]), int(off2[-1]), int(lm_off[-1]), int(directions)
+
+    def run_host(self, xyz1, xyz2, lm1, lm2, T21=None, T12=None):
+        """host numpy in -> host numpy out (H2D, kernels, D2H, sync inside)."""
+        xyz1, xyz2, lm1, lm2 = _f64(xyz1), _f64(xyz2), _f64(lm1), _f64(lm2)
+        if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(lm1) != self.sumK or len(lm2) != self.sumK:
+            raise ValueError("array sizes do not match the planned batch")
+        if T21 is None and self.directions & DIR_T21:
+            T21 = np.empty(self.n2, np.int64)
+        if T12 is None and self.directions & DIR_T12:
+            T12 = np.empty(self.n1, np.int64)
+        self._check(self.lib.lip_batch_run_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, lm1.ctypes.data, lm2.ctypes.data,
+                                                T21.ctypes.data if T21 is not None else None,
+                                                T12.ctypes.data if T12 is not None else None))
+        return T21, T12
+
+    def run_host_ptr(self, xyz1, xyz2, lm1, lm2, T21, T12):
+        """same, raw addresses (pinned buffers of the bench)."""
+        self._check(self.lib.lip_batch_run_host(self.h, xyz1, xyz2, lm1, lm2, T21, T12))
+
+    def run_device(self, xyz1, xyz2, lm1, lm2, T21, T12, stream=0):
+        """device addresses in/out, enqueued on `stream` (0 = the context's own stream); no sync."""
+        self._check(self.lib.lip_batch_run_device(self.h, xyz1, xyz2, lm1, lm2, T21, T12, stream))
+
+    def transforms(self, filled=True):
+        K = self.sumK
+        out = {}
+        R21, t21, R12, t12 = (np.empty((K, 3, 3)), np.empty((K, 3)), np.empty((K, 3, 3)), np.empty((K, 3)))
+        i21, s21, i12, s12 = (np.empty(K, np.int32) for _ in range(4))
+        self._check(self.lib.lip_batch_get_transforms(self.h, int(bool(filled)), _ptr(R21, c_double), _ptr(t21, c_double),
+                                                      _ptr(i21, c_int32), _ptr(s21, c_int32), _ptr(R12, c_double),
+                                                      _ptr(t12, c_double), _ptr(i12, c_int32), _ptr(s12, c_int32)))
+        out.update(R21=R21, t21=t21, iters21=i21, status21=s21, R12=R12, t12=t12, iters12=i12, status12=s12)
+        return out
+
+    def landmark_nn(self, side):
+        n = self.n1 if side == 1 else self.n2
+        nn, d = np.empty((n, 2), np.int32), np.empty((n, 2))
+        self._check(self.lib.lip_batch_get_landmark_nn(self.h, side, _ptr(nn, c_int32), _ptr(d, c_double)))
+        return nn, d
+
+    def counters(self):
+        c = np.zeros(8, np.int64)
+        self._check(self.lib.lip_batch_get_counters(self.h, _ptr(c, c_int64)))
+        return dict(small_icps=int(c[0]), big_icps=int(c[1]), icp_f64_rescans=int(c[2]), map_f64_rescans=int(c[3]),
+                    map_ring2=int(c[4]), map_fullscan=int(c[5]), launches=int(c[6]))
+
+    # ---- single functions ---------------------------------------------------------------------
+    def icp(self, src, src_off, tgt, tgt_off):
+        src, tgt, src_off, tgt_off = _f64(src), _f64(tgt), _i64(src_off), _i64(tgt_off)
+        P = len(src_off) - 1
+        R, t = np.empty((P, 3, 3)), np.empty((P, 3))
+        it, st = np.empty(P, np.int32), np.empty(P, np.int32)
+        self._check(self.lib.lip_icp_host(self.h, P, _ptr(src, c_double), _ptr(src_off, c_int64), _ptr(tgt, c_double),
+                                          _ptr(tgt_off, c_int64), _ptr(R, c_double), _ptr(t, c_double),
+                                          _ptr(it, c_int32), _ptr(st, c_int32)))
+        return R, t, it, st
+
+    def nn(self, src, tgt):
+        src, tgt = _f64(src), _f64(tgt)
+        d, i = np.empty(len(src)), np.empty(len(src), np.int64)
+        self._check(self.lib.lip_nn_host(self.h, _ptr(src, c_double), len(src), _ptr(tgt, c_double), len(tgt),
+                                         _ptr(d, c_double), _ptr(i, c_int64)))
+        return d, i
+
+    def kabsch(self, A, B):
+        A, B = _f64(A), _f64(B)
+        R, t, st = np.empty((3, 3)), np.empty(3), np.zeros(1, np.int32)
+        self._check(self.lib.lip_kabsch_host(self.h, _ptr(A, c_double), _ptr(B, c_double), len(A), _ptr(R, c_double),
+                                             _ptr(t, c_double), _ptr(st, c_int32)))
+        return R, t, int(st[0])
+
+    def triangle_angles(self, abc):
+        abc = _f64(abc)
+        out = np.empty_like(abc)
+        self._check(self.lib.lip_triangle_angles_host(self.h, _ptr(abc, c_double), len(abc), _ptr(out, c_double)))
+        return out
+
+
+_default = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    """process-wide context per device (device defaults to LOCAL_RANK, else 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

@@ -1,0 +1,258 @@
+// Device-side building blocks shared by the local-ICP kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define LIP_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+// Batch layout in HBM.  Meshes are numbered side-major: m in [0,S) = mesh1 of pair m (frame 1),
+// m in [S,2S) = mesh2 of pair m-S.  "Unified" vertex index u = position in [xyz1 | xyz2];
+// "bin" b = unified landmark index in [lm1 | lm2].  Bin b of mesh m holds the vertices of m whose
+// nearest landmark is b; the ICP of bin b has src = bin b and tgt = the same landmark of the
+// partner mesh, bin (b + sumK) mod 2 sumK.
+// ---------------------------------------------------------------------------------------------
+struct GridHdr {
+    double c[3];     // centre of the bounding box: fp32 coordinates are taken relative to it
+    double sum[3];   // sum of the vertices (mean-shift fallback of the fill step)
+    float gmin[3];   // grid origin (bbox min, centred)
+    float inv_h, h;  // cell size
+    int dim[3];      // cells per axis
+    int mask;        // hash table size - 1 (power of two)
+    float mabs;      // max |centred coordinate| over the mesh
+    int n;
+};
+
+struct LipArgs {
+    int S, M, B, sumK, n1_total, n_total, dir_mask, n_tiles;
+    const double *xyz1, *xyz2, *lm1, *lm2;
+    const int* mesh_ubase;   // [M+1] unified vertex base of each mesh
+    const int* mesh_bin;     // [M+1] first bin (= unified landmark index) of each mesh
+    const int* mesh_tab;     // [M+1] first entry of each mesh's hash table in grid_start
+    const int* bin_mesh;     // [B]   mesh of each bin
+    const int* tile_mesh;    // [n_tiles] blend/query tiles: mesh and first local vertex
+    const int* tile_first;   // [n_tiles]
+    int *nn0, *nn1;          // [n_total] nearest / second nearest landmark (local index)
+    double *d0, *d1;         // [n_total] their distances
+    int* bin_off;            // [B+1] unified start of each bin in part_vid
+    int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
+    double *icp_R, *icp_t;   // [B*9], [B*3]
+    int *icp_iters, *icp_status;   // [B]
+    double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
+    int* sched;              // [0] n_small [1] n_big [2] small cursor
+    int *small_list, *big_list;    // [B]
+    float4* grid_pts;        // [n_total] cell-sorted centred fp32 points, .w = local vertex id
+    int* grid_start;         // hash tables, mesh m at mesh_tab[m], size mask+3
+    GridHdr* grid_hdr;       // [M]
+    long long *T12, *T21;    // outputs (unified order: T12 over xyz1, T21 over xyz2)
+    double* q_dist;          // raw-query mode: distance output over xyz2 (or nullptr)
+    unsigned long long* counters;  // [8]
+    int max_iter;
+    double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
+};
+
+__device__ __forceinline__ const double* mesh_xyz(const LipArgs& a, int m) {
+    int ub = a.mesh_ubase[m];
+    return (m < a.S) ? a.xyz1 + 3 * (size_t)ub : a.xyz2 + 3 * (size_t)(ub - a.n1_total);
+}
+__device__ __forceinline__ const double* mesh_lm(const LipArgs& a, int m) {
+    int lb = a.mesh_bin[m];
+    return (m < a.S) ? a.lm1 + 3 * (size_t)lb : a.lm2 + 3 * (size_t)(lb - a.sumK);
+}
+__device__ __forceinline__ int pair_mesh(const LipArgs& a, int m) { return m < a.S ? m + a.S : m - a.S; }
+__device__ __forceinline__ int pair_bin(const LipArgs& a, int b) { return b < a.sumK ? b + a.sumK : b - a.sumK; }
+// is mesh m the SOURCE of a requested direction?  T21 (bit 0): src = mesh2 (m >= S)
+__device__ __forceinline__ bool src_active(const LipArgs& a, int m) {
+    return (m >= a.S) ? (a.dir_mask & 1) : (a.dir_mask & 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions (xor butterfly: every lane ends with the bit-identical result)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LIP_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(LIP_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(LIP_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(LIP_FULL, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact float64 squared distance in the operation order of sklearn's rdist (x, then y, then z;
+// every product and sum rounded separately — no FMA contraction), so that exact ties resolve on
+// the same values the reference sees.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rdist64(double ax, double ay, double az, double bx, double by, double bz) {
+    double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// fp32 top-2 tracking: best, second best and index of the best
+__device__ __forceinline__ void nn_update(float d, int j, float& best, float& sec, int& idx) {
+    sec = fminf(sec, fmaxf(d, best));
+    idx = (d < best) ? j : idx;
+    best = fminf(best, d);
+}
+// bound on |d2_fp32 - d2_exact| given the per-component error e of a coordinate difference
+__device__ __forceinline__ float d2_err(float d2, float e) {
+    return 3.5f * sqrtf(d2) * e + 3.0f * e * e + 5e-7f * d2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 helpers (row-major)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const double* A, const double* Bm, double* C) {  // C = A*B (C may alias B)
+    double r[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = r[i];
+}
+__device__ __forceinline__ void mat3_vec(const double* A, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = A[0] * x + A[1] * y + A[2] * z;
+    oy = A[3] * x + A[4] * y + A[5] * z;
+    oz = A[6] * x + A[7] * y + A[8] * z;
+}
+
+__host__ __device__ __forceinline__ double rcp_approx(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return (double)(1.0f / (float)x);     // host build (unit test harness): same ~20-bit precision class
+#endif
+}
+__host__ __device__ __forceinline__ double rsqrt_approx(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return (double)(1.0f / sqrtf((float)x));
+#endif
+}
+__host__ __device__ __forceinline__ double rsqrt_full(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// One-sided Jacobi step on columns p,q of A (and V).  tan(theta) only has to be approximately the
+// annihilating one (the sweeps are iterated to convergence), so it comes from the ~20-bit MUFU
+// reciprocal / rsqrt; cos and sin are then derived from it in full precision so that every step is
+// an exact rotation and V stays orthogonal.
+#define LIP_JACOBI_PAIR(AP0, AP1, AP2, AQ0, AQ1, AQ2, VP0, VP1, VP2, VQ0, VQ1, VQ2)              \
+    {                                                                                            \
+        double al = AP0 * AP0 + AP1 * AP1 + AP2 * AP2;                                           \
+        double be = AQ0 * AQ0 + AQ1 * AQ1 + AQ2 * AQ2;                                           \
+        double ga = AP0 * AQ0 + AP1 * AQ1 + AP2 * AQ2;                                           \
+        if (ga * ga > 1e-30 * al * be) {                                                         \
+            double ze = (be - al) * rcp_approx(2.0 * ga);                                        \
+            double az = fabs(ze), tt;                                                            \
+            if (az > 1e7) tt = 0.5 * rcp_approx(ze);                                             \
+            else {                                                                               \
+                double w1 = 1.0 + ze * ze;                                                       \
+                tt = copysign(rcp_approx(az + w1 * rsqrt_approx(w1)), ze);                       \
+            }                                                                                    \
+            double cs = rsqrt_full(1.0 + tt * tt), sn = cs * tt, x;                               \
+            x = AP0; AP0 = cs * x - sn * AQ0; AQ0 = sn * x + cs * AQ0;                           \
+            x = AP1; AP1 = cs * x - sn * AQ1; AQ1 = sn * x + cs * AQ1;                           \
+            x = AP2; AP2 = cs * x - sn * AQ2; AQ2 = sn * x + cs * AQ2;                           \
+            x = VP0; VP0 = cs * x - sn * VQ0; VQ0 = sn * x + cs * VQ0;                           \
+            x = VP1; VP1 = cs * x - sn * VQ1; VQ1 = sn * x + cs * VQ1;                           \
+            x = VP2; VP2 = cs * x - sn * VQ2; VQ2 = sn * x + cs * VQ2;                           \
+            any = true;                                                                          \
+        }                                                                                        \
+    }
+
+#define LIP_SWAP_COL(SA, A0, A1, A2, V0, V1, V2, SB, B0, B1, B2, W0, W1, W2)                      \
+    if (SA < SB) {                                                                               \
+        double x;                                                                                \
+        x = SA; SA = SB; SB = x; x = A0; A0 = B0; B0 = x; x = A1; A1 = B1; B1 = x;               \
+        x = A2; A2 = B2; B2 = x; x = V0; V0 = W0; W0 = x; x = V1; V1 = W1; W1 = x;               \
+        x = V2; V2 = W2; W2 = x;                                                                 \
+    }
+
+// Kabsch rotation from the cross-covariance H (row-major, H = sum (a - ca)(b - cb)^T):
+// the proper rotation R (det +1) maximising trace(R H), i.e. numpy's V U^T with the row of Vt of the
+// smallest singular value flipped when det < 0 (registration_icp.py:30-36).  Only the two leading
+// singular pairs are needed; the third follows by cross products, which IS the reflection fix.
+// Returns 0, or 1 when H has rank < 2 (R not unique; a minimal rotation u0 -> v0 is returned).
+__host__ __device__ __noinline__ int kabsch_rotation(const double* H, double* R) {
+    // a_k = column k of H (left singular side), v_k = column k of V
+    double a00 = H[0], a01 = H[3], a02 = H[6];
+    double a10 = H[1], a11 = H[4], a12 = H[7];
+    double a20 = H[2], a21 = H[5], a22 = H[8];
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool any = false;
+        LIP_JACOBI_PAIR(a00, a01, a02, a10, a11, a12, v00, v01, v02, v10, v11, v12)
+        LIP_JACOBI_PAIR(a00, a01, a02, a20, a21, a22, v00, v01, v02, v20, v21, v22)
+        LIP_JACOBI_PAIR(a10, a11, a12, a20, a21, a22, v10, v11, v12, v20, v21, v22)
+        if (!any) break;
+    }
+    // H V = [sigma_k u_k]: squared singular values are the squared column norms
+    double s0 = a00 * a00 + a01 * a01 + a02 * a02;
+    double s1 = a10 * a10 + a11 * a11 + a12 * a12;
+    double s2 = a20 * a20 + a21 * a21 + a22 * a22;
+    LIP_SWAP_COL(s0, a00, a01, a02, v00, v01, v02, s1, a10, a11, a12, v10, v11, v12)
+    LIP_SWAP_COL(s0, a00, a01, a02, v00, v01, v02, s2, a20, a21, a22, v20, v21, v22)
+    LIP_SWAP_COL(s1, a10, a11, a12, v10, v11, v12, s2, a20, a21, a22, v20, v21, v22)
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    if (!(s0 > 1e-280)) return 1;                            // H == 0: identity
+    double x;
+    x = 1.0 / sqrt(a00 * a00 + a01 * a01 + a02 * a02); double u00 = a00 * x, u01 = a01 * x, u02 = a02 * x;
+    x = 1.0 / sqrt(v00 * v00 + v01 * v01 + v02 * v02); v00 *= x; v01 *= x; v02 *= x;
+    if (!(s1 > 1e-24 * s0)) {
+        // rank 1: minimal rotation taking u0 to v0
+        double c = u00 * v00 + u01 * v01 + u02 * v02;
+        double wx = u01 * v02 - u02 * v01, wy = u02 * v00 - u00 * v02, wz = u00 * v01 - u01 * v00;
+        if (c > -1.0 + 1e-12) {
+            double k = 1.0 / (1.0 + c);
+            R[0] = 1 - k * (wy * wy + wz * wz); R[1] = -wz + k * wx * wy;       R[2] = wy + k * wx * wz;
+            R[3] = wz + k * wx * wy;            R[4] = 1 - k * (wx * wx + wz * wz); R[5] = -wx + k * wy * wz;
+            R[6] = -wy + k * wx * wz;           R[7] = wx + k * wy * wz;        R[8] = 1 - k * (wx * wx + wy * wy);
+        } else {
+            // u0 = -v0: half turn about an axis orthogonal to u0
+            double px = (fabs(u00) < 0.9) ? 1.0 : 0.0, py = 1.0 - px, pz = 0.0;
+            double ax = u01 * pz - u02 * py, ay = u02 * px - u00 * pz, az = u00 * py - u01 * px;
+            double k = 1.0 / sqrt(ax * ax + ay * ay + az * az);
+            ax *= k; ay *= k; az *= k;
+            R[0] = 2 * ax * ax - 1; R[1] = 2 * ax * ay;     R[2] = 2 * ax * az;
+            R[3] = 2 * ay * ax;     R[4] = 2 * ay * ay - 1; R[5] = 2 * ay * az;
+            R[6] = 2 * az * ax;     R[7] = 2 * az * ay;     R[8] = 2 * az * az - 1;
+        }
+        return 1;
+    }
+    // second pair: re-orthogonalise against the first (the Jacobi columns already are, to rounding)
+    x = a10 * u00 + a11 * u01 + a12 * u02; a10 -= x * u00; a11 -= x * u01; a12 -= x * u02;
+    x = 1.0 / sqrt(a10 * a10 + a11 * a11 + a12 * a12); double u10 = a10 * x, u11 = a11 * x, u12 = a12 * x;
+    x = v10 * v00 + v11 * v01 + v12 * v02; v10 -= x * v00; v11 -= x * v01; v12 -= x * v02;
+    x = 1.0 / sqrt(v10 * v10 + v11 * v11 + v12 * v12); v10 *= x; v11 *= x; v12 *= x;
+    double u20 = u01 * u12 - u02 * u11, u21 = u02 * u10 - u00 * u12, u22 = u00 * u11 - u01 * u10;
+    v20 = v01 * v12 - v02 * v11; v21 = v02 * v10 - v00 * v12; v22 = v00 * v11 - v01 * v10;
+    // R = V U^T : R[i][j] = sum_k v_k[i] u_k[j]
+    R[0] = v00 * u00 + v10 * u10 + v20 * u20; R[1] = v00 * u01 + v10 * u11 + v20 * u21; R[2] = v00 * u02 + v10 * u12 + v20 * u22;
+    R[3] = v01 * u00 + v11 * u10 + v21 * u20; R[4] = v01 * u01 + v11 * u11 + v21 * u21; R[5] = v01 * u02 + v11 * u12 + v21 * u22;
+    R[6] = v02 * u00 + v12 * u10 + v22 * u20; R[7] = v02 * u01 + v12 * u11 + v22 * u21; R[8] = v02 * u02 + v12 * u12 + v22 * u22;
+    return 0;
+}

@@ -1,0 +1,858 @@
+// Kernels of the local-ICP hot path (sm_100a).  See DESIGN.md for the data layout and the
+// roofline of each kernel.  Reference file:line citations are relative to the reference root.
+#pragma once
+#include "lip_device.cuh"
+
+#define LIP_SMALL_CAP 128     // partitions with <= this many src AND tgt points: one warp, all in SMEM
+#define LIP_SMALL_WARPS 4
+#define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
+#define LIP_BIG_THREADS 256
+#define LIP_TILE 128          // vertices per CTA of the blend / query kernels
+
+// =============================================================================================
+// K0  landmark assignment + stable partition of every mesh by nearest landmark
+//     replaces KDTree(lm).query(xyz, k=2) and the boolean masks NN_skel[:,0]==i
+//     (p2p_matching_in_organ/p2p_matching_seg_icp.py:388-392, 413-414).  One CTA per mesh.
+// =============================================================================================
+__global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
+    extern __shared__ double smem_d[];
+    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const double* xyz = mesh_xyz(a, m);
+    const double* lm = mesh_lm(a, m);
+    double* lmS = smem_d;
+    int* hist = (int*)(lmS + 3 * K);
+    int* excl = hist + K;                                   // K+1 entries
+    for (int i = tid; i < 3 * K; i += blockDim.x) lmS[i] = lm[i];
+    for (int i = tid; i < K; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int v = tid; v < n; v += blockDim.x) {
+        const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+        double best = INFINITY, sec = INFINITY;
+        int i0 = 0, i1 = 0;
+        for (int i = 0; i < K; ++i) {                       // index order, strict '<': sklearn single-leaf scan
+            double d = rdist64(x, y, z, lmS[3 * i], lmS[3 * i + 1], lmS[3 * i + 2]);
+            if (d < best) { sec = best; i1 = i0; best = d; i0 = i; }
+            else if (d < sec) { sec = d; i1 = i; }
+        }
+        if (K == 1) { sec = best; i1 = i0; }
+        a.nn0[ub + v] = i0; a.nn1[ub + v] = i1;
+        a.d0[ub + v] = sqrt(best); a.d1[ub + v] = sqrt(sec);
+        atomicAdd(&hist[i0], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {                                        // exclusive scan of the K bin counts
+        int running = 0;
+        for (int base = 0; base < K; base += 32) {
+            int i = base + lane;
+            int c = (i < K) ? hist[i] : 0, inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
+            if (i < K) excl[i] = running + inc - c;
+            running += __shfl_sync(LIP_FULL, inc, 31);
+        }
+        if (lane == 0) excl[K] = running;
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += blockDim.x) a.bin_off[bb + i] = ub + excl[i];
+    if (m == a.M - 1 && tid == 0) a.bin_off[a.B] = a.n_total;
+    // stable compaction: one warp per bin walks the mesh in vertex order
+    for (int i = warp; i < K; i += nwarps) {
+        int pos = ub + excl[i];
+        for (int base = 0; base < n; base += 32) {
+            int v = base + lane;
+            bool pred = (v < n) && (a.nn0[ub + v] == i);
+            unsigned mask = __ballot_sync(LIP_FULL, pred);
+            if (pred) a.part_vid[pos + __popc(mask & ((1u << lane) - 1))] = v;
+            pos += __popc(mask);
+        }
+    }
+}
+
+// =============================================================================================
+// ICP scheduling: one thread per bin; empty src or tgt -> "no ICP" (p2p_matching_seg_icp.py:415-419)
+// =============================================================================================
+__global__ void icp_schedule_kernel(LipArgs a) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    int m = a.bin_mesh[b];
+    a.icp_iters[b] = 0;
+    a.icp_status[b] = 0;
+    if (!src_active(a, m)) return;
+    int pb = pair_bin(a, b);
+    int ns = a.bin_off[b + 1] - a.bin_off[b], nt = a.bin_off[pb + 1] - a.bin_off[pb];
+    if (ns == 0 || nt == 0) return;
+    if (ns <= LIP_SMALL_CAP && nt <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
+    else a.big_list[atomicAdd(&a.sched[1], 1)] = b;
+}
+
+// =============================================================================================
+// K1-K3  partition ICP, whole iteration loop on device (registration/registration_icp.py:60-98)
+//   NN (get_NN_in_target :49-57): fp32 brute force over the SMEM-staged target in coordinates
+//   centred on the target centroid, top-2 tracking; a query whose two best candidates are closer
+//   than the fp32 error bound is re-evaluated in float64 (lowest index wins an exact tie).
+//   Kabsch (get_best_fit_transform :8-46): float64 sums reduced over the warp with a fixed butterfly,
+//   3x3 Jacobi SVD in registers; accumulate R,t; cost/stop test (:86-88) — all uniform per warp.
+// =============================================================================================
+struct IcpState {            // uniform across the lanes/threads working on one partition
+    double R[9], t[3];       // accumulated transform in centred coordinates
+    double Ri[9], ti[3];     // last increment
+};
+
+__device__ __forceinline__ void icp_state_init(IcpState& s, double tix, double tiy, double tiz) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { s.R[i] = (i % 4 == 0) ? 1.0 : 0.0; s.Ri[i] = s.R[i]; }
+    s.t[0] = s.t[1] = s.t[2] = 0.0;
+    s.ti[0] = tix; s.ti[1] = tiy; s.ti[2] = tiz;
+}
+// R <- Ri R ; t <- Ri t + ti   (registration_icp.py:83-84)
+__device__ __forceinline__ void icp_state_accumulate(IcpState& s) {
+    mat3_mul(s.Ri, s.R, s.R);
+    double x, y, z;
+    mat3_vec(s.Ri, s.t[0], s.t[1], s.t[2], x, y, z);
+    s.t[0] = x + s.ti[0]; s.t[1] = y + s.ti[1]; s.t[2] = z + s.ti[2];
+}
+// acc: 0 sum dist | 1..3 sum p | 4..6 sum b | 7..15 sum p_i b_j | 16 pairs kept
+// Kabsch increment from the reduced sums; returns 1 if the solve was rank deficient
+__device__ __forceinline__ int icp_kabsch_step(const double* acc, IcpState& s) {
+    double n = acc[16];
+    if (!(n > 0.0)) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s.Ri[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        s.ti[0] = s.ti[1] = s.ti[2] = 0.0;
+        return 1;
+    }
+    double inv = 1.0 / n;
+    double ca[3] = {acc[1] * inv, acc[2] * inv, acc[3] * inv};
+    double cb[3] = {acc[4] * inv, acc[5] * inv, acc[6] * inv};
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[3 * i + j] = acc[7 + 3 * i + j] - n * ca[i] * cb[j];
+    int deg = kabsch_rotation(H, s.Ri);
+    double x, y, z;
+    mat3_vec(s.Ri, ca[0], ca[1], ca[2], x, y, z);
+    s.ti[0] = cb[0] - x; s.ti[1] = cb[1] - y; s.ti[2] = cb[2] - z;
+    return deg;
+}
+// final transform back to the original frame: y - c = R (x - c) + t~  =>  t = t~ + c - R c
+__device__ __forceinline__ void icp_store(const LipArgs& a, int b, const IcpState& s, double cx, double cy, double cz,
+                                          int iters, int status) {
+    double x, y, z;
+    mat3_vec(s.R, cx, cy, cz, x, y, z);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.icp_R[9 * (size_t)b + i] = s.R[i];
+    a.icp_t[3 * (size_t)b] = s.t[0] + cx - x;
+    a.icp_t[3 * (size_t)b + 1] = s.t[1] + cy - y;
+    a.icp_t[3 * (size_t)b + 2] = s.t[2] + cz - z;
+    a.icp_iters[b] = iters;
+    a.icp_status[b] = status;
+}
+
+// scan `cnt` fp32 target points (index base `j0`) for two queries at once
+__device__ __forceinline__ void nn_scan2(const float4* __restrict__ tf, int cnt, int j0,
+                                         float ax, float ay, float az, float bx, float by, float bz,
+                                         float& besta, float& seca, int& ia, float& bestb, float& secb, int& ib) {
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+        const float4 t = tf[j];
+        float dx = t.x - ax, dy = t.y - ay, dz = t.z - az;
+        float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+        nn_update(d, j0 + j, besta, seca, ia);
+        dx = t.x - bx; dy = t.y - by; dz = t.z - bz;
+        d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+        nn_update(d, j0 + j, bestb, secb, ib);
+    }
+}
+
+template <int CAP>
+struct IcpSmallSmem {
+    float4 tf[CAP];                       // centred fp32 target (search)
+    double tx[CAP], ty[CAP], tz[CAP];     // centred fp64 target (Kabsch sums, exact re-evaluation)
+    double sx[CAP], sy[CAP], sz[CAP];     // centred fp64 source (original positions)
+};
+
+template <int CAP>
+__device__ __forceinline__ void icp_small_finish(const IcpSmallSmem<CAP>& sm, int nt, bool valid, float best, float sec,
+                                                 int idx, float mabs, double px, double py, double pz, double reject,
+                                                 double* acc, unsigned long long* counters) {
+    if (!valid) return;
+    float fx = (float)px, fy = (float)py, fz = (float)pz;
+    float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) + mabs);
+    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {   // near tie: decide in float64, lowest index
+        double bd = INFINITY;
+        for (int j = 0; j < nt; ++j) {
+            double d = rdist64(px, py, pz, sm.tx[j], sm.ty[j], sm.tz[j]);
+            if (d < bd) { bd = d; idx = j; }
+        }
+        atomicAdd(&counters[2], 1ull);
+    }
+    double bx = sm.tx[idx], by = sm.ty[idx], bz = sm.tz[idx];
+    double d = sqrt(rdist64(px, py, pz, bx, by, bz));
+    acc[0] += d;
+    if (d <= reject) {
+        acc[1] += px; acc[2] += py; acc[3] += pz;
+        acc[4] += bx; acc[5] += by; acc[6] += bz;
+        acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
+        acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
+        acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
+        acc[16] += 1.0;
+    }
+}
+
+template <int CAP>
+__device__ void icp_one_small(const LipArgs& a, int b, IcpSmallSmem<CAP>& sm, int lane) {
+    const int pb = pair_bin(a, b);
+    const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
+    const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
+    const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
+    const double* xs = mesh_xyz(a, ms);
+    const double* xt = mesh_xyz(a, mt);
+    const int* vs = a.part_vid + so;
+    const int* vt = a.part_vid + to;
+    // ---- stage the target, centred on its centroid -------------------------------------------------
+    double cx = 0, cy = 0, cz = 0;
+    for (int j = lane; j < nt; j += 32) {
+        size_t v = (size_t)vt[j];
+        double x = xt[3 * v], y = xt[3 * v + 1], z = xt[3 * v + 2];
+        sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z;
+        cx += x; cy += y; cz += z;
+    }
+    cx = warp_sum(cx) / nt; cy = warp_sum(cy) / nt; cz = warp_sum(cz) / nt;
+    __syncwarp();
+    float mabs = 0.f;
+    double mtx = 0, mty = 0, mtz = 0;
+    for (int j = lane; j < nt; j += 32) {
+        double x = sm.tx[j] - cx, y = sm.ty[j] - cy, z = sm.tz[j] - cz;
+        sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z;
+        sm.tf[j] = make_float4((float)x, (float)y, (float)z, 0.f);
+        mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf((float)x), fabsf((float)y)), fabsf((float)z)));
+        mtx += x; mty += y; mtz += z;
+    }
+    mabs = warp_maxf(mabs);
+    mtx = warp_sum(mtx) / nt; mty = warp_sum(mty) / nt; mtz = warp_sum(mtz) / nt;
+    double msx = 0, msy = 0, msz = 0;
+    for (int q = lane; q < ns; q += 32) {
+        size_t v = (size_t)vs[q];
+        double x = xs[3 * v] - cx, y = xs[3 * v + 1] - cy, z = xs[3 * v + 2] - cz;
+        sm.sx[q] = x; sm.sy[q] = y; sm.sz[q] = z;
+        msx += x; msy += y; msz += z;
+    }
+    msx = warp_sum(msx) / ns; msy = warp_sum(msy) / ns; msz = warp_sum(msz) / ns;
+    __syncwarp();
+    // ---- the ICP loop ---------------------------------------------------------------------------------
+    IcpState st;
+    icp_state_init(st, mtx - msx, mty - msy, mtz - msz);    // t_init = mean(tgt) - mean(src)   (:70)
+    double prev = 0.0;
+    int iters = 0, status = 1;
+    for (int it = 0; it < a.max_iter; ++it) {
+        icp_state_accumulate(st);
+        double acc[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) acc[i] = 0.0;
+        for (int q0 = 0; q0 < ns; q0 += 64) {
+            const int qa = q0 + lane, qb = qa + 32;
+            const bool va = qa < ns, vb = qb < ns;
+            const int ra = va ? qa : ns - 1, rb = vb ? qb : ns - 1;
+            double pax, pay, paz, pbx, pby, pbz;
+            mat3_vec(st.R, sm.sx[ra], sm.sy[ra], sm.sz[ra], pax, pay, paz);
+            pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
+            mat3_vec(st.R, sm.sx[rb], sm.sy[rb], sm.sz[rb], pbx, pby, pbz);
+            pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+            float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
+            int ia = 0, ib = 0;
+            nn_scan2(sm.tf, nt, 0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
+                     besta, seca, ia, bestb, secb, ib);
+            icp_small_finish<CAP>(sm, nt, va, besta, seca, ia, mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+            icp_small_finish<CAP>(sm, nt, vb, bestb, secb, ib, mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
+        }
+#pragma unroll
+        for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
+        const double cost = acc[0] / ns;                    // np.mean(distance)   (:86)
+        iters = it + 1;
+        if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;   // (:87)
+        prev = cost;
+        if (icp_kabsch_step(acc, st)) status = 2;
+    }
+    if (lane == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
+}
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) icp_small_kernel(LipArgs a) {
+    __shared__ IcpSmallSmem<CAP> sm_all[WARPS];
+    IcpSmallSmem<CAP>& sm = sm_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int n_small = a.sched[0];
+    for (;;) {                                              // persistent warps, dynamic partition queue
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&a.sched[2], 1);
+        w = __shfl_sync(LIP_FULL, w, 0);
+        if (w >= n_small) break;
+        icp_one_small<CAP>(a, a.small_list[w], sm, lane);
+        __syncwarp();
+    }
+}
+
+// ---- CTA-per-partition variant for partitions that do not fit the per-warp SMEM budget ----------
+// (K == 1 whole-segment ICP, p2p_matching_seg_icp.py:440-449, and direct my_icp calls)
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {   // all threads get the sum
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < LIP_BIG_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+__device__ __forceinline__ void icp_big_finish(const LipArgs& a, const double* xt, const int* vt, int nt, bool valid,
+                                               float best, float sec, int idx, float mabs, double cx, double cy,
+                                               double cz, double px, double py, double pz, double* acc) {
+    if (!valid) return;
+    float fx = (float)px, fy = (float)py, fz = (float)pz;
+    float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) + mabs);
+    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
+        double bd = INFINITY;
+        for (int j = 0; j < nt; ++j) {
+            size_t v = (size_t)vt[j];
+            double d = rdist64(px, py, pz, xt[3 * v] - cx, xt[3 * v + 1] - cy, xt[3 * v + 2] - cz);
+            if (d < bd) { bd = d; idx = j; }
+        }
+        atomicAdd(&a.counters[2], 1ull);
+    }
+    size_t v = (size_t)vt[idx];
+    double bx = xt[3 * v] - cx, by = xt[3 * v + 1] - cy, bz = xt[3 * v + 2] - cz;
+    double d = sqrt(rdist64(px, py, pz, bx, by, bz));
+    acc[0] += d;
+    if (d <= a.reject_dist) {
+        acc[1] += px; acc[2] += py; acc[3] += pz;
+        acc[4] += bx; acc[5] += by; acc[6] += bz;
+        acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
+        acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
+        acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
+        acc[16] += 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
+    __shared__ float4 tf[LIP_BIG_CAP];
+    __shared__ double red[LIP_BIG_THREADS / 32];
+    __shared__ double red17[LIP_BIG_THREADS / 32][17];
+    __shared__ float redf[LIP_BIG_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_big = a.sched[1];
+    for (int w = blockIdx.x; w < n_big; w += gridDim.x) {
+        const int b = a.big_list[w], pb = pair_bin(a, b);
+        const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
+        const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
+        const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
+        const double* xs = mesh_xyz(a, ms);
+        const double* xt = mesh_xyz(a, mt);
+        const int* vs = a.part_vid + so;
+        const int* vt = a.part_vid + to;
+        double sx = 0, sy = 0, sz = 0;
+        for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
+            size_t v = (size_t)vt[j];
+            sx += xt[3 * v]; sy += xt[3 * v + 1]; sz += xt[3 * v + 2];
+        }
+        const double cx = block_sum(sx, red, tid) / nt, cy = block_sum(sy, red, tid) / nt, cz = block_sum(sz, red, tid) / nt;
+        float mabs = 0.f;
+        sx = sy = sz = 0;
+        for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
+            size_t v = (size_t)vt[j];
+            double x = xt[3 * v] - cx, y = xt[3 * v + 1] - cy, z = xt[3 * v + 2] - cz;
+            mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf((float)x), fabsf((float)y)), fabsf((float)z)));
+            sx += x; sy += y; sz += z;
+        }
+        const double mtx = block_sum(sx, red, tid) / nt, mty = block_sum(sy, red, tid) / nt, mtz = block_sum(sz, red, tid) / nt;
+        mabs = warp_maxf(mabs);
+        __syncthreads();
+        if (lane == 0) redf[warp] = mabs;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LIP_BIG_THREADS / 32; ++k) mabs = fmaxf(mabs, redf[k]);
+        sx = sy = sz = 0;
+        for (int q = tid; q < ns; q += LIP_BIG_THREADS) {
+            size_t v = (size_t)vs[q];
+            sx += xs[3 * v] - cx; sy += xs[3 * v + 1] - cy; sz += xs[3 * v + 2] - cz;
+        }
+        const double msx = block_sum(sx, red, tid) / ns, msy = block_sum(sy, red, tid) / ns, msz = block_sum(sz, red, tid) / ns;
+        const bool resident = nt <= LIP_BIG_CAP;
+        __syncthreads();
+        if (resident) {
+            for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
+                size_t v = (size_t)vt[j];
+                tf[j] = make_float4((float)(xt[3 * v] - cx), (float)(xt[3 * v + 1] - cy), (float)(xt[3 * v + 2] - cz), 0.f);
+            }
+            __syncthreads();
+        }
+        IcpState st;
+        icp_state_init(st, mtx - msx, mty - msy, mtz - msz);
+        double prev = 0.0;
+        int iters = 0, status = 1;
+        for (int it = 0; it < a.max_iter; ++it) {
+            icp_state_accumulate(st);
+            double acc[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) acc[i] = 0.0;
+            for (int q0 = 0; q0 < ns; q0 += 2 * LIP_BIG_THREADS) {
+                const int qa = q0 + tid, qb = qa + LIP_BIG_THREADS;
+                const bool va = qa < ns, vb = qb < ns;
+                const size_t ra = (size_t)vs[va ? qa : ns - 1], rb = (size_t)vs[vb ? qb : ns - 1];
+                double pax, pay, paz, pbx, pby, pbz;
+                mat3_vec(st.R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
+                pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
+                mat3_vec(st.R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
+                pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+                float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
+                int ia = 0, ib = 0;
+                for (int t0 = 0; t0 < nt; t0 += LIP_BIG_CAP) {
+                    const int cnt = min(LIP_BIG_CAP, nt - t0);
+                    if (!resident) {
+                        __syncthreads();
+                        for (int j = tid; j < cnt; j += LIP_BIG_THREADS) {
+                            size_t v = (size_t)vt[t0 + j];
+                            tf[j] = make_float4((float)(xt[3 * v] - cx), (float)(xt[3 * v + 1] - cy),
+                                                (float)(xt[3 * v + 2] - cz), 0.f);
+                        }
+                        __syncthreads();
+                    }
+                    nn_scan2(tf, cnt, t0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
+                             besta, seca, ia, bestb, secb, ib);
+                }
+                icp_big_finish(a, xt, vt, nt, va, besta, seca, ia, mabs, cx, cy, cz, pax, pay, paz, acc);
+                icp_big_finish(a, xt, vt, nt, vb, bestb, secb, ib, mabs, cx, cy, cz, pbx, pby, pbz, acc);
+            }
+#pragma unroll
+            for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 17; ++i) red17[warp][i] = acc[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < LIP_BIG_THREADS / 32; ++k) s += red17[k][i];
+                acc[i] = s;
+            }
+            const double cost = acc[0] / ns;
+            iters = it + 1;
+            if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;
+            prev = cost;
+            if (icp_kabsch_step(acc, st)) status = 2;
+        }
+        if (tid == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// fill of missing transforms (p2p_matching_seg_icp.py:422-437): one thread per source mesh
+// =============================================================================================
+__global__ void fill_kernel(LipArgs a) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= a.M || !src_active(a, m)) return;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    for (int i = 0; i < K; ++i) {
+        const int b = bb + i;
+        int from = -1;                                       // -1: identity + mean shift
+        bool own = a.icp_status[b] != 0;
+        if (!own) {
+            if (i > 0) from = b - 1;                         // already filled (ascending pass)
+            else if (K > 1 && a.icp_status[b + 1] != 0) from = b + 1;
+        }
+        if (own) {
+            for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = a.icp_R[9 * (size_t)b + k];
+            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = a.icp_t[3 * (size_t)b + k];
+        } else if (from == b - 1) {
+            for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = a.fill_R[9 * (size_t)from + k];
+            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = a.fill_t[3 * (size_t)from + k];
+        } else if (from == b + 1) {
+            for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = a.icp_R[9 * (size_t)from + k];
+            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = a.icp_t[3 * (size_t)from + k];
+        } else {
+            const GridHdr& hs = a.grid_hdr[m];
+            const GridHdr& ht = a.grid_hdr[pair_mesh(a, m)];
+            for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = (k % 4 == 0) ? 1.0 : 0.0;
+            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = ht.sum[k] / ht.n - hs.sum[k] / hs.n;
+        }
+    }
+}
+
+// =============================================================================================
+// K5  uniform-grid spatial hash of every mesh (replaces KDTree(xyz1), p2p_matching_seg_icp.py:452):
+//     bbox + vertex sum, cell size from a sampled nearest-neighbour spacing, cell hash -> counting
+//     sort (histogram, prefix scan, scatter) into cell-ordered float4 points.  One CTA per mesh.
+// =============================================================================================
+__device__ __forceinline__ int cell_hash(int cx, int cy, int cz, int mask) {
+    return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & mask;
+}
+__device__ __forceinline__ int cell_coord(float x, float g, float inv_h, int dim) {
+    float c = floorf((x - g) * inv_h);
+    c = fminf(fmaxf(c, -4.0f), (float)(dim + 3));
+    return (int)c;
+}
+
+__global__ void __launch_bounds__(256) grid_build_kernel(LipArgs a, int need_all) {
+    __shared__ double redd[8][9];
+    __shared__ float samp[32];
+    __shared__ GridHdr hdr;
+    __shared__ int carry;
+    __shared__ int wsum[8];
+    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // only targets of a requested direction need a grid, but every mesh needs hdr.sum / hdr.n
+    const bool want_grid = need_all || src_active(a, pair_mesh(a, m));
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const double* xyz = mesh_xyz(a, m);
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, sm[3] = {0, 0, 0};
+    for (int v = tid; v < n; v += 256) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double x = xyz[3 * (size_t)v + k];
+            mn[k] = fmin(mn[k], x); mx[k] = fmax(mx[k], x); sm[k] += x;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); sm[k] = warp_sum(sm[k]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { redd[warp][k] = mn[k]; redd[warp][3 + k] = mx[k]; redd[warp][6 + k] = sm[k]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ext = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            double lo = redd[0][k], hi = redd[0][3 + k], s = redd[0][6 + k];
+            for (int w = 1; w < 8; ++w) { lo = fmin(lo, redd[w][k]); hi = fmax(hi, redd[w][3 + k]); s += redd[w][6 + k]; }
+            hdr.c[k] = 0.5 * (lo + hi);
+            hdr.sum[k] = s;
+            hdr.gmin[k] = (float)(lo - hdr.c[k]);
+            ext = fmaxf(ext, (float)(hi - lo));
+        }
+        hdr.mabs = 0.5f * ext * 1.0001f + 1e-30f;
+        hdr.h = ext;                                         // provisional: extent, finalised below
+        hdr.n = n;
+        hdr.mask = a.mesh_tab[m + 1] - a.mesh_tab[m] - 3;
+    }
+    __syncthreads();
+    if (!want_grid) {
+        if (tid == 0) a.grid_hdr[m] = hdr;
+        return;
+    }
+    const double c0 = hdr.c[0], c1 = hdr.c[1], c2 = hdr.c[2];
+    // sampled nearest-neighbour spacing -> cell size h = 4 * mean spacing (about 4 points per cell on a surface)
+    const int nsamp = min(32, n);
+    for (int k = warp; k < nsamp; k += 8) {
+        const int sv = (int)(((long long)k * n) / nsamp);
+        const float qx = (float)(xyz[3 * (size_t)sv] - c0), qy = (float)(xyz[3 * (size_t)sv + 1] - c1),
+                    qz = (float)(xyz[3 * (size_t)sv + 2] - c2);
+        float best = INFINITY;
+        for (int j = lane; j < n; j += 32) {
+            float dx = (float)(xyz[3 * (size_t)j] - c0) - qx, dy = (float)(xyz[3 * (size_t)j + 1] - c1) - qy,
+                  dz = (float)(xyz[3 * (size_t)j + 2] - c2) - qz;
+            float d = dx * dx + dy * dy + dz * dz;
+            if (j != sv) best = fminf(best, d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(LIP_FULL, best, o));
+        if (lane == 0) samp[k] = best;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ext = hdr.h, s = 0.f;
+        int cnt = 0;
+        for (int k = 0; k < nsamp; ++k)
+            if (samp[k] < INFINITY) { s += sqrtf(samp[k]); ++cnt; }
+        float h = (cnt > 0) ? 4.0f * s / cnt : 1.0f;
+        h = fmaxf(h, ext * (1.0f / 1000.0f));
+        if (!(h > 1e-30f)) h = 1.0f;
+        hdr.h = h;
+        hdr.inv_h = 1.0f / h;
+        for (int k = 0; k < 3; ++k) hdr.dim[k] = 0;          // filled from the points below (max cell + 1)
+        a.grid_hdr[m] = hdr;
+    }
+    __syncthreads();
+    const float inv_h = hdr.inv_h, g0 = hdr.gmin[0], g1 = hdr.gmin[1], g2 = hdr.gmin[2];
+    const int mask = hdr.mask;
+    int* tab = a.grid_start + a.mesh_tab[m];                 // mask+3 entries, zeroed by the host
+    int dmax[3] = {0, 0, 0};
+    for (int v = tid; v < n; v += 256) {
+        float x = (float)(xyz[3 * (size_t)v] - c0), y = (float)(xyz[3 * (size_t)v + 1] - c1), z = (float)(xyz[3 * (size_t)v + 2] - c2);
+        int cx = max(cell_coord(x, g0, inv_h, 1 << 20), 0), cy = max(cell_coord(y, g1, inv_h, 1 << 20), 0),
+            cz = max(cell_coord(z, g2, inv_h, 1 << 20), 0);
+        dmax[0] = max(dmax[0], cx); dmax[1] = max(dmax[1], cy); dmax[2] = max(dmax[2], cz);
+        atomicAdd(&tab[cell_hash(cx, cy, cz, mask) + 2], 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax[k] = max(dmax[k], __shfl_xor_sync(LIP_FULL, dmax[k], o));
+        if (lane == 0) atomicMax(&a.grid_hdr[m].dim[k], dmax[k] + 1);
+    }
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    // inclusive scan of tab[0 .. mask+2] in place: afterwards tab[b+1] = first slot of bucket b
+    const int total = mask + 3;
+    for (int base = 0; base < total; base += 256) {
+        int i = base + tid;
+        int c = (i < total) ? tab[i] : 0, inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (i < total) tab[i] = inc + off;
+        __syncthreads();
+        if (tid == 255) carry = inc + off;
+        __syncthreads();
+    }
+    // scatter: atomicAdd on tab[b+1] hands out the slots; afterwards tab[b] .. tab[b+1] brackets bucket b
+    float4* pts = a.grid_pts + ub;
+    for (int v = tid; v < n; v += 256) {
+        float x = (float)(xyz[3 * (size_t)v] - c0), y = (float)(xyz[3 * (size_t)v + 1] - c1), z = (float)(xyz[3 * (size_t)v + 2] - c2);
+        int cx = max(cell_coord(x, g0, inv_h, 1 << 20), 0), cy = max(cell_coord(y, g1, inv_h, 1 << 20), 0),
+            cz = max(cell_coord(z, g2, inv_h, 1 << 20), 0);
+        int slot = atomicAdd(&tab[cell_hash(cx, cy, cz, mask) + 1], 1);
+        pts[slot] = make_float4(x, y, z, __int_as_float(v));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact nearest neighbour of one query in a hashed grid: ring 1 (27 cells), ring 2 (98 more), then a
+// full scan; a ring result is accepted only if the best distance is inside the searched block.
+// ---------------------------------------------------------------------------------------------
+struct NNResult { int idx; int level; };
+
+__device__ __forceinline__ void grid_visit32(const int* __restrict__ tab, const float4* __restrict__ pts, int bucket,
+                                             float qx, float qy, float qz, float& best, float& sec, int& idx) {
+    const int s = __ldg(&tab[bucket]), e = __ldg(&tab[bucket + 1]);
+    for (int j = s; j < e; ++j) {
+        const float4 p = __ldg(&pts[j]);
+        float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+        float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+        nn_update(d, __float_as_int(p.w), best, sec, idx);
+    }
+}
+__device__ __forceinline__ void grid_visit64(const int* __restrict__ tab, const float4* __restrict__ pts,
+                                             const double* __restrict__ xyz, int bucket, double qx, double qy, double qz,
+                                             double& best, int& idx) {
+    const int s = __ldg(&tab[bucket]), e = __ldg(&tab[bucket + 1]);
+    for (int j = s; j < e; ++j) {
+        const int v = __float_as_int(__ldg(&pts[j]).w);
+        double d = rdist64(qx, qy, qz, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+        if (d < best || (d == best && v < idx)) { best = d; idx = v; }
+    }
+}
+
+// q64: query in ORIGINAL coordinates (float64); returns local vertex index of the nearest target
+__device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __restrict__ tab,
+                                                 const float4* __restrict__ pts, const double* __restrict__ xyz,
+                                                 double q0, double q1, double q2, unsigned long long* counters,
+                                                 double* dist_out) {
+    const float qx = (float)(q0 - h.c[0]), qy = (float)(q1 - h.c[1]), qz = (float)(q2 - h.c[2]);
+    const int cx = cell_coord(qx, h.gmin[0], h.inv_h, h.dim[0]), cy = cell_coord(qy, h.gmin[1], h.inv_h, h.dim[1]),
+              cz = cell_coord(qz, h.gmin[2], h.inv_h, h.dim[2]);
+    float best = INFINITY, sec = INFINITY;
+    int idx = -1, level = 1;
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= h.dim[2]) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= h.dim[1]) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx;
+                if (x < 0 || x >= h.dim[0]) continue;
+                grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx);
+            }
+        }
+    }
+    float g = 0.999f * h.h;
+    if (!(best <= g * g)) {
+        level = 2;
+        for (int dz = -2; dz <= 2; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= h.dim[2]) continue;
+            for (int dy = -2; dy <= 2; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= h.dim[1]) continue;
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int x = cx + dx;
+                    if (x < 0 || x >= h.dim[0]) continue;
+                    if (max(max(abs(dx), abs(dy)), abs(dz)) < 2) continue;
+                    grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx);
+                }
+            }
+        }
+        g = 2.0f * 0.999f * h.h;
+        if (!(best <= g * g)) {
+            level = 3;
+            best = sec = INFINITY;
+            for (int j = 0; j < h.n; ++j) {
+                const float4 p = __ldg(&pts[j]);
+                float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+                nn_update(d, __float_as_int(p.w), best, sec, idx);
+            }
+        }
+    }
+    if (level == 2) atomicAdd(&counters[4], 1ull);
+    if (level == 3) atomicAdd(&counters[5], 1ull);
+    // anything outside the searched block is at least g away: it competes with `sec`
+    if (level < 3) sec = fminf(sec, g * g);
+    const float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + h.mabs);
+    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
+        // near tie (or best close to the certified radius): decide in float64 on the original coordinates
+        atomicAdd(&counters[3], 1ull);
+        double bd = INFINITY;
+        int bi = 0x7fffffff;
+        if (level < 3) {
+            const int r = level;
+            for (int dz = -r; dz <= r; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= h.dim[2]) continue;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= h.dim[1]) continue;
+                    for (int dx = -r; dx <= r; ++dx) {
+                        const int x = cx + dx;
+                        if (x < 0 || x >= h.dim[0]) continue;
+                        grid_visit64(tab, pts, xyz, cell_hash(x, y, z, h.mask), q0, q1, q2, bd, bi);
+                    }
+                }
+            }
+            const double gg = (double)g * 0.999;
+            if (!(bd <= gg * gg)) level = 3;                 // not certifiable in float64: full scan
+        }
+        if (level == 3) {
+            bd = INFINITY; bi = 0x7fffffff;
+            for (int v = 0; v < h.n; ++v) {
+                double d = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (d < bd) { bd = d; bi = v; }
+            }
+        }
+        idx = bi;
+    }
+    if (dist_out) {
+        *dist_out = sqrt(rdist64(q0, q1, q2, xyz[3 * (size_t)idx], xyz[3 * (size_t)idx + 1], xyz[3 * (size_t)idx + 2]));
+    }
+    NNResult r; r.idx = idx; r.level = level;
+    return r;
+}
+
+// =============================================================================================
+// K4  per-point two-transform blend + final nearest neighbour in the whole target mesh
+//     (p2p_matching_seg_icp.py:452-489; get_triangle_angles :27-34 fused, cos(arccos(x)) == x)
+// =============================================================================================
+__global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
+    const int m = a.tile_mesh[blockIdx.x];
+    const int v = a.tile_first[blockIdx.x] + threadIdx.x;
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    if (v >= n) return;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const double* xyz = mesh_xyz(a, m);
+    const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+    const int u = ub + v;
+    const int ia = a.nn0[u], ib = a.nn1[u];
+    double f0 = 0.5, f1 = 0.5;
+    if (K > 1) {
+        const double* lm = mesh_lm(a, m);
+        const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
+        const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
+        const double da = a.d0[u], db = a.d1[u];
+        // get_triangle_angles(g, da, db): B opposite da, C opposite db
+        double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
+        double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
+        cosB = fmin(fmax(cosB, -1.0), 1.0);
+        cosC = fmin(fmax(cosC, -1.0), 1.0);
+        if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
+        else {
+            const double cb = fabs(cosB), cc = fabs(cosC);
+            f0 = cb / (cb + cc); f1 = cc / (cb + cc);
+        }
+    }
+    const double* Ra = a.fill_R + 9 * (size_t)(bb + ia);
+    const double* ta = a.fill_t + 3 * (size_t)(bb + ia);
+    const double* Rb = a.fill_R + 9 * (size_t)(bb + ib);
+    const double* tb = a.fill_t + 3 * (size_t)(bb + ib);
+    double ax, ay, az, bx, by, bz;
+    mat3_vec(Ra, x, y, z, ax, ay, az);
+    mat3_vec(Rb, x, y, z, bx, by, bz);
+    const double q0 = f0 * (ax + ta[0]) + f1 * (bx + tb[0]);
+    const double q1 = f0 * (ay + ta[1]) + f1 * (by + tb[1]);
+    const double q2 = f0 * (az + ta[2]) + f1 * (bz + tb[2]);
+    const int mt = pair_mesh(a, m);
+    const GridHdr h = a.grid_hdr[mt];
+    NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
+                              q0, q1, q2, a.counters, nullptr);
+    if (m < a.S) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
+}
+
+// raw query: nearest target (mesh1 side) of every mesh2-side vertex, with distance (get_NN_in_target)
+__global__ void __launch_bounds__(LIP_TILE) nn_query_kernel(LipArgs a) {
+    const int m = a.tile_mesh[blockIdx.x];
+    const int v = a.tile_first[blockIdx.x] + threadIdx.x;
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    if (v >= n) return;
+    const double* xyz = mesh_xyz(a, m);
+    const int mt = pair_mesh(a, m);
+    const GridHdr h = a.grid_hdr[mt];
+    double dist;
+    NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
+                              xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.counters, &dist);
+    const int u = ub + v;
+    if (m < a.S) a.T12[u] = r.idx; else { a.T21[u - a.n1_total] = r.idx; if (a.q_dist) a.q_dist[u - a.n1_total] = dist; }
+}
+
+// =============================================================================================
+// get_best_fit_transform on its own (registration_icp.py:8-46): one CTA
+// =============================================================================================
+__global__ void __launch_bounds__(256) kabsch_kernel(const double* __restrict__ A, const double* __restrict__ Bp, int n,
+                                                     double* R_out, double* t_out, int* status) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += 256) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s[k] += A[3 * (size_t)i + k]; s[3 + k] += Bp[3 * (size_t)i + k]; }
+    }
+    double ca[3], cb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ca[k] = block_sum(s[k], red, tid) / n; cb[k] = block_sum(s[3 + k], red, tid) / n; }
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += 256) {
+        double a0 = A[3 * (size_t)i] - ca[0], a1 = A[3 * (size_t)i + 1] - ca[1], a2 = A[3 * (size_t)i + 2] - ca[2];
+        double b0 = Bp[3 * (size_t)i] - cb[0], b1 = Bp[3 * (size_t)i + 1] - cb[1], b2 = Bp[3 * (size_t)i + 2] - cb[2];
+        H[0] += a0 * b0; H[1] += a0 * b1; H[2] += a0 * b2;
+        H[3] += a1 * b0; H[4] += a1 * b1; H[5] += a1 * b2;
+        H[6] += a2 * b0; H[7] += a2 * b1; H[8] += a2 * b2;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = block_sum(H[k], red, tid);
+    if (tid == 0) {
+        double R[9];
+        int deg = kabsch_rotation(H, R);
+        double x, y, z;
+        mat3_vec(R, ca[0], ca[1], ca[2], x, y, z);
+        for (int k = 0; k < 9; ++k) R_out[k] = R[k];
+        t_out[0] = cb[0] - x; t_out[1] = cb[1] - y; t_out[2] = cb[2] - z;
+        *status = deg ? 2 : 1;
+    }
+}
+
+// get_triangle_angles (p2p_matching_seg_icp.py:27-34), n triangles
+__global__ void triangle_angles_kernel(const double* __restrict__ abc, int n, double eps, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double sa = abc[3 * (size_t)i], sb = abc[3 * (size_t)i + 1], sc = abc[3 * (size_t)i + 2];
+    out[3 * (size_t)i] = acos((sb * sb + sc * sc - sa * sa) / (2 * sc * sb + eps));
+    out[3 * (size_t)i + 1] = acos((sc * sc + sa * sa - sb * sb) / (2 * sa * sc + eps));
+    out[3 * (size_t)i + 2] = acos((sa * sa + sb * sb - sc * sc) / (2 * sa * sb + eps));
+}

@@ -1,0 +1,507 @@
+// liblocalicp.so — C ABI (include/local_icp.h) over the sm_100a kernels in lip_kernels.cuh.
+// Host side: batch planning (CSR -> mesh / bin / tile descriptors), workspace, launches.
+#include "../../include/local_icp.h"
+#include "lip_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#ifndef LIP_ARCH
+#define LIP_ARCH 100
+#endif
+
+namespace {
+
+std::string g_startup_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
+
+}  // namespace
+
+struct lip_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int small_blocks_per_sm = 1, big_blocks_per_sm = 1;
+    cudaStream_t stream = nullptr;
+    lip_params params;
+    std::string err;
+    // plan
+    bool planned = false;
+    int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0;
+    int M = 0, B = 0, n_tiles = 0, tab_total = 0, directions = 3;
+    std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first;
+    DevBuf d_plan;      // all plan arrays in one allocation
+    int *mesh_ubase = nullptr, *mesh_bin = nullptr, *mesh_tab = nullptr, *bin_mesh = nullptr, *tile_mesh = nullptr,
+        *tile_first = nullptr;
+    // workspace
+    DevBuf ws;
+    LipArgs args;
+    // device copies of host-API inputs / outputs
+    DevBuf in_xyz1, in_xyz2, in_lm1, in_lm2, out_T21, out_T12, misc;
+    int64_t last_launches = 0;
+};
+
+namespace {
+
+int fail(lip_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_startup_error = msg;
+    return code;
+}
+#define LIP_CUDA(c, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, LIP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int next_pow2(int64_t x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// carve the workspace and fill the LipArgs pointers that do not depend on the run
+int carve_workspace(lip_ctx* c) {
+    const size_t n = (size_t)(c->n1 + c->n2), B = (size_t)c->B, M = (size_t)c->M;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t o_nn0 = take(n * 4), o_nn1 = take(n * 4), o_d0 = take(n * 8), o_d1 = take(n * 8);
+    const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4);
+    const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
+    const size_t o_fR = take(B * 72), o_ft = take(B * 24);
+    const size_t o_sched = take(8 * 4), o_small = take(B * 4), o_big = take(B * 4);
+    const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
+    const size_t o_cnt = take(8 * 8);
+    LIP_CUDA(c, c->ws.ensure(off));
+    char* base = c->ws.as<char>();
+    LipArgs& a = c->args;
+    a.nn0 = (int*)(base + o_nn0); a.nn1 = (int*)(base + o_nn1);
+    a.d0 = (double*)(base + o_d0); a.d1 = (double*)(base + o_d1);
+    a.bin_off = (int*)(base + o_binoff); a.part_vid = (int*)(base + o_vid);
+    a.icp_R = (double*)(base + o_R); a.icp_t = (double*)(base + o_t);
+    a.icp_iters = (int*)(base + o_it); a.icp_status = (int*)(base + o_stat);
+    a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft);
+    a.sched = (int*)(base + o_sched); a.small_list = (int*)(base + o_small); a.big_list = (int*)(base + o_big);
+    a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
+    a.counters = (unsigned long long*)(base + o_cnt);
+    return LIP_OK;
+}
+
+void set_param_args(lip_ctx* c) {
+    LipArgs& a = c->args;
+    a.max_iter = c->params.max_iter;
+    a.rise_tol = c->params.cost_rise_tol;
+    a.flat_tol = c->params.cost_flat_tol;
+    a.obtuse_cos = std::sin(c->params.obtuse_eps);          // C > pi/2 - eps  <=>  cos C < sin(eps)
+    a.cos_den_eps = c->params.cos_den_eps;
+    a.reject_dist = c->params.reject_dist;
+}
+
+int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+    if (!c) return LIP_EINVAL;
+    c->planned = false;
+    if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
+    if ((directions & LIP_DIR_BOTH) == 0) return fail(c, LIP_EINVAL, "plan: directions must include T21 and/or T12");
+    if (off1[0] != 0 || off2[0] != 0 || lm_off[0] != 0) return fail(c, LIP_EINVAL, "plan: offsets must start at 0");
+    int64_t maxK = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        if (off1[s + 1] <= off1[s] || off2[s + 1] <= off2[s])
+            return fail(c, LIP_EINVAL, "plan: segment pair " + std::to_string(s) + " has an empty mesh");
+        int64_t K = lm_off[s + 1] - lm_off[s];
+        if (K <= 0) return fail(c, LIP_EINVAL, "plan: segment pair " + std::to_string(s) + " has no landmarks");
+        if (K > LIP_MAX_LANDMARKS) return fail(c, LIP_EINVAL, "plan: more than LIP_MAX_LANDMARKS landmarks in a segment");
+        maxK = std::max(maxK, K);
+    }
+    const int64_t n1 = off1[S], n2 = off2[S], sumK = lm_off[S];
+    if (n1 + n2 >= (int64_t)1 << 30 || 2 * S >= (int64_t)1 << 28)
+        return fail(c, LIP_EINVAL, "plan: batch too large for 32-bit indexing; split it");
+    c->S = S; c->n1 = n1; c->n2 = n2; c->sumK = sumK; c->maxK = maxK;
+    c->M = (int)(2 * S); c->B = (int)(2 * sumK); c->directions = directions & LIP_DIR_BOTH;
+    const int M = c->M;
+    c->h_mesh_ubase.assign(M + 1, 0); c->h_mesh_bin.assign(M + 1, 0); c->h_mesh_tab.assign(M + 1, 0);
+    c->h_bin_mesh.assign(c->B, 0);
+    for (int64_t s = 0; s <= S; ++s) {
+        if (s < S) {
+            c->h_mesh_ubase[s] = (int)off1[s]; c->h_mesh_ubase[S + s] = (int)(n1 + off2[s]);
+            c->h_mesh_bin[s] = (int)lm_off[s]; c->h_mesh_bin[S + s] = (int)(sumK + lm_off[s]);
+        }
+    }
+    c->h_mesh_ubase[M] = (int)(n1 + n2);
+    c->h_mesh_bin[M] = (int)(2 * sumK);
+    int64_t tab = 0;
+    for (int m = 0; m < M; ++m) {
+        c->h_mesh_tab[m] = (int)tab;
+        int64_t n = c->h_mesh_ubase[m + 1] - c->h_mesh_ubase[m];
+        tab += next_pow2(std::max<int64_t>(n, 32)) + 2;
+        if (tab >= (int64_t)1 << 30) return fail(c, LIP_EINVAL, "plan: hash tables too large");
+        for (int b = c->h_mesh_bin[m]; b < c->h_mesh_bin[m + 1]; ++b) c->h_bin_mesh[b] = m;
+    }
+    c->h_mesh_tab[M] = (int)tab;
+    c->tab_total = (int)tab;
+    // tiles of the per-vertex kernels: source meshes of the requested directions
+    c->h_tile_mesh.clear(); c->h_tile_first.clear();
+    for (int m = 0; m < M; ++m) {
+        bool active = (m >= S) ? (c->directions & 1) : (c->directions & 2);
+        if (!active) continue;
+        int n = c->h_mesh_ubase[m + 1] - c->h_mesh_ubase[m];
+        for (int f = 0; f < n; f += LIP_TILE) { c->h_tile_mesh.push_back(m); c->h_tile_first.push_back(f); }
+    }
+    c->n_tiles = (int)c->h_tile_mesh.size();
+    // upload
+    size_t off = 0;
+    auto take = [&](size_t cnt) { size_t o = off; off = align_up(off + cnt * 4); return o; };
+    const size_t o0 = take(M + 1), o1 = take(M + 1), o2 = take(M + 1), o3 = take(c->B), o4 = take(c->n_tiles), o5 = take(c->n_tiles);
+    LIP_CUDA(c, c->d_plan.ensure(off));
+    char* base = c->d_plan.as<char>();
+    c->mesh_ubase = (int*)(base + o0); c->mesh_bin = (int*)(base + o1); c->mesh_tab = (int*)(base + o2);
+    c->bin_mesh = (int*)(base + o3); c->tile_mesh = (int*)(base + o4); c->tile_first = (int*)(base + o5);
+    auto up = [&](int* d, const std::vector<int>& h) {
+        return h.empty() ? cudaSuccess : cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    };
+    LIP_CUDA(c, up(c->mesh_ubase, c->h_mesh_ubase)); LIP_CUDA(c, up(c->mesh_bin, c->h_mesh_bin));
+    LIP_CUDA(c, up(c->mesh_tab, c->h_mesh_tab)); LIP_CUDA(c, up(c->bin_mesh, c->h_bin_mesh));
+    LIP_CUDA(c, up(c->tile_mesh, c->h_tile_mesh)); LIP_CUDA(c, up(c->tile_first, c->h_tile_first));
+    LIP_CUDA(c, cudaStreamSynchronize(c->stream));           // host vectors may be rewritten by the next plan
+    int rc = carve_workspace(c);
+    if (rc) return rc;
+    LipArgs& a = c->args;
+    a.S = (int)S; a.M = M; a.B = c->B; a.sumK = (int)sumK; a.n1_total = (int)n1; a.n_total = (int)(n1 + n2);
+    a.dir_mask = c->directions; a.n_tiles = c->n_tiles;
+    a.mesh_ubase = c->mesh_ubase; a.mesh_bin = c->mesh_bin; a.mesh_tab = c->mesh_tab; a.bin_mesh = c->bin_mesh;
+    a.tile_mesh = c->tile_mesh; a.tile_first = c->tile_first;
+    a.q_dist = nullptr;
+    c->planned = true;
+    return LIP_OK;
+}
+
+int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+               long long* T21, long long* T12, double* q_dist, int stages, cudaStream_t st) {
+    if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
+    LipArgs& a = c->args;
+    a.xyz1 = xyz1; a.xyz2 = xyz2; a.lm1 = lm1; a.lm2 = lm2; a.T21 = T21; a.T12 = T12; a.q_dist = q_dist;
+    set_param_args(c);
+    int64_t launches = 0;
+    LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 8 * 4, st));
+    LIP_CUDA(c, cudaMemsetAsync(a.counters, 0, 8 * 8, st));
+    if (stages & ST_PARTITION) {
+        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 2 + 1) * 4;
+        landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
+        ++launches;
+    }
+    if (stages & ST_ICP) {
+        icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
+        int gs = c->sm_count * c->small_blocks_per_sm;
+        gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
+        icp_small_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+        // a partition is "big" only if src or tgt exceeds LIP_SMALL_CAP points
+        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
+        int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
+        icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
+        launches += 3;
+    }
+    if (stages & (ST_GRID | ST_GRID_ALL)) {
+        LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, st));
+        grid_build_kernel<<<c->M, 256, 0, st>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
+        ++launches;
+    }
+    if (stages & ST_FILL) {
+        fill_kernel<<<(c->M + 127) / 128, 128, 0, st>>>(a);
+        ++launches;
+    }
+    if ((stages & ST_BLEND) && c->n_tiles > 0) {
+        blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
+        ++launches;
+    }
+    if ((stages & ST_QUERY) && c->n_tiles > 0) {
+        nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
+        ++launches;
+    }
+    LIP_CUDA(c, cudaGetLastError());
+    c->last_launches = launches;
+    return LIP_OK;
+}
+
+const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID | ST_FILL | ST_BLEND;
+
+}  // namespace
+
+extern "C" {
+
+int lip_version(void) { return 1; }
+int lip_compiled_arch(void) { return LIP_ARCH; }
+
+void lip_default_params(lip_params* p) {
+    if (!p) return;
+    p->max_iter = 500;
+    p->cost_rise_tol = 1e-4;
+    p->cost_flat_tol = 0.01;
+    p->obtuse_eps = 1e-5;
+    p->cos_den_eps = 1e-5;
+    p->reject_dist = std::numeric_limits<double>::infinity();
+}
+
+const char* lip_last_error(const lip_ctx* ctx) { return ctx ? ctx->err.c_str() : g_startup_error.c_str(); }
+
+int lip_create(lip_ctx** out, int device) {
+    if (!out) return LIP_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, LIP_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (device < 0 || device >= count) return fail(nullptr, LIP_EINVAL, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
+    if (prop.major * 10 + prop.minor != LIP_ARCH)
+        return fail(nullptr, LIP_ENODEV, "liblocalicp was built for sm_" + std::to_string(LIP_ARCH) + "a only; device is sm_" +
+                                             std::to_string(prop.major * 10 + prop.minor));
+    lip_ctx* c = new lip_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    lip_default_params(&c->params);
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_small_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS>,
+                                                      LIP_SMALL_WARPS * 32, 0) == cudaSuccess && nb > 0)
+        c->small_blocks_per_sm = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
+        c->big_blocks_per_sm = nb;
+    cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         LIP_MAX_LANDMARKS * 32 + 64);
+    memset(&c->args, 0, sizeof(c->args));
+    *out = c;
+    return LIP_OK;
+}
+
+void lip_destroy(lip_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc})
+        b->release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int lip_set_params(lip_ctx* c, const lip_params* p) {
+    if (!c || !p) return LIP_EINVAL;
+    if (p->max_iter < 1) return fail(c, LIP_EINVAL, "max_iter must be >= 1");
+    c->params = *p;
+    return LIP_OK;
+}
+
+int lip_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return LIP_EINVAL;
+    return cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? LIP_OK : LIP_ECUDA;
+}
+int lip_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LIP_OK : LIP_ECUDA; }
+
+int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+    if (!c) return LIP_EINVAL;
+    cudaSetDevice(c->device);
+    return plan_impl(c, S, off1, off2, lm_off, directions);
+}
+
+int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                         int64_t* T21, int64_t* T12, void* stream) {
+    if (!c) return LIP_EINVAL;
+    if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
+    if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
+    cudaSetDevice(c->device);
+    return run_stages(c, xyz1, xyz2, lm1, lm2, (long long*)T21, (long long*)T12, nullptr, kFullPipeline,
+                      stream ? (cudaStream_t)stream : c->stream);
+}
+
+int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                       int64_t* T21, int64_t* T12) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
+    if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
+    if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
+    int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
+                        c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
+    if (rc) return rc;
+    if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
+    if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    return LIP_OK;
+}
+
+int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, int32_t* iters21, int32_t* status21,
+                             double* R12, double* t12, int32_t* iters12, int32_t* status12) {
+    if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    const LipArgs& a = c->args;
+    const size_t K = (size_t)c->sumK;
+    const double* R = filled ? a.fill_R : a.icp_R;
+    const double* t = filled ? a.fill_t : a.icp_t;
+    // bins [0, sumK): src = mesh1 -> T12 ICPs ; bins [sumK, 2 sumK): src = mesh2 -> T21 ICPs
+    if (R12) LIP_CUDA(c, cudaMemcpy(R12, R, K * 72, cudaMemcpyDeviceToHost));
+    if (t12) LIP_CUDA(c, cudaMemcpy(t12, t, K * 24, cudaMemcpyDeviceToHost));
+    if (iters12) LIP_CUDA(c, cudaMemcpy(iters12, a.icp_iters, K * 4, cudaMemcpyDeviceToHost));
+    if (status12) LIP_CUDA(c, cudaMemcpy(status12, a.icp_status, K * 4, cudaMemcpyDeviceToHost));
+    if (R21) LIP_CUDA(c, cudaMemcpy(R21, R + 9 * K, K * 72, cudaMemcpyDeviceToHost));
+    if (t21) LIP_CUDA(c, cudaMemcpy(t21, t + 3 * K, K * 24, cudaMemcpyDeviceToHost));
+    if (iters21) LIP_CUDA(c, cudaMemcpy(iters21, a.icp_iters + K, K * 4, cudaMemcpyDeviceToHost));
+    if (status21) LIP_CUDA(c, cudaMemcpy(status21, a.icp_status + K, K * 4, cudaMemcpyDeviceToHost));
+    return LIP_OK;
+}
+
+int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
+    if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (side != 1 && side != 2) return fail(c, LIP_EINVAL, "side must be 1 or 2");
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    const LipArgs& a = c->args;
+    const size_t first = side == 1 ? 0 : (size_t)c->n1, n = side == 1 ? (size_t)c->n1 : (size_t)c->n2;
+    std::vector<int> i0(n), i1(n);
+    std::vector<double> e0(n), e1(n);
+    LIP_CUDA(c, cudaMemcpy(i0.data(), a.nn0 + first, n * 4, cudaMemcpyDeviceToHost));
+    LIP_CUDA(c, cudaMemcpy(i1.data(), a.nn1 + first, n * 4, cudaMemcpyDeviceToHost));
+    LIP_CUDA(c, cudaMemcpy(e0.data(), a.d0 + first, n * 8, cudaMemcpyDeviceToHost));
+    LIP_CUDA(c, cudaMemcpy(e1.data(), a.d1 + first, n * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        if (nn) { nn[2 * i] = i0[i]; nn[2 * i + 1] = i1[i]; }
+        if (dist) { dist[2 * i] = e0[i]; dist[2 * i + 1] = e1[i]; }
+    }
+    return LIP_OK;
+}
+
+int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
+    if (!c || !c->planned || !counters) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    unsigned long long h[8];
+    int sched[8];
+    LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    LIP_CUDA(c, cudaMemcpy(sched, c->args.sched, sizeof(sched), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];
+    counters[0] = sched[0]; counters[1] = sched[1];
+    counters[6] = c->last_launches;
+    return LIP_OK;
+}
+
+int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_off, const double* tgt,
+                 const int64_t* tgt_off, double* R, double* t, int32_t* iters, int32_t* status) {
+    if (!c) return LIP_EINVAL;
+    if (P <= 0 || !src || !src_off || !tgt || !tgt_off) return fail(c, LIP_EINVAL, "icp: bad arguments");
+    cudaSetDevice(c->device);
+    std::vector<int64_t> lm_off(P + 1);
+    for (int64_t i = 0; i <= P; ++i) lm_off[i] = i;
+    // mesh1 = target, mesh2 = source, one (unused) landmark per mesh -> one whole-mesh partition each
+    int rc = plan_impl(c, P, tgt_off, src_off, lm_off.data(), LIP_DIR_T21);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, tgt, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, src, b2, cudaMemcpyHostToDevice, st));
+    // the landmark of mesh m is read at lm[3*m]; any finite point will do (P <= n because no mesh is empty)
+    rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_xyz1.as<double>(), c->in_xyz2.as<double>(),
+                    nullptr, nullptr, nullptr, ST_PARTITION | ST_ICP, st);
+    if (rc) return rc;
+    const LipArgs& a = c->args;
+    const size_t K = (size_t)P;
+    if (R) LIP_CUDA(c, cudaMemcpyAsync(R, a.icp_R + 9 * K, K * 72, cudaMemcpyDeviceToHost, st));
+    if (t) LIP_CUDA(c, cudaMemcpyAsync(t, a.icp_t + 3 * K, K * 24, cudaMemcpyDeviceToHost, st));
+    if (iters) LIP_CUDA(c, cudaMemcpyAsync(iters, a.icp_iters + K, K * 4, cudaMemcpyDeviceToHost, st));
+    if (status) LIP_CUDA(c, cudaMemcpyAsync(status, a.icp_status + K, K * 4, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    c->planned = false;                                      // internal plan: not a user batch
+    return LIP_OK;
+}
+
+int lip_nn_host(lip_ctx* c, const double* src, int64_t n, const double* tgt, int64_t m, double* dist, int64_t* idx) {
+    if (!c) return LIP_EINVAL;
+    if (n <= 0 || m <= 0 || !src || !tgt || !idx) return fail(c, LIP_EINVAL, "nn: bad arguments");
+    cudaSetDevice(c->device);
+    const int64_t off1[2] = {0, m}, off2[2] = {0, n}, lmo[2] = {0, 1};
+    int rc = plan_impl(c, 1, off1, off2, lmo, LIP_DIR_T21);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    LIP_CUDA(c, c->in_xyz1.ensure((size_t)m * 24)); LIP_CUDA(c, c->in_xyz2.ensure((size_t)n * 24));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)n * 8)); LIP_CUDA(c, c->misc.ensure((size_t)n * 8));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, tgt, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, src, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_xyz1.as<double>(), c->in_xyz2.as<double>(),
+                    c->out_T21.as<long long>(), nullptr, c->misc.as<double>(), ST_GRID | ST_QUERY, st);
+    if (rc) return rc;
+    LIP_CUDA(c, cudaMemcpyAsync(idx, c->out_T21.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (dist) LIP_CUDA(c, cudaMemcpyAsync(dist, c->misc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    c->planned = false;
+    return LIP_OK;
+}
+
+int lip_kabsch_host(lip_ctx* c, const double* A, const double* Bp, int64_t n, double* R, double* t, int32_t* status) {
+    if (!c) return LIP_EINVAL;
+    if (n <= 0 || n >= ((int64_t)1 << 30) || !A || !Bp || !R || !t) return fail(c, LIP_EINVAL, "kabsch: bad arguments");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    LIP_CUDA(c, c->in_xyz1.ensure((size_t)n * 24)); LIP_CUDA(c, c->in_xyz2.ensure((size_t)n * 24));
+    LIP_CUDA(c, c->misc.ensure(128));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, A, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, Bp, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    double* d = c->misc.as<double>();
+    kabsch_kernel<<<1, 256, 0, st>>>(c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), (int)n, d, d + 9, (int*)(d + 12));
+    LIP_CUDA(c, cudaGetLastError());
+    double h[13];
+    LIP_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    memcpy(R, h, 72); memcpy(t, h + 9, 24);
+    if (status) memcpy(status, h + 12, 4);
+    c->last_launches = 1;
+    return LIP_OK;
+}
+
+int lip_triangle_angles_host(lip_ctx* c, const double* abc, int64_t n, double* angles) {
+    if (!c) return LIP_EINVAL;
+    if (n <= 0 || n >= ((int64_t)1 << 30) || !abc || !angles) return fail(c, LIP_EINVAL, "triangle_angles: bad arguments");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    LIP_CUDA(c, c->in_xyz1.ensure((size_t)n * 24)); LIP_CUDA(c, c->in_xyz2.ensure((size_t)n * 24));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, abc, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    triangle_angles_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(c->in_xyz1.as<double>(), (int)n, c->params.cos_den_eps,
+                                                                  c->in_xyz2.as<double>());
+    LIP_CUDA(c, cudaGetLastError());
+    LIP_CUDA(c, cudaMemcpyAsync(angles, c->in_xyz2.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    c->last_launches = 1;
+    return LIP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+/*
+ * local_icp.h — C ABI of liblocalicp.so: B200 (sm_100a) local-ICP point-to-point matching.
+ *
+ * Drop-in boundary for the hot path of romi/4d_plant_analysis (paths below are relative to the
+ * reference root).  The reference has no FFI of its own — its boundary is five Python functions —
+ * so each entry point names the Python function whose arithmetic it replaces; INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; float64 coordinates in row-major (n,3) arrays exactly as numpy
+ *     hands them over; int64 CSR offsets; int64 index outputs (numpy intp), like the reference.
+ *   - *_host entry points take HOST pointers (pageable or pinned) and do H2D, kernels, D2H and a
+ *     stream synchronise; *_device entry points take DEVICE pointers, enqueue on `stream`
+ *     (a cudaStream_t passed as void*) and return without synchronising.
+ *   - every function returns 0 on success, a negative LIP_E* code otherwise;
+ *     lip_last_error(ctx) gives the message.
+ *   - there is no CPU path: without a CUDA device lip_create fails with LIP_ENODEV.
+ */
+#ifndef LOCAL_ICP_H
+#define LOCAL_ICP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIP_OK        0
+#define LIP_ENODEV   -1   /* no CUDA device / CUDA runtime error at start-up */
+#define LIP_EINVAL   -2   /* bad argument (empty mesh, K mismatch, K too large, null pointer ...) */
+#define LIP_ECUDA    -3   /* CUDA runtime error, see lip_last_error */
+#define LIP_ENOPLAN  -4   /* run called before plan */
+
+#define LIP_DIR_T21   1   /* mesh2 -> mesh1 map  (p2p_matching_seg_icp.py:173) */
+#define LIP_DIR_T12   2   /* mesh1 -> mesh2 map  (p2p_matching_seg_icp.py:175) */
+#define LIP_DIR_BOTH  3
+
+#define LIP_MAX_LANDMARKS 2048   /* per segment */
+
+typedef struct lip_ctx lip_ctx;
+
+/* Constants the reference hard-codes (registration/registration_icp.py:79,87;
+ * p2p_matching_in_organ/p2p_matching_seg_icp.py:30-32,471).  lip_default_params fills the
+ * reference values; reject_dist is the north star's correspondence-reject hook — the reference
+ * rejects nothing, so the default is +inf. */
+typedef struct lip_params {
+    int32_t max_iter;        /* 500 */
+    double  cost_rise_tol;   /* 1e-4 */
+    double  cost_flat_tol;   /* 0.01 */
+    double  obtuse_eps;      /* 1e-5 */
+    double  cos_den_eps;     /* 1e-5 */
+    double  reject_dist;     /* +inf: pairs farther than this are left out of the Kabsch sums */
+} lip_params;
+
+void lip_default_params(lip_params* p);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int  lip_create(lip_ctx** ctx, int device);
+void lip_destroy(lip_ctx* ctx);
+const char* lip_last_error(const lip_ctx* ctx);   /* ctx may be NULL: start-up error */
+int  lip_set_params(lip_ctx* ctx, const lip_params* p);
+/* pinned host memory for the *_host entry points (optional; any host pointer works) */
+int  lip_host_alloc(void** p, uint64_t bytes);
+int  lip_host_free(void* p);
+
+/* ---- batched segment-pair maps --------------------------------------------------------------
+ * Replaces, for S matched segment pairs at once, the pair of calls
+ *   T21 = get_p2p_mapping_from_segments_using_icp(mesh1, mesh2, lm1, lm2, vs)
+ *   T12 = get_p2p_mapping_from_segments_using_icp(mesh2, mesh1, lm2, lm1, vs)
+ * (p2p_matching_in_organ/p2p_matching_seg_icp.py:383-489, call site :173-176), including
+ * my_icp / get_best_fit_transform / get_NN_in_target (registration/registration_icp.py:8-98) and
+ * the sklearn KDTree queries they make.
+ *
+ * lip_batch_plan: CSR description of the batch (host arrays, copied).
+ *   off1, off2 : (S+1) vertex offsets of mesh1 / mesh2 of every pair;  lm_off : (S+1) landmark
+ *   offsets (lm1 and lm2 of a pair have the same count, p2p_matching_seg_icp.py:408-416).
+ * lip_batch_run_*:
+ *   xyz1 (off1[S],3), xyz2 (off2[S],3), lm1, lm2 (lm_off[S],3) float64.
+ *   T21 (off2[S]) : T21[off2[s]+i] = index in mesh1 of pair s matched to vertex i of mesh2;
+ *   T12 (off1[S]) likewise.  Either may be NULL when its direction is not requested. */
+int lip_batch_plan(lip_ctx* ctx, int64_t S, const int64_t* off1, const int64_t* off2,
+                   const int64_t* lm_off, int directions);
+int lip_batch_run_host(lip_ctx* ctx, const double* xyz1, const double* xyz2,
+                       const double* lm1, const double* lm2, int64_t* T21, int64_t* T12);
+int lip_batch_run_device(lip_ctx* ctx, const double* d_xyz1, const double* d_xyz2,
+                         const double* d_lm1, const double* d_lm2,
+                         int64_t* d_T21, int64_t* d_T12, void* stream);
+
+/* Per-landmark results of the last run, copied to host (any pointer may be NULL).
+ * Row b of the "21" arrays is landmark b of the flattened lm arrays for the mesh2 -> mesh1 ICPs
+ * (src = mesh2 vertices nearest lm2[b], tgt = mesh1 vertices nearest lm1[b]); "12" is the swap.
+ *   R (sumK,3,3), t (sumK,3): my_icp's R, t (x -> R x + t) — AFTER the fill of
+ *   p2p_matching_seg_icp.py:422-437 if filled != 0, raw (garbage where status==0) otherwise;
+ *   iters: NN passes; status: 0 = no ICP (empty src or tgt partition), 1 = ran,
+ *   2 = ran and a Kabsch solve was rank-deficient (R is not unique, SURVEY.md §7 hard part 2). */
+int lip_batch_get_transforms(lip_ctx* ctx, int filled,
+                             double* R21, double* t21, int32_t* iters21, int32_t* status21,
+                             double* R12, double* t12, int32_t* iters12, int32_t* status12);
+/* Landmark assignment of the last run: two nearest landmarks (local index in the pair's lm array)
+ * and their distances for every vertex: KDTree(lm).query(xyz, k=2) of p2p_matching_seg_icp.py:388-392.
+ * nn (n,2) int32, dist (n,2) float64; side 1 -> mesh1 vertices (off1 order), 2 -> mesh2. */
+int lip_batch_get_landmark_nn(lip_ctx* ctx, int side, int32_t* nn, double* dist);
+/* counters of the last run: [0] small-partition ICPs, [1] large-partition ICPs, [2] float64
+ * re-evaluations of near-tied neighbours in ICP, [3] same in the final map, [4] final-map queries
+ * that needed ring 2, [5] that fell back to a full scan, [6] kernels launched by the last run */
+int lip_batch_get_counters(lip_ctx* ctx, int64_t counters[8]);
+
+/* ---- the three registration_icp.py functions on their own ----------------------------------- */
+/* my_icp for P independent (src, tgt) problems in CSR form (registration_icp.py:60-98):
+ * src (src_off[P],3), tgt (tgt_off[P],3) -> R (P,3,3), t (P,3) with x -> R x + t, iters (P). */
+int lip_icp_host(lip_ctx* ctx, int64_t P, const double* src, const int64_t* src_off,
+                 const double* tgt, const int64_t* tgt_off,
+                 double* R, double* t, int32_t* iters, int32_t* status);
+/* get_NN_in_target (registration_icp.py:49-57): for each of n src points the exact Euclidean
+ * nearest of m tgt points: dist (n) float64 (sqrt applied), idx (n) int64. */
+int lip_nn_host(lip_ctx* ctx, const double* src, int64_t n, const double* tgt, int64_t m,
+                double* dist, int64_t* idx);
+/* get_best_fit_transform (registration_icp.py:8-46): Kabsch fit of n paired points A -> B:
+ * R (3,3), t (3) with B ~ R A + t. */
+int lip_kabsch_host(lip_ctx* ctx, const double* A, const double* B, int64_t n,
+                    double* R, double* t, int32_t* status);
+/* get_triangle_angles (p2p_matching_seg_icp.py:27-34) for n triangles: abc (n,3) side lengths ->
+ * angles (n,3) in radians, opposite a, b, c. */
+int lip_triangle_angles_host(lip_ctx* ctx, const double* abc, int64_t n, double* angles);
+
+/* library/ABI version and the SM architecture the kernels were compiled for (100) */
+int lip_version(void);
+int lip_compiled_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCAL_ICP_H */

@@ -1,0 +1,273 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors of the unmodified
+reference and against the oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): NN / map indices identical except where the two candidates'
+distances differ by < 1e-6 relative; R, t within 1e-5 on partitions whose Kabsch solves are not rank
+deficient; identical iteration counts.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_segments, load_golden
+from oracle import local_icp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RT_TOL = 1e-5          # north_star: rotations / translations within 1e-5
+TIE_RTOL = 1e-6        # north_star: ties within 1e-6 relative distance
+
+
+@pytest.fixture(scope="module")
+def L():
+    mod = importlib.import_module("4d_plant_analysis_b200")
+    mod.default_context()          # raises without a B200 + built library: no fallback
+    return mod
+
+
+def _batch_from_golden(L, g):
+    return L.SegmentPairBatch(g["xyz1"], g["xyz2"], g["off1"], g["off2"], g["lm1"], g["lm2"], g["lm_off"],
+                              np.zeros(len(g["off1"]) - 1, np.int32))
+
+
+def _assert_map_equal_up_to_ties(T_gpu, T_ref, x_query, x_target, what):
+    bad = np.nonzero(T_gpu != T_ref)[0]
+    for i in bad:
+        da = np.linalg.norm(x_query[i] - x_target[T_gpu[i]])
+        db = np.linalg.norm(x_query[i] - x_target[T_ref[i]])
+        assert abs(da - db) <= TIE_RTOL * max(da, db), f"{what}: vertex {i}: gpu {T_gpu[i]} (d={da}) ref {T_ref[i]} (d={db})"
+    return len(bad)
+
+
+def _check_against_reference_rows(res, g, keys=("21", "12")):
+    """per-partition R, t, iterations against golden rows recorded from the reference's my_icp"""
+    raw = res.transforms["raw"]
+    n_checked = 0
+    for d in keys:
+        v = g["v" + d]
+        st = raw["status" + d]
+        np.testing.assert_array_equal(st != 0, v, err_msg=f"which ICPs ran ({d})")
+        ok = v & (st == 1)
+        np.testing.assert_array_equal(raw["iters" + d][ok], g["it" + d][ok], err_msg=f"iteration counts ({d})")
+        np.testing.assert_allclose(raw["R" + d][ok], g["R" + d][ok], rtol=0, atol=RT_TOL)
+        np.testing.assert_allclose(raw["t" + d][ok], g["t" + d][ok], rtol=0, atol=RT_TOL)
+        n_checked += int(ok.sum())
+    return n_checked
+
+
+@pytest.mark.parametrize("case", ["c1_small", "c2_small", "c3_small", "c5_small"])
+def test_golden_batch(L, case):
+    g = load_golden(case)
+    res = L.local_icp_batch(_batch_from_golden(L, g), details=True)
+    assert res.T21.dtype == np.int64 and res.T12.dtype == np.int64
+    n_checked = _check_against_reference_rows(res, g)
+    assert n_checked >= 0.9 * (g["v21"].sum() + g["v12"].sum())
+    n_ties = 0
+    for s, x1, x2, l1, l2 in golden_segments(g):
+        a, b, c, d = g["off1"][s], g["off1"][s + 1], g["off2"][s], g["off2"][s + 1]
+        det = {}
+        O.segment_map(x1, x2, l1, l2, nn="kdtree", details=det)
+        n_ties += _assert_map_equal_up_to_ties(res.T21[c:d], g["T21"][c:d], det["x2t"], x1, f"{case} T21 seg {s}")
+        det = {}
+        O.segment_map(x2, x1, l2, l1, nn="kdtree", details=det)
+        n_ties += _assert_map_equal_up_to_ties(res.T12[a:b], g["T12"][a:b], det["x2t"], x2, f"{case} T12 seg {s}")
+    assert n_ties <= 1e-3 * (len(res.T21) + len(res.T12))
+
+
+def test_golden_tiny_edge_cases(L):
+    """1..90-point meshes, K = 1..4: rank-deficient partitions are excluded from the R/t comparison
+    (their rotation is not unique), everything else must match."""
+    g = load_golden("tiny")
+    res = L.local_icp_batch(_batch_from_golden(L, g), details=True)
+    raw = res.transforms["raw"]
+    for d in ("21", "12"):
+        np.testing.assert_array_equal(raw["status" + d] != 0, g["v" + d])
+        ok = raw["status" + d] == 1
+        np.testing.assert_allclose(raw["R" + d][ok], g["R" + d][ok], rtol=0, atol=RT_TOL)
+        np.testing.assert_allclose(raw["t" + d][ok], g["t" + d][ok], rtol=0, atol=RT_TOL)
+        np.testing.assert_array_equal(raw["iters" + d][ok], g["it" + d][ok])
+    assert ((res.T21 >= 0).all() and (res.T12 >= 0).all())
+    for s in range(len(g["off1"]) - 1):
+        T21, T12 = res.maps(s)
+        assert T21.max() < g["off1"][s + 1] - g["off1"][s] and T12.max() < g["off2"][s + 1] - g["off2"][s]
+        e, f = g["lm_off"][s], g["lm_off"][s + 1]
+        if (raw["status21"][e:f] == 1).all():
+            np.testing.assert_array_equal(T21, g["T21"][g["off2"][s]:g["off2"][s + 1]])
+        if (raw["status12"][e:f] == 1).all():
+            np.testing.assert_array_equal(T12, g["T12"][g["off1"][s]:g["off1"][s + 1]])
+
+
+def test_landmark_assignment_matches_kdtree(L):
+    g = load_golden("c3_small")
+    ctx = L.default_context()
+    ctx.plan(g["off1"], g["off2"], g["lm_off"])
+    ctx.run_host(g["xyz1"], g["xyz2"], g["lm1"], g["lm2"])
+    nn1, d1 = ctx.landmark_nn(1)
+    nn2, d2 = ctx.landmark_nn(2)
+    for s, x1, x2, l1, l2 in golden_segments(g):
+        k = 2 if len(l1) > 1 else 1
+        for x, l, nn, dd, off in ((x1, l1, nn1, d1, g["off1"]), (x2, l2, nn2, d2, g["off2"])):
+            dr, ir = O.knn(x, l, k, "kdtree")
+            np.testing.assert_array_equal(nn[off[s]:off[s + 1], :k], ir)
+            np.testing.assert_allclose(dd[off[s]:off[s + 1], :k], dr, rtol=1e-15, atol=0)
+
+
+def test_reference_functions_unit_vectors(L):
+    u = load_golden("unit")
+    T, R, t = L.my_icp(u["icp_src"], u["icp_tgt"])
+    assert T.shape == (4, 4) and R.shape == (3, 3) and t.shape == (3, 1)
+    np.testing.assert_allclose(R, u["icp_R"], atol=RT_TOL)
+    np.testing.assert_allclose(t, u["icp_t"], atol=RT_TOL)
+    np.testing.assert_allclose(T, u["icp_T"], atol=RT_TOL)
+    d, i = L.get_NN_in_target(u["icp_src"], u["icp_tgt"])
+    assert d.shape == (len(u["icp_src"]), 1) and i.shape == (len(u["icp_src"]),) and i.dtype == np.int64
+    np.testing.assert_array_equal(i, u["nn_i"])
+    np.testing.assert_allclose(d, u["nn_d"], rtol=1e-14)
+    T, R, t = L.get_best_fit_transform(u["kab_A"], u["kab_B"])
+    assert t.shape == (3,)
+    np.testing.assert_allclose(R, u["kab_R"], atol=1e-12)
+    np.testing.assert_allclose(t, u["kab_t"], atol=1e-11)
+    np.testing.assert_allclose(T, u["kab_T"], atol=1e-11)
+    T, R, t = L.get_best_fit_transform(u["kab3_A"], u["kab3_B"])          # reflection branch
+    np.testing.assert_allclose(R, u["kab3_R"], atol=1e-12)
+    np.testing.assert_allclose(t, u["kab3_t"], atol=1e-11)
+    for (a, b, c), ang in zip(u["tri_in"], u["tri_out"]):
+        np.testing.assert_allclose(L.get_triangle_angles(a, b, c), ang, rtol=1e-14)
+
+
+def test_nn_exact_against_float64_brute_force(L):
+    rng = np.random.default_rng(3)
+    for n, m, scale, offset in [(1000, 37, 1.0, 0.0), (5000, 4000, 30.0, 100.0), (333, 1, 5.0, -50.0),
+                                (20000, 20000, 80.0, 10.0)]:
+        tgt = rng.normal(size=(m, 3)) * scale * [1.0, 0.2, 0.05] + offset
+        src = rng.normal(size=(n, 3)) * scale * [1.2, 0.25, 0.3] + offset
+        src[:5] += 50 * scale                                # far queries: ring search cannot certify -> full scan
+        d, i = L.get_NN_in_target(src, tgt)
+        dr, ir = O._knn_brute(src, tgt, 1)
+        np.testing.assert_array_equal(i, ir[:, 0])
+        np.testing.assert_allclose(d[:, 0], dr[:, 0], rtol=1e-14)
+
+
+def test_nn_duplicate_targets_lowest_index(L):
+    rng = np.random.default_rng(4)
+    tgt = rng.normal(size=(60, 3))
+    tgt[40] = tgt[7]                                           # exact duplicates: lowest index must win
+    tgt[55] = tgt[7]
+    src = np.repeat(tgt[7][None], 10, 0) + rng.normal(size=(10, 3)) * 1e-3
+    _, i = L.get_NN_in_target(src, tgt)
+    assert (i == 7).all()
+
+
+@pytest.mark.parametrize("config,scale", [(1, 1.0), (2, 0.34), (3, 0.3), (5, 0.02)])
+def test_configs_against_oracle(L, config, scale):
+    """seeded BASELINE configs at sizes the oracle finishes in seconds; both directions, whole batch"""
+    b = L.make_config(config, scale=scale)
+    res = L.local_icp_batch(b, details=True)
+    raw = res.transforms["raw"]
+    n_ties = n_part = 0
+    for s in range(b.n_segments):
+        x1, x2, l1, l2 = b.segment(s)
+        e, f = b.lm_off[s], b.lm_off[s + 1]
+        for (xt, xs, lt, ls, T, d, o) in ((x1, x2, l1, l2, res.maps(s)[0], "21", b.off2),
+                                          (x2, x1, l2, l1, res.maps(s)[1], "12", b.off1)):
+            det = {}
+            T_or = O.segment_map(xt, xs, lt, ls, nn="kdtree", details=det)
+            st = raw["status" + d][e:f]
+            np.testing.assert_array_equal(st != 0, det["valid"])
+            ok = st == 1
+            np.testing.assert_array_equal(raw["iters" + d][e:f][ok], det["iters"][ok])
+            np.testing.assert_allclose(res.transforms["R" + d][e:f][ok], det["R"][ok], rtol=0, atol=RT_TOL)
+            np.testing.assert_allclose(res.transforms["t" + d][e:f][ok], det["t"][ok], rtol=0, atol=RT_TOL)
+            n_part += int(ok.sum())
+            if ok.all():
+                n_ties += _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, f"C{config} seg {s} T{d}")
+    assert n_part > 0
+    assert n_ties <= 1e-3 * b.n_correspondences
+
+
+def test_full_size_properties_c5(L):
+    """BASELINE config 5 at full size (1M points/frame, 2,000 segment pairs): size-independent properties"""
+    b = L.make_config(5)
+    assert b.n_segments == 2000 and b.off1[-1] > 900_000
+    r1 = L.local_icp_batch(b, details=True)
+    r2 = L.local_icp_batch(b)
+    np.testing.assert_array_equal(r1.T21, r2.T21)           # bit-deterministic run to run
+    np.testing.assert_array_equal(r1.T12, r2.T12)
+    n1, n2 = np.diff(b.off1), np.diff(b.off2)
+    assert (r1.T21 >= 0).all() and (r1.T21 < np.repeat(n1, n2)).all()
+    assert (r1.T12 >= 0).all() and (r1.T12 < np.repeat(n2, n1)).all()
+    tr = r1.transforms
+    ok = tr["raw"]["status21"] == 1
+    R = tr["R21"][ok]
+    np.testing.assert_allclose(np.einsum("nij,nkj->nik", R, R), np.broadcast_to(np.eye(3), R.shape), atol=1e-12)
+    np.testing.assert_allclose(np.linalg.det(R), 1.0, atol=1e-12)
+    assert 3 <= tr["raw"]["iters21"][ok].min() and tr["raw"]["iters21"][ok].max() <= 500
+    # every map entry is the true nearest neighbour of the blended point: verify 20 random segment pairs on the CPU
+    rng = np.random.default_rng(0)
+    for s in rng.choice(b.n_segments, 20, replace=False):
+        x1, x2, l1, l2 = b.segment(int(s))
+        det = {}
+        T_or = O.segment_map(x1, x2, l1, l2, nn="brute", details=det)
+        _assert_map_equal_up_to_ties(r1.maps(int(s))[0], T_or, det["x2t"], x1, f"C5 seg {s}")
+    # cycle consistency T12[T21[i]] lands near i for most points (sanity of the registration itself)
+    s = 0
+    T21, T12 = r1.maps(s)
+    x2 = b.segment(s)[1]
+    assert np.median(np.linalg.norm(x2[T12[T21]] - x2, axis=1)) < 2.0
+
+
+def test_invalid_inputs_raise(L):
+    x = np.random.default_rng(0).normal(size=(10, 3))
+    lm = x[:2]
+    with pytest.raises(ValueError):
+        L.local_icp_batch([(x, np.zeros((0, 3)), lm, lm)])
+    with pytest.raises(ValueError):
+        L.local_icp_batch([(x, x, lm, x[:3])])
+    xn = x.copy(); xn[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        L.local_icp_batch([(x, xn, lm, lm)])
+    with pytest.raises(ValueError):
+        L.my_icp(xn, x)
+    with pytest.raises(ValueError):
+        L.get_NN_in_target(x, np.zeros((0, 3)))
+    with pytest.raises(AssertionError):
+        L.get_best_fit_transform(x, x[:5])
+    with pytest.raises(AssertionError):
+        L.get_triangle_angles(1.0, 1.0, 3.0)
+
+
+class _Mesh:
+    def __init__(self, v):
+        self.vertices, self.vertex_colors = v, None
+
+
+def test_drop_in_segment_function_and_install(L):
+    import sys, types
+    g = load_golden("c1_small")
+    s, x1, x2, l1, l2 = next(golden_segments(g))
+    m1, m2 = _Mesh(x1.copy()), _Mesh(x2.copy())
+    np.random.seed(123)
+    T21 = L.get_p2p_mapping_from_segments_using_icp(m1, m2, l1, l2, 0.4)
+    after = np.random.random()
+    np.random.seed(123); np.random.random((len(l1), 3)); expect = np.random.random()
+    assert after == expect                                   # same consumption of the global RNG as the reference (:394)
+    assert T21.dtype == np.int64 and T21.shape == (len(x2),)
+    np.testing.assert_array_equal(m1.vertices, x1)           # inputs untouched
+    assert m1.vertex_colors is not None and len(m1.vertex_colors) == len(x1)
+    np.testing.assert_array_equal(T21, g["T21"][g["off2"][s]:g["off2"][s + 1]])
+    # install(): the reference resolves the hot functions as module globals at call time
+    reg = types.ModuleType("registration.registration_icp")
+    seg = types.ModuleType("p2p_matching_in_organ.p2p_matching_seg_icp")
+    saved = {k: sys.modules.get(k) for k in (reg.__name__, seg.__name__)}
+    sys.modules[reg.__name__], sys.modules[seg.__name__] = reg, seg
+    try:
+        done = L.install()
+        assert seg.get_p2p_mapping_from_segments_using_icp is L.get_p2p_mapping_from_segments_using_icp
+        assert reg.my_icp is L.my_icp and seg.my_icp is L.my_icp and len(done) == 6
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
