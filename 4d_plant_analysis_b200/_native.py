@@ -42,6 +42,9 @@ SIGNATURES = {
     "lip_batch_get_transforms": (c_int, [c_void_p, c_int, _D, _D, _I32, _I32, _D, _D, _I32, _I32]),
     "lip_batch_get_landmark_nn": (c_int, [c_void_p, c_int, _I32, _D]),
     "lip_batch_get_counters": (c_int, [c_void_p, _I64]),
+    "lip_set_profiling": (c_int, [c_void_p, c_int]),
+    "lip_batch_get_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
+    "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
     "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
     "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
     "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
@@ -216,7 +219,23 @@ class Context:
         c = np.zeros(8, np.int64)
         self._check(self.lib.lip_batch_get_counters(self.h, _ptr(c, c_int64)))
         return dict(small_icps=int(c[0]), big_icps=int(c[1]), icp_f64_rescans=int(c[2]), map_f64_rescans=int(c[3]),
-                    map_ring2=int(c[4]), map_fullscan=int(c[5]), launches=int(c[6]))
+                    map_ring2=int(c[4]), map_fullscan=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
+
+    STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_small_kernel", "icp_big_kernel",
+              "grid_build_kernel", "fill_kernel", "blend_nn_kernel")
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.lip_set_profiling(self.h, int(bool(on))))
+
+    def stage_ms(self):
+        ms = np.zeros(7, np.float32)
+        self._check(self.lib.lip_batch_get_stage_ms(self.h, ms.ctypes.data_as(POINTER(ctypes.c_float))))
+        return dict(zip(self.STAGES, (float(x) for x in ms)))
+
+    def bin_offsets(self):
+        off = np.empty(2 * self.sumK + 1, np.int32)
+        self._check(self.lib.lip_batch_get_bin_offsets(self.h, _ptr(off, c_int32)))
+        return off
 
     # ---- single functions ---------------------------------------------------------------------
     def icp(self, src, src_off, tgt, tgt_off):

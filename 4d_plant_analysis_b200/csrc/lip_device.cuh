@@ -48,7 +48,7 @@ struct LipArgs {
     long long *T12, *T21;    // outputs (unified order: T12 over xyz1, T21 over xyz2)
     double* q_dist;          // raw-query mode: distance output over xyz2 (or nullptr)
     unsigned long long* counters;  // [8]
-    int max_iter;
+    int max_iter, profile;   // profile != 0: count evaluated candidate pairs (counters[7])
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };
 

@@ -631,8 +631,10 @@ __global__ void __launch_bounds__(256) grid_build_kernel(LipArgs a, int need_all
 struct NNResult { int idx; int level; };
 
 __device__ __forceinline__ void grid_visit32(const int* __restrict__ tab, const float4* __restrict__ pts, int bucket,
-                                             float qx, float qy, float qz, float& best, float& sec, int& idx) {
+                                             float qx, float qy, float qz, float& best, float& sec, int& idx,
+                                             int& visited) {
     const int s = __ldg(&tab[bucket]), e = __ldg(&tab[bucket + 1]);
+    visited += e - s;
     for (int j = s; j < e; ++j) {
         const float4 p = __ldg(&pts[j]);
         float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
@@ -655,12 +657,12 @@ __device__ __forceinline__ void grid_visit64(const int* __restrict__ tab, const 
 __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __restrict__ tab,
                                                  const float4* __restrict__ pts, const double* __restrict__ xyz,
                                                  double q0, double q1, double q2, unsigned long long* counters,
-                                                 double* dist_out) {
+                                                 double* dist_out, int profile) {
     const float qx = (float)(q0 - h.c[0]), qy = (float)(q1 - h.c[1]), qz = (float)(q2 - h.c[2]);
     const int cx = cell_coord(qx, h.gmin[0], h.inv_h, h.dim[0]), cy = cell_coord(qy, h.gmin[1], h.inv_h, h.dim[1]),
               cz = cell_coord(qz, h.gmin[2], h.inv_h, h.dim[2]);
     float best = INFINITY, sec = INFINITY;
-    int idx = -1, level = 1;
+    int idx = -1, level = 1, visited = 0;
     for (int dz = -1; dz <= 1; ++dz) {
         const int z = cz + dz;
         if (z < 0 || z >= h.dim[2]) continue;
@@ -670,9 +672,13 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
             for (int dx = -1; dx <= 1; ++dx) {
                 const int x = cx + dx;
                 if (x < 0 || x >= h.dim[0]) continue;
-                grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx);
+                grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx, visited);
             }
         }
+    }
+    if (profile) {                                           // ring-1 candidates = the algorithmic pair count
+        unsigned tot = __reduce_add_sync(__activemask(), (unsigned)visited);
+        if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&counters[7], (unsigned long long)tot);
     }
     float g = 0.999f * h.h;
     if (!(best <= g * g)) {
@@ -687,7 +693,7 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
                     const int x = cx + dx;
                     if (x < 0 || x >= h.dim[0]) continue;
                     if (max(max(abs(dx), abs(dy)), abs(dz)) < 2) continue;
-                    grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx);
+                    grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx, visited);
                 }
             }
         }
@@ -791,7 +797,7 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const int mt = pair_mesh(a, m);
     const GridHdr h = a.grid_hdr[mt];
     NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
-                              q0, q1, q2, a.counters, nullptr);
+                              q0, q1, q2, a.counters, nullptr, a.profile);
     if (m < a.S) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
 }
 
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(LIP_TILE) nn_query_kernel(LipArgs a) {
     const GridHdr h = a.grid_hdr[mt];
     double dist;
     NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
-                              xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.counters, &dist);
+                              xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.counters, &dist, a.profile);
     const int u = ub + v;
     if (m < a.S) a.T12[u] = r.idx; else { a.T21[u - a.n1_total] = r.idx; if (a.q_dist) a.q_dist[u - a.n1_total] = dist; }
 }

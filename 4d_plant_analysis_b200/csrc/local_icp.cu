@@ -35,6 +35,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+#define LIP_N_STAGES 7
 enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
 
 }  // namespace
@@ -60,6 +61,10 @@ struct lip_ctx {
     // device copies of host-API inputs / outputs
     DevBuf in_xyz1, in_xyz2, in_lm1, in_lm2, out_T21, out_T12, misc;
     int64_t last_launches = 0;
+    // optional per-stage CUDA-event timing (lip_set_profiling)
+    bool profiling = false;
+    cudaEvent_t ev[LIP_N_STAGES + 1] = {};
+    bool ev_valid = false;
 };
 
 namespace {
@@ -114,6 +119,7 @@ void set_param_args(lip_ctx* c) {
     a.obtuse_cos = std::sin(c->params.obtuse_eps);          // C > pi/2 - eps  <=>  cos C < sin(eps)
     a.cos_den_eps = c->params.cos_den_eps;
     a.reject_dist = c->params.reject_dist;
+    a.profile = c->profiling ? 1 : 0;
 }
 
 int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
@@ -200,33 +206,43 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     a.xyz1 = xyz1; a.xyz2 = xyz2; a.lm1 = lm1; a.lm2 = lm2; a.T21 = T21; a.T12 = T12; a.q_dist = q_dist;
     set_param_args(c);
     int64_t launches = 0;
+    int evi = 0;
+    auto mark = [&]() { if (c->profiling) cudaEventRecord(c->ev[evi], st); ++evi; };
+    c->ev_valid = false;
     LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 8 * 4, st));
     LIP_CUDA(c, cudaMemsetAsync(a.counters, 0, 8 * 8, st));
+    mark();                                                  // 0
     if (stages & ST_PARTITION) {
         size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 2 + 1) * 4;
         landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
         ++launches;
     }
+    mark();                                                  // 1: after partition
     if (stages & ST_ICP) {
         icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
         int gs = c->sm_count * c->small_blocks_per_sm;
         gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
+        mark();                                              // 2: after schedule
         icp_small_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+        mark();                                              // 3: after small ICP
         // a partition is "big" only if src or tgt exceeds LIP_SMALL_CAP points
         int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
         int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
         icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
         launches += 3;
-    }
+    } else { mark(); mark(); }
+    mark();                                                  // 4: after big ICP
     if (stages & (ST_GRID | ST_GRID_ALL)) {
         LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, st));
         grid_build_kernel<<<c->M, 256, 0, st>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
         ++launches;
     }
+    mark();                                                  // 5: after grid build
     if (stages & ST_FILL) {
         fill_kernel<<<(c->M + 127) / 128, 128, 0, st>>>(a);
         ++launches;
     }
+    mark();                                                  // 6: after fill
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
         blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
@@ -235,8 +251,10 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
+    mark();                                                  // 7: after blend / query
     LIP_CUDA(c, cudaGetLastError());
     c->last_launches = launches;
+    c->ev_valid = c->profiling;
     return LIP_OK;
 }
 
@@ -300,6 +318,7 @@ void lip_destroy(lip_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc})
         b->release();
     cudaStreamDestroy(c->stream);
@@ -412,6 +431,34 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];
     counters[0] = sched[0]; counters[1] = sched[1];
     counters[6] = c->last_launches;
+    return LIP_OK;
+}
+
+int lip_set_profiling(lip_ctx* c, int on) {
+    if (!c) return LIP_EINVAL;
+    cudaSetDevice(c->device);
+    if (on && !c->ev[0]) {
+        for (int i = 0; i <= LIP_N_STAGES; ++i) LIP_CUDA(c, cudaEventCreate(&c->ev[i]));
+    }
+    c->profiling = on != 0;
+    c->ev_valid = false;
+    return LIP_OK;
+}
+
+int lip_batch_get_stage_ms(lip_ctx* c, float ms[LIP_N_STAGES]) {
+    if (!c || !ms) return LIP_EINVAL;
+    if (!c->ev_valid) return fail(c, LIP_ENOPLAN, "stage times: profiling was not enabled for the last run");
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, cudaEventSynchronize(c->ev[LIP_N_STAGES]));
+    for (int i = 0; i < LIP_N_STAGES; ++i) LIP_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return LIP_OK;
+}
+
+int lip_batch_get_bin_offsets(lip_ctx* c, int32_t* bin_off) {
+    if (!c || !c->planned || !bin_off) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    LIP_CUDA(c, cudaMemcpy(bin_off, c->args.bin_off, ((size_t)c->B + 1) * 4, cudaMemcpyDeviceToHost));
     return LIP_OK;
 }
 

@@ -206,9 +206,11 @@ def _frame_pair(config, frame_index, S, kind, **kw):
     return segs
 
 
-def make_config(config: int, *, scale: float = 1.0, frame_pairs: int | None = None) -> SegmentPairBatch:
+def make_config(config: int, *, scale: float = 1.0, frame_pairs: int | None = None,
+                frame_offset: int = 0) -> SegmentPairBatch:
     """config 1..5 = BASELINE.json configs[0..4]. ``scale`` < 1 shrinks the number of segment pairs
-    (parity-sized cases); ``frame_pairs`` overrides the number of frame pairs (C4: 15)."""
+    (parity-sized cases); ``frame_pairs`` overrides the number of frame pairs (C4: 15);
+    ``frame_offset`` shifts the frame index that seeds each frame pair (distinct data per rank)."""
     if config == 1:      # tomato: ~20k pts/frame, ~30 segments
         fps, S, kind, kw = frame_pairs or 1, 30, "tomato", {}
     elif config == 2:    # maize: ~50k pts/frame, 12 long ribbons
@@ -223,7 +225,8 @@ def make_config(config: int, *, scale: float = 1.0, frame_pairs: int | None = No
         raise ValueError(f"unknown config {config}")
     S = max(1, int(round(S * scale)))
     segs, fp = [], []
-    for f in range(fps):
+    for f0 in range(fps):
+        f = f0 + frame_offset
         if config == 5:
             rng = np.random.default_rng(1000 * config + f)
             these = [make_segment_pair(rng, kind="tomato", n1=int(rng.uniform(400, 600)),
@@ -231,5 +234,5 @@ def make_config(config: int, *, scale: float = 1.0, frame_pairs: int | None = No
         else:
             these = _frame_pair(config, f, S, kind, **kw)
         segs += these
-        fp += [f] * len(these)
+        fp += [f0] * len(these)
     return batch_from_segments(segs, np.asarray(fp, np.int32), name=f"C{config}")

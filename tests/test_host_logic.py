@@ -1,0 +1,113 @@
+"""CPU tests of the host-side logic: the C-ABI library exports what include/local_icp.h declares,
+the generator, the sharding, and the world_size-2 gather over gloo."""
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    native = importlib.import_module("4d_plant_analysis_b200._native")
+    native.build()
+    lib = native.load()
+    header = open(os.path.join(ROOT, "include", "local_icp.h")).read()
+    declared = set(re.findall(r"\b(lip_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in local_icp.h but not exported"
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    assert lib.lip_compiled_arch() == 100
+    p = native.LipParams()
+    lib.lip_default_params(__import__("ctypes").byref(p))
+    assert (p.max_iter, p.cost_rise_tol, p.cost_flat_tol, p.obtuse_eps, p.cos_den_eps) == (500, 1e-4, 0.01, 1e-5, 1e-5)
+    assert p.reject_dist == float("inf")
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = importlib.import_module("4d_plant_analysis_b200")
+    with pytest.raises(L.NativeError):
+        L.default_context()
+    x = np.random.default_rng(0).normal(size=(20, 3))
+    with pytest.raises(L.NativeError):
+        L.my_icp(x, x)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "4d_plant_analysis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_generator_is_deterministic_and_shaped(syn):
+    a, b = syn.make_config(1), syn.make_config(1)
+    np.testing.assert_array_equal(a.xyz1, b.xyz1)
+    np.testing.assert_array_equal(a.lm2, b.lm2)
+    assert a.n_segments == 30 and 15000 < a.off1[-1] < 26000
+    K = np.diff(a.lm_off)
+    assert K.min() >= 2 and K.max() <= 20
+    c3 = syn.make_config(3, scale=0.5)
+    assert (np.diff(c3.lm_off) == 1).any()
+    c4 = syn.make_config(4, scale=0.1)
+    assert c4.n_frame_pairs == 15
+    sub = a.take([3, 7])
+    np.testing.assert_array_equal(sub.segment(1)[0], a.segment(7)[0])
+
+
+def test_sharding():
+    D = importlib.import_module("4d_plant_analysis_b200.distributed")
+    costs = np.array([5.0, 1, 1, 1, 4, 3, 2, 2])
+    sh = D.shard_segments(costs, 3)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(8))
+    loads = [costs[s].sum() for s in sh]
+    assert max(loads) - min(loads) <= 2
+    fp = np.repeat(np.arange(15), 2)
+    sh = D.shard_segments(np.ones(30), 8, fp)
+    assert [len(s) // 2 for s in sh] == [2, 2, 2, 2, 2, 2, 2, 1]
+
+
+_WORKER = r'''
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["LIP_ROOT"])
+import torch.distributed as dist
+dist.init_process_group("gloo")
+D = importlib.import_module("4d_plant_analysis_b200.distributed")
+syn = importlib.import_module("4d_plant_analysis_b200.synthetic")
+from oracle import local_icp_oracle as O      # the CPU checker stands in for the GPU compute in this host-logic test
+b = syn.make_config(1, scale=0.2)
+def compute(sub):
+    T21, T12 = [], []
+    for s in range(sub.n_segments):
+        a, c = O.segment_pair_maps(*sub.segment(s), nn="brute")
+        T21.append(a); T12.append(c)
+    return np.concatenate(T21), np.concatenate(T12)
+T21, T12, mine = D.local_icp_distributed(b, compute=compute, gather=True)
+R21, R12 = compute(b)
+assert np.array_equal(T21, R21) and np.array_equal(T12, R12), "gathered maps differ from the single-process result"
+assert 0 < len(mine) < b.n_segments
+print("rank", dist.get_rank(), "ok", len(mine))
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gather_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, LIP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
