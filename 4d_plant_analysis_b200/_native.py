@@ -221,14 +221,14 @@ class Context:
         return dict(small_icps=int(c[0]), big_icps=int(c[1]), icp_f64_rescans=int(c[2]), map_f64_rescans=int(c[3]),
                     map_ring2=int(c[4]), map_fullscan=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
 
-    STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_small_kernel", "icp_big_kernel",
-              "grid_build_kernel", "fill_kernel", "blend_nn_kernel")
+    STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_warp_kernel_small", "icp_warp_kernel_medium",
+              "icp_big_kernel", "grid_build_kernel", "fill_kernel", "blend_nn_kernel", "far_nn_kernel")
 
     def set_profiling(self, on=True):
         self._check(self.lib.lip_set_profiling(self.h, int(bool(on))))
 
     def stage_ms(self):
-        ms = np.zeros(7, np.float32)
+        ms = np.zeros(len(self.STAGES), np.float32)
         self._check(self.lib.lip_batch_get_stage_ms(self.h, ms.ctypes.data_as(POINTER(ctypes.c_float))))
         return dict(zip(self.STAGES, (float(x) for x in ms)))
 

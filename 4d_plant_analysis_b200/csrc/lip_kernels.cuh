@@ -5,6 +5,8 @@
 
 #define LIP_SMALL_CAP 128     // partitions with <= this many src AND tgt points: one warp, all in SMEM
 #define LIP_SMALL_WARPS 4
+#define LIP_MEDIUM_CAP 640    // up to this many: still one warp, fp32 tile in SMEM, float64 from global
+#define LIP_MEDIUM_WARPS 4
 #define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 256
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
@@ -83,7 +85,9 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     int pb = pair_bin(a, b);
     int ns = a.bin_off[b + 1] - a.bin_off[b], nt = a.bin_off[pb + 1] - a.bin_off[pb];
     if (ns == 0 || nt == 0) return;
-    if (ns <= LIP_SMALL_CAP && nt <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
+    const int mx = max(ns, nt);
+    if (mx <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
+    else if (mx <= LIP_MEDIUM_CAP) a.medium_list[atomicAdd(&a.sched[4], 1)] = b;
     else a.big_list[atomicAdd(&a.sched[1], 1)] = b;
 }
 
@@ -167,29 +171,51 @@ __device__ __forceinline__ void nn_scan2(const float4* __restrict__ tf, int cnt,
     }
 }
 
-template <int CAP>
-struct IcpSmallSmem {
-    float4 tf[CAP];                       // centred fp32 target (search)
-    double tx[CAP], ty[CAP], tz[CAP];     // centred fp64 target (Kabsch sums, exact re-evaluation)
-    double sx[CAP], sy[CAP], sz[CAP];     // centred fp64 source (original positions)
+// Per-warp SMEM of the warp-per-partition kernel.  SMEM64 = true (small partitions): float64 copies
+// of source and target live in SMEM too; false (medium partitions): only the fp32 search tile is
+// staged and the float64 coordinates are gathered from global memory (L1/L2 resident) when needed.
+template <int CAP, bool SMEM64>
+struct IcpWarpSmem {
+    float4 tf[CAP];                                      // centred fp32 target (search)
+    double tx[SMEM64 ? CAP : 1], ty[SMEM64 ? CAP : 1], tz[SMEM64 ? CAP : 1];   // centred fp64 target
+    double sx[SMEM64 ? CAP : 1], sy[SMEM64 ? CAP : 1], sz[SMEM64 ? CAP : 1];   // centred fp64 source
 };
 
-template <int CAP>
-__device__ __forceinline__ void icp_small_finish(const IcpSmallSmem<CAP>& sm, int nt, bool valid, float best, float sec,
-                                                 int idx, float mabs, double px, double py, double pz, double reject,
-                                                 double* acc, unsigned long long* counters) {
+template <int CAP, bool SMEM64>
+struct IcpWarpView {                                     // one partition as seen by its warp
+    IcpWarpSmem<CAP, SMEM64>& sm;
+    const double *xs, *xt;                               // mesh vertex arrays (original coordinates)
+    const int *vs, *vt;                                  // member lists (local vertex ids)
+    double cx, cy, cz;                                   // target centroid
+    __device__ __forceinline__ void tgt(int j, double& x, double& y, double& z) const {
+        if (SMEM64) { x = sm.tx[j]; y = sm.ty[j]; z = sm.tz[j]; }
+        else { size_t v = (size_t)vt[j]; x = xt[3 * v] - cx; y = xt[3 * v + 1] - cy; z = xt[3 * v + 2] - cz; }
+    }
+    __device__ __forceinline__ void src(int q, double& x, double& y, double& z) const {
+        if (SMEM64) { x = sm.sx[q]; y = sm.sy[q]; z = sm.sz[q]; }
+        else { size_t v = (size_t)vs[q]; x = xs[3 * v] - cx; y = xs[3 * v + 1] - cy; z = xs[3 * v + 2] - cz; }
+    }
+};
+
+template <int CAP, bool SMEM64>
+__device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& w, int nt, bool valid, float best,
+                                                float sec, int idx, float mabs, double px, double py, double pz,
+                                                double reject, double* acc, unsigned long long* counters) {
     if (!valid) return;
     float fx = (float)px, fy = (float)py, fz = (float)pz;
     float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) + mabs);
     if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {   // near tie: decide in float64, lowest index
         double bd = INFINITY;
         for (int j = 0; j < nt; ++j) {
-            double d = rdist64(px, py, pz, sm.tx[j], sm.ty[j], sm.tz[j]);
+            double tx, ty, tz;
+            w.tgt(j, tx, ty, tz);
+            double d = rdist64(px, py, pz, tx, ty, tz);
             if (d < bd) { bd = d; idx = j; }
         }
         atomicAdd(&counters[2], 1ull);
     }
-    double bx = sm.tx[idx], by = sm.ty[idx], bz = sm.tz[idx];
+    double bx, by, bz;
+    w.tgt(idx, bx, by, bz);
     double d = sqrt(rdist64(px, py, pz, bx, by, bz));
     acc[0] += d;
     if (d <= reject) {
@@ -202,31 +228,30 @@ __device__ __forceinline__ void icp_small_finish(const IcpSmallSmem<CAP>& sm, in
     }
 }
 
-template <int CAP>
-__device__ void icp_one_small(const LipArgs& a, int b, IcpSmallSmem<CAP>& sm, int lane) {
+template <int CAP, bool SMEM64>
+__device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& sm, int lane) {
     const int pb = pair_bin(a, b);
     const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
     const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
     const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
-    const double* xs = mesh_xyz(a, ms);
-    const double* xt = mesh_xyz(a, mt);
-    const int* vs = a.part_vid + so;
-    const int* vt = a.part_vid + to;
+    IcpWarpView<CAP, SMEM64> w{sm, mesh_xyz(a, ms), mesh_xyz(a, mt), a.part_vid + so, a.part_vid + to, 0.0, 0.0, 0.0};
     // ---- stage the target, centred on its centroid -------------------------------------------------
     double cx = 0, cy = 0, cz = 0;
     for (int j = lane; j < nt; j += 32) {
-        size_t v = (size_t)vt[j];
-        double x = xt[3 * v], y = xt[3 * v + 1], z = xt[3 * v + 2];
-        sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z;
+        size_t v = (size_t)w.vt[j];
+        double x = w.xt[3 * v], y = w.xt[3 * v + 1], z = w.xt[3 * v + 2];
+        if (SMEM64) { sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z; }
         cx += x; cy += y; cz += z;
     }
     cx = warp_sum(cx) / nt; cy = warp_sum(cy) / nt; cz = warp_sum(cz) / nt;
+    w.cx = cx; w.cy = cy; w.cz = cz;
     __syncwarp();
     float mabs = 0.f;
     double mtx = 0, mty = 0, mtz = 0;
     for (int j = lane; j < nt; j += 32) {
-        double x = sm.tx[j] - cx, y = sm.ty[j] - cy, z = sm.tz[j] - cz;
-        sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z;
+        double x, y, z;
+        if (SMEM64) { x = sm.tx[j] - cx; y = sm.ty[j] - cy; z = sm.tz[j] - cz; sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z; }
+        else w.tgt(j, x, y, z);
         sm.tf[j] = make_float4((float)x, (float)y, (float)z, 0.f);
         mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf((float)x), fabsf((float)y)), fabsf((float)z)));
         mtx += x; mty += y; mtz += z;
@@ -235,9 +260,9 @@ __device__ void icp_one_small(const LipArgs& a, int b, IcpSmallSmem<CAP>& sm, in
     mtx = warp_sum(mtx) / nt; mty = warp_sum(mty) / nt; mtz = warp_sum(mtz) / nt;
     double msx = 0, msy = 0, msz = 0;
     for (int q = lane; q < ns; q += 32) {
-        size_t v = (size_t)vs[q];
-        double x = xs[3 * v] - cx, y = xs[3 * v + 1] - cy, z = xs[3 * v + 2] - cz;
-        sm.sx[q] = x; sm.sy[q] = y; sm.sz[q] = z;
+        size_t v = (size_t)w.vs[q];
+        double x = w.xs[3 * v] - cx, y = w.xs[3 * v + 1] - cy, z = w.xs[3 * v + 2] - cz;
+        if (SMEM64) { sm.sx[q] = x; sm.sy[q] = y; sm.sz[q] = z; }
         msx += x; msy += y; msz += z;
     }
     msx = warp_sum(msx) / ns; msy = warp_sum(msy) / ns; msz = warp_sum(msz) / ns;
@@ -255,18 +280,19 @@ __device__ void icp_one_small(const LipArgs& a, int b, IcpSmallSmem<CAP>& sm, in
         for (int q0 = 0; q0 < ns; q0 += 64) {
             const int qa = q0 + lane, qb = qa + 32;
             const bool va = qa < ns, vb = qb < ns;
-            const int ra = va ? qa : ns - 1, rb = vb ? qb : ns - 1;
-            double pax, pay, paz, pbx, pby, pbz;
-            mat3_vec(st.R, sm.sx[ra], sm.sy[ra], sm.sz[ra], pax, pay, paz);
+            double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
+            w.src(va ? qa : ns - 1, sax, say, saz);
+            w.src(vb ? qb : ns - 1, sbx, sby, sbz);
+            mat3_vec(st.R, sax, say, saz, pax, pay, paz);
             pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-            mat3_vec(st.R, sm.sx[rb], sm.sy[rb], sm.sz[rb], pbx, pby, pbz);
+            mat3_vec(st.R, sbx, sby, sbz, pbx, pby, pbz);
             pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
             float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
             int ia = 0, ib = 0;
             nn_scan2(sm.tf, nt, 0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
                      besta, seca, ia, bestb, secb, ib);
-            icp_small_finish<CAP>(sm, nt, va, besta, seca, ia, mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
-            icp_small_finish<CAP>(sm, nt, vb, bestb, secb, ib, mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
+            icp_warp_finish<CAP, SMEM64>(w, nt, va, besta, seca, ia, mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+            icp_warp_finish<CAP, SMEM64>(w, nt, vb, bestb, secb, ib, mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
         }
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
@@ -279,18 +305,22 @@ __device__ void icp_one_small(const LipArgs& a, int b, IcpSmallSmem<CAP>& sm, in
     if (lane == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
 }
 
-template <int CAP, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) icp_small_kernel(LipArgs a) {
-    __shared__ IcpSmallSmem<CAP> sm_all[WARPS];
-    IcpSmallSmem<CAP>& sm = sm_all[threadIdx.x >> 5];
+// LIST 0: small partitions (sched[0] entries of small_list, cursor sched[2]);
+// LIST 1: medium partitions (sched[4] entries of medium_list, cursor sched[5])
+template <int CAP, int WARPS, bool SMEM64>
+__global__ void __launch_bounds__(WARPS * 32) icp_warp_kernel(LipArgs a) {
+    __shared__ IcpWarpSmem<CAP, SMEM64> sm_all[WARPS];
+    IcpWarpSmem<CAP, SMEM64>& sm = sm_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int n_small = a.sched[0];
+    const int n_items = SMEM64 ? a.sched[0] : a.sched[4];
+    const int* list = SMEM64 ? a.small_list : a.medium_list;
+    int* cursor = SMEM64 ? &a.sched[2] : &a.sched[5];
     for (;;) {                                              // persistent warps, dynamic partition queue
         int w = 0;
-        if (lane == 0) w = atomicAdd(&a.sched[2], 1);
+        if (lane == 0) w = atomicAdd(cursor, 1);
         w = __shfl_sync(LIP_FULL, w, 0);
-        if (w >= n_small) break;
-        icp_one_small<CAP>(a, a.small_list[w], sm, lane);
+        if (w >= n_items) break;
+        icp_one_warp<CAP, SMEM64>(a, list[w], sm, lane);
         __syncwarp();
     }
 }
@@ -698,21 +728,14 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
             }
         }
         g = 2.0f * 0.999f * h.h;
-        if (!(best <= g * g)) {
-            level = 3;
-            best = sec = INFINITY;
-            for (int j = 0; j < h.n; ++j) {
-                const float4 p = __ldg(&pts[j]);
-                float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-                float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-                nn_update(d, __float_as_int(p.w), best, sec, idx);
-            }
+        if (!(best <= g * g)) {                              // still not certifiable: hand over to far_nn_kernel
+            NNResult r; r.idx = -1; r.level = 3;
+            return r;
         }
     }
     if (level == 2) atomicAdd(&counters[4], 1ull);
-    if (level == 3) atomicAdd(&counters[5], 1ull);
     // anything outside the searched block is at least g away: it competes with `sec`
-    if (level < 3) sec = fminf(sec, g * g);
+    sec = fminf(sec, g * g);
     const float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + h.mabs);
     if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
         // near tie (or best close to the certified radius): decide in float64 on the original coordinates
@@ -751,6 +774,12 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
     }
     NNResult r; r.idx = idx; r.level = level;
     return r;
+}
+
+__device__ __forceinline__ void far_push(const LipArgs& a, int u, int mt, double q0, double q1, double q2) {
+    const int slot = atomicAdd(&a.sched[3], 1);
+    a.far_list[2 * (size_t)slot] = u; a.far_list[2 * (size_t)slot + 1] = mt;
+    a.far_q[3 * (size_t)slot] = q0; a.far_q[3 * (size_t)slot + 1] = q1; a.far_q[3 * (size_t)slot + 2] = q2;
 }
 
 // =============================================================================================
@@ -798,6 +827,7 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const GridHdr h = a.grid_hdr[mt];
     NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
                               q0, q1, q2, a.counters, nullptr, a.profile);
+    if (r.idx < 0) { far_push(a, u, mt, q0, q1, q2); return; }
     if (m < a.S) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
 }
 
@@ -814,7 +844,72 @@ __global__ void __launch_bounds__(LIP_TILE) nn_query_kernel(LipArgs a) {
     NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
                               xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.counters, &dist, a.profile);
     const int u = ub + v;
+    if (r.idx < 0) { far_push(a, u, mt, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]); return; }
     if (m < a.S) a.T12[u] = r.idx; else { a.T21[u - a.n1_total] = r.idx; if (a.q_dist) a.q_dist[u - a.n1_total] = dist; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// queries the ring search could not certify (farther than two cells from every target point, e.g.
+// the grown tip of a leaf): one WARP per query scans the whole target mesh, lanes striding over the
+// cell-sorted float4 points (coalesced), warp-shuffle argmin, same float64 tie rule.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) far_nn_kernel(LipArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int n_far = a.sched[3];
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&a.sched[6], 1);
+        w = __shfl_sync(LIP_FULL, w, 0);
+        if (w >= n_far) break;
+        const int u = a.far_list[2 * (size_t)w], mt = a.far_list[2 * (size_t)w + 1];
+        const double q0 = a.far_q[3 * (size_t)w], q1 = a.far_q[3 * (size_t)w + 1], q2 = a.far_q[3 * (size_t)w + 2];
+        const GridHdr& h = a.grid_hdr[mt];
+        const float4* __restrict__ pts = a.grid_pts + a.mesh_ubase[mt];
+        const double* __restrict__ xyz = mesh_xyz(a, mt);
+        const int n = h.n;
+        const float qx = (float)(q0 - h.c[0]), qy = (float)(q1 - h.c[1]), qz = (float)(q2 - h.c[2]);
+        float best = INFINITY, sec = INFINITY;
+        int idx = 0;
+        for (int j = lane; j < n; j += 32) {
+            const float4 p = __ldg(&pts[j]);
+            float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+            nn_update(d, __float_as_int(p.w), best, sec, idx);
+        }
+        float ball = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ball = fminf(ball, __shfl_xor_sync(LIP_FULL, ball, o));
+        const int win = __ffs(__ballot_sync(LIP_FULL, best == ball)) - 1;
+        float sall = (lane == win) ? sec : best;             // runner-up over the whole warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sall = fminf(sall, __shfl_xor_sync(LIP_FULL, sall, o));
+        idx = __shfl_sync(LIP_FULL, idx, win);
+        const float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + h.mabs);
+        if (sall - ball <= d2_err(ball, e) + d2_err(sall, e)) {
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int v = lane; v < n; v += 32) {
+                double d = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (d < bd) { bd = d; bi = v; }              // ascending v per lane: lowest index kept
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double od = __shfl_xor_sync(LIP_FULL, bd, o);
+                int oi = __shfl_xor_sync(LIP_FULL, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            idx = bi;
+            if (lane == 0) atomicAdd(&a.counters[3], 1ull);
+        }
+        if (lane == 0) {
+            if (u < a.n1_total) a.T12[u] = idx;
+            else {
+                a.T21[u - a.n1_total] = idx;
+                if (a.q_dist)
+                    a.q_dist[u - a.n1_total] = sqrt(rdist64(q0, q1, q2, xyz[3 * (size_t)idx], xyz[3 * (size_t)idx + 1], xyz[3 * (size_t)idx + 2]));
+            }
+        }
+    }
 }
 
 // =============================================================================================

@@ -35,7 +35,6 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-#define LIP_N_STAGES 7
 enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
 
 }  // namespace
@@ -43,7 +42,7 @@ enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 
 struct lip_ctx {
     int device = 0;
     int sm_count = 0;
-    int small_blocks_per_sm = 1, big_blocks_per_sm = 1;
+    int small_blocks_per_sm = 1, medium_blocks_per_sm = 1, big_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
     lip_params params;
     std::string err;
@@ -93,7 +92,8 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
     const size_t o_fR = take(B * 72), o_ft = take(B * 24);
-    const size_t o_sched = take(8 * 4), o_small = take(B * 4), o_big = take(B * 4);
+    const size_t o_sched = take(8 * 4), o_small = take(B * 4), o_med = take(B * 4), o_big = take(B * 4);
+    const size_t o_far = take(n * 8), o_farq = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
     LIP_CUDA(c, c->ws.ensure(off));
@@ -105,7 +105,8 @@ int carve_workspace(lip_ctx* c) {
     a.icp_R = (double*)(base + o_R); a.icp_t = (double*)(base + o_t);
     a.icp_iters = (int*)(base + o_it); a.icp_status = (int*)(base + o_stat);
     a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft);
-    a.sched = (int*)(base + o_sched); a.small_list = (int*)(base + o_small); a.big_list = (int*)(base + o_big);
+    a.sched = (int*)(base + o_sched); a.small_list = (int*)(base + o_small); a.medium_list = (int*)(base + o_med);
+    a.big_list = (int*)(base + o_big); a.far_list = (int*)(base + o_far); a.far_q = (double*)(base + o_farq);
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
     return LIP_OK;
@@ -211,7 +212,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     c->ev_valid = false;
     LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 8 * 4, st));
     LIP_CUDA(c, cudaMemsetAsync(a.counters, 0, 8 * 8, st));
-    mark();                                                  // 0
+    mark();                                                  // event 0
     if (stages & ST_PARTITION) {
         size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 2 + 1) * 4;
         landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
@@ -220,29 +221,34 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     mark();                                                  // 1: after partition
     if (stages & ST_ICP) {
         icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
+        mark();                                              // 2: after schedule
         int gs = c->sm_count * c->small_blocks_per_sm;
         gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
-        mark();                                              // 2: after schedule
-        icp_small_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+        icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
         mark();                                              // 3: after small ICP
-        // a partition is "big" only if src or tgt exceeds LIP_SMALL_CAP points
-        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
+        // a partition is "medium"/"big" only if src or tgt exceeds LIP_SMALL_CAP / LIP_MEDIUM_CAP points
+        int gm = c->sm_count * c->medium_blocks_per_sm;
+        int64_t mbound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
+        gm = (int)std::max<int64_t>(1, std::min<int64_t>(gm, (mbound + LIP_MEDIUM_WARPS - 1) / LIP_MEDIUM_WARPS));
+        icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, st>>>(a);
+        mark();                                              // 4: after medium ICP
+        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_MEDIUM_CAP + 1);
         int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
         icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
-        launches += 3;
-    } else { mark(); mark(); }
-    mark();                                                  // 4: after big ICP
+        launches += 4;
+    } else { mark(); mark(); mark(); }
+    mark();                                                  // 5: after big ICP
     if (stages & (ST_GRID | ST_GRID_ALL)) {
         LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, st));
         grid_build_kernel<<<c->M, 256, 0, st>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
         ++launches;
     }
-    mark();                                                  // 5: after grid build
+    mark();                                                  // 6: after grid build
     if (stages & ST_FILL) {
         fill_kernel<<<(c->M + 127) / 128, 128, 0, st>>>(a);
         ++launches;
     }
-    mark();                                                  // 6: after fill
+    mark();                                                  // 7: after fill
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
         blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
@@ -251,7 +257,13 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
-    mark();                                                  // 7: after blend / query
+    mark();                                                  // 8: after blend / query
+    if ((stages & (ST_QUERY | ST_BLEND)) && c->n_tiles > 0) {
+        int gf = std::max(1, std::min(c->sm_count * 8, (a.n_total + 3) / 4));
+        far_nn_kernel<<<gf, 128, 0, st>>>(a);
+        ++launches;
+    }
+    mark();                                                  // 9: after far queries
     LIP_CUDA(c, cudaGetLastError());
     c->last_launches = launches;
     c->ev_valid = c->profiling;
@@ -302,9 +314,12 @@ int lip_create(lip_ctx** out, int device) {
         return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
     }
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_small_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS>,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true>,
                                                       LIP_SMALL_WARPS * 32, 0) == cudaSuccess && nb > 0)
         c->small_blocks_per_sm = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false>,
+                                                      LIP_MEDIUM_WARPS * 32, 0) == cudaSuccess && nb > 0)
+        c->medium_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
     cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,7 +444,7 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
     LIP_CUDA(c, cudaMemcpy(sched, c->args.sched, sizeof(sched), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];
-    counters[0] = sched[0]; counters[1] = sched[1];
+    counters[0] = sched[0] + sched[4]; counters[1] = sched[1]; counters[5] = sched[3];
     counters[6] = c->last_launches;
     return LIP_OK;
 }

@@ -202,7 +202,8 @@ def run_b200(args):
     d_in = [torch.from_numpy(a).to(dev) for a in (batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)]
     d_T21 = torch.empty(int(batch.off2[-1]), dtype=torch.int64, device=dev)
     d_T12 = torch.empty(int(batch.off1[-1]), dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # a real (non-null) stream: handle 0 would select the library's own
+    torch.cuda.set_stream(stream)
 
     def step_device():
         ctx.run_device(d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), d_in[3].data_ptr(),
@@ -290,8 +291,11 @@ def run_b200(args):
     ns = np.concatenate([sizes[sumK:], sizes[:sumK]])          # rows in "21 then 12" order: src sizes
     nt = np.concatenate([sizes[:sumK], sizes[sumK:]])
     iters = np.concatenate([tr["iters21"], tr["iters12"]]).astype(np.float64)
-    small = (ns <= 128) & (nt <= 128)
-    pairs = {"icp_small_kernel": float((iters * ns * nt)[small].sum()), "icp_big_kernel": float((iters * ns * nt)[~small].sum()),
+    mx = np.maximum(ns, nt)
+    w = iters * ns * nt                                        # evaluated (source, candidate) pairs per partition
+    pairs = {"icp_warp_kernel_small": float(w[mx <= 128].sum()),
+             "icp_warp_kernel_medium": float(w[(mx > 128) & (mx <= 640)].sum()),
+             "icp_big_kernel": float(w[mx > 640].sum()),
              "blend_nn_kernel": float(counters["map_ring1_pairs"])}
     dom = max(pairs, key=lambda k: stage[k])
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12       # TFLOP/s, FP32 FMA pipe at the max SM clock
