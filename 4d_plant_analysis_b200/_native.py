@@ -219,10 +219,10 @@ class Context:
         c = np.zeros(8, np.int64)
         self._check(self.lib.lip_batch_get_counters(self.h, _ptr(c, c_int64)))
         return dict(small_icps=int(c[0]), big_icps=int(c[1]), icp_f64_rescans=int(c[2]), map_f64_rescans=int(c[3]),
-                    map_ring2=int(c[4]), map_fullscan=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
+                    map_retry=int(c[4]), map_far=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
 
     STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_warp_kernel_small", "icp_warp_kernel_medium",
-              "icp_big_kernel", "grid_build_kernel", "fill_kernel", "blend_nn_kernel", "far_nn_kernel")
+              "icp_big_kernel", "grid_build_kernel", "blend_nn_kernel", "retry_nn_kernel", "far_nn_kernel")
 
     def set_profiling(self, on=True):
         self._check(self.lib.lip_set_profiling(self.h, int(bool(on))))

@@ -87,7 +87,13 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     if (ns == 0 || nt == 0) return;
     const int mx = max(ns, nt);
     if (mx <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
-    else if (mx <= LIP_MEDIUM_CAP) a.medium_list[atomicAdd(&a.sched[4], 1)] = b;
+    else if (mx <= LIP_MEDIUM_CAP) {
+        // four work classes, heaviest first: the persistent warps drain class 3, then 2, 1, 0 (longest tasks first)
+        const long long w = (long long)ns * nt;
+        const int cls = (w > 160000) ? 3 : (w > 70000) ? 2 : (w > 30000) ? 1 : 0;
+        a.medium_list[(size_t)cls * a.B + atomicAdd(&a.sched[8 + cls], 1)] = b;
+        atomicAdd(&a.sched[4], 1);
+    }
     else a.big_list[atomicAdd(&a.sched[1], 1)] = b;
 }
 
@@ -320,7 +326,14 @@ __global__ void __launch_bounds__(WARPS * 32) icp_warp_kernel(LipArgs a) {
         if (lane == 0) w = atomicAdd(cursor, 1);
         w = __shfl_sync(LIP_FULL, w, 0);
         if (w >= n_items) break;
-        icp_one_warp<CAP, SMEM64>(a, list[w], sm, lane);
+        int b;
+        if (SMEM64) b = list[w];
+        else {                                               // medium: class 3 first
+            int c = 3, r = w;
+            while (c > 0 && r >= a.sched[8 + c]) { r -= a.sched[8 + c]; --c; }
+            b = list[(size_t)c * a.B + r];
+        }
+        icp_one_warp<CAP, SMEM64>(a, b, sm, lane);
         __syncwarp();
     }
 }
@@ -683,7 +696,71 @@ __device__ __forceinline__ void grid_visit64(const int* __restrict__ tab, const 
     }
 }
 
-// q64: query in ORIGINAL coordinates (float64); returns local vertex index of the nearest target
+// scan the cells at Chebyshev distance r_lo..r_hi from (cx,cy,cz)
+__device__ __forceinline__ void grid_ring_scan32(const GridHdr& h, const int* __restrict__ tab, const float4* __restrict__ pts,
+                                                 int cx, int cy, int cz, int r_lo, int r_hi, float qx, float qy, float qz,
+                                                 float& best, float& sec, int& idx, int& visited) {
+    for (int dz = -r_hi; dz <= r_hi; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= h.dim[2]) continue;
+        for (int dy = -r_hi; dy <= r_hi; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= h.dim[1]) continue;
+            for (int dx = -r_hi; dx <= r_hi; ++dx) {
+                const int x = cx + dx;
+                if (x < 0 || x >= h.dim[0]) continue;
+                if (max(max(abs(dx), abs(dy)), abs(dz)) < r_lo) continue;
+                grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx, visited);
+            }
+        }
+    }
+}
+
+// Given the fp32 result of a search that covered every cell within `level` rings of the query's cell and
+// found best <= (0.999 level h)^2: resolve near ties in float64 on the original coordinates and return
+// the index of the exact nearest neighbour (lowest index on an exact tie).
+__device__ __forceinline__ int grid_finish(const GridHdr& h, const int* __restrict__ tab, const float4* __restrict__ pts,
+                                           const double* __restrict__ xyz, double q0, double q1, double q2, float qx,
+                                           float qy, float qz, int cx, int cy, int cz, int level, float best, float sec,
+                                           int idx, unsigned long long* counters) {
+    const float g = 0.999f * h.h * (float)level;
+    // anything outside the searched block is at least g away: it competes with `sec`
+    sec = fminf(sec, g * g);
+    const float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + h.mabs);
+    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
+        // near tie (or best close to the certified radius): decide in float64
+        atomicAdd(&counters[3], 1ull);
+        double bd = INFINITY;
+        int bi = 0x7fffffff;
+        for (int dz = -level; dz <= level; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= h.dim[2]) continue;
+            for (int dy = -level; dy <= level; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= h.dim[1]) continue;
+                for (int dx = -level; dx <= level; ++dx) {
+                    const int x = cx + dx;
+                    if (x < 0 || x >= h.dim[0]) continue;
+                    grid_visit64(tab, pts, xyz, cell_hash(x, y, z, h.mask), q0, q1, q2, bd, bi);
+                }
+            }
+        }
+        const double gg = (double)g * 0.999;
+        if (!(bd <= gg * gg)) {                              // not certifiable in float64 either: full scan
+            bd = INFINITY; bi = 0x7fffffff;
+            for (int v = 0; v < h.n; ++v) {
+                double d = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (d < bd) { bd = d; bi = v; }
+            }
+        }
+        idx = bi;
+    }
+    return idx;
+}
+
+// One thread, one query (ORIGINAL float64 coordinates): ring 1 (27 cells), then ring 2 (98 more); a ring
+// result is accepted only if the best distance is inside the searched block.  idx = -1: not certifiable
+// within two rings — the caller hands the query to far_nn_kernel.
 __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __restrict__ tab,
                                                  const float4* __restrict__ pts, const double* __restrict__ xyz,
                                                  double q0, double q1, double q2, unsigned long long* counters,
@@ -693,19 +770,7 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
               cz = cell_coord(qz, h.gmin[2], h.inv_h, h.dim[2]);
     float best = INFINITY, sec = INFINITY;
     int idx = -1, level = 1, visited = 0;
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int z = cz + dz;
-        if (z < 0 || z >= h.dim[2]) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
-            if (y < 0 || y >= h.dim[1]) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx;
-                if (x < 0 || x >= h.dim[0]) continue;
-                grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx, visited);
-            }
-        }
-    }
+    grid_ring_scan32(h, tab, pts, cx, cy, cz, 0, 1, qx, qy, qz, best, sec, idx, visited);
     if (profile) {                                           // ring-1 candidates = the algorithmic pair count
         unsigned tot = __reduce_add_sync(__activemask(), (unsigned)visited);
         if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&counters[7], (unsigned long long)tot);
@@ -713,62 +778,15 @@ __device__ __forceinline__ NNResult grid_nearest(const GridHdr& h, const int* __
     float g = 0.999f * h.h;
     if (!(best <= g * g)) {
         level = 2;
-        for (int dz = -2; dz <= 2; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= h.dim[2]) continue;
-            for (int dy = -2; dy <= 2; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= h.dim[1]) continue;
-                for (int dx = -2; dx <= 2; ++dx) {
-                    const int x = cx + dx;
-                    if (x < 0 || x >= h.dim[0]) continue;
-                    if (max(max(abs(dx), abs(dy)), abs(dz)) < 2) continue;
-                    grid_visit32(tab, pts, cell_hash(x, y, z, h.mask), qx, qy, qz, best, sec, idx, visited);
-                }
-            }
-        }
+        atomicAdd(&counters[4], 1ull);
+        grid_ring_scan32(h, tab, pts, cx, cy, cz, 2, 2, qx, qy, qz, best, sec, idx, visited);
         g = 2.0f * 0.999f * h.h;
-        if (!(best <= g * g)) {                              // still not certifiable: hand over to far_nn_kernel
+        if (!(best <= g * g)) {
             NNResult r; r.idx = -1; r.level = 3;
             return r;
         }
     }
-    if (level == 2) atomicAdd(&counters[4], 1ull);
-    // anything outside the searched block is at least g away: it competes with `sec`
-    sec = fminf(sec, g * g);
-    const float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + h.mabs);
-    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
-        // near tie (or best close to the certified radius): decide in float64 on the original coordinates
-        atomicAdd(&counters[3], 1ull);
-        double bd = INFINITY;
-        int bi = 0x7fffffff;
-        if (level < 3) {
-            const int r = level;
-            for (int dz = -r; dz <= r; ++dz) {
-                const int z = cz + dz;
-                if (z < 0 || z >= h.dim[2]) continue;
-                for (int dy = -r; dy <= r; ++dy) {
-                    const int y = cy + dy;
-                    if (y < 0 || y >= h.dim[1]) continue;
-                    for (int dx = -r; dx <= r; ++dx) {
-                        const int x = cx + dx;
-                        if (x < 0 || x >= h.dim[0]) continue;
-                        grid_visit64(tab, pts, xyz, cell_hash(x, y, z, h.mask), q0, q1, q2, bd, bi);
-                    }
-                }
-            }
-            const double gg = (double)g * 0.999;
-            if (!(bd <= gg * gg)) level = 3;                 // not certifiable in float64: full scan
-        }
-        if (level == 3) {
-            bd = INFINITY; bi = 0x7fffffff;
-            for (int v = 0; v < h.n; ++v) {
-                double d = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
-                if (d < bd) { bd = d; bi = v; }
-            }
-        }
-        idx = bi;
-    }
+    idx = grid_finish(h, tab, pts, xyz, q0, q1, q2, qx, qy, qz, cx, cy, cz, level, best, sec, idx, counters);
     if (dist_out) {
         *dist_out = sqrt(rdist64(q0, q1, q2, xyz[3 * (size_t)idx], xyz[3 * (size_t)idx + 1], xyz[3 * (size_t)idx + 2]));
     }
@@ -781,54 +799,170 @@ __device__ __forceinline__ void far_push(const LipArgs& a, int u, int mt, double
     a.far_list[2 * (size_t)slot] = u; a.far_list[2 * (size_t)slot + 1] = mt;
     a.far_q[3 * (size_t)slot] = q0; a.far_q[3 * (size_t)slot + 1] = q1; a.far_q[3 * (size_t)slot + 2] = q2;
 }
+__device__ __forceinline__ void retry_push(const LipArgs& a, int u, int mt, double q0, double q1, double q2) {
+    const int slot = atomicAdd(&a.sched[7], 1);
+    a.retry_list[2 * (size_t)slot] = u; a.retry_list[2 * (size_t)slot + 1] = mt;
+    a.retry_q[3 * (size_t)slot] = q0; a.retry_q[3 * (size_t)slot + 1] = q1; a.retry_q[3 * (size_t)slot + 2] = q2;
+}
+
+// Which ICP result does landmark i of a mesh use after the fill of p2p_matching_seg_icp.py:422-437?
+// Ascending pass: a missing entry takes entry i-1 (already filled), entry 0 takes entry 1 if that ran,
+// otherwise identity + mean shift.  Returns the bin whose raw (R,t) applies, or -1 for the default.
+__device__ __forceinline__ int fill_source(const LipArgs& a, int bb, int K, int i) {
+    int j = i;
+    while (j > 0 && a.icp_status[bb + j] == 0) --j;
+    if (a.icp_status[bb + j] != 0) return bb + j;
+    return (K > 1 && a.icp_status[bb + 1] != 0) ? bb + 1 : -1;
+}
+__device__ __forceinline__ void fill_apply(const LipArgs& a, int m, int src, double x, double y, double z, double& ox,
+                                           double& oy, double& oz) {
+    if (src >= 0) {
+        const double* R = a.icp_R + 9 * (size_t)src;
+        const double* t = a.icp_t + 3 * (size_t)src;
+        mat3_vec(R, x, y, z, ox, oy, oz);
+        ox += t[0]; oy += t[1]; oz += t[2];
+    } else {                                                 // identity, t = mean(target mesh) - mean(source mesh)
+        const GridHdr& hs = a.grid_hdr[m];
+        const GridHdr& ht = a.grid_hdr[pair_mesh(a, m)];
+        ox = x + (ht.sum[0] / ht.n - hs.sum[0] / hs.n);
+        oy = y + (ht.sum[1] / ht.n - hs.sum[1] / hs.n);
+        oz = z + (ht.sum[2] / ht.n - hs.sum[2] / hs.n);
+    }
+}
 
 // =============================================================================================
 // K4  per-point two-transform blend + final nearest neighbour in the whole target mesh
-//     (p2p_matching_seg_icp.py:452-489; get_triangle_angles :27-34 fused, cos(arccos(x)) == x)
+//     (p2p_matching_seg_icp.py:452-489; get_triangle_angles :27-34 fused, cos(arccos(x)) == x;
+//     the fill of :422-437 is resolved on the fly).
+//     Queries are taken in partition order (part_vid): the 32 queries of a warp belong to the same
+//     landmark blob, so their cell neighbourhoods overlap.  The warp takes the bounding box of its
+//     queries' cells (+1 ring), each lane looks up one cell of the box (hash + table loads in
+//     parallel), and the non-empty cells are then scanned by ALL lanes together: the target points are
+//     warp-uniform (broadcast) loads and every lane updates its own query — no divergence.
 // =============================================================================================
+#define LIP_BOX_MAX 512       // cells in the warp's box
+#define LIP_BOX_POINTS 384    // target points in the box beyond which the per-query path is cheaper
 __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const int m = a.tile_mesh[blockIdx.x];
-    const int v = a.tile_first[blockIdx.x] + threadIdx.x;
+    const int slot = a.tile_first[blockIdx.x] + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
-    if (v >= n) return;
+    const bool valid = slot < n;
     const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
-    const double* xyz = mesh_xyz(a, m);
-    const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+    const int v = valid ? a.part_vid[ub + slot] : 0;
     const int u = ub + v;
-    const int ia = a.nn0[u], ib = a.nn1[u];
-    double f0 = 0.5, f1 = 0.5;
-    if (K > 1) {
-        const double* lm = mesh_lm(a, m);
-        const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
-        const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
-        const double da = a.d0[u], db = a.d1[u];
-        // get_triangle_angles(g, da, db): B opposite da, C opposite db
-        double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
-        double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
-        cosB = fmin(fmax(cosB, -1.0), 1.0);
-        cosC = fmin(fmax(cosC, -1.0), 1.0);
-        if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
-        else {
-            const double cb = fabs(cosB), cc = fabs(cosC);
-            f0 = cb / (cb + cc); f1 = cc / (cb + cc);
-        }
-    }
-    const double* Ra = a.fill_R + 9 * (size_t)(bb + ia);
-    const double* ta = a.fill_t + 3 * (size_t)(bb + ia);
-    const double* Rb = a.fill_R + 9 * (size_t)(bb + ib);
-    const double* tb = a.fill_t + 3 * (size_t)(bb + ib);
-    double ax, ay, az, bx, by, bz;
-    mat3_vec(Ra, x, y, z, ax, ay, az);
-    mat3_vec(Rb, x, y, z, bx, by, bz);
-    const double q0 = f0 * (ax + ta[0]) + f1 * (bx + tb[0]);
-    const double q1 = f0 * (ay + ta[1]) + f1 * (by + tb[1]);
-    const double q2 = f0 * (az + ta[2]) + f1 * (bz + tb[2]);
     const int mt = pair_mesh(a, m);
-    const GridHdr h = a.grid_hdr[mt];
-    NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
-                              q0, q1, q2, a.counters, nullptr, a.profile);
-    if (r.idx < 0) { far_push(a, u, mt, q0, q1, q2); return; }
-    if (m < a.S) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
+    double q0 = 0, q1 = 0, q2 = 0;
+    if (valid) {
+        const double* xyz = mesh_xyz(a, m);
+        const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+        const int ia = a.nn0[u], ib = a.nn1[u];
+        double f0 = 0.5, f1 = 0.5;
+        if (K > 1) {
+            const double* lm = mesh_lm(a, m);
+            const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
+            const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
+            const double da = a.d0[u], db = a.d1[u];
+            // get_triangle_angles(g, da, db): B opposite da, C opposite db
+            double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
+            double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
+            cosB = fmin(fmax(cosB, -1.0), 1.0);
+            cosC = fmin(fmax(cosC, -1.0), 1.0);
+            if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
+            else {
+                const double cb = fabs(cosB), cc = fabs(cosC);
+                f0 = cb / (cb + cc); f1 = cc / (cb + cc);
+            }
+        }
+        double ax, ay, az, bx, by, bz;
+        const int sa = fill_source(a, bb, K, ia);
+        fill_apply(a, m, sa, x, y, z, ax, ay, az);
+        if (ib == ia) { bx = ax; by = ay; bz = az; }
+        else fill_apply(a, m, fill_source(a, bb, K, ib), x, y, z, bx, by, bz);
+        q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
+    }
+    // ---- warp-cooperative ring-1 search in the target's hashed grid ------------------------------------
+    const GridHdr& h = a.grid_hdr[mt];
+    const int* __restrict__ tab = a.grid_start + a.mesh_tab[mt];
+    const float4* __restrict__ pts = a.grid_pts + a.mesh_ubase[mt];
+    const float hh = h.h, inv_h = h.inv_h;
+    const int d0 = h.dim[0], d1 = h.dim[1], d2 = h.dim[2], mask = h.mask;
+    const float qx = (float)(q0 - h.c[0]), qy = (float)(q1 - h.c[1]), qz = (float)(q2 - h.c[2]);
+    // query cell, clamped to one cell outside the grid so that far-away queries keep the box finite
+    const int cx = min(max(cell_coord(qx, h.gmin[0], inv_h, d0), -1), d0);
+    const int cy = min(max(cell_coord(qy, h.gmin[1], inv_h, d1), -1), d1);
+    const int cz = min(max(cell_coord(qz, h.gmin[2], inv_h, d2), -1), d2);
+    const int BIG = 1 << 28;
+    const int lox = max(__reduce_min_sync(LIP_FULL, valid ? cx : BIG) - 1, 0), hix = min(__reduce_max_sync(LIP_FULL, valid ? cx : -BIG) + 1, d0 - 1);
+    const int loy = max(__reduce_min_sync(LIP_FULL, valid ? cy : BIG) - 1, 0), hiy = min(__reduce_max_sync(LIP_FULL, valid ? cy : -BIG) + 1, d1 - 1);
+    const int loz = max(__reduce_min_sync(LIP_FULL, valid ? cz : BIG) - 1, 0), hiz = min(__reduce_max_sync(LIP_FULL, valid ? cz : -BIG) + 1, d2 - 1);
+    const int sx = hix - lox + 1, sy = hiy - loy + 1, sz = hiz - loz + 1;
+    float best = INFINITY, sec = INFINITY;
+    int idx = -1;
+    bool certified = false;
+    if (sx > 0 && sy > 0 && sz > 0 && (long long)sx * sy * sz <= LIP_BOX_MAX) {
+        const int ncell = sx * sy * sz;
+        int visited = 0, mine = 0;
+        bool overflow = false;
+        for (int base = 0; base < ncell && !overflow; base += 32) {
+            const int k = base + lane;
+            int s = 0, e = 0, x = 0, y = 0, z = 0;
+            if (k < ncell) {
+                x = lox + k % sx; y = loy + (k / sx) % sy; z = loz + k / (sx * sy);
+                const int bucket = cell_hash(x, y, z, mask);
+                s = __ldg(&tab[bucket]); e = __ldg(&tab[bucket + 1]);
+            }
+            // the same bucket twice in one batch (hash collision inside the box) would count a point twice
+            const int key = (e > s) ? s : -1 - lane;
+            const unsigned same = __match_any_sync(LIP_FULL, key);
+            if ((same & ((1u << lane) - 1)) != 0) e = s;
+            unsigned nonempty = __ballot_sync(LIP_FULL, e > s);
+            while (nonempty) {
+                const int kk = __ffs(nonempty) - 1;
+                nonempty &= nonempty - 1;
+                const int ss = __shfl_sync(LIP_FULL, s, kk), ee = __shfl_sync(LIP_FULL, e, kk);
+                visited += ee - ss;
+                if (visited > LIP_BOX_POINTS) { overflow = true; break; }   // box too populated: per-query path is cheaper
+                if (a.profile) {                             // pairs inside the query's own 27 cells = algorithmic count
+                    const int bx = __shfl_sync(LIP_FULL, x, kk), by = __shfl_sync(LIP_FULL, y, kk), bz = __shfl_sync(LIP_FULL, z, kk);
+                    if (valid && max(max(abs(bx - cx), abs(by - cy)), abs(bz - cz)) <= 1) mine += ee - ss;
+                }
+                for (int j = ss; j < ee; ++j) {
+                    const float4 p = __ldg(&pts[j]);
+                    float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                    float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+                    nn_update(d, __float_as_int(p.w), best, sec, idx);
+                }
+            }
+        }
+        if (a.profile) {
+            const unsigned tot = __reduce_add_sync(LIP_FULL, (unsigned)mine);
+            if (lane == 0) atomicAdd(&a.counters[7], (unsigned long long)tot);
+        }
+        const float g = 0.999f * hh;
+        certified = valid && !overflow && (best <= g * g);   // the box contains ring 1 of every lane's own cell
+    }
+    if (!valid) return;
+    if (certified) {
+        idx = grid_finish(h, tab, pts, mesh_xyz(a, mt), q0, q1, q2, qx, qy, qz, cx, cy, cz, 1, best, sec, idx, a.counters);
+        if (m < a.S) a.T12[u] = idx; else a.T21[u - a.n1_total] = idx;
+    } else {
+        retry_push(a, u, mt, q0, q1, q2);                    // ring 2 / far: second pass, compacted
+    }
+}
+
+// queries the cooperative pass could not certify: one thread per query, ring 1 + ring 2, else far list
+__global__ void __launch_bounds__(128) retry_nn_kernel(LipArgs a) {
+    const int n_retry = a.sched[7];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_retry; i += gridDim.x * blockDim.x) {
+        const int u = a.retry_list[2 * (size_t)i], mt = a.retry_list[2 * (size_t)i + 1];
+        const double q0 = a.retry_q[3 * (size_t)i], q1 = a.retry_q[3 * (size_t)i + 1], q2 = a.retry_q[3 * (size_t)i + 2];
+        const GridHdr h = a.grid_hdr[mt];
+        NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
+                                  q0, q1, q2, a.counters, nullptr, 0);
+        if (r.idx < 0) { far_push(a, u, mt, q0, q1, q2); continue; }
+        if (u < a.n1_total) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
+    }
 }
 
 // raw query: nearest target (mesh1 side) of every mesh2-side vertex, with distance (get_NN_in_target)

@@ -44,6 +44,9 @@ struct lip_ctx {
     int sm_count = 0;
     int small_blocks_per_sm = 1, medium_blocks_per_sm = 1, big_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, medium ICP, grid build
+    cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    bool fill_done = false;
     lip_params params;
     std::string err;
     // plan
@@ -92,8 +95,8 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
     const size_t o_fR = take(B * 72), o_ft = take(B * 24);
-    const size_t o_sched = take(8 * 4), o_small = take(B * 4), o_med = take(B * 4), o_big = take(B * 4);
-    const size_t o_far = take(n * 8), o_farq = take(n * 24);
+    const size_t o_sched = take(16 * 4), o_small = take(B * 4), o_med = take(4 * B * 4), o_big = take(B * 4);
+    const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
     LIP_CUDA(c, c->ws.ensure(off));
@@ -107,6 +110,7 @@ int carve_workspace(lip_ctx* c) {
     a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft);
     a.sched = (int*)(base + o_sched); a.small_list = (int*)(base + o_small); a.medium_list = (int*)(base + o_med);
     a.big_list = (int*)(base + o_big); a.far_list = (int*)(base + o_far); a.far_q = (double*)(base + o_farq);
+    a.retry_list = (int*)(base + o_re); a.retry_q = (double*)(base + o_req);
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
     return LIP_OK;
@@ -208,10 +212,16 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     set_param_args(c);
     int64_t launches = 0;
     int evi = 0;
+    // While profiling, everything runs back to back on `st` so that the events bracket one kernel each;
+    // otherwise the three ICP kernels and the grid build run as concurrent branches (their tails overlap).
+    const bool serial = c->profiling;
     auto mark = [&]() { if (c->profiling) cudaEventRecord(c->ev[evi], st); ++evi; };
+    cudaStream_t s_big = serial ? st : c->side[0], s_med = serial ? st : c->side[1], s_grid = serial ? st : c->side[2];
     c->ev_valid = false;
-    LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 8 * 4, st));
+    c->fill_done = false;
+    LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 16 * 4, st));
     LIP_CUDA(c, cudaMemsetAsync(a.counters, 0, 8 * 8, st));
+    if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
     if (stages & ST_PARTITION) {
         size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 2 + 1) * 4;
@@ -219,36 +229,51 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         ++launches;
     }
     mark();                                                  // 1: after partition
+    bool forked_icp = false, forked_grid = false;
     if (stages & ST_ICP) {
         icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
         mark();                                              // 2: after schedule
-        int gs = c->sm_count * c->small_blocks_per_sm;
-        gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
-        icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
-        mark();                                              // 3: after small ICP
-        // a partition is "medium"/"big" only if src or tgt exceeds LIP_SMALL_CAP / LIP_MEDIUM_CAP points
+        if (!serial) {
+            LIP_CUDA(c, cudaEventRecord(c->ev_fork, st));
+            LIP_CUDA(c, cudaStreamWaitEvent(s_big, c->ev_fork, 0));
+            LIP_CUDA(c, cudaStreamWaitEvent(s_med, c->ev_fork, 0));
+            forked_icp = true;
+        }
+        // longest tasks first: CTA-per-partition (big), then medium, then small partitions
+        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_MEDIUM_CAP + 1);
+        int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
         int gm = c->sm_count * c->medium_blocks_per_sm;
         int64_t mbound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
         gm = (int)std::max<int64_t>(1, std::min<int64_t>(gm, (mbound + LIP_MEDIUM_WARPS - 1) / LIP_MEDIUM_WARPS));
-        icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, st>>>(a);
-        mark();                                              // 4: after medium ICP
-        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_MEDIUM_CAP + 1);
-        int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
-        icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
+        int gs = c->sm_count * c->small_blocks_per_sm;
+        gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
+        if (serial) {
+            icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+            mark();                                          // 3: after small ICP
+            icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, st>>>(a);
+            mark();                                          // 4: after medium ICP
+            icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
+        } else {
+            icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, s_big>>>(a);
+            icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, s_med>>>(a);
+            icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+            mark(); mark();
+        }
         launches += 4;
     } else { mark(); mark(); mark(); }
     mark();                                                  // 5: after big ICP
     if (stages & (ST_GRID | ST_GRID_ALL)) {
-        LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, st));
-        grid_build_kernel<<<c->M, 256, 0, st>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
+        if (!serial) { LIP_CUDA(c, cudaStreamWaitEvent(s_grid, c->ev_begin, 0)); forked_grid = true; }
+        LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, s_grid));
+        grid_build_kernel<<<c->M, 256, 0, s_grid>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
         ++launches;
     }
     mark();                                                  // 6: after grid build
-    if (stages & ST_FILL) {
-        fill_kernel<<<(c->M + 127) / 128, 128, 0, st>>>(a);
-        ++launches;
+    if (forked_icp) {
+        LIP_CUDA(c, cudaEventRecord(c->ev_join[0], s_big)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
+        LIP_CUDA(c, cudaEventRecord(c->ev_join[1], s_med)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
     }
-    mark();                                                  // 7: after fill
+    if (forked_grid) { LIP_CUDA(c, cudaEventRecord(c->ev_join[2], s_grid)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[2], 0)); }
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
         blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
@@ -257,7 +282,13 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
-    mark();                                                  // 8: after blend / query
+    mark();                                                  // 7: after blend / query
+    if ((stages & ST_BLEND) && c->n_tiles > 0) {
+        int gr = std::max(1, std::min(c->sm_count * 8, (a.n_total + 127) / 128));
+        retry_nn_kernel<<<gr, 128, 0, st>>>(a);
+        ++launches;
+    }
+    mark();                                                  // 8: after retry
     if ((stages & (ST_QUERY | ST_BLEND)) && c->n_tiles > 0) {
         int gf = std::max(1, std::min(c->sm_count * 8, (a.n_total + 3) / 4));
         far_nn_kernel<<<gf, 128, 0, st>>>(a);
@@ -270,7 +301,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     return LIP_OK;
 }
 
-const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID | ST_FILL | ST_BLEND;
+const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // the fill is resolved inside blend_nn_kernel
 
 }  // namespace
 
@@ -313,6 +344,12 @@ int lip_create(lip_ctx** out, int device) {
         delete c;
         return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
     }
+    for (int i = 0; i < 3; ++i) {
+        cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true>,
                                                       LIP_SMALL_WARPS * 32, 0) == cudaSuccess && nb > 0)
@@ -334,6 +371,9 @@ void lip_destroy(lip_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc})
         b->release();
     cudaStreamDestroy(c->stream);
@@ -401,6 +441,12 @@ int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, i
     LIP_CUDA(c, cudaDeviceSynchronize());
     const LipArgs& a = c->args;
     const size_t K = (size_t)c->sumK;
+    if (filled && !c->fill_done) {                           // the hot path resolves the fill on the fly; materialise it here
+        fill_kernel<<<(c->M + 127) / 128, 128, 0, c->stream>>>(a);
+        LIP_CUDA(c, cudaGetLastError());
+        LIP_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->fill_done = true;
+    }
     const double* R = filled ? a.fill_R : a.icp_R;
     const double* t = filled ? a.fill_t : a.icp_t;
     // bins [0, sumK): src = mesh1 -> T12 ICPs ; bins [sumK, 2 sumK): src = mesh2 -> T21 ICPs
@@ -440,11 +486,11 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     cudaSetDevice(c->device);
     LIP_CUDA(c, cudaDeviceSynchronize());
     unsigned long long h[8];
-    int sched[8];
+    int sched[16];
     LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
     LIP_CUDA(c, cudaMemcpy(sched, c->args.sched, sizeof(sched), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];
-    counters[0] = sched[0] + sched[4]; counters[1] = sched[1]; counters[5] = sched[3];
+    counters[0] = sched[0] + sched[4]; counters[1] = sched[1]; counters[5] = sched[3]; counters[4] = sched[7];
     counters[6] = c->last_launches;
     return LIP_OK;
 }
