@@ -177,6 +177,55 @@ __device__ __forceinline__ void nn_scan2(const float4* __restrict__ tf, int cnt,
     }
 }
 
+// ---- blocked fp32 scan of an SMEM target tile (warp-per-partition kernels) ----------------------------
+// Per (query, candidate) pair the loop keeps only the two smallest scores (3 min/max ops); WHICH
+// candidate is best is recorded per block of 8 candidates (one compare+select per block) and recovered
+// afterwards by re-evaluating that block with the identical instruction sequence.
+// DOT = true scores with c = |y|^2 - 2 q.y (3 FMAs; |y|^2 precomputed in .w, the query passed as -2q):
+// same argmin as the squared distance |q - y|^2 = c + |q|^2, used when the partition is compact enough
+// for the cancellation error to stay small; DOT = false scores with the difference form.
+#define LIP_NN_BLOCK 8
+template <bool DOT>
+__device__ __forceinline__ float nn_score(const float4 t, float mx, float my, float mz) {
+    if (DOT) return fmaf(mx, t.x, fmaf(my, t.y, fmaf(mz, t.z, t.w)));
+    float dx = t.x - mx, dy = t.y - my, dz = t.z - mz;
+    float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+    return d;
+}
+struct NNTop2 { float best, sec; int blk; };
+
+template <bool DOT, int Q>
+__device__ __forceinline__ void nn_scan_blocks(const float4* __restrict__ tf, int nt_pad, const float (&m)[Q][3], NNTop2 (&r)[Q]) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { r[q].best = INFINITY; r[q].sec = INFINITY; r[q].blk = 0; }
+    for (int jb = 0; jb < nt_pad; jb += LIP_NN_BLOCK) {
+        float prev[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) prev[q] = r[q].best;
+#pragma unroll
+        for (int k = 0; k < LIP_NN_BLOCK; ++k) {
+            const float4 t = tf[jb + k];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float c = nn_score<DOT>(t, m[q][0], m[q][1], m[q][2]);
+                r[q].sec = fminf(r[q].sec, fmaxf(c, r[q].best));
+                r[q].best = fminf(r[q].best, c);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) r[q].blk = (r[q].best < prev[q]) ? jb : r[q].blk;
+    }
+}
+// index of the first candidate of block `blk` whose score equals `best` (bitwise: same instruction sequence)
+template <bool DOT>
+__device__ __forceinline__ int nn_block_index(const float4* __restrict__ tf, int blk, float best, float mx, float my, float mz) {
+    int idx = blk;
+#pragma unroll
+    for (int k = LIP_NN_BLOCK - 1; k >= 0; --k)
+        if (nn_score<DOT>(tf[blk + k], mx, my, mz) == best) idx = blk + k;
+    return idx;
+}
+
 // Per-warp SMEM of the warp-per-partition kernel.  SMEM64 = true (small partitions): float64 copies
 // of source and target live in SMEM too; false (medium partitions): only the fp32 search tile is
 // staged and the float64 coordinates are gathered from global memory (L1/L2 resident) when needed.
@@ -203,14 +252,23 @@ struct IcpWarpView {                                     // one partition as see
     }
 };
 
-template <int CAP, bool SMEM64>
-__device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& w, int nt, bool valid, float best,
-                                                float sec, int idx, float mabs, double px, double py, double pz,
-                                                double reject, double* acc, unsigned long long* counters) {
+template <int CAP, bool SMEM64, bool DOT>
+__device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& w, int nt, bool valid, const NNTop2& r,
+                                                float mx, float my, float mz, float mabs, double px, double py,
+                                                double pz, double reject, double* acc, unsigned long long* counters) {
     if (!valid) return;
-    float fx = (float)px, fy = (float)py, fz = (float)pz;
-    float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) + mabs);
-    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {   // near tie: decide in float64, lowest index
+    int idx = nn_block_index<DOT>(w.sm.tf, r.blk, r.best, mx, my, mz);
+    const float fx = (float)px, fy = (float)py, fz = (float)pz;
+    const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
+    const float e = 1.2e-7f * (qabs + mabs);
+    float tol;
+    if (DOT) {                                               // scores are c = d2 - |q|^2
+        const float qq = fx * fx + fy * fy + fz * fz;
+        tol = d2_err(fmaxf(r.best + qq, 0.f), e) + d2_err(fmaxf(r.sec + qq, 0.f), e) + 2.2e-6f * (mabs * mabs + qabs * mabs);
+    } else {
+        tol = d2_err(r.best, e) + d2_err(r.sec, e);
+    }
+    if (!(r.sec - r.best > tol)) {                           // near tie: decide in float64, lowest index
         double bd = INFINITY;
         for (int j = 0; j < nt; ++j) {
             double tx, ty, tz;
@@ -231,6 +289,42 @@ __device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& 
         acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
         acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
         acc[16] += 1.0;
+    }
+}
+
+// one NN pass of the partition: every source point against the staged target; accumulates the Kabsch sums
+template <int CAP, bool SMEM64, bool DOT>
+__device__ __forceinline__ void icp_warp_pass(const LipArgs& a, const IcpWarpView<CAP, SMEM64>& w, const IcpState& st,
+                                              int ns, int nt, int nt_pad, float mabs, int lane, double* acc) {
+    const float sc = DOT ? -2.0f : 1.0f;
+    int q0 = 0;
+    for (; q0 + 32 < ns; q0 += 64) {                         // two queries per lane while more than 32 remain
+        const int qa = q0 + lane, qb = qa + 32;
+        const bool vb = qb < ns;
+        double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
+        w.src(qa, sax, say, saz);
+        w.src(vb ? qb : ns - 1, sbx, sby, sbz);
+        mat3_vec(st.R, sax, say, saz, pax, pay, paz);
+        pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
+        mat3_vec(st.R, sbx, sby, sbz, pbx, pby, pbz);
+        pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+        const float m[2][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}, {sc * (float)pbx, sc * (float)pby, sc * (float)pbz}};
+        NNTop2 r[2];
+        nn_scan_blocks<DOT, 2>(w.sm.tf, nt_pad, m, r);
+        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, true, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, vb, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
+    }
+    if (q0 < ns) {                                           // at most 32 left: one query per lane
+        const int qa = q0 + lane;
+        const bool va = qa < ns;
+        double sax, say, saz, pax, pay, paz;
+        w.src(va ? qa : ns - 1, sax, say, saz);
+        mat3_vec(st.R, sax, say, saz, pax, pay, paz);
+        pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
+        const float m[1][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}};
+        NNTop2 r[1];
+        nn_scan_blocks<DOT, 1>(w.sm.tf, nt_pad, m, r);
+        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, va, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
     }
 }
 
@@ -258,11 +352,17 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
         double x, y, z;
         if (SMEM64) { x = sm.tx[j] - cx; y = sm.ty[j] - cy; z = sm.tz[j] - cz; sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z; }
         else w.tgt(j, x, y, z);
-        sm.tf[j] = make_float4((float)x, (float)y, (float)z, 0.f);
-        mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf((float)x), fabsf((float)y)), fabsf((float)z)));
+        const float fx = (float)x, fy = (float)y, fz = (float)z;
+        sm.tf[j] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));   // .w = |y|^2 for the dot-form score
+        mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)));
         mtx += x; mty += y; mtz += z;
     }
     mabs = warp_maxf(mabs);
+    // dot-form scores only while the cancellation error stays far below the point spacing
+    const bool use_dot = mabs <= 24.0f;
+    const int nt_pad = (nt + LIP_NN_BLOCK - 1) / LIP_NN_BLOCK * LIP_NN_BLOCK;
+    if (lane < nt_pad - nt)                                   // sentinels: never the best, never a runner-up
+        sm.tf[nt + lane] = use_dot ? make_float4(0.f, 0.f, 0.f, 3.0e38f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
     mtx = warp_sum(mtx) / nt; mty = warp_sum(mty) / nt; mtz = warp_sum(mtz) / nt;
     double msx = 0, msy = 0, msz = 0;
     for (int q = lane; q < ns; q += 32) {
@@ -283,23 +383,8 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
         double acc[17];
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-        for (int q0 = 0; q0 < ns; q0 += 64) {
-            const int qa = q0 + lane, qb = qa + 32;
-            const bool va = qa < ns, vb = qb < ns;
-            double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
-            w.src(va ? qa : ns - 1, sax, say, saz);
-            w.src(vb ? qb : ns - 1, sbx, sby, sbz);
-            mat3_vec(st.R, sax, say, saz, pax, pay, paz);
-            pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-            mat3_vec(st.R, sbx, sby, sbz, pbx, pby, pbz);
-            pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
-            float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
-            int ia = 0, ib = 0;
-            nn_scan2(sm.tf, nt, 0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
-                     besta, seca, ia, bestb, secb, ib);
-            icp_warp_finish<CAP, SMEM64>(w, nt, va, besta, seca, ia, mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
-            icp_warp_finish<CAP, SMEM64>(w, nt, vb, bestb, secb, ib, mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
-        }
+        if (use_dot) icp_warp_pass<CAP, SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, acc);
+        else icp_warp_pass<CAP, SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, acc);
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
         const double cost = acc[0] / ns;                    // np.mean(distance)   (:86)
@@ -314,7 +399,7 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
 // LIST 0: small partitions (sched[0] entries of small_list, cursor sched[2]);
 // LIST 1: medium partitions (sched[4] entries of medium_list, cursor sched[5])
 template <int CAP, int WARPS, bool SMEM64>
-__global__ void __launch_bounds__(WARPS * 32) icp_warp_kernel(LipArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, 4) icp_warp_kernel(LipArgs a) {
     __shared__ IcpWarpSmem<CAP, SMEM64> sm_all[WARPS];
     IcpWarpSmem<CAP, SMEM64>& sm = sm_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -834,14 +919,11 @@ __device__ __forceinline__ void fill_apply(const LipArgs& a, int m, int src, dou
 // K4  per-point two-transform blend + final nearest neighbour in the whole target mesh
 //     (p2p_matching_seg_icp.py:452-489; get_triangle_angles :27-34 fused, cos(arccos(x)) == x;
 //     the fill of :422-437 is resolved on the fly).
-//     Queries are taken in partition order (part_vid): the 32 queries of a warp belong to the same
-//     landmark blob, so their cell neighbourhoods overlap.  The warp takes the bounding box of its
-//     queries' cells (+1 ring), each lane looks up one cell of the box (hash + table loads in
-//     parallel), and the non-empty cells are then scanned by ALL lanes together: the target points are
-//     warp-uniform (broadcast) loads and every lane updates its own query — no divergence.
+//     Queries are taken in partition order (part_vid): the threads of a CTA work on one landmark blob,
+//     so the target cells and points they touch stay in L1.  Each thread first issues the 27 cell
+//     look-ups of its ring (independent loads), then walks the candidates of the non-empty cells in one
+//     flattened loop; queries that ring 1 cannot certify go to a compacted retry list.
 // =============================================================================================
-#define LIP_BOX_MAX 512       // cells in the warp's box
-#define LIP_BOX_POINTS 384    // target points in the box beyond which the per-query path is cheaper
 __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const int m = a.tile_mesh[blockIdx.x];
     const int slot = a.tile_first[blockIdx.x] + threadIdx.x;
@@ -881,77 +963,60 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
         else fill_apply(a, m, fill_source(a, bb, K, ib), x, y, z, bx, by, bz);
         q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
     }
-    // ---- warp-cooperative ring-1 search in the target's hashed grid ------------------------------------
+    if (!valid) return;
+    // ---- ring-1 search in the target's hashed grid ------------------------------------------------------
     const GridHdr& h = a.grid_hdr[mt];
     const int* __restrict__ tab = a.grid_start + a.mesh_tab[mt];
     const float4* __restrict__ pts = a.grid_pts + a.mesh_ubase[mt];
-    const float hh = h.h, inv_h = h.inv_h;
-    const int d0 = h.dim[0], d1 = h.dim[1], d2 = h.dim[2], mask = h.mask;
     const float qx = (float)(q0 - h.c[0]), qy = (float)(q1 - h.c[1]), qz = (float)(q2 - h.c[2]);
-    // query cell, clamped to one cell outside the grid so that far-away queries keep the box finite
-    const int cx = min(max(cell_coord(qx, h.gmin[0], inv_h, d0), -1), d0);
-    const int cy = min(max(cell_coord(qy, h.gmin[1], inv_h, d1), -1), d1);
-    const int cz = min(max(cell_coord(qz, h.gmin[2], inv_h, d2), -1), d2);
-    const int BIG = 1 << 28;
-    const int lox = max(__reduce_min_sync(LIP_FULL, valid ? cx : BIG) - 1, 0), hix = min(__reduce_max_sync(LIP_FULL, valid ? cx : -BIG) + 1, d0 - 1);
-    const int loy = max(__reduce_min_sync(LIP_FULL, valid ? cy : BIG) - 1, 0), hiy = min(__reduce_max_sync(LIP_FULL, valid ? cy : -BIG) + 1, d1 - 1);
-    const int loz = max(__reduce_min_sync(LIP_FULL, valid ? cz : BIG) - 1, 0), hiz = min(__reduce_max_sync(LIP_FULL, valid ? cz : -BIG) + 1, d2 - 1);
-    const int sx = hix - lox + 1, sy = hiy - loy + 1, sz = hiz - loz + 1;
-    float best = INFINITY, sec = INFINITY;
-    int idx = -1;
-    bool certified = false;
-    if (sx > 0 && sy > 0 && sz > 0 && (long long)sx * sy * sz <= LIP_BOX_MAX) {
-        const int ncell = sx * sy * sz;
-        int visited = 0, mine = 0;
-        bool overflow = false;
-        for (int base = 0; base < ncell && !overflow; base += 32) {
-            const int k = base + lane;
-            int s = 0, e = 0, x = 0, y = 0, z = 0;
-            if (k < ncell) {
-                x = lox + k % sx; y = loy + (k / sx) % sy; z = loz + k / (sx * sy);
-                const int bucket = cell_hash(x, y, z, mask);
-                s = __ldg(&tab[bucket]); e = __ldg(&tab[bucket + 1]);
-            }
-            // the same bucket twice in one batch (hash collision inside the box) would count a point twice
-            const int key = (e > s) ? s : -1 - lane;
-            const unsigned same = __match_any_sync(LIP_FULL, key);
-            if ((same & ((1u << lane) - 1)) != 0) e = s;
-            unsigned nonempty = __ballot_sync(LIP_FULL, e > s);
-            while (nonempty) {
-                const int kk = __ffs(nonempty) - 1;
-                nonempty &= nonempty - 1;
-                const int ss = __shfl_sync(LIP_FULL, s, kk), ee = __shfl_sync(LIP_FULL, e, kk);
-                visited += ee - ss;
-                if (visited > LIP_BOX_POINTS) { overflow = true; break; }   // box too populated: per-query path is cheaper
-                if (a.profile) {                             // pairs inside the query's own 27 cells = algorithmic count
-                    const int bx = __shfl_sync(LIP_FULL, x, kk), by = __shfl_sync(LIP_FULL, y, kk), bz = __shfl_sync(LIP_FULL, z, kk);
-                    if (valid && max(max(abs(bx - cx), abs(by - cy)), abs(bz - cz)) <= 1) mine += ee - ss;
-                }
-                for (int j = ss; j < ee; ++j) {
-                    const float4 p = __ldg(&pts[j]);
-                    float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-                    float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-                    nn_update(d, __float_as_int(p.w), best, sec, idx);
-                }
-            }
-        }
-        if (a.profile) {
-            const unsigned tot = __reduce_add_sync(LIP_FULL, (unsigned)mine);
-            if (lane == 0) atomicAdd(&a.counters[7], (unsigned long long)tot);
-        }
-        const float g = 0.999f * hh;
-        certified = valid && !overflow && (best <= g * g);   // the box contains ring 1 of every lane's own cell
+    const int d0 = h.dim[0], d1 = h.dim[1], d2 = h.dim[2], mask = h.mask;
+    const int cx = cell_coord(qx, h.gmin[0], h.inv_h, d0), cy = cell_coord(qy, h.gmin[1], h.inv_h, d1),
+              cz = cell_coord(qz, h.gmin[2], h.inv_h, d2);
+    // pass A: the 27 table look-ups, branch-free and independent (all loads in flight together);
+    // non-empty cells are compacted into a per-thread list
+    int rs[27], re[27];
+    int nc = 0;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const int x = cx + (k % 3) - 1, y = cy + ((k / 3) % 3) - 1, z = cz + (k / 9) - 1;
+        const bool in = (unsigned)x < (unsigned)d0 && (unsigned)y < (unsigned)d1 && (unsigned)z < (unsigned)d2;
+        const int bucket = in ? cell_hash(x, y, z, mask) : 0;
+        const int s = __ldg(&tab[bucket]), e = __ldg(&tab[bucket + 1]);
+        if (in && e > s) { rs[nc] = s; re[nc] = e; ++nc; }
     }
-    if (!valid) return;
-    if (certified) {
+    // pass B: one candidate per iteration whatever cell it comes from (lanes stay together until the
+    // lane with the most candidates finishes)
+    float best = INFINITY, sec = INFINITY;
+    int idx = -1, visited = 0;
+    if (nc > 0) {
+        int c = 0, j = rs[0], e = re[0];
+        for (;;) {
+            const float4 p = __ldg(&pts[j]);
+            float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+            nn_update(d, __float_as_int(p.w), best, sec, idx);
+            ++visited;
+            if (++j == e) {
+                if (++c == nc) break;
+                j = rs[c]; e = re[c];
+            }
+        }
+    }
+    if (a.profile) {                                         // ring-1 candidates = the algorithmic pair count
+        const unsigned act = __activemask();
+        const unsigned tot = __reduce_add_sync(act, (unsigned)visited);
+        if (lane == __ffs(act) - 1) atomicAdd(&a.counters[7], (unsigned long long)tot);
+    }
+    const float g = 0.999f * h.h;
+    if (best <= g * g) {                                     // certified: nothing outside ring 1 can be closer
         idx = grid_finish(h, tab, pts, mesh_xyz(a, mt), q0, q1, q2, qx, qy, qz, cx, cy, cz, 1, best, sec, idx, a.counters);
         if (m < a.S) a.T12[u] = idx; else a.T21[u - a.n1_total] = idx;
     } else {
-        retry_push(a, u, mt, q0, q1, q2);                    // ring 2 / far: second pass, compacted
+        retry_push(a, u, mt, q0, q1, q2);                    // ring 2 / far: second pass over the compacted list
     }
 }
 
-// queries the cooperative pass could not certify: one thread per query, ring 1 + ring 2, else far list
+// queries ring 1 could not certify: one thread per query, ring 1 + ring 2, else far list
 __global__ void __launch_bounds__(128) retry_nn_kernel(LipArgs a) {
     const int n_retry = a.sched[7];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_retry; i += gridDim.x * blockDim.x) {
