@@ -40,8 +40,10 @@ struct LipArgs {
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
-    int* sched;              // [0] n_small [1] n_big [2] small cursor [3] n_far [4] n_medium [5] medium cursor [6] far cursor [7] n_retry [8..11] medium class counts
-    int *small_list, *medium_list, *big_list;    // [B]
+    int* sched;              // [32] [0] n_small [1] n_big [2] small cursor [3] n_far [4] n_medium [5] medium cursor
+                             //      [6] far cursor [7] n_retry [8..11] medium class counts [12..15] big class counts
+                             //      [16] big cursor
+    int *small_list, *medium_list, *big_list;    // [B], [4B] (four work classes), [4B]
     int* far_list;           // [n_total] unified ids of queries whose ring search could not certify
     double* far_q;           // [3 * n_total] their blended positions
     int* retry_list;         // [2 * n_total] (unified id, target mesh) of queries the cooperative pass left open

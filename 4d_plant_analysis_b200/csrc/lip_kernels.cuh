@@ -5,7 +5,7 @@
 
 #define LIP_SMALL_CAP 128     // partitions with <= this many src AND tgt points: one warp, all in SMEM
 #define LIP_SMALL_WARPS 4
-#define LIP_MEDIUM_CAP 640    // up to this many: still one warp, fp32 tile in SMEM, float64 from global
+#define LIP_MEDIUM_CAP 256    // up to this many: still one warp, fp32 tile in SMEM, float64 from global
 #define LIP_MEDIUM_WARPS 4
 #define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 256
@@ -90,11 +90,16 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     else if (mx <= LIP_MEDIUM_CAP) {
         // four work classes, heaviest first: the persistent warps drain class 3, then 2, 1, 0 (longest tasks first)
         const long long w = (long long)ns * nt;
-        const int cls = (w > 160000) ? 3 : (w > 70000) ? 2 : (w > 30000) ? 1 : 0;
+        const int cls = (w > 45000) ? 3 : (w > 30000) ? 2 : (w > 18000) ? 1 : 0;
         a.medium_list[(size_t)cls * a.B + atomicAdd(&a.sched[8 + cls], 1)] = b;
         atomicAdd(&a.sched[4], 1);
     }
-    else a.big_list[atomicAdd(&a.sched[1], 1)] = b;
+    else {
+        const long long w = (long long)ns * nt;
+        const int cls = (w > 1000000) ? 3 : (w > 400000) ? 2 : (w > 150000) ? 1 : 0;
+        a.big_list[(size_t)cls * a.B + atomicAdd(&a.sched[12 + cls], 1)] = b;
+        atomicAdd(&a.sched[1], 1);
+    }
 }
 
 // =============================================================================================
@@ -236,28 +241,29 @@ struct IcpWarpSmem {
     double sx[SMEM64 ? CAP : 1], sy[SMEM64 ? CAP : 1], sz[SMEM64 ? CAP : 1];   // centred fp64 source
 };
 
-template <int CAP, bool SMEM64>
-struct IcpWarpView {                                     // one partition as seen by its warp
-    IcpWarpSmem<CAP, SMEM64>& sm;
+template <bool SMEM64>
+struct IcpView {                                         // one partition as seen by the warp / CTA working on it
+    const float4* tf;                                    // staged centred fp32 target (SMEM)
+    const double *tx, *ty, *tz, *sx, *sy, *sz;           // SMEM64: centred float64 target / source in SMEM
     const double *xs, *xt;                               // mesh vertex arrays (original coordinates)
     const int *vs, *vt;                                  // member lists (local vertex ids)
     double cx, cy, cz;                                   // target centroid
     __device__ __forceinline__ void tgt(int j, double& x, double& y, double& z) const {
-        if (SMEM64) { x = sm.tx[j]; y = sm.ty[j]; z = sm.tz[j]; }
+        if (SMEM64) { x = tx[j]; y = ty[j]; z = tz[j]; }
         else { size_t v = (size_t)vt[j]; x = xt[3 * v] - cx; y = xt[3 * v + 1] - cy; z = xt[3 * v + 2] - cz; }
     }
     __device__ __forceinline__ void src(int q, double& x, double& y, double& z) const {
-        if (SMEM64) { x = sm.sx[q]; y = sm.sy[q]; z = sm.sz[q]; }
+        if (SMEM64) { x = sx[q]; y = sy[q]; z = sz[q]; }
         else { size_t v = (size_t)vs[q]; x = xs[3 * v] - cx; y = xs[3 * v + 1] - cy; z = xs[3 * v + 2] - cz; }
     }
 };
 
-template <int CAP, bool SMEM64, bool DOT>
-__device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& w, int nt, bool valid, const NNTop2& r,
+template <bool SMEM64, bool DOT>
+__device__ __forceinline__ void icp_finish(const IcpView<SMEM64>& w, int nt, bool valid, const NNTop2& r,
                                                 float mx, float my, float mz, float mabs, double px, double py,
                                                 double pz, double reject, double* acc, unsigned long long* counters) {
     if (!valid) return;
-    int idx = nn_block_index<DOT>(w.sm.tf, r.blk, r.best, mx, my, mz);
+    int idx = nn_block_index<DOT>(w.tf, r.blk, r.best, mx, my, mz);
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
     const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
     const float e = 1.2e-7f * (qabs + mabs);
@@ -293,13 +299,14 @@ __device__ __forceinline__ void icp_warp_finish(const IcpWarpView<CAP, SMEM64>& 
 }
 
 // one NN pass of the partition: every source point against the staged target; accumulates the Kabsch sums
-template <int CAP, bool SMEM64, bool DOT>
-__device__ __forceinline__ void icp_warp_pass(const LipArgs& a, const IcpWarpView<CAP, SMEM64>& w, const IcpState& st,
-                                              int ns, int nt, int nt_pad, float mabs, int lane, double* acc) {
+// (lane, stride) = (lane, 32) for a warp, (thread, blockDim) for a CTA
+template <bool SMEM64, bool DOT>
+__device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>& w, const IcpState& st, int ns, int nt,
+                                         int nt_pad, float mabs, int lane, int stride, double* acc) {
     const float sc = DOT ? -2.0f : 1.0f;
     int q0 = 0;
-    for (; q0 + 32 < ns; q0 += 64) {                         // two queries per lane while more than 32 remain
-        const int qa = q0 + lane, qb = qa + 32;
+    for (; q0 + stride < ns; q0 += 2 * stride) {             // two queries per lane while more than `stride` remain
+        const int qa = q0 + lane, qb = qa + stride;
         const bool vb = qb < ns;
         double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
         w.src(qa, sax, say, saz);
@@ -310,11 +317,11 @@ __device__ __forceinline__ void icp_warp_pass(const LipArgs& a, const IcpWarpVie
         pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
         const float m[2][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}, {sc * (float)pbx, sc * (float)pby, sc * (float)pbz}};
         NNTop2 r[2];
-        nn_scan_blocks<DOT, 2>(w.sm.tf, nt_pad, m, r);
-        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, true, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
-        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, vb, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
+        nn_scan_blocks<DOT, 2>(w.tf, nt_pad, m, r);
+        icp_finish<SMEM64, DOT>(w, nt, true, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+        icp_finish<SMEM64, DOT>(w, nt, vb, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
     }
-    if (q0 < ns) {                                           // at most 32 left: one query per lane
+    if (q0 < ns) {                                           // at most `stride` left: one query per lane
         const int qa = q0 + lane;
         const bool va = qa < ns;
         double sax, say, saz, pax, pay, paz;
@@ -323,8 +330,8 @@ __device__ __forceinline__ void icp_warp_pass(const LipArgs& a, const IcpWarpVie
         pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
         const float m[1][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}};
         NNTop2 r[1];
-        nn_scan_blocks<DOT, 1>(w.sm.tf, nt_pad, m, r);
-        icp_warp_finish<CAP, SMEM64, DOT>(w, nt, va, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+        nn_scan_blocks<DOT, 1>(w.tf, nt_pad, m, r);
+        icp_finish<SMEM64, DOT>(w, nt, va, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
     }
 }
 
@@ -334,7 +341,8 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
     const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
     const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
     const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
-    IcpWarpView<CAP, SMEM64> w{sm, mesh_xyz(a, ms), mesh_xyz(a, mt), a.part_vid + so, a.part_vid + to, 0.0, 0.0, 0.0};
+    IcpView<SMEM64> w{sm.tf, sm.tx, sm.ty, sm.tz, sm.sx, sm.sy, sm.sz, mesh_xyz(a, ms), mesh_xyz(a, mt),
+                      a.part_vid + so, a.part_vid + to, 0.0, 0.0, 0.0};
     // ---- stage the target, centred on its centroid -------------------------------------------------
     double cx = 0, cy = 0, cz = 0;
     for (int j = lane; j < nt; j += 32) {
@@ -383,8 +391,8 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
         double acc[17];
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-        if (use_dot) icp_warp_pass<CAP, SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, acc);
-        else icp_warp_pass<CAP, SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, acc);
+        if (use_dot) icp_pass<SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, acc);
+        else icp_pass<SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, acc);
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
         const double cost = acc[0] / ns;                    // np.mean(distance)   (:86)
@@ -470,10 +478,18 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
     __shared__ double red[LIP_BIG_THREADS / 32];
     __shared__ double red17[LIP_BIG_THREADS / 32][17];
     __shared__ float redf[LIP_BIG_THREADS / 32];
+    __shared__ int s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_big = a.sched[1];
-    for (int w = blockIdx.x; w < n_big; w += gridDim.x) {
-        const int b = a.big_list[w], pb = pair_bin(a, b);
+    for (;;) {                                              // persistent CTAs, heaviest class first
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&a.sched[16], 1);      // big cursor
+        __syncthreads();
+        const int wi = s_item;
+        if (wi >= n_big) break;
+        int cls = 3, ri = wi;
+        while (cls > 0 && ri >= a.sched[12 + cls]) { ri -= a.sched[12 + cls]; --cls; }
+        const int b = a.big_list[(size_t)cls * a.B + ri], pb = pair_bin(a, b);
         const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
         const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
         const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
@@ -508,15 +524,24 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
             sx += xs[3 * v] - cx; sy += xs[3 * v + 1] - cy; sz += xs[3 * v + 2] - cz;
         }
         const double msx = block_sum(sx, red, tid) / ns, msy = block_sum(sy, red, tid) / ns, msz = block_sum(sz, red, tid) / ns;
+        // resident: the whole target fits the SMEM tile -> staged once, blocked top-2 scan (same as the warp kernels)
         const bool resident = nt <= LIP_BIG_CAP;
+        const bool use_dot = mabs <= 24.0f;
+        const int nt_pad = (nt + LIP_NN_BLOCK - 1) / LIP_NN_BLOCK * LIP_NN_BLOCK;
         __syncthreads();
         if (resident) {
-            for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
-                size_t v = (size_t)vt[j];
-                tf[j] = make_float4((float)(xt[3 * v] - cx), (float)(xt[3 * v + 1] - cy), (float)(xt[3 * v + 2] - cz), 0.f);
+            for (int j = tid; j < nt_pad; j += LIP_BIG_THREADS) {
+                if (j < nt) {
+                    size_t v = (size_t)vt[j];
+                    const float fx = (float)(xt[3 * v] - cx), fy = (float)(xt[3 * v + 1] - cy), fz = (float)(xt[3 * v + 2] - cz);
+                    tf[j] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+                } else {
+                    tf[j] = use_dot ? make_float4(0.f, 0.f, 0.f, 3.0e38f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+                }
             }
             __syncthreads();
         }
+        IcpView<false> view{tf, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xs, xt, vs, vt, cx, cy, cz};
         IcpState st;
         icp_state_init(st, mtx - msx, mty - msy, mtz - msz);
         double prev = 0.0;
@@ -526,20 +551,24 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
             double acc[17];
 #pragma unroll
             for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-            for (int q0 = 0; q0 < ns; q0 += 2 * LIP_BIG_THREADS) {
-                const int qa = q0 + tid, qb = qa + LIP_BIG_THREADS;
-                const bool va = qa < ns, vb = qb < ns;
-                const size_t ra = (size_t)vs[va ? qa : ns - 1], rb = (size_t)vs[vb ? qb : ns - 1];
-                double pax, pay, paz, pbx, pby, pbz;
-                mat3_vec(st.R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
-                pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-                mat3_vec(st.R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
-                pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
-                float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
-                int ia = 0, ib = 0;
-                for (int t0 = 0; t0 < nt; t0 += LIP_BIG_CAP) {
-                    const int cnt = min(LIP_BIG_CAP, nt - t0);
-                    if (!resident) {
+            if (resident) {
+                if (use_dot) icp_pass<false, true>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, acc);
+                else icp_pass<false, false>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, acc);
+            } else {
+                // target larger than the tile: stream it through SMEM, per-pair index tracking
+                for (int q0 = 0; q0 < ns; q0 += 2 * LIP_BIG_THREADS) {
+                    const int qa = q0 + tid, qb = qa + LIP_BIG_THREADS;
+                    const bool va = qa < ns, vb = qb < ns;
+                    const size_t ra = (size_t)vs[va ? qa : ns - 1], rb = (size_t)vs[vb ? qb : ns - 1];
+                    double pax, pay, paz, pbx, pby, pbz;
+                    mat3_vec(st.R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
+                    pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
+                    mat3_vec(st.R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
+                    pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+                    float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
+                    int ia = 0, ib = 0;
+                    for (int t0 = 0; t0 < nt; t0 += LIP_BIG_CAP) {
+                        const int cnt = min(LIP_BIG_CAP, nt - t0);
                         __syncthreads();
                         for (int j = tid; j < cnt; j += LIP_BIG_THREADS) {
                             size_t v = (size_t)vt[t0 + j];
@@ -547,12 +576,12 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
                                                 (float)(xt[3 * v + 2] - cz), 0.f);
                         }
                         __syncthreads();
+                        nn_scan2(tf, cnt, t0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
+                                 besta, seca, ia, bestb, secb, ib);
                     }
-                    nn_scan2(tf, cnt, t0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
-                             besta, seca, ia, bestb, secb, ib);
+                    icp_big_finish(a, xt, vt, nt, va, besta, seca, ia, mabs, cx, cy, cz, pax, pay, paz, acc);
+                    icp_big_finish(a, xt, vt, nt, vb, bestb, secb, ib, mabs, cx, cy, cz, pbx, pby, pbz, acc);
                 }
-                icp_big_finish(a, xt, vt, nt, va, besta, seca, ia, mabs, cx, cy, cz, pax, pay, paz, acc);
-                icp_big_finish(a, xt, vt, nt, vb, bestb, secb, ib, mabs, cx, cy, cz, pbx, pby, pbz, acc);
             }
 #pragma unroll
             for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
@@ -576,7 +605,6 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
             if (icp_kabsch_step(acc, st)) status = 2;
         }
         if (tid == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
-        __syncthreads();
     }
 }
 
@@ -984,21 +1012,28 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
         const int s = __ldg(&tab[bucket]), e = __ldg(&tab[bucket + 1]);
         if (in && e > s) { rs[nc] = s; re[nc] = e; ++nc; }
     }
-    // pass B: one candidate per iteration whatever cell it comes from (lanes stay together until the
-    // lane with the most candidates finishes)
+    // pass B: the non-empty cells, four candidates per step under predication (a cell holds ~4 points);
+    // the only divergent branch is the step to the next cell
     float best = INFINITY, sec = INFINITY;
     int idx = -1, visited = 0;
     if (nc > 0) {
         int c = 0, j = rs[0], e = re[0];
+        visited = e - j;
         for (;;) {
-            const float4 p = __ldg(&pts[j]);
-            float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-            float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-            nn_update(d, __float_as_int(p.w), best, sec, idx);
-            ++visited;
-            if (++j == e) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (j + k < e) {
+                    const float4 p = __ldg(&pts[j + k]);
+                    float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                    float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
+                    nn_update(d, __float_as_int(p.w), best, sec, idx);
+                }
+            }
+            j += 4;
+            if (j >= e) {
                 if (++c == nc) break;
                 j = rs[c]; e = re[c];
+                visited += e - j;
             }
         }
     }

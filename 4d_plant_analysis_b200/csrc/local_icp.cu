@@ -95,7 +95,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
     const size_t o_fR = take(B * 72), o_ft = take(B * 24);
-    const size_t o_sched = take(16 * 4), o_small = take(B * 4), o_med = take(4 * B * 4), o_big = take(B * 4);
+    const size_t o_sched = take(32 * 4), o_small = take(B * 4), o_med = take(4 * B * 4), o_big = take(4 * B * 4);
     const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
@@ -219,7 +219,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     cudaStream_t s_big = serial ? st : c->side[0], s_med = serial ? st : c->side[1], s_grid = serial ? st : c->side[2];
     c->ev_valid = false;
     c->fill_done = false;
-    LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 16 * 4, st));
+    LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 32 * 4, st));
     LIP_CUDA(c, cudaMemsetAsync(a.counters, 0, 8 * 8, st));
     if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
@@ -486,7 +486,7 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     cudaSetDevice(c->device);
     LIP_CUDA(c, cudaDeviceSynchronize());
     unsigned long long h[8];
-    int sched[16];
+    int sched[32];
     LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
     LIP_CUDA(c, cudaMemcpy(sched, c->args.sched, sizeof(sched), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];

@@ -294,8 +294,8 @@ def run_b200(args):
     mx = np.maximum(ns, nt)
     w = iters * ns * nt                                        # evaluated (source, candidate) pairs per partition
     pairs = {"icp_warp_kernel_small": float(w[mx <= 128].sum()),
-             "icp_warp_kernel_medium": float(w[(mx > 128) & (mx <= 640)].sum()),
-             "icp_big_kernel": float(w[mx > 640].sum()),
+             "icp_warp_kernel_medium": float(w[(mx > 128) & (mx <= 256)].sum()),
+             "icp_big_kernel": float(w[mx > 256].sum()),
              "blend_nn_kernel": float(counters["map_ring1_pairs"])}
     dom = max(pairs, key=lambda k: stage[k])
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12       # TFLOP/s, FP32 FMA pipe at the max SM clock
