@@ -37,6 +37,7 @@ struct LipArgs {
     double *d0, *d1;         // [n_total] their distances
     int* bin_off;            // [B+1] unified start of each bin in part_vid
     int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
+    int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step

@@ -10,6 +10,9 @@
 #define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 256
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
+#ifndef LIP_WARP_MINBLOCKS
+#define LIP_WARP_MINBLOCKS 5   // CTAs per SM the warp-per-partition kernels are compiled for (register cap 96)
+#endif
 
 // =============================================================================================
 // K0  landmark assignment + stable partition of every mesh by nearest landmark
@@ -110,32 +113,42 @@ __global__ void icp_schedule_kernel(LipArgs a) {
 //   Kabsch (get_best_fit_transform :8-46): float64 sums reduced over the warp with a fixed butterfly,
 //   3x3 Jacobi SVD in registers; accumulate R,t; cost/stop test (:86-88) — all uniform per warp.
 // =============================================================================================
-struct IcpState {            // uniform across the lanes/threads working on one partition
+// ICP state of one partition.  It lives in SHARED memory (one per warp / CTA): every lane computes the
+// identical update and stores the identical values, so the state costs no registers across the NN scan.
+struct IcpState {
     double R[9], t[3];       // accumulated transform in centred coordinates
     double Ri[9], ti[3];     // last increment
 };
 
-__device__ __forceinline__ void icp_state_init(IcpState& s, double tix, double tiy, double tiz) {
+__device__ __forceinline__ void icp_state_init(IcpState* s, double tix, double tiy, double tiz) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { s.R[i] = (i % 4 == 0) ? 1.0 : 0.0; s.Ri[i] = s.R[i]; }
-    s.t[0] = s.t[1] = s.t[2] = 0.0;
-    s.ti[0] = tix; s.ti[1] = tiy; s.ti[2] = tiz;
+    for (int i = 0; i < 9; ++i) { s->R[i] = (i % 4 == 0) ? 1.0 : 0.0; s->Ri[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    s->t[0] = s->t[1] = s->t[2] = 0.0;
+    s->ti[0] = tix; s->ti[1] = tiy; s->ti[2] = tiz;
 }
 // R <- Ri R ; t <- Ri t + ti   (registration_icp.py:83-84)
-__device__ __forceinline__ void icp_state_accumulate(IcpState& s) {
-    mat3_mul(s.Ri, s.R, s.R);
+__device__ __forceinline__ void icp_state_accumulate(IcpState* s) {
+    double Ri[9], R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { Ri[i] = s->Ri[i]; R[i] = s->R[i]; }
+    const double t0 = s->t[0], t1 = s->t[1], t2 = s->t[2];
+    mat3_mul(Ri, R, R);
     double x, y, z;
-    mat3_vec(s.Ri, s.t[0], s.t[1], s.t[2], x, y, z);
-    s.t[0] = x + s.ti[0]; s.t[1] = y + s.ti[1]; s.t[2] = z + s.ti[2];
+    mat3_vec(Ri, t0, t1, t2, x, y, z);
+    x += s->ti[0]; y += s->ti[1]; z += s->ti[2];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s->R[i] = R[i];
+    s->t[0] = x; s->t[1] = y; s->t[2] = z;
 }
 // acc: 0 sum dist | 1..3 sum p | 4..6 sum b | 7..15 sum p_i b_j | 16 pairs kept
 // Kabsch increment from the reduced sums; returns 1 if the solve was rank deficient
-__device__ __forceinline__ int icp_kabsch_step(const double* acc, IcpState& s) {
+__device__ __forceinline__ int icp_kabsch_step(const double* acc, IcpState* s) {
     double n = acc[16];
+    double Ri[9];
     if (!(n > 0.0)) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) s.Ri[i] = (i % 4 == 0) ? 1.0 : 0.0;
-        s.ti[0] = s.ti[1] = s.ti[2] = 0.0;
+        for (int i = 0; i < 9; ++i) s->Ri[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        s->ti[0] = s->ti[1] = s->ti[2] = 0.0;
         return 1;
     }
     double inv = 1.0 / n;
@@ -146,22 +159,24 @@ __device__ __forceinline__ int icp_kabsch_step(const double* acc, IcpState& s) {
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) H[3 * i + j] = acc[7 + 3 * i + j] - n * ca[i] * cb[j];
-    int deg = kabsch_rotation(H, s.Ri);
+    int deg = kabsch_rotation(H, Ri);
     double x, y, z;
-    mat3_vec(s.Ri, ca[0], ca[1], ca[2], x, y, z);
-    s.ti[0] = cb[0] - x; s.ti[1] = cb[1] - y; s.ti[2] = cb[2] - z;
+    mat3_vec(Ri, ca[0], ca[1], ca[2], x, y, z);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s->Ri[i] = Ri[i];
+    s->ti[0] = cb[0] - x; s->ti[1] = cb[1] - y; s->ti[2] = cb[2] - z;
     return deg;
 }
 // final transform back to the original frame: y - c = R (x - c) + t~  =>  t = t~ + c - R c
-__device__ __forceinline__ void icp_store(const LipArgs& a, int b, const IcpState& s, double cx, double cy, double cz,
+__device__ __forceinline__ void icp_store(const LipArgs& a, int b, const IcpState* s, double cx, double cy, double cz,
                                           int iters, int status) {
     double x, y, z;
-    mat3_vec(s.R, cx, cy, cz, x, y, z);
+    mat3_vec(s->R, cx, cy, cz, x, y, z);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) a.icp_R[9 * (size_t)b + i] = s.R[i];
-    a.icp_t[3 * (size_t)b] = s.t[0] + cx - x;
-    a.icp_t[3 * (size_t)b + 1] = s.t[1] + cy - y;
-    a.icp_t[3 * (size_t)b + 2] = s.t[2] + cz - z;
+    for (int i = 0; i < 9; ++i) a.icp_R[9 * (size_t)b + i] = s->R[i];
+    a.icp_t[3 * (size_t)b] = s->t[0] + cx - x;
+    a.icp_t[3 * (size_t)b + 1] = s->t[1] + cy - y;
+    a.icp_t[3 * (size_t)b + 2] = s->t[2] + cz - z;
     a.icp_iters[b] = iters;
     a.icp_status[b] = status;
 }
@@ -258,11 +273,11 @@ struct IcpView {                                         // one partition as see
     }
 };
 
+// resolve the winner of one query from its blocked top-2 result: index inside the winning block, and a
+// float64 re-evaluation of the whole target when the runner-up is within the fp32 error bound
 template <bool SMEM64, bool DOT>
-__device__ __forceinline__ void icp_finish(const IcpView<SMEM64>& w, int nt, bool valid, const NNTop2& r,
-                                                float mx, float my, float mz, float mabs, double px, double py,
-                                                double pz, double reject, double* acc, unsigned long long* counters) {
-    if (!valid) return;
+__device__ __forceinline__ int icp_resolve(const IcpView<SMEM64>& w, int nt, const NNTop2& r, float mx, float my, float mz,
+                                           float mabs, double px, double py, double pz, unsigned long long* counters) {
     int idx = nn_block_index<DOT>(w.tf, r.blk, r.best, mx, my, mz);
     const float fx = (float)px, fy = (float)py, fz = (float)pz;
     const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
@@ -276,6 +291,7 @@ __device__ __forceinline__ void icp_finish(const IcpView<SMEM64>& w, int nt, boo
     }
     if (!(r.sec - r.best > tol)) {                           // near tie: decide in float64, lowest index
         double bd = INFINITY;
+#pragma unroll 1
         for (int j = 0; j < nt; ++j) {
             double tx, ty, tz;
             w.tgt(j, tx, ty, tz);
@@ -284,25 +300,17 @@ __device__ __forceinline__ void icp_finish(const IcpView<SMEM64>& w, int nt, boo
         }
         atomicAdd(&counters[2], 1ull);
     }
-    double bx, by, bz;
-    w.tgt(idx, bx, by, bz);
-    double d = sqrt(rdist64(px, py, pz, bx, by, bz));
-    acc[0] += d;
-    if (d <= reject) {
-        acc[1] += px; acc[2] += py; acc[3] += pz;
-        acc[4] += bx; acc[5] += by; acc[6] += bz;
-        acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
-        acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
-        acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
-        acc[16] += 1.0;
-    }
+    return idx;
 }
 
-// one NN pass of the partition: every source point against the staged target; accumulates the Kabsch sums
-// (lane, stride) = (lane, 32) for a warp, (thread, blockDim) for a CTA
+// One ICP iteration over a partition, (lane, stride) = (lane, 32) for a warp, (thread, blockDim) for a CTA.
+// Phase 1 (get_NN_in_target): every source point against the staged target, winners written to nn_idx.
+// Phase 2 (sums of get_best_fit_transform + cost): float64 accumulation over the (source, winner) pairs.
+// Keeping the phases apart keeps the 17 float64 accumulators out of the registers of the scan loop; each
+// lane reads back only the nn_idx entries it wrote itself.
 template <bool SMEM64, bool DOT>
-__device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>& w, const IcpState& st, int ns, int nt,
-                                         int nt_pad, float mabs, int lane, int stride, double* acc) {
+__device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>& w, const IcpState* st, int ns, int nt,
+                                         int nt_pad, float mabs, int lane, int stride, int* __restrict__ nn_idx, double* acc) {
     const float sc = DOT ? -2.0f : 1.0f;
     int q0 = 0;
     for (; q0 + stride < ns; q0 += 2 * stride) {             // two queries per lane while more than `stride` remain
@@ -311,32 +319,52 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>
         double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
         w.src(qa, sax, say, saz);
         w.src(vb ? qb : ns - 1, sbx, sby, sbz);
-        mat3_vec(st.R, sax, say, saz, pax, pay, paz);
-        pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-        mat3_vec(st.R, sbx, sby, sbz, pbx, pby, pbz);
-        pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+        mat3_vec(st->R, sax, say, saz, pax, pay, paz);
+        pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
+        mat3_vec(st->R, sbx, sby, sbz, pbx, pby, pbz);
+        pbx += st->t[0]; pby += st->t[1]; pbz += st->t[2];
         const float m[2][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}, {sc * (float)pbx, sc * (float)pby, sc * (float)pbz}};
         NNTop2 r[2];
         nn_scan_blocks<DOT, 2>(w.tf, nt_pad, m, r);
-        icp_finish<SMEM64, DOT>(w, nt, true, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
-        icp_finish<SMEM64, DOT>(w, nt, vb, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.reject_dist, acc, a.counters);
+        nn_idx[qa] = icp_resolve<SMEM64, DOT>(w, nt, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.counters);
+        if (vb) nn_idx[qb] = icp_resolve<SMEM64, DOT>(w, nt, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.counters);
     }
     if (q0 < ns) {                                           // at most `stride` left: one query per lane
         const int qa = q0 + lane;
-        const bool va = qa < ns;
-        double sax, say, saz, pax, pay, paz;
-        w.src(va ? qa : ns - 1, sax, say, saz);
-        mat3_vec(st.R, sax, say, saz, pax, pay, paz);
-        pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-        const float m[1][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}};
-        NNTop2 r[1];
-        nn_scan_blocks<DOT, 1>(w.tf, nt_pad, m, r);
-        icp_finish<SMEM64, DOT>(w, nt, va, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.reject_dist, acc, a.counters);
+        if (qa < ns) {
+            double sax, say, saz, pax, pay, paz;
+            w.src(qa, sax, say, saz);
+            mat3_vec(st->R, sax, say, saz, pax, pay, paz);
+            pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
+            const float m[1][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}};
+            NNTop2 r[1];
+            nn_scan_blocks<DOT, 1>(w.tf, nt_pad, m, r);
+            nn_idx[qa] = icp_resolve<SMEM64, DOT>(w, nt, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.counters);
+        }
+    }
+    // ---- phase 2 ----
+    const double reject = a.reject_dist;
+    for (int q = lane; q < ns; q += stride) {
+        double sx, sy, sz, px, py, pz, bx, by, bz;
+        w.src(q, sx, sy, sz);
+        mat3_vec(st->R, sx, sy, sz, px, py, pz);
+        px += st->t[0]; py += st->t[1]; pz += st->t[2];
+        w.tgt(nn_idx[q], bx, by, bz);
+        const double d = sqrt(rdist64(px, py, pz, bx, by, bz));
+        acc[0] += d;
+        if (d <= reject) {
+            acc[1] += px; acc[2] += py; acc[3] += pz;
+            acc[4] += bx; acc[5] += by; acc[6] += bz;
+            acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
+            acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
+            acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
+            acc[16] += 1.0;
+        }
     }
 }
 
 template <int CAP, bool SMEM64>
-__device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& sm, int lane) {
+__device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& sm, IcpState* st, int lane) {
     const int pb = pair_bin(a, b);
     const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
     const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
@@ -382,17 +410,18 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
     msx = warp_sum(msx) / ns; msy = warp_sum(msy) / ns; msz = warp_sum(msz) / ns;
     __syncwarp();
     // ---- the ICP loop ---------------------------------------------------------------------------------
-    IcpState st;
     icp_state_init(st, mtx - msx, mty - msy, mtz - msz);    // t_init = mean(tgt) - mean(src)   (:70)
+    __syncwarp();
     double prev = 0.0;
     int iters = 0, status = 1;
     for (int it = 0; it < a.max_iter; ++it) {
         icp_state_accumulate(st);
+        __syncwarp();
         double acc[17];
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-        if (use_dot) icp_pass<SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, acc);
-        else icp_pass<SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, acc);
+        if (use_dot) icp_pass<SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, a.nn_idx + so, acc);
+        else icp_pass<SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, a.nn_idx + so, acc);
 #pragma unroll
         for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
         const double cost = acc[0] / ns;                    // np.mean(distance)   (:86)
@@ -400,6 +429,7 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
         if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;   // (:87)
         prev = cost;
         if (icp_kabsch_step(acc, st)) status = 2;
+        __syncwarp();
     }
     if (lane == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
 }
@@ -407,9 +437,11 @@ __device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& 
 // LIST 0: small partitions (sched[0] entries of small_list, cursor sched[2]);
 // LIST 1: medium partitions (sched[4] entries of medium_list, cursor sched[5])
 template <int CAP, int WARPS, bool SMEM64>
-__global__ void __launch_bounds__(WARPS * 32, 4) icp_warp_kernel(LipArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, LIP_WARP_MINBLOCKS) icp_warp_kernel(LipArgs a) {
     __shared__ IcpWarpSmem<CAP, SMEM64> sm_all[WARPS];
+    __shared__ IcpState st_all[WARPS];
     IcpWarpSmem<CAP, SMEM64>& sm = sm_all[threadIdx.x >> 5];
+    IcpState* st = &st_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int n_items = SMEM64 ? a.sched[0] : a.sched[4];
     const int* list = SMEM64 ? a.small_list : a.medium_list;
@@ -426,7 +458,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) icp_warp_kernel(LipArgs a) {
             while (c > 0 && r >= a.sched[8 + c]) { r -= a.sched[8 + c]; --c; }
             b = list[(size_t)c * a.B + r];
         }
-        icp_one_warp<CAP, SMEM64>(a, b, sm, lane);
+        icp_one_warp<CAP, SMEM64>(a, b, sm, st, lane);
         __syncwarp();
     }
 }
@@ -479,6 +511,9 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
     __shared__ double red17[LIP_BIG_THREADS / 32][17];
     __shared__ float redf[LIP_BIG_THREADS / 32];
     __shared__ int s_item;
+    __shared__ IcpState st_sh;
+    __shared__ int st_deg;
+    IcpState* st = &st_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_big = a.sched[1];
     for (;;) {                                              // persistent CTAs, heaviest class first
@@ -542,18 +577,20 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
             __syncthreads();
         }
         IcpView<false> view{tf, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xs, xt, vs, vt, cx, cy, cz};
-        IcpState st;
-        icp_state_init(st, mtx - msx, mty - msy, mtz - msz);
+        if (tid < 32) { icp_state_init(st, mtx - msx, mty - msy, mtz - msz); st_deg = 1; }
+        __syncthreads();
         double prev = 0.0;
-        int iters = 0, status = 1;
+        int iters = 0;
         for (int it = 0; it < a.max_iter; ++it) {
-            icp_state_accumulate(st);
+            __syncthreads();                                 // all reads of the previous state are done
+            if (tid < 32) icp_state_accumulate(st);
+            __syncthreads();
             double acc[17];
 #pragma unroll
             for (int i = 0; i < 17; ++i) acc[i] = 0.0;
             if (resident) {
-                if (use_dot) icp_pass<false, true>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, acc);
-                else icp_pass<false, false>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, acc);
+                if (use_dot) icp_pass<false, true>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, a.nn_idx + so, acc);
+                else icp_pass<false, false>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, a.nn_idx + so, acc);
             } else {
                 // target larger than the tile: stream it through SMEM, per-pair index tracking
                 for (int q0 = 0; q0 < ns; q0 += 2 * LIP_BIG_THREADS) {
@@ -561,10 +598,10 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
                     const bool va = qa < ns, vb = qb < ns;
                     const size_t ra = (size_t)vs[va ? qa : ns - 1], rb = (size_t)vs[vb ? qb : ns - 1];
                     double pax, pay, paz, pbx, pby, pbz;
-                    mat3_vec(st.R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
-                    pax += st.t[0]; pay += st.t[1]; paz += st.t[2];
-                    mat3_vec(st.R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
-                    pbx += st.t[0]; pby += st.t[1]; pbz += st.t[2];
+                    mat3_vec(st->R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
+                    pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
+                    mat3_vec(st->R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
+                    pbx += st->t[0]; pby += st->t[1]; pbz += st->t[2];
                     float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
                     int ia = 0, ib = 0;
                     for (int t0 = 0; t0 < nt; t0 += LIP_BIG_CAP) {
@@ -602,9 +639,11 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
             iters = it + 1;
             if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;
             prev = cost;
-            if (icp_kabsch_step(acc, st)) status = 2;
+            // one warp solves the 3x3 problem (all of its lanes identically); the others wait at the barrier above
+            if (tid < 32) { if (icp_kabsch_step(acc, st)) st_deg = 2; }
         }
-        if (tid == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
+        __syncthreads();
+        if (tid == 0) icp_store(a, b, st, cx, cy, cz, iters, st_deg);
     }
 }
 

@@ -92,7 +92,7 @@ int carve_workspace(lip_ctx* c) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     const size_t o_nn0 = take(n * 4), o_nn1 = take(n * 4), o_d0 = take(n * 8), o_d1 = take(n * 8);
-    const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4);
+    const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4), o_nnidx = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
     const size_t o_fR = take(B * 72), o_ft = take(B * 24);
     const size_t o_sched = take(32 * 4), o_small = take(B * 4), o_med = take(4 * B * 4), o_big = take(4 * B * 4);
@@ -104,7 +104,7 @@ int carve_workspace(lip_ctx* c) {
     LipArgs& a = c->args;
     a.nn0 = (int*)(base + o_nn0); a.nn1 = (int*)(base + o_nn1);
     a.d0 = (double*)(base + o_d0); a.d1 = (double*)(base + o_d1);
-    a.bin_off = (int*)(base + o_binoff); a.part_vid = (int*)(base + o_vid);
+    a.bin_off = (int*)(base + o_binoff); a.part_vid = (int*)(base + o_vid); a.nn_idx = (int*)(base + o_nnidx);
     a.icp_R = (double*)(base + o_R); a.icp_t = (double*)(base + o_t);
     a.icp_iters = (int*)(base + o_it); a.icp_status = (int*)(base + o_stat);
     a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft);
