@@ -505,7 +505,7 @@ __device__ __forceinline__ void icp_big_finish(const LipArgs& a, const double* x
     }
 }
 
-__global__ void __launch_bounds__(LIP_BIG_THREADS) icp_big_kernel(LipArgs a) {
+__global__ void __launch_bounds__(LIP_BIG_THREADS, 2) icp_big_kernel(LipArgs a) {
     __shared__ float4 tf[LIP_BIG_CAP];
     __shared__ double red[LIP_BIG_THREADS / 32];
     __shared__ double red17[LIP_BIG_THREADS / 32][17];
