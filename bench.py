@@ -74,6 +74,13 @@ def cpu_throughput(batch, n_proc, repeats=1):
     return n / best, best, n
 
 
+def cpu_sample_frame_pairs(args, cores):
+    """bounded CPU sample: about 10-30 s of CPU work.  One core does roughly 0.4 maize/tomato frame pairs per second
+    (SURVEY.md section 6), i.e. ~2.5 core-seconds per frame pair; config 5 is ~110 core-seconds per frame pair."""
+    per_fp = {1: 2.5, 2: 2.7, 3: 8.8, 4: 2.5 * 15, 5: 110.0}[args.config]
+    return int(max(1, min(args.frame_pairs, round(20.0 / per_fp))))
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -152,7 +159,7 @@ def run_reference(args):
         return
     cores = host_cores()
     a2 = argparse.Namespace(**vars(args))
-    a2.frame_pairs = args.cpu_sample_frame_pairs or max(1, min(args.frame_pairs, (cores + 11) // 12))
+    a2.frame_pairs = args.cpu_sample_frame_pairs or cpu_sample_frame_pairs(args, cores)
     batch = make_workload(a2, 0)
     n_proc = min(cores, batch.n_segments)
     import multiprocessing as mp
@@ -330,7 +337,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         a2 = argparse.Namespace(**vars(args))
-        a2.frame_pairs = args.cpu_sample_frame_pairs or max(1, min(args.frame_pairs, (cores + 11) // 12, 8))
+        a2.frame_pairs = args.cpu_sample_frame_pairs or cpu_sample_frame_pairs(args, cores)
         sample = make_workload(a2, 0)
         n_proc = min(cores, sample.n_segments)
         v, dt, n = cpu_throughput(sample, n_proc)
