@@ -34,6 +34,7 @@ SIGNATURES = {
     "lip_destroy": (None, [c_void_p]),
     "lip_last_error": (c_char_p, [c_void_p]),
     "lip_set_params": (c_int, [c_void_p, c_void_p]),
+    "lip_set_map_mode": (c_int, [c_void_p, c_int]),
     "lip_host_alloc": (c_int, [POINTER(c_void_p), c_uint64]),
     "lip_host_free": (c_int, [c_void_p]),
     "lip_batch_plan": (c_int, [c_void_p, c_int64, _I64, _I64, _I64, c_int]),
@@ -166,6 +167,10 @@ class Context:
             setattr(p, k, v)
         self._check(self.lib.lip_set_params(self.h, byref(p)))
 
+    def set_map_mode(self, mode: int):
+        """0 = landmark-bin tiles (default), 1 = hashed grid; plan again afterwards."""
+        self._check(self.lib.lip_set_map_mode(self.h, int(mode)))
+
     # ---- batch --------------------------------------------------------------------------------
     def plan(self, off1, off2, lm_off, directions=DIR_BOTH):
         off1, off2, lm_off = _i64(off1), _i64(off2), _i64(lm_off)
@@ -222,7 +227,7 @@ class Context:
                     map_retry=int(c[4]), map_far=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
 
     STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_warp_kernel_small", "icp_warp_kernel_medium",
-              "icp_big_kernel", "grid_build_kernel", "blend_nn_kernel", "retry_nn_kernel", "far_nn_kernel")
+              "icp_big_kernel", "grid_build_kernel", "final_map_kernel", "retry_nn_kernel", "far_nn_kernel")
 
     def set_profiling(self, on=True):
         self._check(self.lib.lip_set_profiling(self.h, int(bool(on))))

@@ -38,12 +38,16 @@ struct LipArgs {
     int* bin_off;            // [B+1] unified start of each bin in part_vid
     int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
     int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
+    float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
+    float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
+    int* map_tiles;          // [2 * (n_total / LIP_MAP_TILE + B)] (bin, first slot) of every final-map tile; count in sched[20]
+    double* mesh_sum;        // [M*4] sum of the vertices of every mesh (x, y, z) and the vertex count
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
     int* sched;              // [32] [0] n_small [1] n_big [2] small cursor [3] n_far [4] n_medium [5] medium cursor
                              //      [6] far cursor [7] n_retry [8..11] medium class counts [12..15] big class counts
-                             //      [16] big cursor
+                             //      [16] big cursor [20] number of final-map tiles
     int *small_list, *medium_list, *big_list;    // [B], [4B] (four work classes), [4B]
     int* far_list;           // [n_total] unified ids of queries whose ring search could not certify
     double* far_q;           // [3 * n_total] their blended positions
@@ -56,6 +60,7 @@ struct LipArgs {
     double* q_dist;          // raw-query mode: distance output over xyz2 (or nullptr)
     unsigned long long* counters;  // [8]
     int max_iter, profile;   // profile != 0: count evaluated candidate pairs (counters[7])
+    int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };
 

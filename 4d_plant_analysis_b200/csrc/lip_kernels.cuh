@@ -10,6 +10,10 @@
 #define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 256
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
+#define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA, two queries per thread
+#define LIP_MAP_TILE (2 * LIP_MAP_THREADS)
+#define LIP_MAP_CHUNK 512    // candidates staged per scan
+#define LIP_MAP_BOXBATCH 64
 #ifndef LIP_WARP_MINBLOCKS
 #define LIP_WARP_MINBLOCKS 5   // CTAs per SM the warp-per-partition kernels are compiled for (register cap 96)
 #endif
@@ -21,6 +25,7 @@
 // =============================================================================================
 __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
     extern __shared__ double smem_d[];
+    __shared__ double msum[8][3];
     const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
     const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
@@ -32,8 +37,10 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
     for (int i = tid; i < 3 * K; i += blockDim.x) lmS[i] = lm[i];
     for (int i = tid; i < K; i += blockDim.x) hist[i] = 0;
     __syncthreads();
+    double sx = 0, sy = 0, sz = 0;
     for (int v = tid; v < n; v += blockDim.x) {
         const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+        sx += x; sy += y; sz += z;
         double best = INFINITY, sec = INFINITY;
         int i0 = 0, i1 = 0;
         for (int i = 0; i < K; ++i) {                       // index order, strict '<': sklearn single-leaf scan
@@ -46,7 +53,15 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
         a.d0[ub + v] = sqrt(best); a.d1[ub + v] = sqrt(sec);
         atomicAdd(&hist[i0], 1);
     }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { msum[warp][0] = sx; msum[warp][1] = sy; msum[warp][2] = sz; }
     __syncthreads();
+    if (tid < 3) {                                          // vertex sum of the mesh (mean-shift fallback of the fill step)
+        double s = 0;
+        for (int w = 0; w < nwarps; ++w) s += msum[w][tid];
+        a.mesh_sum[4 * (size_t)m + tid] = s;
+    }
+    if (tid == 3) a.mesh_sum[4 * (size_t)m + 3] = (double)n;
     if (warp == 0) {                                        // exclusive scan of the K bin counts
         int running = 0;
         for (int base = 0; base < K; base += 32) {
@@ -62,15 +77,35 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
     __syncthreads();
     for (int i = tid; i < K; i += blockDim.x) a.bin_off[bb + i] = ub + excl[i];
     if (m == a.M - 1 && tid == 0) a.bin_off[a.B] = a.n_total;
-    // stable compaction: one warp per bin walks the mesh in vertex order
+    // stable compaction: one warp per bin walks the mesh in vertex order.  Besides the member list it writes
+    // the bin's points as fp32 offsets from the bin's own landmark (the search tiles of the ICP and of the
+    // final map are assembled from these with coalesced 16-byte loads) and their bounding box.
     for (int i = warp; i < K; i += nwarps) {
         int pos = ub + excl[i];
+        const double lx = lmS[3 * i], ly = lmS[3 * i + 1], lz = lmS[3 * i + 2];
+        float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
         for (int base = 0; base < n; base += 32) {
             int v = base + lane;
             bool pred = (v < n) && (a.nn0[ub + v] == i);
             unsigned mask = __ballot_sync(LIP_FULL, pred);
-            if (pred) a.part_vid[pos + __popc(mask & ((1u << lane) - 1))] = v;
+            if (pred) {
+                const int p = pos + __popc(mask & ((1u << lane) - 1));
+                const float fx = (float)(xyz[3 * (size_t)v] - lx), fy = (float)(xyz[3 * (size_t)v + 1] - ly),
+                            fz = (float)(xyz[3 * (size_t)v + 2] - lz);
+                a.part_vid[p] = v;
+                a.bin_pts[p] = make_float4(fx, fy, fz, __int_as_float(v));
+                lo0 = fminf(lo0, fx); lo1 = fminf(lo1, fy); lo2 = fminf(lo2, fz);
+                hi0 = fmaxf(hi0, fx); hi1 = fmaxf(hi1, fy); hi2 = fmaxf(hi2, fz);
+            }
             pos += __popc(mask);
+        }
+        lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
+        hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
+        if (lane == 0) {
+            float* bx = a.bin_box + 8 * (size_t)(bb + i);
+            bx[0] = lo0; bx[1] = lo1; bx[2] = lo2; bx[3] = hi0; bx[4] = hi1; bx[5] = hi2;
+            bx[6] = fmaxf(fmaxf(fmaxf(fabsf(lo0), fabsf(hi0)), fmaxf(fabsf(lo1), fabsf(hi1))), fmaxf(fabsf(lo2), fabsf(hi2)));
+            bx[7] = 0.f;
         }
     }
 }
@@ -87,6 +122,11 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     if (!src_active(a, m)) return;
     int pb = pair_bin(a, b);
     int ns = a.bin_off[b + 1] - a.bin_off[b], nt = a.bin_off[pb + 1] - a.bin_off[pb];
+    if (ns > 0) {                                            // tiles of the final map: up to LIP_MAP_TILE queries of one bin
+        const int nt_map = (ns + LIP_MAP_TILE - 1) / LIP_MAP_TILE;
+        const int slot = atomicAdd(&a.sched[20], nt_map);
+        for (int i = 0; i < nt_map; ++i) { a.map_tiles[2 * (size_t)(slot + i)] = b; a.map_tiles[2 * (size_t)(slot + i) + 1] = i * LIP_MAP_TILE; }
+    }
     if (ns == 0 || nt == 0) return;
     const int mx = max(ns, nt);
     if (mx <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
@@ -672,10 +712,10 @@ __global__ void fill_kernel(LipArgs a) {
             for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = a.icp_R[9 * (size_t)from + k];
             for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = a.icp_t[3 * (size_t)from + k];
         } else {
-            const GridHdr& hs = a.grid_hdr[m];
-            const GridHdr& ht = a.grid_hdr[pair_mesh(a, m)];
+            const double* hs = a.mesh_sum + 4 * (size_t)m;
+            const double* ht = a.mesh_sum + 4 * (size_t)pair_mesh(a, m);
             for (int k = 0; k < 9; ++k) a.fill_R[9 * (size_t)b + k] = (k % 4 == 0) ? 1.0 : 0.0;
-            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = ht.sum[k] / ht.n - hs.sum[k] / hs.n;
+            for (int k = 0; k < 3; ++k) a.fill_t[3 * (size_t)b + k] = ht[k] / ht[3] - hs[k] / hs[3];
         }
     }
 }
@@ -974,12 +1014,44 @@ __device__ __forceinline__ void fill_apply(const LipArgs& a, int m, int src, dou
         mat3_vec(R, x, y, z, ox, oy, oz);
         ox += t[0]; oy += t[1]; oz += t[2];
     } else {                                                 // identity, t = mean(target mesh) - mean(source mesh)
-        const GridHdr& hs = a.grid_hdr[m];
-        const GridHdr& ht = a.grid_hdr[pair_mesh(a, m)];
-        ox = x + (ht.sum[0] / ht.n - hs.sum[0] / hs.n);
-        oy = y + (ht.sum[1] / ht.n - hs.sum[1] / hs.n);
-        oz = z + (ht.sum[2] / ht.n - hs.sum[2] / hs.n);
+        const double* hs = a.mesh_sum + 4 * (size_t)m;
+        const double* ht = a.mesh_sum + 4 * (size_t)pair_mesh(a, m);
+        ox = x + (ht[0] / ht[3] - hs[0] / hs[3]);
+        oy = y + (ht[1] / ht[3] - hs[1] / hs[3]);
+        oz = z + (ht[2] / ht[3] - hs[2] / hs[3]);
     }
+}
+
+// The blended position of vertex v of source mesh m (p2p_matching_seg_icp.py:454-487): weights from the
+// triangle (landmark gap, d_a, d_b) — get_triangle_angles :27-34 fused, cos(arccos(x)) == x — and the two
+// landmark transforms after the fill of :422-437, all in float64.
+__device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int K, int v, double& q0, double& q1, double& q2) {
+    const int u = a.mesh_ubase[m] + v;
+    const double* xyz = mesh_xyz(a, m);
+    const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+    const int ia = a.nn0[u], ib = a.nn1[u];
+    double f0 = 0.5, f1 = 0.5;
+    if (K > 1) {
+        const double* lm = mesh_lm(a, m);
+        const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
+        const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
+        const double da = a.d0[u], db = a.d1[u];
+        // get_triangle_angles(g, da, db): B opposite da, C opposite db
+        double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
+        double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
+        cosB = fmin(fmax(cosB, -1.0), 1.0);
+        cosC = fmin(fmax(cosC, -1.0), 1.0);
+        if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
+        else {
+            const double cb = fabs(cosB), cc = fabs(cosC);
+            f0 = cb / (cb + cc); f1 = cc / (cb + cc);
+        }
+    }
+    double ax, ay, az, bx, by, bz;
+    fill_apply(a, m, fill_source(a, bb, K, ia), x, y, z, ax, ay, az);
+    if (ib == ia) { bx = ax; by = ay; bz = az; }
+    else fill_apply(a, m, fill_source(a, bb, K, ib), x, y, z, bx, by, bz);
+    q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
 }
 
 // =============================================================================================
@@ -1002,34 +1074,7 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const int u = ub + v;
     const int mt = pair_mesh(a, m);
     double q0 = 0, q1 = 0, q2 = 0;
-    if (valid) {
-        const double* xyz = mesh_xyz(a, m);
-        const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
-        const int ia = a.nn0[u], ib = a.nn1[u];
-        double f0 = 0.5, f1 = 0.5;
-        if (K > 1) {
-            const double* lm = mesh_lm(a, m);
-            const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
-            const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
-            const double da = a.d0[u], db = a.d1[u];
-            // get_triangle_angles(g, da, db): B opposite da, C opposite db
-            double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
-            double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
-            cosB = fmin(fmax(cosB, -1.0), 1.0);
-            cosC = fmin(fmax(cosC, -1.0), 1.0);
-            if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
-            else {
-                const double cb = fabs(cosB), cc = fabs(cosC);
-                f0 = cb / (cb + cc); f1 = cc / (cb + cc);
-            }
-        }
-        double ax, ay, az, bx, by, bz;
-        const int sa = fill_source(a, bb, K, ia);
-        fill_apply(a, m, sa, x, y, z, ax, ay, az);
-        if (ib == ia) { bx = ax; by = ay; bz = az; }
-        else fill_apply(a, m, fill_source(a, bb, K, ib), x, y, z, bx, by, bz);
-        q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
-    }
+    if (valid) blend_query(a, m, bb, K, v, q0, q1, q2);
     if (!valid) return;
     // ---- ring-1 search in the target's hashed grid ------------------------------------------------------
     const GridHdr& h = a.grid_hdr[mt];
@@ -1087,6 +1132,288 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
         if (m < a.S) a.T12[u] = idx; else a.T21[u - a.n1_total] = idx;
     } else {
         retry_push(a, u, mt, q0, q1, q2);                    // ring 2 / far: second pass over the compacted list
+    }
+}
+
+// =============================================================================================
+// K4' final map on landmark-bin tiles (default; the hashed-grid variant above is kept for A/B evidence)
+//     The partition step has already sorted every mesh by nearest landmark, so the target mesh comes as
+//     K spatially compact bins with known bounding boxes — that IS the spatial index.  A CTA takes up to
+//     LIP_MAP_TILE queries of ONE source bin (icp_schedule_kernel builds the tile list), stages the target
+//     bin of the same landmark into SMEM and scans it (round 0); then every target bin whose box is closer
+//     to some query than that query's current best is staged and scanned too (round 1).  After round 1
+//     every query has seen every point that could be its nearest neighbour, so the result is exact without
+//     any fallback path.  All lanes read the same candidate (SMEM broadcast); the per-pair cost is 3 FFMA
+//     + ~1.1 min/max (scores c = |y|^2 - 2 q.y, block minima, winner recovered per block of 8).
+// =============================================================================================
+__device__ __forceinline__ float tile_score(const float4 t, const float* m) {
+    return fmaf(m[0], t.x, fmaf(m[1], t.y, fmaf(m[2], t.z, t.w)));
+}
+// blocked scan of an SMEM tile: per block of 8 candidates only the block minimum enters the top-2 tracking
+template <int Q>
+__device__ __forceinline__ void tile_scan(const float4* __restrict__ tp, int npad, const float (&m)[2][3], float (&best)[2],
+                                          float (&sec)[2], int (&blk)[2]) {
+#pragma unroll 1
+    for (int jb = 0; jb < npad; jb += 8) {
+        float4 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = tp[jb + k];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float c[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = tile_score(t[k], m[q]);
+            float bm = fminf(fminf(c[0], c[1]), c[2]);
+            bm = fminf(fminf(bm, c[3]), c[4]);
+            bm = fminf(fminf(bm, c[5]), c[6]);
+            bm = fminf(bm, c[7]);
+            sec[q] = fminf(sec[q], fmaxf(bm, best[q]));
+            blk[q] = (bm < best[q]) ? jb : blk[q];
+            best[q] = fminf(best[q], bm);
+        }
+    }
+}
+// winner of block `blk` (first candidate whose score equals `best` bitwise: same instruction sequence) and the
+// smallest score among the other seven
+__device__ __forceinline__ void tile_recover(const float4* __restrict__ tp, const int* __restrict__ tv, int blk, float best,
+                                             const float* m, int& idx, float& sec_in) {
+    int pos = -1;
+    float s2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float c = tile_score(tp[blk + k], m);
+        if (c == best && pos < 0) pos = blk + k;
+        else s2 = fminf(s2, c);
+    }
+    idx = tv[pos < 0 ? blk : pos];
+    sec_in = s2;
+}
+// Bound on |evaluated - exact| of the dot-form score of a candidate at distance <= sqrt(d2) of a query with
+// |q|^2 = qq: three FMAs and the stored |y|^2 (three roundings), every partial result bounded by
+// |y|^2 + 2 |q| |y| with |y| <= |q| + d.   6 u (.) with u = 2^-24, times 1.5 for slack.
+__device__ __forceinline__ float dot_err(float qq, float d2) {
+    const float nq = sqrtf(qq), ny = nq + 1.001f * sqrtf(d2) + 1e-3f;
+    return 5.4e-7f * fmaf(ny, ny, 2.f * nq * ny);
+}
+
+__global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) {
+    __shared__ float4 tp[LIP_MAP_CHUNK];
+    __shared__ int tv[LIP_MAP_CHUNK];
+    __shared__ unsigned need[LIP_MAX_LANDMARKS / 32];
+    __shared__ float sbox[LIP_MAP_BOXBATCH][8];
+    __shared__ float red[LIP_MAP_THREADS / 32][8];
+    if ((int)blockIdx.x >= a.sched[20]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = a.map_tiles[2 * (size_t)blockIdx.x], first = a.map_tiles[2 * (size_t)blockIdx.x + 1];
+    const int m = a.bin_mesh[b];
+    const int ub = a.mesh_ubase[m];
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const int mt = pair_mesh(a, m), bbt = a.mesh_bin[mt];
+    const int home = b - bb;                                 // the queries' nearest landmark (local index)
+    const double* __restrict__ lmt = mesh_lm(a, mt);
+    const int so = a.bin_off[b];
+    const int nq = min(LIP_MAP_TILE, a.bin_off[b + 1] - so - first);
+    const double C0 = lmt[3 * home], C1 = lmt[3 * home + 1], C2 = lmt[3 * home + 2];     // tile origin: the target's landmark
+    float mq[2][3], qq[2], qabs[2], best[2], sec[2], sec_in[2];
+    int idx[2], blk[2], vq[2];
+    bool valid[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int slot = first + tid + k * LIP_MAP_THREADS;
+        valid[k] = tid + k * LIP_MAP_THREADS < nq;
+        vq[k] = valid[k] ? a.part_vid[so + slot] : 0;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (valid[k]) {
+            double q0, q1, q2;
+            blend_query(a, m, bb, K, vq[k], q0, q1, q2);
+            fx = (float)(q0 - C0); fy = (float)(q1 - C1); fz = (float)(q2 - C2);
+        }
+        mq[k][0] = -2.f * fx; mq[k][1] = -2.f * fy; mq[k][2] = -2.f * fz;
+        qq[k] = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+        qabs[k] = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
+        best[k] = INFINITY; sec[k] = INFINITY; sec_in[k] = INFINITY; idx[k] = -1; blk[k] = 0;
+    }
+    const bool two = nq > LIP_MAP_THREADS;                   // uniform: second query slot in use
+    for (int i = tid; i < (K + 31) / 32; i += LIP_MAP_THREADS) need[i] = 0u;
+    float mabs = 0.f;                                        // max |coordinate| staged so far (uniform)
+    int fill = 0;
+    long long staged = 0;
+
+    auto flush = [&]() {
+        const int npad = (fill + 7) & ~7;
+        if (tid < npad - fill) { tp[fill + tid] = make_float4(0.f, 0.f, 0.f, 3.0e38f); tv[fill + tid] = 0x7fffffff; }
+        __syncthreads();
+        const float prev0 = best[0], prev1 = best[1];
+        if (two) tile_scan<2>(tp, npad, mq, best, sec, blk);
+        else tile_scan<1>(tp, npad, mq, best, sec, blk);
+        if (best[0] < prev0) tile_recover(tp, tv, blk[0], best[0], mq[0], idx[0], sec_in[0]);
+        if (best[1] < prev1) tile_recover(tp, tv, blk[1], best[1], mq[1], idx[1], sec_in[1]);
+        __syncthreads();
+        staged += fill;
+        fill = 0;
+    };
+    auto stage_bin = [&](int j) {
+        const int s = a.bin_off[bbt + j], e = a.bin_off[bbt + j + 1];
+        if (e == s) return;
+        const float sh0 = (float)(lmt[3 * j] - C0), sh1 = (float)(lmt[3 * j + 1] - C1), sh2 = (float)(lmt[3 * j + 2] - C2);
+        mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
+        int p = s;
+        while (p < e) {
+            const int cnt = min(e - p, LIP_MAP_CHUNK - fill);
+            for (int i = tid; i < cnt; i += LIP_MAP_THREADS) {
+                const float4 t = a.bin_pts[p + i];
+                const float x = t.x + sh0, y = t.y + sh1, z = t.z + sh2;
+                tp[fill + i] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
+                tv[fill + i] = __float_as_int(t.w);
+            }
+            fill += cnt; p += cnt;
+            if (fill == LIP_MAP_CHUNK) flush();
+        }
+    };
+
+    // ---- round 0: the target bin of the queries' own landmark ------------------------------------------------
+    stage_bin(home);
+    if (fill > 0) flush();
+
+    // ---- round 1: every other bin that could hold something closer ---------------------------------------
+    if (K > 1) {
+        // CTA-wide bounds: box of the queries, largest current best distance, largest |q|
+        float v[8];
+        v[6] = 0.f; v[7] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!valid[k]) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float f = -0.5f * mq[k][c]; v[c] = fminf(v[c], f); v[3 + c] = fmaxf(v[3 + c], f); }
+            v[6] = fmaxf(v[6], fmaxf(best[k] + qq[k], 0.f));
+            v[7] = fmaxf(v[7], qabs[k]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = -warp_maxf(-v[c]);
+#pragma unroll
+        for (int c = 3; c < 8; ++c) v[c] = warp_maxf(v[c]);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) red[warp][c] = v[c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < LIP_MAP_THREADS / 32; ++w) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = fminf(v[c], red[w][c]);
+#pragma unroll
+            for (int c = 3; c < 8; ++c) v[c] = fmaxf(v[c], red[w][c]);
+        }
+        const float rmax2 = v[6], qabs_max = v[7];
+        const float qq_max = 3.f * qabs_max * qabs_max;
+        for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXBATCH) {
+            __syncthreads();
+            if (tid < LIP_MAP_BOXBATCH) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
+                const int j = j0 + tid;
+                float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
+                if (j < K && j != home && a.bin_off[bbt + j + 1] > a.bin_off[bbt + j]) {
+                    const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
+                    float bb2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float sh = (float)(lmt[3 * j + c] - (c == 0 ? C0 : c == 1 ? C1 : C2));
+                        lo[c] = bx[c] + sh; hi[c] = bx[3 + c] + sh;
+                        mb = fmaxf(mb, fmaxf(fabsf(lo[c]), fabsf(hi[c])));
+                        const float d = fmaxf(fmaxf(lo[c] - v[3 + c], v[c] - hi[c]), 0.f);
+                        bb2 = fmaf(d, d, bb2);
+                    }
+                    const float e = 4e-7f * (qabs_max + fmaxf(mb, mabs));
+                    const float rhs = rmax2 + d2_err(rmax2, e) + dot_err(qq_max, rmax2);
+                    const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
+                    flag = (lhs > rhs) ? 0.f : 1.f;          // (NaN compares false -> kept)
+                }
+                sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
+                sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
+                sbox[tid][6] = mb; sbox[tid][7] = flag;
+            }
+            __syncthreads();
+            unsigned w0 = 0u, w1 = 0u;
+            const int jn = min(LIP_MAP_BOXBATCH, K - j0);
+            for (int t = 0; t < jn; ++t) {
+                if (sbox[t][7] == 0.f) continue;             // uniform
+                bool nd = false;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!valid[k]) continue;
+                    float bd2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float f = -0.5f * mq[k][c];
+                        const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
+                        bd2 = fmaf(d, d, bd2);
+                    }
+                    const float bd = fmaxf(best[k] + qq[k], 0.f);
+                    const float e = 4e-7f * (qabs[k] + fmaxf(sbox[t][6], mabs));
+                    const float tol = d2_err(bd, e) + d2_err(bd2, e) + dot_err(qq[k], bd);
+                    nd = nd || !(bd2 - bd > tol);
+                }
+                if (nd) { if (t < 32) w0 |= 1u << t; else w1 |= 1u << (t - 32); }
+            }
+            w0 = __reduce_or_sync(LIP_FULL, w0); w1 = __reduce_or_sync(LIP_FULL, w1);
+            if (lane == 0) {
+                if (w0) atomicOr(&need[j0 / 32], w0);
+                if (w1) atomicOr(&need[j0 / 32 + 1], w1);
+            }
+        }
+        __syncthreads();
+        for (int w = 0; w < (K + 31) / 32; ++w) {
+            unsigned bits = need[w];                          // uniform
+            while (bits) {
+                const int j = 32 * w + __ffs(bits) - 1;
+                bits &= bits - 1;
+                stage_bin(j);
+            }
+        }
+        if (fill > 0) flush();
+    }
+    if (a.profile && tid == 0) atomicAdd(&a.counters[7], (unsigned long long)(staged * nq));
+
+    // ---- result: near ties are decided in float64 over everything that was staged, a warp per query -------
+    const double* __restrict__ xt = mesh_xyz(a, mt);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float d2b = fmaxf(best[k] + qq[k], 0.f), d2s = fmaxf(fminf(sec[k], sec_in[k]) + qq[k], 0.f);
+        const float e = 4e-7f * (qabs[k] + mabs);
+        const float tol = d2_err(d2b, e) + d2_err(d2s, e) + 2.f * dot_err(qq[k], d2s);
+        int res = idx[k];
+        const bool tie = valid[k] && !(d2s - d2b > tol);
+        unsigned ties = __ballot_sync(LIP_FULL, tie);
+        if (ties && lane == 0) atomicAdd(&a.counters[3], (unsigned long long)__popc(ties));
+        while (ties) {
+            const int src = __ffs(ties) - 1;
+            ties &= ties - 1;
+            double q0 = 0, q1 = 0, q2 = 0;
+            if (lane == src) blend_query(a, m, bb, K, vq[k], q0, q1, q2);
+            q0 = __shfl_sync(LIP_FULL, q0, src); q1 = __shfl_sync(LIP_FULL, q1, src); q2 = __shfl_sync(LIP_FULL, q2, src);
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int j = 0; j < K; ++j) {
+                if (j != home && !((need[j >> 5] >> (j & 31)) & 1u)) continue;
+                for (int p = a.bin_off[bbt + j] + lane; p < a.bin_off[bbt + j + 1]; p += 32) {
+                    const int vv = a.part_vid[p];
+                    const double d = rdist64(q0, q1, q2, xt[3 * (size_t)vv], xt[3 * (size_t)vv + 1], xt[3 * (size_t)vv + 2]);
+                    if (d < bd || (d == bd && vv < bi)) { bd = d; bi = vv; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(LIP_FULL, bd, o);
+                const int oi = __shfl_xor_sync(LIP_FULL, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (lane == src) res = bi;
+        }
+        if (valid[k]) {
+            const int u = ub + vq[k];
+            if (m < a.S) a.T12[u] = res; else a.T21[u - a.n1_total] = res;
+        }
     }
 }
 

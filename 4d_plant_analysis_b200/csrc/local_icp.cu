@@ -47,6 +47,9 @@ struct lip_ctx {
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, medium ICP, grid build
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool fill_done = false;
+    int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
+    int plan_tile = LIP_TILE;
+    size_t max_map_tiles = 0;
     lip_params params;
     std::string err;
     // plan
@@ -99,6 +102,9 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
+    const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
+    c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
+    const size_t o_mt = take(c->max_map_tiles * 8);
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
     LipArgs& a = c->args;
@@ -113,6 +119,8 @@ int carve_workspace(lip_ctx* c) {
     a.retry_list = (int*)(base + o_re); a.retry_q = (double*)(base + o_req);
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
+    a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
+    a.map_tiles = (int*)(base + o_mt);
     return LIP_OK;
 }
 
@@ -125,9 +133,11 @@ void set_param_args(lip_ctx* c) {
     a.cos_den_eps = c->params.cos_den_eps;
     a.reject_dist = c->params.reject_dist;
     a.profile = c->profiling ? 1 : 0;
+    a.map_mode = c->map_mode;
 }
 
-int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions,
+              int tile = LIP_TILE) {
     if (!c) return LIP_EINVAL;
     c->planned = false;
     if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
@@ -174,9 +184,10 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
         bool active = (m >= S) ? (c->directions & 1) : (c->directions & 2);
         if (!active) continue;
         int n = c->h_mesh_ubase[m + 1] - c->h_mesh_ubase[m];
-        for (int f = 0; f < n; f += LIP_TILE) { c->h_tile_mesh.push_back(m); c->h_tile_first.push_back(f); }
+        for (int f = 0; f < n; f += tile) { c->h_tile_mesh.push_back(m); c->h_tile_first.push_back(f); }
     }
     c->n_tiles = (int)c->h_tile_mesh.size();
+    c->plan_tile = tile;
     // upload
     size_t off = 0;
     auto take = [&](size_t cnt) { size_t o = off; off = align_up(off + cnt * 4); return o; };
@@ -262,7 +273,8 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         launches += 4;
     } else { mark(); mark(); mark(); }
     mark();                                                  // 5: after big ICP
-    if (stages & (ST_GRID | ST_GRID_ALL)) {
+    const bool tiles = (stages & ST_BLEND) && c->map_mode == 0;      // final map on landmark-bin tiles: no grid needed
+    if ((stages & (ST_GRID | ST_GRID_ALL)) && !tiles) {
         if (!serial) { LIP_CUDA(c, cudaStreamWaitEvent(s_grid, c->ev_begin, 0)); forked_grid = true; }
         LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, s_grid));
         grid_build_kernel<<<c->M, 256, 0, s_grid>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
@@ -275,7 +287,8 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     }
     if (forked_grid) { LIP_CUDA(c, cudaEventRecord(c->ev_join[2], s_grid)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[2], 0)); }
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
-        blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
+        if (tiles) blend_tile_kernel<<<(unsigned)c->max_map_tiles, LIP_MAP_THREADS, 0, st>>>(a);
+        else blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
     if ((stages & ST_QUERY) && c->n_tiles > 0) {
@@ -283,13 +296,13 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         ++launches;
     }
     mark();                                                  // 7: after blend / query
-    if ((stages & ST_BLEND) && c->n_tiles > 0) {
+    if ((stages & ST_BLEND) && !tiles && c->n_tiles > 0) {
         int gr = std::max(1, std::min(c->sm_count * 8, (a.n_total + 127) / 128));
         retry_nn_kernel<<<gr, 128, 0, st>>>(a);
         ++launches;
     }
     mark();                                                  // 8: after retry
-    if ((stages & (ST_QUERY | ST_BLEND)) && c->n_tiles > 0) {
+    if ((stages & (ST_QUERY | ST_BLEND)) && !tiles && c->n_tiles > 0) {
         int gf = std::max(1, std::min(c->sm_count * 8, (a.n_total + 3) / 4));
         far_nn_kernel<<<gf, 128, 0, st>>>(a);
         ++launches;
@@ -384,6 +397,14 @@ int lip_set_params(lip_ctx* c, const lip_params* p) {
     if (!c || !p) return LIP_EINVAL;
     if (p->max_iter < 1) return fail(c, LIP_EINVAL, "max_iter must be >= 1");
     c->params = *p;
+    return LIP_OK;
+}
+
+int lip_set_map_mode(lip_ctx* c, int mode) {
+    if (!c) return LIP_EINVAL;
+    if (mode != 0 && mode != 1) return fail(c, LIP_EINVAL, "map mode must be 0 (landmark-bin tiles) or 1 (hashed grid)");
+    if (mode != c->map_mode) c->planned = false;             // the tile list depends on the mode: plan again
+    c->map_mode = mode;
     return LIP_OK;
 }
 

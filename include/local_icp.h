@@ -59,6 +59,10 @@ int  lip_create(lip_ctx** ctx, int device);
 void lip_destroy(lip_ctx* ctx);
 const char* lip_last_error(const lip_ctx* ctx);   /* ctx may be NULL: start-up error */
 int  lip_set_params(lip_ctx* ctx, const lip_params* p);
+/* Final dense map (p2p_matching_seg_icp.py:452,488, KDTree(xyz1).query): 0 (default) = exact search on
+ * landmark-bin tiles (blend_tile_kernel), 1 = exact search in a hashed uniform grid (grid_build_kernel +
+ * blend_nn_kernel + retry/far passes).  Same results; call before lip_batch_plan. */
+int  lip_set_map_mode(lip_ctx* ctx, int mode);
 /* pinned host memory for the *_host entry points (optional; any host pointer works) */
 int  lip_host_alloc(void** p, uint64_t bytes);
 int  lip_host_free(void* p);
