@@ -41,14 +41,15 @@ struct LipArgs {
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
     float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
     int* map_tiles;          // [2 * (n_total / LIP_MAP_TILE + B)] (bin, first slot) of every final-map tile; count in sched[20]
+    double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number
     double* mesh_sum;        // [M*4] sum of the vertices of every mesh (x, y, z) and the vertex count
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
-    int* sched;              // [32] [0] n_small [1] n_big [2] small cursor [3] n_far [4] n_medium [5] medium cursor
-                             //      [6] far cursor [7] n_retry [8..11] medium class counts [12..15] big class counts
+    int* sched;              // [32] [0] partitions of icp_group_kernel [1] n_big [2] group task cursor [3] n_far
+                             //      [6] far cursor [7] n_retry [12..15] big class counts [24..31] group class counts
                              //      [16] big cursor [20] number of final-map tiles
-    int *small_list, *medium_list, *big_list;    // [B], [4B] (four work classes), [4B]
+    int *warp_list, *big_list;     // [8B] (eight work classes), [4B] (four)
     int* far_list;           // [n_total] unified ids of queries whose ring search could not certify
     double* far_q;           // [3 * n_total] their blended positions
     int* retry_list;         // [2 * n_total] (unified id, target mesh) of queries the cooperative pass left open

@@ -3,10 +3,10 @@
 #pragma once
 #include "lip_device.cuh"
 
-#define LIP_SMALL_CAP 128     // partitions with <= this many src AND tgt points: one warp, all in SMEM
-#define LIP_SMALL_WARPS 4
-#define LIP_MEDIUM_CAP 256    // up to this many: still one warp, fp32 tile in SMEM, float64 from global
-#define LIP_MEDIUM_WARPS 4
+#define LIP_WARP_CAP 256      // partitions with <= this many src AND tgt points: icp_group_kernel (a warp per partition)
+#define LIP_ICP_WARPS 4       // warps per CTA of icp_group_kernel
+#define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp
+#define LIP_ICP_GMAX 8        // partitions per warp task: their 3x3 solves run SIMT, one lane per partition
 #define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 256
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
@@ -77,35 +77,63 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
     __syncthreads();
     for (int i = tid; i < K; i += blockDim.x) a.bin_off[bb + i] = ub + excl[i];
     if (m == a.M - 1 && tid == 0) a.bin_off[a.B] = a.n_total;
-    // stable compaction: one warp per bin walks the mesh in vertex order.  Besides the member list it writes
-    // the bin's points as fp32 offsets from the bin's own landmark (the search tiles of the ICP and of the
-    // final map are assembled from these with coalesced 16-byte loads) and their bounding box.
+    // Stable partition of the vertices by nearest landmark (ascending vertex id inside a bin, as the boolean
+    // masks of the reference give it), one chunk of blockDim vertices at a time: rank inside the warp by
+    // __match_any_sync, offsets of the earlier warps of the chunk from per-warp bin counts, running bin
+    // cursors across chunks.  Besides the member list it writes the bin's points as fp32 offsets from the
+    // bin's own landmark: the search tiles of the ICP and of the final map are assembled from these with
+    // coalesced 16-byte loads.
+    int* running = excl + K + 1;                            // K cursors
+    int* wcnt = running + K;                                // nwarps x K per-warp counts of the current chunk
+    for (int i = tid; i < K; i += blockDim.x) running[i] = excl[i];
+    for (int i = tid; i < nwarps * K; i += blockDim.x) wcnt[i] = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int v = base + tid;
+        const int bin = (v < n) ? a.nn0[ub + v] : -1;
+        const unsigned peers = __match_any_sync(LIP_FULL, bin);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        if (bin >= 0 && rank == 0) wcnt[warp * K + bin] = __popc(peers);
+        __syncthreads();
+        if (bin >= 0) {
+            int pos = ub + running[bin] + rank;
+            for (int w = 0; w < warp; ++w) pos += wcnt[w * K + bin];
+            const float fx = (float)(xyz[3 * (size_t)v] - lmS[3 * bin]), fy = (float)(xyz[3 * (size_t)v + 1] - lmS[3 * bin + 1]),
+                        fz = (float)(xyz[3 * (size_t)v + 2] - lmS[3 * bin + 2]);
+            a.part_vid[pos] = v;
+            a.bin_pts[pos] = make_float4(fx, fy, fz, __int_as_float(v));
+        }
+        __syncthreads();
+        if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the chunk
+            atomicAdd(&running[bin], __popc(peers));         // integer adds commute: the cursors stay deterministic
+            wcnt[warp * K + bin] = 0;
+        }
+        __syncthreads();
+    }
+    // per bin: bounding box of the fp32 offsets and the float64 mean of the vertices, in member order
+    // (the means give my_icp's initial translation, registration_icp.py:70, and the centre of the ICP frame)
     for (int i = warp; i < K; i += nwarps) {
-        int pos = ub + excl[i];
-        const double lx = lmS[3 * i], ly = lmS[3 * i + 1], lz = lmS[3 * i + 2];
+        const int s0 = ub + excl[i], e0 = ub + excl[i + 1];
         float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
-        for (int base = 0; base < n; base += 32) {
-            int v = base + lane;
-            bool pred = (v < n) && (a.nn0[ub + v] == i);
-            unsigned mask = __ballot_sync(LIP_FULL, pred);
-            if (pred) {
-                const int p = pos + __popc(mask & ((1u << lane) - 1));
-                const float fx = (float)(xyz[3 * (size_t)v] - lx), fy = (float)(xyz[3 * (size_t)v + 1] - ly),
-                            fz = (float)(xyz[3 * (size_t)v + 2] - lz);
-                a.part_vid[p] = v;
-                a.bin_pts[p] = make_float4(fx, fy, fz, __int_as_float(v));
-                lo0 = fminf(lo0, fx); lo1 = fminf(lo1, fy); lo2 = fminf(lo2, fz);
-                hi0 = fmaxf(hi0, fx); hi1 = fmaxf(hi1, fy); hi2 = fmaxf(hi2, fz);
-            }
-            pos += __popc(mask);
+        double bx0 = 0, bx1 = 0, bx2 = 0;
+        for (int p = s0 + lane; p < e0; p += 32) {
+            const float4 t = a.bin_pts[p];
+            lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
+            hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
+            const size_t v = (size_t)__float_as_int(t.w);
+            bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
         }
         lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
         hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
+        bx0 = warp_sum(bx0); bx1 = warp_sum(bx1); bx2 = warp_sum(bx2);
         if (lane == 0) {
             float* bx = a.bin_box + 8 * (size_t)(bb + i);
             bx[0] = lo0; bx[1] = lo1; bx[2] = lo2; bx[3] = hi0; bx[4] = hi1; bx[5] = hi2;
             bx[6] = fmaxf(fmaxf(fmaxf(fabsf(lo0), fabsf(hi0)), fmaxf(fabsf(lo1), fabsf(hi1))), fmaxf(fabsf(lo2), fabsf(hi2)));
             bx[7] = 0.f;
+            double* bs = a.bin_sum + 4 * (size_t)(bb + i);
+            const double cnt = (double)(e0 - s0);
+            bs[0] = bx0 / cnt; bs[1] = bx1 / cnt; bs[2] = bx2 / cnt; bs[3] = cnt;     // (NaN for an empty bin: never read)
         }
     }
 }
@@ -129,20 +157,80 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     }
     if (ns == 0 || nt == 0) return;
     const int mx = max(ns, nt);
-    if (mx <= LIP_SMALL_CAP) a.small_list[atomicAdd(&a.sched[0], 1)] = b;
-    else if (mx <= LIP_MEDIUM_CAP) {
-        // four work classes, heaviest first: the persistent warps drain class 3, then 2, 1, 0 (longest tasks first)
-        const long long w = (long long)ns * nt;
-        const int cls = (w > 45000) ? 3 : (w > 30000) ? 2 : (w > 18000) ? 1 : 0;
-        a.medium_list[(size_t)cls * a.B + atomicAdd(&a.sched[8 + cls], 1)] = b;
-        atomicAdd(&a.sched[4], 1);
-    }
-    else {
-        const long long w = (long long)ns * nt;
+    const long long w = (long long)ns * nt;
+    if (mx <= LIP_WARP_CAP) {
+        // eight work classes (factor 2 apart); the persistent warps take groups of partitions heaviest class first
+        int cls = 0;
+        for (long long t = 1024; t <= w && cls < 7; t <<= 1) ++cls;
+        a.warp_list[(size_t)cls * a.B + atomicAdd(&a.sched[24 + cls], 1)] = b;
+        atomicAdd(&a.sched[0], 1);
+    } else {
         const int cls = (w > 1000000) ? 3 : (w > 400000) ? 2 : (w > 150000) ? 1 : 0;
         a.big_list[(size_t)cls * a.B + atomicAdd(&a.sched[12 + cls], 1)] = b;
         atomicAdd(&a.sched[1], 1);
     }
+}
+
+// =============================================================================================
+// Scan primitives shared by the ICP kernels and the final map: an SMEM tile of fp32 candidates (float4,
+// DOT form: .w = |y|^2 and the query passed as m = -2q, score c = |y|^2 - 2 q.y = d^2 - |q|^2 in 3 FFMA;
+// difference form: m = q, score d^2) is scanned by all lanes at once (broadcast reads).  Per block of 8
+// candidates only the block minimum enters the top-2 tracking (FMNMX3), the winner's position is
+// recovered afterwards by re-evaluating its block with the identical instruction sequence.
+// =============================================================================================
+template <bool DOT>
+__device__ __forceinline__ float tile_score(const float4 t, const float* m) {
+    if (DOT) return fmaf(m[0], t.x, fmaf(m[1], t.y, fmaf(m[2], t.z, t.w)));
+    const float dx = t.x - m[0], dy = t.y - m[1], dz = t.z - m[2];
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+template <int Q, bool DOT>
+__device__ __forceinline__ void tile_scan(const float4* __restrict__ tp, int npad, const float (&m)[2][3], float (&best)[2],
+                                          float (&sec)[2], int (&blk)[2]) {
+#pragma unroll 1
+    for (int jb = 0; jb < npad; jb += 8) {
+        float4 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = tp[jb + k];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float c[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = tile_score<DOT>(t[k], m[q]);
+            float bm = fminf(fminf(c[0], c[1]), c[2]);
+            bm = fminf(fminf(bm, c[3]), c[4]);
+            bm = fminf(fminf(bm, c[5]), c[6]);
+            bm = fminf(bm, c[7]);
+            sec[q] = fminf(sec[q], fmaxf(bm, best[q]));
+            blk[q] = (bm < best[q]) ? jb : blk[q];
+            best[q] = fminf(best[q], bm);
+        }
+    }
+}
+// position of the winner of block `blk` (first candidate whose score equals `best` bitwise) and the smallest
+// score among the other seven
+template <bool DOT>
+__device__ __forceinline__ int tile_recover(const float4* __restrict__ tp, int blk, float best, const float* m, float& sec_in) {
+    int pos = -1;
+    float s2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float c = tile_score<DOT>(tp[blk + k], m);
+        if (c == best && pos < 0) pos = blk + k;
+        else s2 = fminf(s2, c);
+    }
+    sec_in = s2;
+    return pos < 0 ? blk : pos;
+}
+__device__ __forceinline__ float4 tile_sentinel(bool dot) {       // never the best, never a runner-up
+    return dot ? make_float4(0.f, 0.f, 0.f, 3.0e38f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+}
+// Bound on |evaluated - exact| of the dot-form score of a candidate at distance <= sqrt(d2) of a query with
+// |q|^2 = qq: three FMAs and the stored |y|^2 (three roundings), every partial result bounded by
+// |y|^2 + 2 |q| |y| with |y| <= |q| + d.   6 u (.) with u = 2^-24, times 1.5 for slack.
+__device__ __forceinline__ float dot_err(float qq, float d2) {
+    const float nq = sqrtf(qq), ny = nq + 1.001f * sqrtf(d2) + 1e-3f;
+    return 5.4e-7f * fmaf(ny, ny, 2.f * nq * ny);
 }
 
 // =============================================================================================
@@ -286,16 +374,6 @@ __device__ __forceinline__ int nn_block_index(const float4* __restrict__ tf, int
     return idx;
 }
 
-// Per-warp SMEM of the warp-per-partition kernel.  SMEM64 = true (small partitions): float64 copies
-// of source and target live in SMEM too; false (medium partitions): only the fp32 search tile is
-// staged and the float64 coordinates are gathered from global memory (L1/L2 resident) when needed.
-template <int CAP, bool SMEM64>
-struct IcpWarpSmem {
-    float4 tf[CAP];                                      // centred fp32 target (search)
-    double tx[SMEM64 ? CAP : 1], ty[SMEM64 ? CAP : 1], tz[SMEM64 ? CAP : 1];   // centred fp64 target
-    double sx[SMEM64 ? CAP : 1], sy[SMEM64 ? CAP : 1], sz[SMEM64 ? CAP : 1];   // centred fp64 source
-};
-
 template <bool SMEM64>
 struct IcpView {                                         // one partition as seen by the warp / CTA working on it
     const float4* tf;                                    // staged centred fp32 target (SMEM)
@@ -403,102 +481,190 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>
     }
 }
 
-template <int CAP, bool SMEM64>
-__device__ void icp_one_warp(const LipArgs& a, int b, IcpWarpSmem<CAP, SMEM64>& sm, IcpState* st, int lane) {
-    const int pb = pair_bin(a, b);
-    const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
-    const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
-    const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
-    IcpView<SMEM64> w{sm.tf, sm.tx, sm.ty, sm.tz, sm.sx, sm.sy, sm.sz, mesh_xyz(a, ms), mesh_xyz(a, mt),
-                      a.part_vid + so, a.part_vid + to, 0.0, 0.0, 0.0};
-    // ---- stage the target, centred on its centroid -------------------------------------------------
-    double cx = 0, cy = 0, cz = 0;
-    for (int j = lane; j < nt; j += 32) {
-        size_t v = (size_t)w.vt[j];
-        double x = w.xt[3 * v], y = w.xt[3 * v + 1], z = w.xt[3 * v + 2];
-        if (SMEM64) { sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z; }
-        cx += x; cy += y; cz += z;
+// ---- warp-per-partition, groups of partitions per warp task ---------------------------------------------
+// A persistent warp takes a task of g <= LIP_ICP_GMAX partitions of similar size.  Every NN pass is
+// warp-cooperative (one partition after the other: tile staged from bin_pts with coalesced 16-byte loads,
+// lanes own the queries); the serial part of an iteration — cost / stop test, 3x3 Kabsch solve, transform
+// accumulation — runs SIMT across the task's partitions, lane p working for partition p, so its cost is
+// shared by g partitions instead of being paid 32-fold redundantly by every one.
+struct IcpGroupSmem {
+    float4 tf[LIP_ICP_CHUNK + 8];                         // fp32 search tile (offsets from the target landmark)
+    IcpState st[LIP_ICP_GMAX];
+    double acc[LIP_ICP_GMAX][17];
+};
+
+template <bool DOT>
+__device__ __forceinline__ void group_stage(const LipArgs& a, float4* tf, int to, int c0, int cnt, int lane,
+                                            float sh0, float sh1, float sh2) {
+    const int npad = (cnt + 7) & ~7;
+    for (int j = lane; j < npad; j += 32) {
+        float4 t = tile_sentinel(DOT);
+        if (j < cnt) {
+            t = a.bin_pts[to + c0 + j];
+            t.x += sh0; t.y += sh1; t.z += sh2;
+            t.w = DOT ? fmaf(t.x, t.x, fmaf(t.y, t.y, t.z * t.z)) : 0.f;
+        }
+        tf[j] = t;
     }
-    cx = warp_sum(cx) / nt; cy = warp_sum(cy) / nt; cz = warp_sum(cz) / nt;
-    w.cx = cx; w.cy = cy; w.cz = cz;
-    __syncwarp();
-    float mabs = 0.f;
-    double mtx = 0, mty = 0, mtz = 0;
-    for (int j = lane; j < nt; j += 32) {
-        double x, y, z;
-        if (SMEM64) { x = sm.tx[j] - cx; y = sm.ty[j] - cy; z = sm.tz[j] - cz; sm.tx[j] = x; sm.ty[j] = y; sm.tz[j] = z; }
-        else w.tgt(j, x, y, z);
-        const float fx = (float)x, fy = (float)y, fz = (float)z;
-        sm.tf[j] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));   // .w = |y|^2 for the dot-form score
-        mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)));
-        mtx += x; mty += y; mtz += z;
-    }
-    mabs = warp_maxf(mabs);
-    // dot-form scores only while the cancellation error stays far below the point spacing
-    const bool use_dot = mabs <= 24.0f;
-    const int nt_pad = (nt + LIP_NN_BLOCK - 1) / LIP_NN_BLOCK * LIP_NN_BLOCK;
-    if (lane < nt_pad - nt)                                   // sentinels: never the best, never a runner-up
-        sm.tf[nt + lane] = use_dot ? make_float4(0.f, 0.f, 0.f, 3.0e38f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
-    mtx = warp_sum(mtx) / nt; mty = warp_sum(mty) / nt; mtz = warp_sum(mtz) / nt;
-    double msx = 0, msy = 0, msz = 0;
-    for (int q = lane; q < ns; q += 32) {
-        size_t v = (size_t)w.vs[q];
-        double x = w.xs[3 * v] - cx, y = w.xs[3 * v + 1] - cy, z = w.xs[3 * v + 2] - cz;
-        if (SMEM64) { sm.sx[q] = x; sm.sy[q] = y; sm.sz[q] = z; }
-        msx += x; msy += y; msz += z;
-    }
-    msx = warp_sum(msx) / ns; msy = warp_sum(msy) / ns; msz = warp_sum(msz) / ns;
-    __syncwarp();
-    // ---- the ICP loop ---------------------------------------------------------------------------------
-    icp_state_init(st, mtx - msx, mty - msy, mtz - msz);    // t_init = mean(tgt) - mean(src)   (:70)
-    __syncwarp();
-    double prev = 0.0;
-    int iters = 0, status = 1;
-    for (int it = 0; it < a.max_iter; ++it) {
-        icp_state_accumulate(st);
-        __syncwarp();
-        double acc[17];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-        if (use_dot) icp_pass<SMEM64, true>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, a.nn_idx + so, acc);
-        else icp_pass<SMEM64, false>(a, w, st, ns, nt, nt_pad, mabs, lane, 32, a.nn_idx + so, acc);
-#pragma unroll
-        for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
-        const double cost = acc[0] / ns;                    // np.mean(distance)   (:86)
-        iters = it + 1;
-        if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;   // (:87)
-        prev = cost;
-        if (icp_kabsch_step(acc, st)) status = 2;
-        __syncwarp();
-    }
-    if (lane == 0) icp_store(a, b, st, cx, cy, cz, iters, status);
 }
 
-// LIST 0: small partitions (sched[0] entries of small_list, cursor sched[2]);
-// LIST 1: medium partitions (sched[4] entries of medium_list, cursor sched[5])
-template <int CAP, int WARPS, bool SMEM64>
-__global__ void __launch_bounds__(WARPS * 32, LIP_WARP_MINBLOCKS) icp_warp_kernel(LipArgs a) {
-    __shared__ IcpWarpSmem<CAP, SMEM64> sm_all[WARPS];
-    __shared__ IcpState st_all[WARPS];
-    IcpWarpSmem<CAP, SMEM64>& sm = sm_all[threadIdx.x >> 5];
-    IcpState* st = &st_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const int n_items = SMEM64 ? a.sched[0] : a.sched[4];
-    const int* list = SMEM64 ? a.small_list : a.medium_list;
-    int* cursor = SMEM64 ? &a.sched[2] : &a.sched[5];
-    for (;;) {                                              // persistent warps, dynamic partition queue
-        int w = 0;
-        if (lane == 0) w = atomicAdd(cursor, 1);
-        w = __shfl_sync(LIP_FULL, w, 0);
-        if (w >= n_items) break;
-        int b;
-        if (SMEM64) b = list[w];
-        else {                                               // medium: class 3 first
-            int c = 3, r = w;
-            while (c > 0 && r >= a.sched[8 + c]) { r -= a.sched[8 + c]; --c; }
-            b = list[(size_t)c * a.B + r];
+// one NN pass + sums of partition (src bin at so/ns, tgt bin at to/nt, origin c = the target's landmark)
+template <bool DOT>
+__device__ __forceinline__ void group_pass(const LipArgs& a, IcpGroupSmem& sm, int p, int lane, int so, int ns, int to, int nt,
+                                           const double* __restrict__ xs, const double* __restrict__ xt,
+                                           double c0, double c1, double c2, float sh0, float sh1, float sh2, float mabs) {
+    const IcpState* st = &sm.st[p];
+    const int* __restrict__ vs = a.part_vid + so;
+    const int* __restrict__ vt = a.part_vid + to;
+    int* __restrict__ nn_idx = a.nn_idx + so;
+    const float sc = DOT ? -2.0f : 1.0f;
+    const bool one_chunk = nt <= LIP_ICP_CHUNK;
+    if (one_chunk) { __syncwarp(); group_stage<DOT>(a, sm.tf, to, 0, nt, lane, sh0, sh1, sh2); __syncwarp(); }
+    for (int q0 = 0; q0 < ns; q0 += 64) {
+        const bool two = ns - q0 > 32;                       // uniform
+        const int qi[2] = {q0 + lane, q0 + lane + 32};
+        double pq[2][3];
+        float m[2][3], best[2], sec[2], sec_in[2];
+        int blk[2], idx[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const size_t v = (size_t)vs[min(qi[k], ns - 1)];
+            mat3_vec(st->R, xs[3 * v] - c0, xs[3 * v + 1] - c1, xs[3 * v + 2] - c2, pq[k][0], pq[k][1], pq[k][2]);
+            pq[k][0] += st->t[0]; pq[k][1] += st->t[1]; pq[k][2] += st->t[2];
+            m[k][0] = sc * (float)pq[k][0]; m[k][1] = sc * (float)pq[k][1]; m[k][2] = sc * (float)pq[k][2];
+            best[k] = INFINITY; sec[k] = INFINITY; sec_in[k] = INFINITY; blk[k] = 0; idx[k] = 0;
         }
-        icp_one_warp<CAP, SMEM64>(a, b, sm, st, lane);
+        for (int t0 = 0; t0 < nt; t0 += LIP_ICP_CHUNK) {
+            const int cnt = min(LIP_ICP_CHUNK, nt - t0), npad = (cnt + 7) & ~7;
+            if (!one_chunk) { __syncwarp(); group_stage<DOT>(a, sm.tf, to, t0, cnt, lane, sh0, sh1, sh2); __syncwarp(); }
+            const float prev0 = best[0], prev1 = best[1];
+            if (two) tile_scan<2, DOT>(sm.tf, npad, m, best, sec, blk);
+            else tile_scan<1, DOT>(sm.tf, npad, m, best, sec, blk);
+            if (best[0] < prev0) idx[0] = t0 + tile_recover<DOT>(sm.tf, blk[0], best[0], m[0], sec_in[0]);
+            if (best[1] < prev1) idx[1] = t0 + tile_recover<DOT>(sm.tf, blk[1], best[1], m[1], sec_in[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (qi[k] >= ns) continue;
+            const float fx = (float)pq[k][0], fy = (float)pq[k][1], fz = (float)pq[k][2];
+            const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
+            const float e = 2.4e-7f * (qabs + mabs);
+            const float qq = DOT ? fmaf(fx, fx, fmaf(fy, fy, fz * fz)) : 0.f;
+            const float d2b = fmaxf(best[k] + qq, 0.f), d2s = fmaxf(fminf(sec[k], sec_in[k]) + qq, 0.f);
+            float tol = d2_err(d2b, e) + d2_err(d2s, e);
+            if (DOT) tol += 2.f * dot_err(qq, d2s);
+            if (!(d2s - d2b > tol)) {                        // near tie: decide in float64, lowest index
+                double bd = INFINITY;
+#pragma unroll 1
+                for (int j = 0; j < nt; ++j) {
+                    const size_t v = (size_t)vt[j];
+                    const double d = rdist64(pq[k][0], pq[k][1], pq[k][2], xt[3 * v] - c0, xt[3 * v + 1] - c1, xt[3 * v + 2] - c2);
+                    if (d < bd) { bd = d; idx[k] = j; }
+                }
+                atomicAdd(&a.counters[2], 1ull);
+            }
+            nn_idx[qi[k]] = idx[k];
+        }
+    }
+    // ---- sums of get_best_fit_transform + cost over the (source, winner) pairs, float64 ----
+    double acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = 0.0;
+    const double reject = a.reject_dist;
+    for (int q = lane; q < ns; q += 32) {
+        const size_t v = (size_t)vs[q], w = (size_t)vt[nn_idx[q]];
+        double px, py, pz;
+        mat3_vec(st->R, xs[3 * v] - c0, xs[3 * v + 1] - c1, xs[3 * v + 2] - c2, px, py, pz);
+        px += st->t[0]; py += st->t[1]; pz += st->t[2];
+        const double bx = xt[3 * w] - c0, by = xt[3 * w + 1] - c1, bz = xt[3 * w + 2] - c2;
+        const double d = sqrt(rdist64(px, py, pz, bx, by, bz));
+        acc[0] += d;
+        if (d <= reject) {
+            acc[1] += px; acc[2] += py; acc[3] += pz;
+            acc[4] += bx; acc[5] += by; acc[6] += bz;
+            acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
+            acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
+            acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
+            acc[16] += 1.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) sm.acc[p][i] = acc[i];
+    }
+}
+
+__global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_group_kernel(LipArgs a) {
+    __shared__ IcpGroupSmem sm_all[LIP_ICP_WARPS];
+    IcpGroupSmem& sm = sm_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int n_items = a.sched[0];
+    // group size: as large as leaves every resident warp a few tasks
+    int G = n_items / (int)(gridDim.x * LIP_ICP_WARPS * 3);
+    G = max(1, min(G, LIP_ICP_GMAX));
+    const int n_tasks = (n_items + G - 1) / G;
+    for (;;) {                                              // persistent warps, dynamic task queue, heaviest class first
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&a.sched[2], 1);
+        w = __shfl_sync(LIP_FULL, w, 0);
+        if (w >= n_tasks) break;
+        const int first = w * G, g = min(G, n_items - first);
+        // ---- lane p < g owns partition p of the task -------------------------------------------------------
+        int b = 0, own_ns = 1, iters = 0, status = 1;
+        bool active = lane < g;
+        double prev = 0.0;
+        if (active) {
+            int c = 7, r = first + lane;
+            while (c > 0 && r >= a.sched[24 + c]) { r -= a.sched[24 + c]; --c; }
+            b = a.warp_list[(size_t)c * a.B + r];
+            const int pb = pair_bin(a, b);
+            own_ns = a.bin_off[b + 1] - a.bin_off[b];
+            const double* ss = a.bin_sum + 4 * (size_t)b;
+            const double* ts = a.bin_sum + 4 * (size_t)pb;
+            // increment 0: identity, t = mean(tgt) - mean(src)   (registration_icp.py:70)
+            icp_state_init(&sm.st[lane], ts[0] - ss[0], ts[1] - ss[1], ts[2] - ss[2]);
+        }
+        __syncwarp();
+        for (int it = 0; it < a.max_iter; ++it) {
+            unsigned todo = __ballot_sync(LIP_FULL, active);
+            if (!todo) break;
+            if (active) icp_state_accumulate(&sm.st[lane]);     // R <- Ri R ; t <- Ri t + ti   (:83-84)
+            __syncwarp();
+            while (todo) {                                      // NN pass + sums, one partition after the other
+                const int p = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int bp = __shfl_sync(LIP_FULL, b, p), pb = pair_bin(a, bp);
+                const int so = a.bin_off[bp], ns = a.bin_off[bp + 1] - so;
+                const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
+                const int ms = a.bin_mesh[bp], mt = pair_mesh(a, ms);
+                // frame of the ICP: centred on the target centroid; the tile points are stored as offsets from the
+                // target's landmark, so they are shifted by (landmark - centroid) when staged
+                const double* lmt = mesh_lm(a, mt) + 3 * (size_t)(pb - a.mesh_bin[mt]);
+                const double* ct = a.bin_sum + 4 * (size_t)pb;
+                const float sh0 = (float)(lmt[0] - ct[0]), sh1 = (float)(lmt[1] - ct[1]), sh2 = (float)(lmt[2] - ct[2]);
+                const float mabs = a.bin_box[8 * (size_t)pb + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2));
+                // dot-form scores only while the cancellation error stays far below the point spacing
+                if (mabs <= 24.0f) group_pass<true>(a, sm, p, lane, so, ns, to, nt, mesh_xyz(a, ms), mesh_xyz(a, mt), ct[0], ct[1], ct[2], sh0, sh1, sh2, mabs);
+                else group_pass<false>(a, sm, p, lane, so, ns, to, nt, mesh_xyz(a, ms), mesh_xyz(a, mt), ct[0], ct[1], ct[2], sh0, sh1, sh2, mabs);
+            }
+            __syncwarp();
+            if (active) {                                       // SIMT over the task's partitions
+                const double cost = sm.acc[lane][0] / own_ns;   // np.mean(distance)   (:86)
+                iters = it + 1;
+                if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) active = false;   // (:87)
+                else {
+                    prev = cost;
+                    if (icp_kabsch_step(sm.acc[lane], &sm.st[lane])) status = 2;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < g) {
+            const double* ct = a.bin_sum + 4 * (size_t)pair_bin(a, b);
+            icp_store(a, b, &sm.st[lane], ct[0], ct[1], ct[2], iters, status);
+        }
         __syncwarp();
     }
 }
@@ -1146,56 +1312,6 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
 //     any fallback path.  All lanes read the same candidate (SMEM broadcast); the per-pair cost is 3 FFMA
 //     + ~1.1 min/max (scores c = |y|^2 - 2 q.y, block minima, winner recovered per block of 8).
 // =============================================================================================
-__device__ __forceinline__ float tile_score(const float4 t, const float* m) {
-    return fmaf(m[0], t.x, fmaf(m[1], t.y, fmaf(m[2], t.z, t.w)));
-}
-// blocked scan of an SMEM tile: per block of 8 candidates only the block minimum enters the top-2 tracking
-template <int Q>
-__device__ __forceinline__ void tile_scan(const float4* __restrict__ tp, int npad, const float (&m)[2][3], float (&best)[2],
-                                          float (&sec)[2], int (&blk)[2]) {
-#pragma unroll 1
-    for (int jb = 0; jb < npad; jb += 8) {
-        float4 t[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = tp[jb + k];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            float c[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c[k] = tile_score(t[k], m[q]);
-            float bm = fminf(fminf(c[0], c[1]), c[2]);
-            bm = fminf(fminf(bm, c[3]), c[4]);
-            bm = fminf(fminf(bm, c[5]), c[6]);
-            bm = fminf(bm, c[7]);
-            sec[q] = fminf(sec[q], fmaxf(bm, best[q]));
-            blk[q] = (bm < best[q]) ? jb : blk[q];
-            best[q] = fminf(best[q], bm);
-        }
-    }
-}
-// winner of block `blk` (first candidate whose score equals `best` bitwise: same instruction sequence) and the
-// smallest score among the other seven
-__device__ __forceinline__ void tile_recover(const float4* __restrict__ tp, const int* __restrict__ tv, int blk, float best,
-                                             const float* m, int& idx, float& sec_in) {
-    int pos = -1;
-    float s2 = INFINITY;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float c = tile_score(tp[blk + k], m);
-        if (c == best && pos < 0) pos = blk + k;
-        else s2 = fminf(s2, c);
-    }
-    idx = tv[pos < 0 ? blk : pos];
-    sec_in = s2;
-}
-// Bound on |evaluated - exact| of the dot-form score of a candidate at distance <= sqrt(d2) of a query with
-// |q|^2 = qq: three FMAs and the stored |y|^2 (three roundings), every partial result bounded by
-// |y|^2 + 2 |q| |y| with |y| <= |q| + d.   6 u (.) with u = 2^-24, times 1.5 for slack.
-__device__ __forceinline__ float dot_err(float qq, float d2) {
-    const float nq = sqrtf(qq), ny = nq + 1.001f * sqrtf(d2) + 1e-3f;
-    return 5.4e-7f * fmaf(ny, ny, 2.f * nq * ny);
-}
-
 __global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) {
     __shared__ float4 tp[LIP_MAP_CHUNK];
     __shared__ int tv[LIP_MAP_CHUNK];
@@ -1244,10 +1360,10 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) 
         if (tid < npad - fill) { tp[fill + tid] = make_float4(0.f, 0.f, 0.f, 3.0e38f); tv[fill + tid] = 0x7fffffff; }
         __syncthreads();
         const float prev0 = best[0], prev1 = best[1];
-        if (two) tile_scan<2>(tp, npad, mq, best, sec, blk);
-        else tile_scan<1>(tp, npad, mq, best, sec, blk);
-        if (best[0] < prev0) tile_recover(tp, tv, blk[0], best[0], mq[0], idx[0], sec_in[0]);
-        if (best[1] < prev1) tile_recover(tp, tv, blk[1], best[1], mq[1], idx[1], sec_in[1]);
+        if (two) tile_scan<2, true>(tp, npad, mq, best, sec, blk);
+        else tile_scan<1, true>(tp, npad, mq, best, sec, blk);
+        if (best[0] < prev0) idx[0] = tv[tile_recover<true>(tp, blk[0], best[0], mq[0], sec_in[0])];
+        if (best[1] < prev1) idx[1] = tv[tile_recover<true>(tp, blk[1], best[1], mq[1], sec_in[1])];
         __syncthreads();
         staged += fill;
         fill = 0;

@@ -42,9 +42,9 @@ enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 
 struct lip_ctx {
     int device = 0;
     int sm_count = 0;
-    int small_blocks_per_sm = 1, medium_blocks_per_sm = 1, big_blocks_per_sm = 1;
+    int group_blocks_per_sm = 1, big_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, medium ICP, grid build
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, (unused), grid build
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool fill_done = false;
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
@@ -98,7 +98,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4), o_nnidx = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
     const size_t o_fR = take(B * 72), o_ft = take(B * 24);
-    const size_t o_sched = take(32 * 4), o_small = take(B * 4), o_med = take(4 * B * 4), o_big = take(4 * B * 4);
+    const size_t o_sched = take(32 * 4), o_warp = take(8 * B * 4), o_big = take(4 * B * 4), o_bsum = take(B * 32);
     const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
@@ -114,7 +114,7 @@ int carve_workspace(lip_ctx* c) {
     a.icp_R = (double*)(base + o_R); a.icp_t = (double*)(base + o_t);
     a.icp_iters = (int*)(base + o_it); a.icp_status = (int*)(base + o_stat);
     a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft);
-    a.sched = (int*)(base + o_sched); a.small_list = (int*)(base + o_small); a.medium_list = (int*)(base + o_med);
+    a.sched = (int*)(base + o_sched); a.warp_list = (int*)(base + o_warp); a.bin_sum = (double*)(base + o_bsum);
     a.big_list = (int*)(base + o_big); a.far_list = (int*)(base + o_far); a.far_q = (double*)(base + o_farq);
     a.retry_list = (int*)(base + o_re); a.retry_q = (double*)(base + o_req);
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
@@ -227,7 +227,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     // otherwise the three ICP kernels and the grid build run as concurrent branches (their tails overlap).
     const bool serial = c->profiling;
     auto mark = [&]() { if (c->profiling) cudaEventRecord(c->ev[evi], st); ++evi; };
-    cudaStream_t s_big = serial ? st : c->side[0], s_med = serial ? st : c->side[1], s_grid = serial ? st : c->side[2];
+    cudaStream_t s_big = serial ? st : c->side[0], s_grid = serial ? st : c->side[2];
     c->ev_valid = false;
     c->fill_done = false;
     LIP_CUDA(c, cudaMemsetAsync(a.sched, 0, 32 * 4, st));
@@ -235,7 +235,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
     if (stages & ST_PARTITION) {
-        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 2 + 1) * 4;
+        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 3 + 1) * 4 + (size_t)c->maxK * 8 * 4;
         landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
         ++launches;
     }
@@ -247,30 +247,24 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         if (!serial) {
             LIP_CUDA(c, cudaEventRecord(c->ev_fork, st));
             LIP_CUDA(c, cudaStreamWaitEvent(s_big, c->ev_fork, 0));
-            LIP_CUDA(c, cudaStreamWaitEvent(s_med, c->ev_fork, 0));
             forked_icp = true;
         }
-        // longest tasks first: CTA-per-partition (big), then medium, then small partitions
-        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_MEDIUM_CAP + 1);
+        // the CTA-per-partition kernel (few, long tasks) runs as a concurrent branch of the group kernel
+        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_WARP_CAP + 1);
         int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
-        int gm = c->sm_count * c->medium_blocks_per_sm;
-        int64_t mbound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_SMALL_CAP + 1);
-        gm = (int)std::max<int64_t>(1, std::min<int64_t>(gm, (mbound + LIP_MEDIUM_WARPS - 1) / LIP_MEDIUM_WARPS));
-        int gs = c->sm_count * c->small_blocks_per_sm;
-        gs = std::max(1, std::min(gs, (c->B + LIP_SMALL_WARPS - 1) / LIP_SMALL_WARPS));
+        int gs = c->sm_count * c->group_blocks_per_sm;
+        gs = std::max(1, std::min(gs, (c->B + LIP_ICP_WARPS - 1) / LIP_ICP_WARPS));
         if (serial) {
-            icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
-            mark();                                          // 3: after small ICP
-            icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, st>>>(a);
-            mark();                                          // 4: after medium ICP
+            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
+            mark();                                          // 3: after the group kernel
+            mark();                                          // 4: (unused)
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
         } else {
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, s_big>>>(a);
-            icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false><<<gm, LIP_MEDIUM_WARPS * 32, 0, s_med>>>(a);
-            icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true><<<gs, LIP_SMALL_WARPS * 32, 0, st>>>(a);
+            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
             mark(); mark();
         }
-        launches += 4;
+        launches += 3;
     } else { mark(); mark(); mark(); }
     mark();                                                  // 5: after big ICP
     const bool tiles = (stages & ST_BLEND) && c->map_mode == 0;      // final map on landmark-bin tiles: no grid needed
@@ -283,7 +277,6 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     mark();                                                  // 6: after grid build
     if (forked_icp) {
         LIP_CUDA(c, cudaEventRecord(c->ev_join[0], s_big)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
-        LIP_CUDA(c, cudaEventRecord(c->ev_join[1], s_med)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
     }
     if (forked_grid) { LIP_CUDA(c, cudaEventRecord(c->ev_join[2], s_grid)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[2], 0)); }
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
@@ -364,16 +357,12 @@ int lip_create(lip_ctx** out, int device) {
     cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_warp_kernel<LIP_SMALL_CAP, LIP_SMALL_WARPS, true>,
-                                                      LIP_SMALL_WARPS * 32, 0) == cudaSuccess && nb > 0)
-        c->small_blocks_per_sm = nb;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_warp_kernel<LIP_MEDIUM_CAP, LIP_MEDIUM_WARPS, false>,
-                                                      LIP_MEDIUM_WARPS * 32, 0) == cudaSuccess && nb > 0)
-        c->medium_blocks_per_sm = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_group_kernel, LIP_ICP_WARPS * 32, 0) == cudaSuccess && nb > 0)
+        c->group_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
     cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         LIP_MAX_LANDMARKS * 32 + 64);
+                         LIP_MAX_LANDMARKS * 68 + 64);
     memset(&c->args, 0, sizeof(c->args));
     *out = c;
     return LIP_OK;
@@ -511,7 +500,7 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
     LIP_CUDA(c, cudaMemcpy(sched, c->args.sched, sizeof(sched), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) counters[i] = (int64_t)h[i];
-    counters[0] = sched[0] + sched[4]; counters[1] = sched[1]; counters[5] = sched[3]; counters[4] = sched[7];
+    counters[0] = sched[0]; counters[1] = sched[1]; counters[5] = sched[3]; counters[4] = sched[7];
     counters[6] = c->last_launches;
     return LIP_OK;
 }

@@ -302,8 +302,7 @@ def run_b200(args):
     iters = np.concatenate([tr["iters21"], tr["iters12"]]).astype(np.float64)
     mx = np.maximum(ns, nt)
     w = iters * ns * nt                                        # evaluated (source, candidate) pairs per partition
-    pairs = {"icp_warp_kernel_small": float(w[mx <= 128].sum()),
-             "icp_warp_kernel_medium": float(w[(mx > 128) & (mx <= 256)].sum()),
+    pairs = {"icp_group_kernel": float(w[mx <= 256].sum()),
              "icp_big_kernel": float(w[mx > 256].sum()),
              "final_map_kernel": float(counters["map_ring1_pairs"])}
     dom = max(pairs, key=lambda k: stage[k])

@@ -104,7 +104,7 @@ int lip_batch_get_transforms(lip_ctx* ctx, int filled,
  * and their distances for every vertex: KDTree(lm).query(xyz, k=2) of p2p_matching_seg_icp.py:388-392.
  * nn (n,2) int32, dist (n,2) float64; side 1 -> mesh1 vertices (off1 order), 2 -> mesh2. */
 int lip_batch_get_landmark_nn(lip_ctx* ctx, int side, int32_t* nn, double* dist);
-/* counters of the last run: [0] warp-per-partition ICPs (small + medium), [1] CTA-per-partition ICPs, [2] float64
+/* counters of the last run: [0] warp-per-partition ICPs (icp_group_kernel), [1] CTA-per-partition ICPs, [2] float64
  * re-evaluations of near-tied neighbours in ICP, [3] same in the final map, [4] final-map queries
  * left open by the warp-cooperative pass (retry_nn_kernel: ring 1 + ring 2 per query), [5] that were handed to the whole-mesh scan (far_nn_kernel), [6] kernels launched by the last run, [7] candidate pairs evaluated in
  * ring 1 of the final map (only counted while profiling is on) */
@@ -113,8 +113,8 @@ int lip_batch_get_counters(lip_ctx* ctx, int64_t counters[8]);
 /* Per-kernel device times of the last run, measured with CUDA events on the stream the kernels were
  * launched on.  Enable with lip_set_profiling before the run; while it is on, the kernels run back to
  * back on one stream (normally the ICP kernels and the grid build run as concurrent branches).
- * ms[0] landmark_partition_kernel, [1] icp_schedule_kernel, [2] icp_warp_kernel (small partitions),
- * [3] icp_warp_kernel (medium), [4] icp_big_kernel, [5] grid_build_kernel (+ its table memset),
+ * ms[0] landmark_partition_kernel, [1] icp_schedule_kernel, [2] icp_group_kernel (warp per partition),
+ * [3] unused (0), [4] icp_big_kernel (CTA per partition), [5] grid_build_kernel (+ its table memset),
  * [6] blend_nn_kernel / nn_query_kernel, [7] retry_nn_kernel, [8] far_nn_kernel. */
 #define LIP_N_STAGES 9
 int lip_set_profiling(lip_ctx* ctx, int on);
