@@ -39,6 +39,7 @@ struct LipArgs {
     int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
     int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
+    double* bin_xyz;         // [3 * n_total] the same vertices in float64, planes x | y | z in part_vid order
     float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
     int* map_tiles;          // [2 * (n_total / LIP_MAP_TILE + B)] (bin, first slot) of every final-map tile; count in sched[20]
     double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number

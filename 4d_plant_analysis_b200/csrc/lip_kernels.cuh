@@ -3,12 +3,15 @@
 #pragma once
 #include "lip_device.cuh"
 
-#define LIP_WARP_CAP 256      // partitions with <= this many src AND tgt points: icp_group_kernel (a warp per partition)
+#define LIP_WARP_CAP 256      // (sizing of launch grids only)
+#ifndef LIP_WARP_WORK
+#define LIP_WARP_WORK 65536    // partitions with n_src * n_tgt <= this: icp_group_kernel (a warp per partition), else CTA
+#endif
 #define LIP_ICP_WARPS 4       // warps per CTA of icp_group_kernel
 #define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp
 #define LIP_ICP_GMAX 8        // partitions per warp task: their 3x3 solves run SIMT, one lane per partition
-#define LIP_BIG_CAP 2048      // tgt tile (float4) of the CTA-per-partition variant
-#define LIP_BIG_THREADS 256
+#define LIP_BIG_CHUNK 1024    // tgt tile (float4) of the CTA-per-partition variant
+#define LIP_BIG_THREADS 128
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
 #define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA, two queries per thread
 #define LIP_MAP_TILE (2 * LIP_MAP_THREADS)
@@ -102,6 +105,9 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
                         fz = (float)(xyz[3 * (size_t)v + 2] - lmS[3 * bin + 2]);
             a.part_vid[pos] = v;
             a.bin_pts[pos] = make_float4(fx, fy, fz, __int_as_float(v));
+            a.bin_xyz[pos] = xyz[3 * (size_t)v];
+            a.bin_xyz[(size_t)a.n_total + pos] = xyz[3 * (size_t)v + 1];
+            a.bin_xyz[2 * (size_t)a.n_total + pos] = xyz[3 * (size_t)v + 2];
         }
         __syncthreads();
         if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the chunk
@@ -156,9 +162,8 @@ __global__ void icp_schedule_kernel(LipArgs a) {
         for (int i = 0; i < nt_map; ++i) { a.map_tiles[2 * (size_t)(slot + i)] = b; a.map_tiles[2 * (size_t)(slot + i) + 1] = i * LIP_MAP_TILE; }
     }
     if (ns == 0 || nt == 0) return;
-    const int mx = max(ns, nt);
     const long long w = (long long)ns * nt;
-    if (mx <= LIP_WARP_CAP) {
+    if (w <= LIP_WARP_WORK) {
         // eight work classes (factor 2 apart); the persistent warps take groups of partitions heaviest class first
         int cls = 0;
         for (long long t = 1024; t <= w && cls < 7; t <<= 1) ++cls;
@@ -309,195 +314,18 @@ __device__ __forceinline__ void icp_store(const LipArgs& a, int b, const IcpStat
     a.icp_status[b] = status;
 }
 
-// scan `cnt` fp32 target points (index base `j0`) for two queries at once
-__device__ __forceinline__ void nn_scan2(const float4* __restrict__ tf, int cnt, int j0,
-                                         float ax, float ay, float az, float bx, float by, float bz,
-                                         float& besta, float& seca, int& ia, float& bestb, float& secb, int& ib) {
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-        const float4 t = tf[j];
-        float dx = t.x - ax, dy = t.y - ay, dz = t.z - az;
-        float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-        nn_update(d, j0 + j, besta, seca, ia);
-        dx = t.x - bx; dy = t.y - by; dz = t.z - bz;
-        d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-        nn_update(d, j0 + j, bestb, secb, ib);
-    }
+// ---- one NN pass + Kabsch sums of a partition, by a warp (NT = 32) or by a CTA (NT = blockDim) -------------
+// The partition's points are read in bin order: a.bin_pts (fp32 offsets from the target's landmark, 16-byte
+// coalesced loads) for the search tile, a.bin_xyz (float64 planes x|y|z in bin order) for everything float64.
+template <int NT>
+__device__ __forceinline__ void coop_sync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
 }
-
-// ---- blocked fp32 scan of an SMEM target tile (warp-per-partition kernels) ----------------------------
-// Per (query, candidate) pair the loop keeps only the two smallest scores (3 min/max ops); WHICH
-// candidate is best is recorded per block of 8 candidates (one compare+select per block) and recovered
-// afterwards by re-evaluating that block with the identical instruction sequence.
-// DOT = true scores with c = |y|^2 - 2 q.y (3 FMAs; |y|^2 precomputed in .w, the query passed as -2q):
-// same argmin as the squared distance |q - y|^2 = c + |q|^2, used when the partition is compact enough
-// for the cancellation error to stay small; DOT = false scores with the difference form.
-#define LIP_NN_BLOCK 8
-template <bool DOT>
-__device__ __forceinline__ float nn_score(const float4 t, float mx, float my, float mz) {
-    if (DOT) return fmaf(mx, t.x, fmaf(my, t.y, fmaf(mz, t.z, t.w)));
-    float dx = t.x - mx, dy = t.y - my, dz = t.z - mz;
-    float d = dx * dx; d = fmaf(dy, dy, d); d = fmaf(dz, dz, d);
-    return d;
-}
-struct NNTop2 { float best, sec; int blk; };
-
-template <bool DOT, int Q>
-__device__ __forceinline__ void nn_scan_blocks(const float4* __restrict__ tf, int nt_pad, const float (&m)[Q][3], NNTop2 (&r)[Q]) {
-#pragma unroll
-    for (int q = 0; q < Q; ++q) { r[q].best = INFINITY; r[q].sec = INFINITY; r[q].blk = 0; }
-    for (int jb = 0; jb < nt_pad; jb += LIP_NN_BLOCK) {
-        float prev[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) prev[q] = r[q].best;
-#pragma unroll
-        for (int k = 0; k < LIP_NN_BLOCK; ++k) {
-            const float4 t = tf[jb + k];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const float c = nn_score<DOT>(t, m[q][0], m[q][1], m[q][2]);
-                r[q].sec = fminf(r[q].sec, fmaxf(c, r[q].best));
-                r[q].best = fminf(r[q].best, c);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < Q; ++q) r[q].blk = (r[q].best < prev[q]) ? jb : r[q].blk;
-    }
-}
-// index of the first candidate of block `blk` whose score equals `best` (bitwise: same instruction sequence)
-template <bool DOT>
-__device__ __forceinline__ int nn_block_index(const float4* __restrict__ tf, int blk, float best, float mx, float my, float mz) {
-    int idx = blk;
-#pragma unroll
-    for (int k = LIP_NN_BLOCK - 1; k >= 0; --k)
-        if (nn_score<DOT>(tf[blk + k], mx, my, mz) == best) idx = blk + k;
-    return idx;
-}
-
-template <bool SMEM64>
-struct IcpView {                                         // one partition as seen by the warp / CTA working on it
-    const float4* tf;                                    // staged centred fp32 target (SMEM)
-    const double *tx, *ty, *tz, *sx, *sy, *sz;           // SMEM64: centred float64 target / source in SMEM
-    const double *xs, *xt;                               // mesh vertex arrays (original coordinates)
-    const int *vs, *vt;                                  // member lists (local vertex ids)
-    double cx, cy, cz;                                   // target centroid
-    __device__ __forceinline__ void tgt(int j, double& x, double& y, double& z) const {
-        if (SMEM64) { x = tx[j]; y = ty[j]; z = tz[j]; }
-        else { size_t v = (size_t)vt[j]; x = xt[3 * v] - cx; y = xt[3 * v + 1] - cy; z = xt[3 * v + 2] - cz; }
-    }
-    __device__ __forceinline__ void src(int q, double& x, double& y, double& z) const {
-        if (SMEM64) { x = sx[q]; y = sy[q]; z = sz[q]; }
-        else { size_t v = (size_t)vs[q]; x = xs[3 * v] - cx; y = xs[3 * v + 1] - cy; z = xs[3 * v + 2] - cz; }
-    }
-};
-
-// resolve the winner of one query from its blocked top-2 result: index inside the winning block, and a
-// float64 re-evaluation of the whole target when the runner-up is within the fp32 error bound
-template <bool SMEM64, bool DOT>
-__device__ __forceinline__ int icp_resolve(const IcpView<SMEM64>& w, int nt, const NNTop2& r, float mx, float my, float mz,
-                                           float mabs, double px, double py, double pz, unsigned long long* counters) {
-    int idx = nn_block_index<DOT>(w.tf, r.blk, r.best, mx, my, mz);
-    const float fx = (float)px, fy = (float)py, fz = (float)pz;
-    const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
-    const float e = 1.2e-7f * (qabs + mabs);
-    float tol;
-    if (DOT) {                                               // scores are c = d2 - |q|^2
-        const float qq = fx * fx + fy * fy + fz * fz;
-        tol = d2_err(fmaxf(r.best + qq, 0.f), e) + d2_err(fmaxf(r.sec + qq, 0.f), e) + 2.2e-6f * (mabs * mabs + qabs * mabs);
-    } else {
-        tol = d2_err(r.best, e) + d2_err(r.sec, e);
-    }
-    if (!(r.sec - r.best > tol)) {                           // near tie: decide in float64, lowest index
-        double bd = INFINITY;
-#pragma unroll 1
-        for (int j = 0; j < nt; ++j) {
-            double tx, ty, tz;
-            w.tgt(j, tx, ty, tz);
-            double d = rdist64(px, py, pz, tx, ty, tz);
-            if (d < bd) { bd = d; idx = j; }
-        }
-        atomicAdd(&counters[2], 1ull);
-    }
-    return idx;
-}
-
-// One ICP iteration over a partition, (lane, stride) = (lane, 32) for a warp, (thread, blockDim) for a CTA.
-// Phase 1 (get_NN_in_target): every source point against the staged target, winners written to nn_idx.
-// Phase 2 (sums of get_best_fit_transform + cost): float64 accumulation over the (source, winner) pairs.
-// Keeping the phases apart keeps the 17 float64 accumulators out of the registers of the scan loop; each
-// lane reads back only the nn_idx entries it wrote itself.
-template <bool SMEM64, bool DOT>
-__device__ __forceinline__ void icp_pass(const LipArgs& a, const IcpView<SMEM64>& w, const IcpState* st, int ns, int nt,
-                                         int nt_pad, float mabs, int lane, int stride, int* __restrict__ nn_idx, double* acc) {
-    const float sc = DOT ? -2.0f : 1.0f;
-    int q0 = 0;
-    for (; q0 + stride < ns; q0 += 2 * stride) {             // two queries per lane while more than `stride` remain
-        const int qa = q0 + lane, qb = qa + stride;
-        const bool vb = qb < ns;
-        double sax, say, saz, sbx, sby, sbz, pax, pay, paz, pbx, pby, pbz;
-        w.src(qa, sax, say, saz);
-        w.src(vb ? qb : ns - 1, sbx, sby, sbz);
-        mat3_vec(st->R, sax, say, saz, pax, pay, paz);
-        pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
-        mat3_vec(st->R, sbx, sby, sbz, pbx, pby, pbz);
-        pbx += st->t[0]; pby += st->t[1]; pbz += st->t[2];
-        const float m[2][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}, {sc * (float)pbx, sc * (float)pby, sc * (float)pbz}};
-        NNTop2 r[2];
-        nn_scan_blocks<DOT, 2>(w.tf, nt_pad, m, r);
-        nn_idx[qa] = icp_resolve<SMEM64, DOT>(w, nt, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.counters);
-        if (vb) nn_idx[qb] = icp_resolve<SMEM64, DOT>(w, nt, r[1], m[1][0], m[1][1], m[1][2], mabs, pbx, pby, pbz, a.counters);
-    }
-    if (q0 < ns) {                                           // at most `stride` left: one query per lane
-        const int qa = q0 + lane;
-        if (qa < ns) {
-            double sax, say, saz, pax, pay, paz;
-            w.src(qa, sax, say, saz);
-            mat3_vec(st->R, sax, say, saz, pax, pay, paz);
-            pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
-            const float m[1][3] = {{sc * (float)pax, sc * (float)pay, sc * (float)paz}};
-            NNTop2 r[1];
-            nn_scan_blocks<DOT, 1>(w.tf, nt_pad, m, r);
-            nn_idx[qa] = icp_resolve<SMEM64, DOT>(w, nt, r[0], m[0][0], m[0][1], m[0][2], mabs, pax, pay, paz, a.counters);
-        }
-    }
-    // ---- phase 2 ----
-    const double reject = a.reject_dist;
-    for (int q = lane; q < ns; q += stride) {
-        double sx, sy, sz, px, py, pz, bx, by, bz;
-        w.src(q, sx, sy, sz);
-        mat3_vec(st->R, sx, sy, sz, px, py, pz);
-        px += st->t[0]; py += st->t[1]; pz += st->t[2];
-        w.tgt(nn_idx[q], bx, by, bz);
-        const double d = sqrt(rdist64(px, py, pz, bx, by, bz));
-        acc[0] += d;
-        if (d <= reject) {
-            acc[1] += px; acc[2] += py; acc[3] += pz;
-            acc[4] += bx; acc[5] += by; acc[6] += bz;
-            acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
-            acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
-            acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
-            acc[16] += 1.0;
-        }
-    }
-}
-
-// ---- warp-per-partition, groups of partitions per warp task ---------------------------------------------
-// A persistent warp takes a task of g <= LIP_ICP_GMAX partitions of similar size.  Every NN pass is
-// warp-cooperative (one partition after the other: tile staged from bin_pts with coalesced 16-byte loads,
-// lanes own the queries); the serial part of an iteration — cost / stop test, 3x3 Kabsch solve, transform
-// accumulation — runs SIMT across the task's partitions, lane p working for partition p, so its cost is
-// shared by g partitions instead of being paid 32-fold redundantly by every one.
-struct IcpGroupSmem {
-    float4 tf[LIP_ICP_CHUNK + 8];                         // fp32 search tile (offsets from the target landmark)
-    IcpState st[LIP_ICP_GMAX];
-    double acc[LIP_ICP_GMAX][17];
-};
-
-template <bool DOT>
-__device__ __forceinline__ void group_stage(const LipArgs& a, float4* tf, int to, int c0, int cnt, int lane,
-                                            float sh0, float sh1, float sh2) {
+template <bool DOT, int NT>
+__device__ __forceinline__ void icp_stage(const LipArgs& a, float4* tf, int to, int c0, int cnt, int tid,
+                                          float sh0, float sh1, float sh2) {
     const int npad = (cnt + 7) & ~7;
-    for (int j = lane; j < npad; j += 32) {
+    for (int j = tid; j < npad; j += NT) {
         float4 t = tile_sentinel(DOT);
         if (j < cnt) {
             t = a.bin_pts[to + c0 + j];
@@ -507,48 +335,49 @@ __device__ __forceinline__ void group_stage(const LipArgs& a, float4* tf, int to
         tf[j] = t;
     }
 }
-
-// one NN pass + sums of partition (src bin at so/ns, tgt bin at to/nt, origin c = the target's landmark)
-template <bool DOT>
-__device__ __forceinline__ void group_pass(const LipArgs& a, IcpGroupSmem& sm, int p, int lane, int so, int ns, int to, int nt,
-                                           const double* __restrict__ xs, const double* __restrict__ xt,
-                                           double c0, double c1, double c2, float sh0, float sh1, float sh2, float mabs) {
-    const IcpState* st = &sm.st[p];
-    const int* __restrict__ vs = a.part_vid + so;
-    const int* __restrict__ vt = a.part_vid + to;
+// source bin at so/ns, target bin at to/nt; frame centred on c (the target centroid); the tile points are the
+// stored offsets shifted by sh = landmark - c.  Returns this thread's partial sums in acc[17]:
+// 0 sum dist | 1..3 sum p | 4..6 sum b | 7..15 sum p_i b_j | 16 pairs kept.
+template <bool DOT, int NT, int CHUNK>
+__device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const IcpState* st, int tid, int so, int ns, int to, int nt,
+                                         double c0, double c1, double c2, float sh0, float sh1, float sh2, float mabs,
+                                         double (&acc)[17]) {
+    const size_t N = (size_t)a.n_total;
+    const double* __restrict__ sx = a.bin_xyz + so;
+    const double* __restrict__ tx = a.bin_xyz + to;
     int* __restrict__ nn_idx = a.nn_idx + so;
     const float sc = DOT ? -2.0f : 1.0f;
-    const bool one_chunk = nt <= LIP_ICP_CHUNK;
-    if (one_chunk) { __syncwarp(); group_stage<DOT>(a, sm.tf, to, 0, nt, lane, sh0, sh1, sh2); __syncwarp(); }
-    for (int q0 = 0; q0 < ns; q0 += 64) {
-        const bool two = ns - q0 > 32;                       // uniform
-        const int qi[2] = {q0 + lane, q0 + lane + 32};
+    const bool one_chunk = nt <= CHUNK;
+    if (one_chunk) { coop_sync<NT>(); icp_stage<DOT, NT>(a, tf, to, 0, nt, tid, sh0, sh1, sh2); coop_sync<NT>(); }
+    for (int q0 = 0; q0 < ns; q0 += 2 * NT) {
+        const bool two = ns - q0 > NT;                       // uniform
+        const int qi[2] = {q0 + tid, q0 + tid + NT};
         double pq[2][3];
         float m[2][3], best[2], sec[2], sec_in[2];
         int blk[2], idx[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const size_t v = (size_t)vs[min(qi[k], ns - 1)];
-            mat3_vec(st->R, xs[3 * v] - c0, xs[3 * v + 1] - c1, xs[3 * v + 2] - c2, pq[k][0], pq[k][1], pq[k][2]);
+            const int q = min(qi[k], ns - 1);
+            mat3_vec(st->R, sx[q] - c0, sx[N + q] - c1, sx[2 * N + q] - c2, pq[k][0], pq[k][1], pq[k][2]);
             pq[k][0] += st->t[0]; pq[k][1] += st->t[1]; pq[k][2] += st->t[2];
             m[k][0] = sc * (float)pq[k][0]; m[k][1] = sc * (float)pq[k][1]; m[k][2] = sc * (float)pq[k][2];
             best[k] = INFINITY; sec[k] = INFINITY; sec_in[k] = INFINITY; blk[k] = 0; idx[k] = 0;
         }
-        for (int t0 = 0; t0 < nt; t0 += LIP_ICP_CHUNK) {
-            const int cnt = min(LIP_ICP_CHUNK, nt - t0), npad = (cnt + 7) & ~7;
-            if (!one_chunk) { __syncwarp(); group_stage<DOT>(a, sm.tf, to, t0, cnt, lane, sh0, sh1, sh2); __syncwarp(); }
+        for (int t0 = 0; t0 < nt; t0 += CHUNK) {
+            const int cnt = min(CHUNK, nt - t0), npad = (cnt + 7) & ~7;
+            if (!one_chunk) { coop_sync<NT>(); icp_stage<DOT, NT>(a, tf, to, t0, cnt, tid, sh0, sh1, sh2); coop_sync<NT>(); }
             const float prev0 = best[0], prev1 = best[1];
-            if (two) tile_scan<2, DOT>(sm.tf, npad, m, best, sec, blk);
-            else tile_scan<1, DOT>(sm.tf, npad, m, best, sec, blk);
-            if (best[0] < prev0) idx[0] = t0 + tile_recover<DOT>(sm.tf, blk[0], best[0], m[0], sec_in[0]);
-            if (best[1] < prev1) idx[1] = t0 + tile_recover<DOT>(sm.tf, blk[1], best[1], m[1], sec_in[1]);
+            if (two) tile_scan<2, DOT>(tf, npad, m, best, sec, blk);
+            else tile_scan<1, DOT>(tf, npad, m, best, sec, blk);
+            if (best[0] < prev0) idx[0] = t0 + tile_recover<DOT>(tf, blk[0], best[0], m[0], sec_in[0]);
+            if (best[1] < prev1) idx[1] = t0 + tile_recover<DOT>(tf, blk[1], best[1], m[1], sec_in[1]);
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (qi[k] >= ns) continue;
             const float fx = (float)pq[k][0], fy = (float)pq[k][1], fz = (float)pq[k][2];
             const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
-            const float e = 2.4e-7f * (qabs + mabs);
+            const float e = 2.4e-7f * (qabs + mabs);         // stored offset, shift and sum: three roundings per coordinate
             const float qq = DOT ? fmaf(fx, fx, fmaf(fy, fy, fz * fz)) : 0.f;
             const float d2b = fmaxf(best[k] + qq, 0.f), d2s = fmaxf(fminf(sec[k], sec_in[k]) + qq, 0.f);
             float tol = d2_err(d2b, e) + d2_err(d2s, e);
@@ -557,8 +386,7 @@ __device__ __forceinline__ void group_pass(const LipArgs& a, IcpGroupSmem& sm, i
                 double bd = INFINITY;
 #pragma unroll 1
                 for (int j = 0; j < nt; ++j) {
-                    const size_t v = (size_t)vt[j];
-                    const double d = rdist64(pq[k][0], pq[k][1], pq[k][2], xt[3 * v] - c0, xt[3 * v + 1] - c1, xt[3 * v + 2] - c2);
+                    const double d = rdist64(pq[k][0], pq[k][1], pq[k][2], tx[j] - c0, tx[N + j] - c1, tx[2 * N + j] - c2);
                     if (d < bd) { bd = d; idx[k] = j; }
                 }
                 atomicAdd(&a.counters[2], 1ull);
@@ -567,16 +395,15 @@ __device__ __forceinline__ void group_pass(const LipArgs& a, IcpGroupSmem& sm, i
         }
     }
     // ---- sums of get_best_fit_transform + cost over the (source, winner) pairs, float64 ----
-    double acc[17];
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = 0.0;
     const double reject = a.reject_dist;
-    for (int q = lane; q < ns; q += 32) {
-        const size_t v = (size_t)vs[q], w = (size_t)vt[nn_idx[q]];
+    for (int q = tid; q < ns; q += NT) {
+        const int w = nn_idx[q];
         double px, py, pz;
-        mat3_vec(st->R, xs[3 * v] - c0, xs[3 * v + 1] - c1, xs[3 * v + 2] - c2, px, py, pz);
+        mat3_vec(st->R, sx[q] - c0, sx[N + q] - c1, sx[2 * N + q] - c2, px, py, pz);
         px += st->t[0]; py += st->t[1]; pz += st->t[2];
-        const double bx = xt[3 * w] - c0, by = xt[3 * w + 1] - c1, bz = xt[3 * w + 2] - c2;
+        const double bx = tx[w] - c0, by = tx[N + w] - c1, bz = tx[2 * N + w] - c2;
         const double d = sqrt(rdist64(px, py, pz, bx, by, bz));
         acc[0] += d;
         if (d <= reject) {
@@ -590,39 +417,63 @@ __device__ __forceinline__ void group_pass(const LipArgs& a, IcpGroupSmem& sm, i
     }
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 17; ++i) sm.acc[p][i] = acc[i];
-    }
 }
+
+// frame of one ICP: centre = target centroid, tile shift = target landmark - centre, bound on |tile coordinate|
+struct IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; };
+__device__ __forceinline__ IcpFrame icp_frame(const LipArgs& a, int b) {
+    IcpFrame f;
+    const int pb = pair_bin(a, b), mt = pair_mesh(a, a.bin_mesh[b]);
+    f.so = a.bin_off[b]; f.ns = a.bin_off[b + 1] - f.so;
+    f.to = a.bin_off[pb]; f.nt = a.bin_off[pb + 1] - f.to;
+    const double* lmt = mesh_lm(a, mt) + 3 * (size_t)(pb - a.mesh_bin[mt]);
+    const double* ct = a.bin_sum + 4 * (size_t)pb;
+    f.c0 = ct[0]; f.c1 = ct[1]; f.c2 = ct[2];
+    f.sh0 = (float)(lmt[0] - ct[0]); f.sh1 = (float)(lmt[1] - ct[1]); f.sh2 = (float)(lmt[2] - ct[2]);
+    f.mabs = a.bin_box[8 * (size_t)pb + 6] + fmaxf(fmaxf(fabsf(f.sh0), fabsf(f.sh1)), fabsf(f.sh2));
+    return f;
+}
+
+// ---- warp-per-partition, groups of partitions per warp task ---------------------------------------------
+// A persistent warp takes a task of g <= LIP_ICP_GMAX partitions of one work class.  Every NN pass is
+// warp-cooperative (one partition after the other, lanes own the queries); the serial part of an iteration —
+// cost / stop test, 3x3 Kabsch solve, transform accumulation — runs SIMT across the task's partitions, lane p
+// working for partition p, so its cost is shared by g partitions instead of being paid 32-fold redundantly.
+struct IcpGroupSmem {
+    float4 tf[LIP_ICP_CHUNK + 8];                         // fp32 search tile
+    IcpState st[LIP_ICP_GMAX];
+    double acc[LIP_ICP_GMAX][17];
+};
+// partitions per task of work class c (n_src * n_tgt in [512 * 2^c, 1024 * 2^c)): heavy classes go one by one
+__device__ __forceinline__ int icp_class_group(int c, int gcap) { return max(1, min(gcap, LIP_ICP_GMAX >> max(c - 3, 0))); }
 
 __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_group_kernel(LipArgs a) {
     __shared__ IcpGroupSmem sm_all[LIP_ICP_WARPS];
     IcpGroupSmem& sm = sm_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int n_items = a.sched[0];
-    // group size: as large as leaves every resident warp a few tasks
-    int G = n_items / (int)(gridDim.x * LIP_ICP_WARPS * 3);
-    G = max(1, min(G, LIP_ICP_GMAX));
-    const int n_tasks = (n_items + G - 1) / G;
+    // group size cap: as large as leaves every resident warp a few tasks
+    const int gcap = max(1, min(n_items / (int)(gridDim.x * LIP_ICP_WARPS * 3), LIP_ICP_GMAX));
+    int n_tasks = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const int G = icp_class_group(c, gcap); n_tasks += (a.sched[24 + c] + G - 1) / G; }
     for (;;) {                                              // persistent warps, dynamic task queue, heaviest class first
         int w = 0;
         if (lane == 0) w = atomicAdd(&a.sched[2], 1);
         w = __shfl_sync(LIP_FULL, w, 0);
         if (w >= n_tasks) break;
-        const int first = w * G, g = min(G, n_items - first);
+        int c = 7, G = icp_class_group(7, gcap), tc = (a.sched[24 + 7] + G - 1) / G;
+        while (c > 0 && w >= tc) { w -= tc; --c; G = icp_class_group(c, gcap); tc = (a.sched[24 + c] + G - 1) / G; }
+        const int first = w * G, g = min(G, a.sched[24 + c] - first);
         // ---- lane p < g owns partition p of the task -------------------------------------------------------
         int b = 0, own_ns = 1, iters = 0, status = 1;
         bool active = lane < g;
         double prev = 0.0;
         if (active) {
-            int c = 7, r = first + lane;
-            while (c > 0 && r >= a.sched[24 + c]) { r -= a.sched[24 + c]; --c; }
-            b = a.warp_list[(size_t)c * a.B + r];
-            const int pb = pair_bin(a, b);
+            b = a.warp_list[(size_t)c * a.B + first + lane];
             own_ns = a.bin_off[b + 1] - a.bin_off[b];
             const double* ss = a.bin_sum + 4 * (size_t)b;
-            const double* ts = a.bin_sum + 4 * (size_t)pb;
+            const double* ts = a.bin_sum + 4 * (size_t)pair_bin(a, b);
             // increment 0: identity, t = mean(tgt) - mean(src)   (registration_icp.py:70)
             icp_state_init(&sm.st[lane], ts[0] - ss[0], ts[1] - ss[1], ts[2] - ss[2]);
         }
@@ -635,19 +486,15 @@ __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_gr
             while (todo) {                                      // NN pass + sums, one partition after the other
                 const int p = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int bp = __shfl_sync(LIP_FULL, b, p), pb = pair_bin(a, bp);
-                const int so = a.bin_off[bp], ns = a.bin_off[bp + 1] - so;
-                const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
-                const int ms = a.bin_mesh[bp], mt = pair_mesh(a, ms);
-                // frame of the ICP: centred on the target centroid; the tile points are stored as offsets from the
-                // target's landmark, so they are shifted by (landmark - centroid) when staged
-                const double* lmt = mesh_lm(a, mt) + 3 * (size_t)(pb - a.mesh_bin[mt]);
-                const double* ct = a.bin_sum + 4 * (size_t)pb;
-                const float sh0 = (float)(lmt[0] - ct[0]), sh1 = (float)(lmt[1] - ct[1]), sh2 = (float)(lmt[2] - ct[2]);
-                const float mabs = a.bin_box[8 * (size_t)pb + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2));
+                const IcpFrame f = icp_frame(a, __shfl_sync(LIP_FULL, b, p));
+                double acc[17];
                 // dot-form scores only while the cancellation error stays far below the point spacing
-                if (mabs <= 24.0f) group_pass<true>(a, sm, p, lane, so, ns, to, nt, mesh_xyz(a, ms), mesh_xyz(a, mt), ct[0], ct[1], ct[2], sh0, sh1, sh2, mabs);
-                else group_pass<false>(a, sm, p, lane, so, ns, to, nt, mesh_xyz(a, ms), mesh_xyz(a, mt), ct[0], ct[1], ct[2], sh0, sh1, sh2, mabs);
+                if (f.mabs <= 24.0f) icp_pass<true, 32, LIP_ICP_CHUNK>(a, sm.tf, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
+                else icp_pass<false, 32, LIP_ICP_CHUNK>(a, sm.tf, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) sm.acc[p][i] = acc[i];
+                }
             }
             __syncwarp();
             if (active) {                                       // SIMT over the task's partitions
@@ -669,187 +516,79 @@ __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_gr
     }
 }
 
-// ---- CTA-per-partition variant for partitions that do not fit the per-warp SMEM budget ----------
-// (K == 1 whole-segment ICP, p2p_matching_seg_icp.py:440-449, and direct my_icp calls)
-__device__ __forceinline__ double block_sum(double v, double* red, int tid) {   // all threads get the sum
+// ---- CTA-per-partition variant for the heavy partitions (n_src * n_tgt > LIP_WARP_WORK: K == 1 whole-segment
+// ICP, p2p_matching_seg_icp.py:440-449, direct my_icp calls, long leaves): same pass, the CTA's threads own the
+// queries, the target streams through one SMEM tile, warp 0 does the serial part.
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {   // 256 threads; all get the sum
     v = warp_sum(v);
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     double s = 0;
 #pragma unroll
-    for (int w = 0; w < LIP_BIG_THREADS / 32; ++w) s += red[w];
+    for (int w = 0; w < 8; ++w) s += red[w];
     return s;
 }
 
-__device__ __forceinline__ void icp_big_finish(const LipArgs& a, const double* xt, const int* vt, int nt, bool valid,
-                                               float best, float sec, int idx, float mabs, double cx, double cy,
-                                               double cz, double px, double py, double pz, double* acc) {
-    if (!valid) return;
-    float fx = (float)px, fy = (float)py, fz = (float)pz;
-    float e = 1.2e-7f * (fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) + mabs);
-    if (sec - best <= d2_err(best, e) + d2_err(sec, e)) {
-        double bd = INFINITY;
-        for (int j = 0; j < nt; ++j) {
-            size_t v = (size_t)vt[j];
-            double d = rdist64(px, py, pz, xt[3 * v] - cx, xt[3 * v + 1] - cy, xt[3 * v + 2] - cz);
-            if (d < bd) { bd = d; idx = j; }
-        }
-        atomicAdd(&a.counters[2], 1ull);
-    }
-    size_t v = (size_t)vt[idx];
-    double bx = xt[3 * v] - cx, by = xt[3 * v + 1] - cy, bz = xt[3 * v + 2] - cz;
-    double d = sqrt(rdist64(px, py, pz, bx, by, bz));
-    acc[0] += d;
-    if (d <= a.reject_dist) {
-        acc[1] += px; acc[2] += py; acc[3] += pz;
-        acc[4] += bx; acc[5] += by; acc[6] += bz;
-        acc[7] += px * bx; acc[8] += px * by; acc[9] += px * bz;
-        acc[10] += py * bx; acc[11] += py * by; acc[12] += py * bz;
-        acc[13] += pz * bx; acc[14] += pz * by; acc[15] += pz * bz;
-        acc[16] += 1.0;
-    }
-}
-
-__global__ void __launch_bounds__(LIP_BIG_THREADS, 2) icp_big_kernel(LipArgs a) {
-    __shared__ float4 tf[LIP_BIG_CAP];
-    __shared__ double red[LIP_BIG_THREADS / 32];
+__global__ void __launch_bounds__(LIP_BIG_THREADS, 4) icp_big_kernel(LipArgs a) {
+    __shared__ float4 tf[LIP_BIG_CHUNK + 8];
     __shared__ double red17[LIP_BIG_THREADS / 32][17];
-    __shared__ float redf[LIP_BIG_THREADS / 32];
-    __shared__ int s_item;
+    __shared__ double tot[17];
+    __shared__ int s_item, s_go, s_status;
     __shared__ IcpState st_sh;
-    __shared__ int st_deg;
     IcpState* st = &st_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_big = a.sched[1];
     for (;;) {                                              // persistent CTAs, heaviest class first
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(&a.sched[16], 1);      // big cursor
+        if (tid == 0) s_item = atomicAdd(&a.sched[16], 1);
         __syncthreads();
         const int wi = s_item;
         if (wi >= n_big) break;
         int cls = 3, ri = wi;
         while (cls > 0 && ri >= a.sched[12 + cls]) { ri -= a.sched[12 + cls]; --cls; }
-        const int b = a.big_list[(size_t)cls * a.B + ri], pb = pair_bin(a, b);
-        const int so = a.bin_off[b], ns = a.bin_off[b + 1] - so;
-        const int to = a.bin_off[pb], nt = a.bin_off[pb + 1] - to;
-        const int ms = a.bin_mesh[b], mt = pair_mesh(a, ms);
-        const double* xs = mesh_xyz(a, ms);
-        const double* xt = mesh_xyz(a, mt);
-        const int* vs = a.part_vid + so;
-        const int* vt = a.part_vid + to;
-        double sx = 0, sy = 0, sz = 0;
-        for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
-            size_t v = (size_t)vt[j];
-            sx += xt[3 * v]; sy += xt[3 * v + 1]; sz += xt[3 * v + 2];
+        const int b = a.big_list[(size_t)cls * a.B + ri];
+        const IcpFrame f = icp_frame(a, b);
+        if (warp == 0) {
+            const double* ss = a.bin_sum + 4 * (size_t)b;
+            const double* ts = a.bin_sum + 4 * (size_t)pair_bin(a, b);
+            icp_state_init(st, ts[0] - ss[0], ts[1] - ss[1], ts[2] - ss[2]);
+            if (lane == 0) { s_go = 1; s_status = 1; }
         }
-        const double cx = block_sum(sx, red, tid) / nt, cy = block_sum(sy, red, tid) / nt, cz = block_sum(sz, red, tid) / nt;
-        float mabs = 0.f;
-        sx = sy = sz = 0;
-        for (int j = tid; j < nt; j += LIP_BIG_THREADS) {
-            size_t v = (size_t)vt[j];
-            double x = xt[3 * v] - cx, y = xt[3 * v + 1] - cy, z = xt[3 * v + 2] - cz;
-            mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf((float)x), fabsf((float)y)), fabsf((float)z)));
-            sx += x; sy += y; sz += z;
-        }
-        const double mtx = block_sum(sx, red, tid) / nt, mty = block_sum(sy, red, tid) / nt, mtz = block_sum(sz, red, tid) / nt;
-        mabs = warp_maxf(mabs);
-        __syncthreads();
-        if (lane == 0) redf[warp] = mabs;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < LIP_BIG_THREADS / 32; ++k) mabs = fmaxf(mabs, redf[k]);
-        sx = sy = sz = 0;
-        for (int q = tid; q < ns; q += LIP_BIG_THREADS) {
-            size_t v = (size_t)vs[q];
-            sx += xs[3 * v] - cx; sy += xs[3 * v + 1] - cy; sz += xs[3 * v + 2] - cz;
-        }
-        const double msx = block_sum(sx, red, tid) / ns, msy = block_sum(sy, red, tid) / ns, msz = block_sum(sz, red, tid) / ns;
-        // resident: the whole target fits the SMEM tile -> staged once, blocked top-2 scan (same as the warp kernels)
-        const bool resident = nt <= LIP_BIG_CAP;
-        const bool use_dot = mabs <= 24.0f;
-        const int nt_pad = (nt + LIP_NN_BLOCK - 1) / LIP_NN_BLOCK * LIP_NN_BLOCK;
-        __syncthreads();
-        if (resident) {
-            for (int j = tid; j < nt_pad; j += LIP_BIG_THREADS) {
-                if (j < nt) {
-                    size_t v = (size_t)vt[j];
-                    const float fx = (float)(xt[3 * v] - cx), fy = (float)(xt[3 * v + 1] - cy), fz = (float)(xt[3 * v + 2] - cz);
-                    tf[j] = make_float4(fx, fy, fz, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
-                } else {
-                    tf[j] = use_dot ? make_float4(0.f, 0.f, 0.f, 3.0e38f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
-                }
-            }
-            __syncthreads();
-        }
-        IcpView<false> view{tf, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xs, xt, vs, vt, cx, cy, cz};
-        if (tid < 32) { icp_state_init(st, mtx - msx, mty - msy, mtz - msz); st_deg = 1; }
-        __syncthreads();
-        double prev = 0.0;
+        double prev = 0.0;                                   // warp 0 only
         int iters = 0;
         for (int it = 0; it < a.max_iter; ++it) {
-            __syncthreads();                                 // all reads of the previous state are done
-            if (tid < 32) icp_state_accumulate(st);
+            __syncthreads();
+            if (!s_go) break;
+            if (warp == 0) icp_state_accumulate(st);
             __syncthreads();
             double acc[17];
-#pragma unroll
-            for (int i = 0; i < 17; ++i) acc[i] = 0.0;
-            if (resident) {
-                if (use_dot) icp_pass<false, true>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, a.nn_idx + so, acc);
-                else icp_pass<false, false>(a, view, st, ns, nt, nt_pad, mabs, tid, LIP_BIG_THREADS, a.nn_idx + so, acc);
-            } else {
-                // target larger than the tile: stream it through SMEM, per-pair index tracking
-                for (int q0 = 0; q0 < ns; q0 += 2 * LIP_BIG_THREADS) {
-                    const int qa = q0 + tid, qb = qa + LIP_BIG_THREADS;
-                    const bool va = qa < ns, vb = qb < ns;
-                    const size_t ra = (size_t)vs[va ? qa : ns - 1], rb = (size_t)vs[vb ? qb : ns - 1];
-                    double pax, pay, paz, pbx, pby, pbz;
-                    mat3_vec(st->R, xs[3 * ra] - cx, xs[3 * ra + 1] - cy, xs[3 * ra + 2] - cz, pax, pay, paz);
-                    pax += st->t[0]; pay += st->t[1]; paz += st->t[2];
-                    mat3_vec(st->R, xs[3 * rb] - cx, xs[3 * rb + 1] - cy, xs[3 * rb + 2] - cz, pbx, pby, pbz);
-                    pbx += st->t[0]; pby += st->t[1]; pbz += st->t[2];
-                    float besta = INFINITY, seca = INFINITY, bestb = INFINITY, secb = INFINITY;
-                    int ia = 0, ib = 0;
-                    for (int t0 = 0; t0 < nt; t0 += LIP_BIG_CAP) {
-                        const int cnt = min(LIP_BIG_CAP, nt - t0);
-                        __syncthreads();
-                        for (int j = tid; j < cnt; j += LIP_BIG_THREADS) {
-                            size_t v = (size_t)vt[t0 + j];
-                            tf[j] = make_float4((float)(xt[3 * v] - cx), (float)(xt[3 * v + 1] - cy),
-                                                (float)(xt[3 * v + 2] - cz), 0.f);
-                        }
-                        __syncthreads();
-                        nn_scan2(tf, cnt, t0, (float)pax, (float)pay, (float)paz, (float)pbx, (float)pby, (float)pbz,
-                                 besta, seca, ia, bestb, secb, ib);
-                    }
-                    icp_big_finish(a, xt, vt, nt, va, besta, seca, ia, mabs, cx, cy, cz, pax, pay, paz, acc);
-                    icp_big_finish(a, xt, vt, nt, vb, bestb, secb, ib, mabs, cx, cy, cz, pbx, pby, pbz, acc);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
-            __syncthreads();
+            if (f.mabs <= 24.0f) icp_pass<true, LIP_BIG_THREADS, LIP_BIG_CHUNK>(a, tf, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
+            else icp_pass<false, LIP_BIG_THREADS, LIP_BIG_CHUNK>(a, tf, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 17; ++i) red17[warp][i] = acc[i];
             }
             __syncthreads();
+            if (warp == 0) {                                 // serial part: all lanes of warp 0 identically
+                if (lane < 17) {
+                    double s = 0;
 #pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                double s = 0;
-#pragma unroll
-                for (int k = 0; k < LIP_BIG_THREADS / 32; ++k) s += red17[k][i];
-                acc[i] = s;
+                    for (int k = 0; k < LIP_BIG_THREADS / 32; ++k) s += red17[k][lane];
+                    tot[lane] = s;
+                }
+                __syncwarp();
+                const double cost = tot[0] / f.ns;
+                iters = it + 1;
+                if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) { if (lane == 0) s_go = 0; }
+                else {
+                    prev = cost;
+                    if (icp_kabsch_step(tot, st) && lane == 0) s_status = 2;
+                }
             }
-            const double cost = acc[0] / ns;
-            iters = it + 1;
-            if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) break;
-            prev = cost;
-            // one warp solves the 3x3 problem (all of its lanes identically); the others wait at the barrier above
-            if (tid < 32) { if (icp_kabsch_step(acc, st)) st_deg = 2; }
         }
         __syncthreads();
-        if (tid == 0) icp_store(a, b, st, cx, cy, cz, iters, st_deg);
+        if (tid == 0) icp_store(a, b, st, f.c0, f.c1, f.c2, iters, s_status);
     }
 }
 

@@ -104,6 +104,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_cnt = take(8 * 8);
     const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
+    const size_t o_bxyz = take(n * 24);
     const size_t o_mt = take(c->max_map_tiles * 8);
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
@@ -121,6 +122,7 @@ int carve_workspace(lip_ctx* c) {
     a.counters = (unsigned long long*)(base + o_cnt);
     a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
     a.map_tiles = (int*)(base + o_mt);
+    a.bin_xyz = (double*)(base + o_bxyz);
     return LIP_OK;
 }
 

@@ -302,8 +302,8 @@ def run_b200(args):
     iters = np.concatenate([tr["iters21"], tr["iters12"]]).astype(np.float64)
     mx = np.maximum(ns, nt)
     w = iters * ns * nt                                        # evaluated (source, candidate) pairs per partition
-    pairs = {"icp_group_kernel": float(w[mx <= 256].sum()),
-             "icp_big_kernel": float(w[mx > 256].sum()),
+    pairs = {"icp_group_kernel": float(w[ns * nt <= 65536].sum()),         # LIP_WARP_WORK
+             "icp_big_kernel": float(w[ns * nt > 65536].sum()),
              "final_map_kernel": float(counters["map_ring1_pairs"])}
     dom = max(pairs, key=lambda k: stage[k])
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12       # TFLOP/s, FP32 FMA pipe at the max SM clock
