@@ -14,6 +14,8 @@
 #ifndef LIP_ARCH
 #define LIP_ARCH 100
 #endif
+#define LIP_PIPELINE_CHUNKS 4             // sub-batches of the pipelined host path
+#define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
 namespace {
 
@@ -50,6 +52,14 @@ struct lip_ctx {
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
     int plan_tile = LIP_TILE;
     size_t max_map_tiles = 0;
+    // host-path pipeline: the batch split into sub-batches, each on its own child context (own stream and
+    // workspace), so that H2D of one, kernels of another and D2H of a third overlap (lip_batch_run_host)
+    std::vector<lip_ctx*> kids;
+    std::vector<int64_t> kid_seg;       // first segment pair of each kid, and S at the end
+    std::vector<int64_t> h_off1, h_off2, h_lm_off;   // the planned CSR (for slicing the host arrays)
+    int n_kids = 0;                     // kids in use by the current plan (0: no split)
+    bool last_run_split = false;
+    bool is_kid = false;
     lip_params params;
     std::string err;
     // plan
@@ -311,6 +321,26 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
 
 const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // the fill is resolved inside blend_nn_kernel
 
+// H2D of one (sub-)batch, the whole pipeline and D2H, all enqueued on the context's stream; no synchronisation
+int host_run_async(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                   int64_t* T21, int64_t* T12) {
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
+    int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
+                        c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
+    if (rc) return rc;
+    if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
+    if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
+    return LIP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -372,6 +402,8 @@ int lip_create(lip_ctx** out, int device) {
 
 void lip_destroy(lip_ctx* c) {
     if (!c) return;
+    for (lip_ctx* k : c->kids) lip_destroy(k);
+    c->kids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -405,10 +437,54 @@ int lip_host_alloc(void** p, uint64_t bytes) {
 }
 int lip_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LIP_OK : LIP_ECUDA; }
 
+// split the planned batch into sub-batches of about equal vertex count for the pipelined host path
+static int plan_kids(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+    c->n_kids = 0;
+    const int64_t n = off1[S] + off2[S];
+    int want = (int)std::min<int64_t>(LIP_PIPELINE_CHUNKS, S);
+    if (n < LIP_PIPELINE_MIN_VERTICES || want < 2) return LIP_OK;
+    c->kid_seg.assign(1, 0);
+    for (int k = 1; k < want; ++k) {                         // cut where the running vertex count passes k/want of the total
+        const int64_t target = n * k / want;
+        int64_t s = c->kid_seg.back() + 1;
+        while (s < S && off1[s] + off2[s] < target) ++s;
+        if (s >= S) break;
+        c->kid_seg.push_back(s);
+    }
+    c->kid_seg.push_back(S);
+    const int nk = (int)c->kid_seg.size() - 1;
+    if (nk < 2) return LIP_OK;
+    while ((int)c->kids.size() < nk) {
+        lip_ctx* k = nullptr;
+        int rc = lip_create(&k, c->device);
+        if (rc) return fail(c, rc, std::string("pipeline context: ") + lip_last_error(nullptr));
+        k->is_kid = true;
+        c->kids.push_back(k);
+    }
+    std::vector<int64_t> o1, o2, ol;
+    for (int k = 0; k < nk; ++k) {
+        const int64_t s0 = c->kid_seg[k], s1 = c->kid_seg[k + 1];
+        o1.assign(off1 + s0, off1 + s1 + 1); o2.assign(off2 + s0, off2 + s1 + 1); ol.assign(lm_off + s0, lm_off + s1 + 1);
+        for (auto& x : o1) x -= off1[s0];
+        for (auto& x : o2) x -= off2[s0];
+        for (auto& x : ol) x -= lm_off[s0];
+        lip_ctx* kc = c->kids[k];
+        kc->params = c->params; kc->map_mode = c->map_mode;
+        int rc = plan_impl(kc, s1 - s0, o1.data(), o2.data(), ol.data(), directions);
+        if (rc) return fail(c, rc, "pipeline plan: " + kc->err);
+    }
+    c->n_kids = nk;
+    return LIP_OK;
+}
+
 int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
     if (!c) return LIP_EINVAL;
     cudaSetDevice(c->device);
-    return plan_impl(c, S, off1, off2, lm_off, directions);
+    int rc = plan_impl(c, S, off1, off2, lm_off, directions);
+    if (rc) return rc;
+    c->h_off1.assign(off1, off1 + S + 1); c->h_off2.assign(off2, off2 + S + 1); c->h_lm_off.assign(lm_off, lm_off + S + 1);
+    c->last_run_split = false;
+    return plan_kids(c, S, off1, off2, lm_off, directions);
 }
 
 int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
@@ -417,6 +493,7 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
+    c->last_run_split = false;
     return run_stages(c, xyz1, xyz2, lm1, lm2, (long long*)T21, (long long*)T12, nullptr, kFullPipeline,
                       stream ? (cudaStream_t)stream : c->stream);
 }
@@ -428,21 +505,24 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
-    cudaStream_t st = c->stream;
-    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
-    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
-    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
-    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
-    int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
-                        c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
+    if (c->n_kids >= 2) {
+        // pipelined: every sub-batch on its own stream — copies in, kernels and copies out of different sub-batches overlap
+        for (int k = 0; k < c->n_kids; ++k) {
+            lip_ctx* kc = c->kids[k];
+            const int64_t s0 = c->kid_seg[k];
+            kc->params = c->params;
+            int rc = host_run_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0],
+                                    lm2 + 3 * c->h_lm_off[s0], T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr);
+            if (rc) return fail(c, rc, "pipeline run: " + kc->err);
+        }
+        for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
+        c->last_run_split = true;
+        return LIP_OK;
+    }
+    c->last_run_split = false;
+    int rc = host_run_async(c, xyz1, xyz2, lm1, lm2, T21, T12);
     if (rc) return rc;
-    if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
-    if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
-    LIP_CUDA(c, cudaStreamSynchronize(st));
+    LIP_CUDA(c, cudaStreamSynchronize(c->stream));
     return LIP_OK;
 }
 
@@ -450,6 +530,17 @@ int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, i
                              double* R12, double* t12, int32_t* iters12, int32_t* status12) {
     if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
+    if (c->last_run_split) {                                 // the last run was pipelined: collect from the sub-batches
+        for (int k = 0; k < c->n_kids; ++k) {
+            const size_t o = (size_t)c->h_lm_off[c->kid_seg[k]];
+            int rc = lip_batch_get_transforms(c->kids[k], filled, R21 ? R21 + 9 * o : nullptr, t21 ? t21 + 3 * o : nullptr,
+                                              iters21 ? iters21 + o : nullptr, status21 ? status21 + o : nullptr,
+                                              R12 ? R12 + 9 * o : nullptr, t12 ? t12 + 3 * o : nullptr,
+                                              iters12 ? iters12 + o : nullptr, status12 ? status12 + o : nullptr);
+            if (rc) return fail(c, rc, c->kids[k]->err);
+        }
+        return LIP_OK;
+    }
     LIP_CUDA(c, cudaDeviceSynchronize());
     const LipArgs& a = c->args;
     const size_t K = (size_t)c->sumK;
@@ -477,6 +568,14 @@ int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
     if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     if (side != 1 && side != 2) return fail(c, LIP_EINVAL, "side must be 1 or 2");
     cudaSetDevice(c->device);
+    if (c->last_run_split) {
+        for (int k = 0; k < c->n_kids; ++k) {
+            const size_t o = (size_t)(side == 1 ? c->h_off1 : c->h_off2)[c->kid_seg[k]];
+            int rc = lip_batch_get_landmark_nn(c->kids[k], side, nn ? nn + 2 * o : nullptr, dist ? dist + 2 * o : nullptr);
+            if (rc) return fail(c, rc, c->kids[k]->err);
+        }
+        return LIP_OK;
+    }
     LIP_CUDA(c, cudaDeviceSynchronize());
     const LipArgs& a = c->args;
     const size_t first = side == 1 ? 0 : (size_t)c->n1, n = side == 1 ? (size_t)c->n1 : (size_t)c->n2;
@@ -496,6 +595,16 @@ int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
 int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     if (!c || !c->planned || !counters) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
+    if (c->last_run_split) {
+        for (int i = 0; i < 8; ++i) counters[i] = 0;
+        for (int k = 0; k < c->n_kids; ++k) {
+            int64_t part[8];
+            int rc = lip_batch_get_counters(c->kids[k], part);
+            if (rc) return fail(c, rc, c->kids[k]->err);
+            for (int i = 0; i < 8; ++i) counters[i] += part[i];
+        }
+        return LIP_OK;
+    }
     LIP_CUDA(c, cudaDeviceSynchronize());
     unsigned long long h[8];
     int sched[32];
@@ -529,6 +638,7 @@ int lip_batch_get_stage_ms(lip_ctx* c, float ms[LIP_N_STAGES]) {
 
 int lip_batch_get_bin_offsets(lip_ctx* c, int32_t* bin_off) {
     if (!c || !c->planned || !bin_off) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (c->last_run_split) return fail(c, LIP_ENOPLAN, "bin offsets: the last run was a pipelined host run; use lip_batch_run_device");
     cudaSetDevice(c->device);
     LIP_CUDA(c, cudaDeviceSynchronize());
     LIP_CUDA(c, cudaMemcpy(bin_off, c->args.bin_off, ((size_t)c->B + 1) * 4, cudaMemcpyDeviceToHost));
