@@ -40,6 +40,7 @@ struct LipArgs {
     int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
     double* bin_xyz;         // [3 * n_total] the same vertices in float64, planes x | y | z in part_vid order
+    double* bin_q;           // [3 * n_total] blended positions of the source vertices (blend_kernel), same layout
     float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
     int* map_tiles;          // [2 * (n_total / LIP_MAP_TILE + B)] (bin, first slot) of every final-map tile; count in sched[20]
     double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number
@@ -49,7 +50,7 @@ struct LipArgs {
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
     int* sched;              // [32] [0] partitions of icp_group_kernel [1] n_big [2] group task cursor [3] n_far
                              //      [6] far cursor [7] n_retry [12..15] big class counts [24..31] group class counts
-                             //      [16] big cursor [20] number of final-map tiles
+                             //      [16] big cursor [20] number of final-map tiles [21] their cursor
     int *warp_list, *big_list;     // [8B] (eight work classes), [4B] (four)
     int* far_list;           // [n_total] unified ids of queries whose ring search could not certify
     double* far_q;           // [3 * n_total] their blended positions

@@ -959,6 +959,24 @@ __device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int
     q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
 }
 
+// One thread per source vertex (bin order): the blended position of p2p_matching_seg_icp.py:454-487 in float64,
+// written as planes x | y | z like bin_xyz.  Streaming and fully parallel, so that the latency of its dependent
+// loads and float64 divisions is not paid inside the search tiles.
+__global__ void __launch_bounds__(256) blend_kernel(LipArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_total) return;
+    // bin of position p: binary search in bin_off (ascending, B+1 entries)
+    int lo = 0, hi = a.B;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.bin_off[mid] <= p) lo = mid; else hi = mid; }
+    const int m = a.bin_mesh[lo];
+    if (!src_active(a, m)) return;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    double q0, q1, q2;
+    blend_query(a, m, bb, K, a.part_vid[p], q0, q1, q2);
+    const size_t N = (size_t)a.n_total;
+    a.bin_q[p] = q0; a.bin_q[N + p] = q1; a.bin_q[2 * N + p] = q2;
+}
+
 // =============================================================================================
 // K4  per-point two-transform blend + final nearest neighbour in the whole target mesh
 //     (p2p_matching_seg_icp.py:452-489; get_triangle_angles :27-34 fused, cos(arccos(x)) == x;
@@ -1051,15 +1069,23 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
 //     any fallback path.  All lanes read the same candidate (SMEM broadcast); the per-pair cost is 3 FFMA
 //     + ~1.1 min/max (scores c = |y|^2 - 2 q.y, block minima, winner recovered per block of 8).
 // =============================================================================================
-__global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) {
-    __shared__ float4 tp[LIP_MAP_CHUNK];
-    __shared__ int tv[LIP_MAP_CHUNK];
-    __shared__ unsigned need[LIP_MAX_LANDMARKS / 32];
-    __shared__ float sbox[LIP_MAP_BOXBATCH][8];
-    __shared__ float red[LIP_MAP_THREADS / 32][8];
-    if ((int)blockIdx.x >= a.sched[20]) return;
+struct MapSmem {
+    float4 tp[LIP_MAP_CHUNK];
+    int tv[LIP_MAP_CHUNK];
+    unsigned need[LIP_MAX_LANDMARKS / 32];
+    float sbox[LIP_MAP_BOXBATCH][8];
+    float red[LIP_MAP_THREADS / 32][8];
+    unsigned cand[2];
+};
+
+__device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int tile) {
+    float4* tp = S.tp;
+    int* tv = S.tv;
+    unsigned* need = S.need;
+    float (*sbox)[8] = S.sbox;
+    float (*red)[8] = S.red;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = a.map_tiles[2 * (size_t)blockIdx.x], first = a.map_tiles[2 * (size_t)blockIdx.x + 1];
+    const int b = a.map_tiles[2 * (size_t)tile], first = a.map_tiles[2 * (size_t)tile + 1];
     const int m = a.bin_mesh[b];
     const int ub = a.mesh_ubase[m];
     const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
@@ -1078,155 +1104,172 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) 
         valid[k] = tid + k * LIP_MAP_THREADS < nq;
         vq[k] = valid[k] ? a.part_vid[so + slot] : 0;
         float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (valid[k]) {
-            double q0, q1, q2;
-            blend_query(a, m, bb, K, vq[k], q0, q1, q2);
-            fx = (float)(q0 - C0); fy = (float)(q1 - C1); fz = (float)(q2 - C2);
+        if (valid[k]) {                                      // blended positions in bin order, written by blend_kernel
+            const size_t N = (size_t)a.n_total, p = (size_t)so + slot;
+            fx = (float)(a.bin_q[p] - C0); fy = (float)(a.bin_q[N + p] - C1); fz = (float)(a.bin_q[2 * N + p] - C2);
         }
         mq[k][0] = -2.f * fx; mq[k][1] = -2.f * fy; mq[k][2] = -2.f * fz;
         qq[k] = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
         qabs[k] = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
         best[k] = INFINITY; sec[k] = INFINITY; sec_in[k] = INFINITY; idx[k] = -1; blk[k] = 0;
     }
-    const bool two = nq > LIP_MAP_THREADS;                   // uniform: second query slot in use
+    // queries in use by this WARP (units of 32 queries are dealt warp 0, warp 1, warp 0, warp 1)
+    const int qw = (nq > LIP_MAP_THREADS + 32 * warp) ? 2 : (nq > 32 * warp) ? 1 : 0;
+    __syncthreads();                                         // the previous tile of this CTA is done with the shared arrays
     for (int i = tid; i < (K + 31) / 32; i += LIP_MAP_THREADS) need[i] = 0u;
     float mabs = 0.f;                                        // max |coordinate| staged so far (uniform)
     int fill = 0;
     long long staged = 0;
 
-    auto flush = [&]() {
-        const int npad = (fill + 7) & ~7;
-        if (tid < npad - fill) { tp[fill + tid] = make_float4(0.f, 0.f, 0.f, 3.0e38f); tv[fill + tid] = 0x7fffffff; }
-        __syncthreads();
-        const float prev0 = best[0], prev1 = best[1];
-        if (two) tile_scan<2, true>(tp, npad, mq, best, sec, blk);
-        else tile_scan<1, true>(tp, npad, mq, best, sec, blk);
-        if (best[0] < prev0) idx[0] = tv[tile_recover<true>(tp, blk[0], best[0], mq[0], sec_in[0])];
-        if (best[1] < prev1) idx[1] = tv[tile_recover<true>(tp, blk[1], best[1], mq[1], sec_in[1])];
-        __syncthreads();
-        staged += fill;
-        fill = 0;
-    };
-    auto stage_bin = [&](int j) {
-        const int s = a.bin_off[bbt + j], e = a.bin_off[bbt + j + 1];
-        if (e == s) return;
-        const float sh0 = (float)(lmt[3 * j] - C0), sh1 = (float)(lmt[3 * j + 1] - C1), sh2 = (float)(lmt[3 * j + 2] - C2);
-        mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
-        int p = s;
-        while (p < e) {
-            const int cnt = min(e - p, LIP_MAP_CHUNK - fill);
-            for (int i = tid; i < cnt; i += LIP_MAP_THREADS) {
-                const float4 t = a.bin_pts[p + i];
-                const float x = t.x + sh0, y = t.y + sh1, z = t.z + sh2;
-                tp[fill + i] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
-                tv[fill + i] = __float_as_int(t.w);
+    // Two rounds through ONE staging / scanning loop (a single copy of the scan code keeps the kernel small):
+    // round 0 stages the target bin of the queries' own landmark, round 1 every other bin that could hold
+    // something closer.
+    const int nwords = (K + 31) / 32;
+    for (int round = 0; round < 2; ++round) {
+        if (round == 1) {
+            if (K <= 1) break;
+            // CTA-wide bounds: box of the queries, largest current best distance, largest |q|
+            float v[8];
+            v[6] = 0.f; v[7] = 0.f;
+    #pragma unroll
+            for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
+    #pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (!valid[k]) continue;
+    #pragma unroll
+                for (int c = 0; c < 3; ++c) { const float f = -0.5f * mq[k][c]; v[c] = fminf(v[c], f); v[3 + c] = fmaxf(v[3 + c], f); }
+                v[6] = fmaxf(v[6], fmaxf(best[k] + qq[k], 0.f));
+                v[7] = fmaxf(v[7], qabs[k]);
             }
-            fill += cnt; p += cnt;
-            if (fill == LIP_MAP_CHUNK) flush();
-        }
-    };
-
-    // ---- round 0: the target bin of the queries' own landmark ------------------------------------------------
-    stage_bin(home);
-    if (fill > 0) flush();
-
-    // ---- round 1: every other bin that could hold something closer ---------------------------------------
-    if (K > 1) {
-        // CTA-wide bounds: box of the queries, largest current best distance, largest |q|
-        float v[8];
-        v[6] = 0.f; v[7] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (!valid[k]) continue;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { const float f = -0.5f * mq[k][c]; v[c] = fminf(v[c], f); v[3 + c] = fmaxf(v[3 + c], f); }
-            v[6] = fmaxf(v[6], fmaxf(best[k] + qq[k], 0.f));
-            v[7] = fmaxf(v[7], qabs[k]);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = -warp_maxf(-v[c]);
-#pragma unroll
-        for (int c = 3; c < 8; ++c) v[c] = warp_maxf(v[c]);
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) red[warp][c] = v[c];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < LIP_MAP_THREADS / 32; ++w) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = fminf(v[c], red[w][c]);
-#pragma unroll
-            for (int c = 3; c < 8; ++c) v[c] = fmaxf(v[c], red[w][c]);
-        }
-        const float rmax2 = v[6], qabs_max = v[7];
-        const float qq_max = 3.f * qabs_max * qabs_max;
-        for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXBATCH) {
-            __syncthreads();
-            if (tid < LIP_MAP_BOXBATCH) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
-                const int j = j0 + tid;
-                float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
-                if (j < K && j != home && a.bin_off[bbt + j + 1] > a.bin_off[bbt + j]) {
-                    const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
-                    float bb2 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float sh = (float)(lmt[3 * j + c] - (c == 0 ? C0 : c == 1 ? C1 : C2));
-                        lo[c] = bx[c] + sh; hi[c] = bx[3 + c] + sh;
-                        mb = fmaxf(mb, fmaxf(fabsf(lo[c]), fabsf(hi[c])));
-                        const float d = fmaxf(fmaxf(lo[c] - v[3 + c], v[c] - hi[c]), 0.f);
-                        bb2 = fmaf(d, d, bb2);
-                    }
-                    const float e = 4e-7f * (qabs_max + fmaxf(mb, mabs));
-                    const float rhs = rmax2 + d2_err(rmax2, e) + dot_err(qq_max, rmax2);
-                    const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
-                    flag = (lhs > rhs) ? 0.f : 1.f;          // (NaN compares false -> kept)
-                }
-                sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
-                sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
-                sbox[tid][6] = mb; sbox[tid][7] = flag;
-            }
-            __syncthreads();
-            unsigned w0 = 0u, w1 = 0u;
-            const int jn = min(LIP_MAP_BOXBATCH, K - j0);
-            for (int t = 0; t < jn; ++t) {
-                if (sbox[t][7] == 0.f) continue;             // uniform
-                bool nd = false;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (!valid[k]) continue;
-                    float bd2 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float f = -0.5f * mq[k][c];
-                        const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
-                        bd2 = fmaf(d, d, bd2);
-                    }
-                    const float bd = fmaxf(best[k] + qq[k], 0.f);
-                    const float e = 4e-7f * (qabs[k] + fmaxf(sbox[t][6], mabs));
-                    const float tol = d2_err(bd, e) + d2_err(bd2, e) + dot_err(qq[k], bd);
-                    nd = nd || !(bd2 - bd > tol);
-                }
-                if (nd) { if (t < 32) w0 |= 1u << t; else w1 |= 1u << (t - 32); }
-            }
-            w0 = __reduce_or_sync(LIP_FULL, w0); w1 = __reduce_or_sync(LIP_FULL, w1);
+    #pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = -warp_maxf(-v[c]);
+    #pragma unroll
+            for (int c = 3; c < 8; ++c) v[c] = warp_maxf(v[c]);
             if (lane == 0) {
-                if (w0) atomicOr(&need[j0 / 32], w0);
-                if (w1) atomicOr(&need[j0 / 32 + 1], w1);
+    #pragma unroll
+                for (int c = 0; c < 8; ++c) red[warp][c] = v[c];
+            }
+            __syncthreads();
+    #pragma unroll
+            for (int w = 0; w < LIP_MAP_THREADS / 32; ++w) {
+    #pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = fminf(v[c], red[w][c]);
+    #pragma unroll
+                for (int c = 3; c < 8; ++c) v[c] = fmaxf(v[c], red[w][c]);
+            }
+            const float rmax2 = v[6], qabs_max = v[7];
+            const float qq_max = 3.f * qabs_max * qabs_max;
+            for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXBATCH) {
+                __syncthreads();
+                if (tid < LIP_MAP_BOXBATCH) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
+                    const int j = j0 + tid;
+                    float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
+                    if (j < K && j != home && a.bin_off[bbt + j + 1] > a.bin_off[bbt + j]) {
+                        const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
+                        float bb2 = 0.f;
+    #pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float sh = (float)(lmt[3 * j + c] - (c == 0 ? C0 : c == 1 ? C1 : C2));
+                            lo[c] = bx[c] + sh; hi[c] = bx[3 + c] + sh;
+                            mb = fmaxf(mb, fmaxf(fabsf(lo[c]), fabsf(hi[c])));
+                            const float d = fmaxf(fmaxf(lo[c] - v[3 + c], v[c] - hi[c]), 0.f);
+                            bb2 = fmaf(d, d, bb2);
+                        }
+                        const float e = 4e-7f * (qabs_max + fmaxf(mb, mabs));
+                        const float rhs = rmax2 + d2_err(rmax2, e) + dot_err(qq_max, rmax2);
+                        const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
+                        flag = (lhs > rhs) ? 0.f : 1.f;          // (NaN compares false -> kept)
+                    }
+                    sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
+                    sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
+                    sbox[tid][6] = mb; sbox[tid][7] = flag;
+                    const unsigned fm = __ballot_sync(LIP_FULL, flag != 0.f);
+                    if (lane == 0) S.cand[warp] = fm;
+                }
+                __syncthreads();
+                unsigned w0 = 0u, w1 = 0u;
+                unsigned long long cm = ((unsigned long long)S.cand[1] << 32) | S.cand[0];     // uniform
+                while (cm) {
+                    const int t = __ffsll((long long)cm) - 1;
+                    cm &= cm - 1;
+                    bool nd = false;
+    #pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (!valid[k]) continue;
+                        float bd2 = 0.f;
+    #pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float f = -0.5f * mq[k][c];
+                            const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
+                            bd2 = fmaf(d, d, bd2);
+                        }
+                        const float bd = fmaxf(best[k] + qq[k], 0.f);
+                        const float e = 4e-7f * (qabs[k] + fmaxf(sbox[t][6], mabs));
+                        const float tol = d2_err(bd, e) + d2_err(bd2, e) + dot_err(qq[k], bd);
+                        nd = nd || !(bd2 - bd > tol);
+                    }
+                    if (nd) { if (t < 32) w0 |= 1u << t; else w1 |= 1u << (t - 32); }
+                }
+                w0 = __reduce_or_sync(LIP_FULL, w0); w1 = __reduce_or_sync(LIP_FULL, w1);
+                if (lane == 0) {
+                    if (w0) atomicOr(&need[j0 / 32], w0);
+                    if (w1) atomicOr(&need[j0 / 32 + 1], w1);
+                }
+            }
+            __syncthreads();
+        }
+        int wi = 0, base = 0, cur_p = 0, cur_e = 0;
+        unsigned bits = 0u;
+        float sh0 = 0.f, sh1 = 0.f, sh2 = 0.f;
+        bool pending_home = round == 0, more = true;
+        while (more) {
+            while (fill < LIP_MAP_CHUNK) {
+                if (cur_p >= cur_e) {                        // next bin of this round (uniform)
+                    int j = -1;
+                    if (round == 0) { if (pending_home) { j = home; pending_home = false; } }
+                    else {
+                        while (bits == 0u && wi < nwords) { bits = need[wi]; base = 32 * wi; ++wi; }
+                        if (bits) { j = base + __ffs(bits) - 1; bits &= bits - 1; }
+                    }
+                    if (j < 0) { more = false; break; }
+                    cur_p = a.bin_off[bbt + j]; cur_e = a.bin_off[bbt + j + 1];
+                    if (cur_e > cur_p) {
+                        sh0 = (float)(lmt[3 * j] - C0); sh1 = (float)(lmt[3 * j + 1] - C1); sh2 = (float)(lmt[3 * j + 2] - C2);
+                        mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
+                    }
+                    continue;
+                }
+                const int cnt = min(cur_e - cur_p, LIP_MAP_CHUNK - fill);
+                for (int i0 = tid; i0 < cnt; i0 += 4 * LIP_MAP_THREADS) {
+                    float4 t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int i = i0 + u * LIP_MAP_THREADS; if (i < cnt) t[u] = a.bin_pts[cur_p + i]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * LIP_MAP_THREADS;
+                        if (i < cnt) {
+                            const float x = t[u].x + sh0, y = t[u].y + sh1, z = t[u].z + sh2;
+                            tp[fill + i] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
+                            tv[fill + i] = __float_as_int(t[u].w);
+                        }
+                    }
+                }
+                fill += cnt; cur_p += cnt;
+            }
+            if (fill > 0) {                                  // scan the staged chunk
+                const int npad = (fill + 7) & ~7;
+                if (tid < npad - fill) { tp[fill + tid] = make_float4(0.f, 0.f, 0.f, 3.0e38f); tv[fill + tid] = 0x7fffffff; }
+                __syncthreads();
+                const float prev0 = best[0], prev1 = best[1];
+                if (qw == 2) tile_scan<2, true>(tp, npad, mq, best, sec, blk);
+                else if (qw == 1) tile_scan<1, true>(tp, npad, mq, best, sec, blk);
+                if (best[0] < prev0) idx[0] = tv[tile_recover<true>(tp, blk[0], best[0], mq[0], sec_in[0])];
+                if (best[1] < prev1) idx[1] = tv[tile_recover<true>(tp, blk[1], best[1], mq[1], sec_in[1])];
+                __syncthreads();
+                staged += fill;
+                fill = 0;
             }
         }
-        __syncthreads();
-        for (int w = 0; w < (K + 31) / 32; ++w) {
-            unsigned bits = need[w];                          // uniform
-            while (bits) {
-                const int j = 32 * w + __ffs(bits) - 1;
-                bits &= bits - 1;
-                stage_bin(j);
-            }
-        }
-        if (fill > 0) flush();
     }
     if (a.profile && tid == 0) atomicAdd(&a.counters[7], (unsigned long long)(staged * nq));
 
@@ -1244,9 +1287,9 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) 
         while (ties) {
             const int src = __ffs(ties) - 1;
             ties &= ties - 1;
-            double q0 = 0, q1 = 0, q2 = 0;
-            if (lane == src) blend_query(a, m, bb, K, vq[k], q0, q1, q2);
-            q0 = __shfl_sync(LIP_FULL, q0, src); q1 = __shfl_sync(LIP_FULL, q1, src); q2 = __shfl_sync(LIP_FULL, q2, src);
+            const size_t N = (size_t)a.n_total;
+            const size_t pq = (size_t)so + first + (tid - lane + src) + k * LIP_MAP_THREADS;     // slot of lane `src`
+            const double q0 = a.bin_q[pq], q1 = a.bin_q[N + pq], q2 = a.bin_q[2 * N + pq];
             double bd = INFINITY;
             int bi = 0x7fffffff;
             for (int j = 0; j < K; ++j) {
@@ -1269,6 +1312,20 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS) blend_tile_kernel(LipArgs a) 
             const int u = ub + vq[k];
             if (m < a.S) a.T12[u] = res; else a.T21[u - a.n1_total] = res;
         }
+    }
+}
+
+__global__ void __launch_bounds__(LIP_MAP_THREADS, 12) blend_tile_kernel(LipArgs a) {
+    __shared__ MapSmem S;
+    __shared__ int s_tile;
+    const int n_tiles = a.sched[20];
+    for (;;) {                                              // persistent CTAs over the tile list
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&a.sched[21], 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        blend_tile(a, S, tile);
     }
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -14,7 +15,7 @@
 #ifndef LIP_ARCH
 #define LIP_ARCH 100
 #endif
-#define LIP_PIPELINE_CHUNKS 4             // sub-batches of the pipelined host path
+#define LIP_PIPELINE_CHUNKS 8             // sub-batches of the pipelined host path
 #define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
 namespace {
@@ -44,7 +45,7 @@ enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 
 struct lip_ctx {
     int device = 0;
     int sm_count = 0;
-    int group_blocks_per_sm = 1, big_blocks_per_sm = 1;
+    int group_blocks_per_sm = 1, big_blocks_per_sm = 1, map_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, (unused), grid build
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -114,7 +115,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_cnt = take(8 * 8);
     const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
-    const size_t o_bxyz = take(n * 24);
+    const size_t o_bxyz = take(n * 24), o_bq = take(n * 24);
     const size_t o_mt = take(c->max_map_tiles * 8);
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
@@ -132,7 +133,7 @@ int carve_workspace(lip_ctx* c) {
     a.counters = (unsigned long long*)(base + o_cnt);
     a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
     a.map_tiles = (int*)(base + o_mt);
-    a.bin_xyz = (double*)(base + o_bxyz);
+    a.bin_xyz = (double*)(base + o_bxyz); a.bin_q = (double*)(base + o_bq);
     return LIP_OK;
 }
 
@@ -292,7 +293,12 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     }
     if (forked_grid) { LIP_CUDA(c, cudaEventRecord(c->ev_join[2], s_grid)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[2], 0)); }
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
-        if (tiles) blend_tile_kernel<<<(unsigned)c->max_map_tiles, LIP_MAP_THREADS, 0, st>>>(a);
+        if (tiles) {
+            blend_kernel<<<(a.n_total + 255) / 256, 256, 0, st>>>(a);
+            ++launches;
+            const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * c->map_blocks_per_sm);
+            blend_tile_kernel<<<(unsigned)gm, LIP_MAP_THREADS, 0, st>>>(a);
+        }
         else blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
@@ -391,6 +397,8 @@ int lip_create(lip_ctx** out, int device) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_group_kernel, LIP_ICP_WARPS * 32, 0) == cudaSuccess && nb > 0)
         c->group_blocks_per_sm = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, blend_tile_kernel, LIP_MAP_THREADS, 0) == cudaSuccess && nb > 0)
+        c->map_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
     cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -441,7 +449,9 @@ int lip_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LIP_OK : LI
 static int plan_kids(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
     c->n_kids = 0;
     const int64_t n = off1[S] + off2[S];
-    int want = (int)std::min<int64_t>(LIP_PIPELINE_CHUNKS, S);
+    int chunks = LIP_PIPELINE_CHUNKS;
+    if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    int want = (int)std::min<int64_t>(chunks, S);
     if (n < LIP_PIPELINE_MIN_VERTICES || want < 2) return LIP_OK;
     c->kid_seg.assign(1, 0);
     for (int k = 1; k < want; ++k) {                         // cut where the running vertex count passes k/want of the total

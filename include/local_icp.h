@@ -82,7 +82,7 @@ int  lip_host_free(void* p);
  *   xyz1 (off1[S],3), xyz2 (off2[S],3), lm1, lm2 (lm_off[S],3) float64.
  *   T21 (off2[S]) : T21[off2[s]+i] = index in mesh1 of pair s matched to vertex i of mesh2;
  *   T12 (off1[S]) likewise.  Either may be NULL when its direction is not requested.
- * lip_batch_run_host on a large batch (>= 400k vertices) runs as a pipeline of up to four sub-batches on their own
+ * lip_batch_run_host on a large batch (>= 400k vertices) runs as a pipeline of up to eight sub-batches on their own
  * streams, so that the copies in, the kernels and the copies out overlap (pinned host buffers make the copies
  * truly asynchronous: lip_host_alloc).  Results are identical to an unsplit run. */
 int lip_batch_plan(lip_ctx* ctx, int64_t S, const int64_t* off1, const int64_t* off2,
