@@ -374,7 +374,6 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            if (qi[k] >= ns) continue;
             const float fx = (float)pq[k][0], fy = (float)pq[k][1], fz = (float)pq[k][2];
             const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
             const float e = 2.4e-7f * (qabs + mabs);         // stored offset, shift and sum: three roundings per coordinate
@@ -382,16 +381,29 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
             const float d2b = fmaxf(best[k] + qq, 0.f), d2s = fmaxf(fminf(sec[k], sec_in[k]) + qq, 0.f);
             float tol = d2_err(d2b, e) + d2_err(d2s, e);
             if (DOT) tol += 2.f * dot_err(qq, d2s);
-            if (!(d2s - d2b > tol)) {                        // near tie: decide in float64, lowest index
+            // near ties are decided in float64 (lowest index), the warp working together on one query at a time
+            unsigned ties = __ballot_sync(LIP_FULL, qi[k] < ns && !(d2s - d2b > tol));
+            if (ties && (tid & 31) == 0) atomicAdd(&a.counters[2], (unsigned long long)__popc(ties));
+            while (ties) {
+                const int src = __ffs(ties) - 1;
+                ties &= ties - 1;
+                const double p0 = __shfl_sync(LIP_FULL, pq[k][0], src), p1 = __shfl_sync(LIP_FULL, pq[k][1], src),
+                             p2 = __shfl_sync(LIP_FULL, pq[k][2], src);
                 double bd = INFINITY;
-#pragma unroll 1
-                for (int j = 0; j < nt; ++j) {
-                    const double d = rdist64(pq[k][0], pq[k][1], pq[k][2], tx[j] - c0, tx[N + j] - c1, tx[2 * N + j] - c2);
-                    if (d < bd) { bd = d; idx[k] = j; }
+                int bj = 0x7fffffff;
+                for (int j = tid & 31; j < nt; j += 32) {
+                    const double d = rdist64(p0, p1, p2, tx[j] - c0, tx[N + j] - c1, tx[2 * N + j] - c2);
+                    if (d < bd) { bd = d; bj = j; }          // ascending j per lane: the lowest index is kept
                 }
-                atomicAdd(&a.counters[2], 1ull);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(LIP_FULL, bd, o);
+                    const int oj = __shfl_xor_sync(LIP_FULL, bj, o);
+                    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                }
+                if ((tid & 31) == src) idx[k] = bj;
             }
-            nn_idx[qi[k]] = idx[k];
+            if (qi[k] < ns) nn_idx[qi[k]] = idx[k];
         }
     }
     // ---- sums of get_best_fit_transform + cost over the (source, winner) pairs, float64 ----

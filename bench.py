@@ -305,6 +305,10 @@ def run_b200(args):
     pairs = {"icp_group_kernel": float(w[ns * nt <= 65536].sum()),         # LIP_WARP_WORK
              "icp_big_kernel": float(w[ns * nt > 65536].sum()),
              "final_map_kernel": float(counters["map_ring1_pairs"])}
+    big = ns * nt > 65536
+    it_stats = {"group": {"n": int((~big & (iters > 0)).sum()), "mean": float(iters[~big & (iters > 0)].mean()), "p99": float(np.percentile(iters[~big & (iters > 0)], 99)), "max": float(iters[~big].max())},
+                "big": {"n": int((big & (iters > 0)).sum()), "mean": float(iters[big & (iters > 0)].mean()) if (big & (iters > 0)).any() else 0.0,
+                        "p99": float(np.percentile(iters[big & (iters > 0)], 99)) if (big & (iters > 0)).any() else 0.0, "max": float(iters[big].max()) if big.any() else 0.0}}
     dom = max(pairs, key=lambda k: stage[k])
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12       # TFLOP/s, FP32 FMA pipe at the max SM clock
     achieved = 8.0 * pairs[dom] / (stage[dom] / 1e3) / 1e12
@@ -334,7 +338,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "frame_pairs_per_s": nfp_all / (e2e_ms / args.steps / 1e3)},
             "gpu_launches": int(launches), "kernels_per_step": counters["launches"],
-            "stage_ms": stage, "counters": counters, "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm}
+            "stage_ms": stage, "counters": counters, "nn_passes": it_stats, "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm}
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         a2 = argparse.Namespace(**vars(args))
