@@ -271,3 +271,38 @@ def test_drop_in_segment_function_and_install(L):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_grid_map_mode_gives_identical_maps(L):
+    """final map: landmark-bin tiles (mode 0, default) and hashed uniform grid (mode 1) are both exact searches"""
+    b = L.make_config(1, scale=1.0)
+    ctx = L.Context(0)
+    out = {}
+    for mode in (0, 1):
+        ctx.set_map_mode(mode)
+        ctx.plan(b.off1, b.off2, b.lm_off)
+        out[mode] = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+        c = ctx.counters()
+        assert (c["map_retry"] > 0) == (mode == 1) or c["map_retry"] == 0
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    ctx.close()
+
+
+def test_pipelined_host_path_equals_single_pass(L, monkeypatch):
+    """lip_batch_run_host splits large batches into sub-batches on their own streams; same results as one pass"""
+    b = L.make_config(2, frame_pairs=8)                      # ~800k vertices: above the pipeline threshold
+    assert b.off1[-1] + b.off2[-1] > 400_000
+    res = {}
+    for chunks in ("1", "8"):
+        monkeypatch.setenv("LIP_PIPELINE_CHUNKS", chunks)
+        ctx = L.Context(0)
+        ctx.plan(b.off1, b.off2, b.lm_off)
+        T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+        res[chunks] = (T21, T12, ctx.transforms(filled=True), ctx.counters())
+        ctx.close()
+    np.testing.assert_array_equal(res["1"][0], res["8"][0])
+    np.testing.assert_array_equal(res["1"][1], res["8"][1])
+    for k in ("R21", "t21", "iters21", "status21", "R12", "t12", "iters12", "status12"):
+        np.testing.assert_array_equal(res["1"][2][k], res["8"][2][k])
+    assert res["1"][3]["small_icps"] + res["1"][3]["big_icps"] == res["8"][3]["small_icps"] + res["8"][3]["big_icps"]
