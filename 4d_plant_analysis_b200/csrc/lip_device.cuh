@@ -24,6 +24,13 @@ struct GridHdr {
     int n;
 };
 
+// one tile of the final map: up to LIP_MAP_TILE queries of source bin b (written by icp_schedule_kernel)
+struct MapTile {
+    int b, first, nq, m, bb, K, bbt, so, ub, ts, te;   // source bin, first slot, queries, mesh, its first bin / bin count, first bin of
+    float home_mabs;                                    // the target mesh, slot bases, target bin of the same landmark [ts, te)
+    double C[3];                                        // tile origin: the target's landmark
+};
+
 struct LipArgs {
     int S, M, B, sumK, n1_total, n_total, dir_mask, n_tiles;
     const double *xyz1, *xyz2, *lm1, *lm2;
@@ -41,8 +48,10 @@ struct LipArgs {
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
     double* bin_xyz;         // [3 * n_total] the same vertices in float64, planes x | y | z in part_vid order
     double* bin_q;           // [3 * n_total] blended positions of the source vertices (blend_kernel), same layout
+    int *pos_bin, *pos_nn1;  // [n_total] bin and second-nearest landmark of every slot (bin order)
+    double* pos_d;           // [2 * n_total] distances to the nearest / second-nearest landmark, planes, bin order
     float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
-    int* map_tiles;          // [2 * (n_total / LIP_MAP_TILE + B)] (bin, first slot) of every final-map tile; count in sched[20]
+    MapTile* map_tiles;      // [n_total / LIP_MAP_TILE + B] final-map tiles; count in sched[20]
     double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number
     double* mesh_sum;        // [M*4] sum of the vertices of every mesh (x, y, z) and the vertex count
     double *icp_R, *icp_t;   // [B*9], [B*3]

@@ -105,9 +105,6 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
                         fz = (float)(xyz[3 * (size_t)v + 2] - lmS[3 * bin + 2]);
             a.part_vid[pos] = v;
             a.bin_pts[pos] = make_float4(fx, fy, fz, __int_as_float(v));
-            a.bin_xyz[pos] = xyz[3 * (size_t)v];
-            a.bin_xyz[(size_t)a.n_total + pos] = xyz[3 * (size_t)v + 1];
-            a.bin_xyz[2 * (size_t)a.n_total + pos] = xyz[3 * (size_t)v + 2];
         }
         __syncthreads();
         if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the chunk
@@ -126,8 +123,13 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
             const float4 t = a.bin_pts[p];
             lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
             hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
-            const size_t v = (size_t)__float_as_int(t.w);
-            bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
+            const size_t v = (size_t)__float_as_int(t.w), N = (size_t)a.n_total;
+            const double x = xyz[3 * v], y = xyz[3 * v + 1], z = xyz[3 * v + 2];
+            bx0 += x; bx1 += y; bx2 += z;
+            // the bin-ordered float64 copies: coalesced stores here, gathers from what this CTA has just written
+            a.bin_xyz[p] = x; a.bin_xyz[N + p] = y; a.bin_xyz[2 * N + p] = z;
+            a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
+            a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
         }
         lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
         hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
@@ -159,7 +161,15 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     if (ns > 0) {                                            // tiles of the final map: up to LIP_MAP_TILE queries of one bin
         const int nt_map = (ns + LIP_MAP_TILE - 1) / LIP_MAP_TILE;
         const int slot = atomicAdd(&a.sched[20], nt_map);
-        for (int i = 0; i < nt_map; ++i) { a.map_tiles[2 * (size_t)(slot + i)] = b; a.map_tiles[2 * (size_t)(slot + i) + 1] = i * LIP_MAP_TILE; }
+        MapTile t;
+        const int mt = pair_mesh(a, m);
+        t.b = b; t.m = m; t.bb = a.mesh_bin[m]; t.K = a.mesh_bin[m + 1] - t.bb; t.bbt = a.mesh_bin[mt];
+        t.so = a.bin_off[b]; t.ub = a.mesh_ubase[m];
+        t.ts = a.bin_off[pb]; t.te = a.bin_off[pb + 1];
+        t.home_mabs = (t.te > t.ts) ? a.bin_box[8 * (size_t)pb + 6] : 0.f;
+        const double* lmh = mesh_lm(a, mt) + 3 * (size_t)(b - t.bb);
+        t.C[0] = lmh[0]; t.C[1] = lmh[1]; t.C[2] = lmh[2];
+        for (int i = 0; i < nt_map; ++i) { t.first = i * LIP_MAP_TILE; t.nq = min(LIP_MAP_TILE, ns - t.first); a.map_tiles[slot + i] = t; }
     }
     if (ns == 0 || nt == 0) return;
     const long long w = (long long)ns * nt;
@@ -942,17 +952,13 @@ __device__ __forceinline__ void fill_apply(const LipArgs& a, int m, int src, dou
 // The blended position of vertex v of source mesh m (p2p_matching_seg_icp.py:454-487): weights from the
 // triangle (landmark gap, d_a, d_b) — get_triangle_angles :27-34 fused, cos(arccos(x)) == x — and the two
 // landmark transforms after the fill of :422-437, all in float64.
-__device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int K, int v, double& q0, double& q1, double& q2) {
-    const int u = a.mesh_ubase[m] + v;
-    const double* xyz = mesh_xyz(a, m);
-    const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
-    const int ia = a.nn0[u], ib = a.nn1[u];
+__device__ __forceinline__ void blend_point(const LipArgs& a, int m, int bb, int K, double x, double y, double z, int ia, int ib,
+                                            double da, double db, double& q0, double& q1, double& q2) {
     double f0 = 0.5, f1 = 0.5;
     if (K > 1) {
         const double* lm = mesh_lm(a, m);
         const double gx = lm[3 * ib] - lm[3 * ia], gy = lm[3 * ib + 1] - lm[3 * ia + 1], gz = lm[3 * ib + 2] - lm[3 * ia + 2];
         const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
-        const double da = a.d0[u], db = a.d1[u];
         // get_triangle_angles(g, da, db): B opposite da, C opposite db
         double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
         double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
@@ -971,20 +977,26 @@ __device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int
     q0 = f0 * ax + f1 * bx; q1 = f0 * ay + f1 * by; q2 = f0 * az + f1 * bz;
 }
 
+__device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int K, int v, double& q0, double& q1, double& q2) {
+    const int u = a.mesh_ubase[m] + v;
+    const double* xyz = mesh_xyz(a, m);
+    blend_point(a, m, bb, K, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.nn0[u], a.nn1[u], a.d0[u], a.d1[u],
+                q0, q1, q2);
+}
+
 // One thread per source vertex (bin order): the blended position of p2p_matching_seg_icp.py:454-487 in float64,
 // written as planes x | y | z like bin_xyz.  Streaming and fully parallel, so that the latency of its dependent
 // loads and float64 divisions is not paid inside the search tiles.
 __global__ void __launch_bounds__(256) blend_kernel(LipArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_total) return;
-    // bin of position p: binary search in bin_off (ascending, B+1 entries)
-    int lo = 0, hi = a.B;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.bin_off[mid] <= p) lo = mid; else hi = mid; }
-    const int m = a.bin_mesh[lo];
+    const int b = a.pos_bin[p], m = a.bin_mesh[b];           // everything per vertex is read in bin order: coalesced
     if (!src_active(a, m)) return;
     const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const size_t N0 = (size_t)a.n_total;
     double q0, q1, q2;
-    blend_query(a, m, bb, K, a.part_vid[p], q0, q1, q2);
+    blend_point(a, m, bb, K, a.bin_xyz[p], a.bin_xyz[N0 + p], a.bin_xyz[2 * N0 + p], b - bb, a.pos_nn1[p], a.pos_d[p], a.pos_d[N0 + p],
+                q0, q1, q2);
     const size_t N = (size_t)a.n_total;
     a.bin_q[p] = q0; a.bin_q[N + p] = q1; a.bin_q[2 * N + p] = q2;
 }
@@ -1088,6 +1100,7 @@ struct MapSmem {
     float sbox[LIP_MAP_BOXBATCH][8];
     float red[LIP_MAP_THREADS / 32][8];
     unsigned cand[2];
+    struct { int start, end; float sh[3]; } sdesc[LIP_MAP_BOXBATCH];   // where the bins of the last box batch are, and their shift
 };
 
 __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int tile) {
@@ -1097,16 +1110,12 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     float (*sbox)[8] = S.sbox;
     float (*red)[8] = S.red;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = a.map_tiles[2 * (size_t)tile], first = a.map_tiles[2 * (size_t)tile + 1];
-    const int m = a.bin_mesh[b];
-    const int ub = a.mesh_ubase[m];
-    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
-    const int mt = pair_mesh(a, m), bbt = a.mesh_bin[mt];
-    const int home = b - bb;                                 // the queries' nearest landmark (local index)
+    const MapTile T = a.map_tiles[tile];                     // one 80-byte descriptor instead of a chain of dependent look-ups
+    const int first = T.first, m = T.m, ub = T.ub, bb = T.bb, K = T.K, bbt = T.bbt, so = T.so, nq = T.nq;
+    const int mt = pair_mesh(a, m);
+    const int home = T.b - bb;                               // the queries' nearest landmark (local index)
     const double* __restrict__ lmt = mesh_lm(a, mt);
-    const int so = a.bin_off[b];
-    const int nq = min(LIP_MAP_TILE, a.bin_off[b + 1] - so - first);
-    const double C0 = lmt[3 * home], C1 = lmt[3 * home + 1], C2 = lmt[3 * home + 2];     // tile origin: the target's landmark
+    const double C0 = T.C[0], C1 = T.C[1], C2 = T.C[2];      // tile origin: the target's landmark
     float mq[2][3], qq[2], qabs[2], best[2], sec[2], sec_in[2];
     int idx[2], blk[2], vq[2];
     bool valid[2];
@@ -1143,30 +1152,30 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
             // CTA-wide bounds: box of the queries, largest current best distance, largest |q|
             float v[8];
             v[6] = 0.f; v[7] = 0.f;
-    #pragma unroll
+#pragma unroll
             for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
-    #pragma unroll
+#pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (!valid[k]) continue;
-    #pragma unroll
+#pragma unroll
                 for (int c = 0; c < 3; ++c) { const float f = -0.5f * mq[k][c]; v[c] = fminf(v[c], f); v[3 + c] = fmaxf(v[3 + c], f); }
                 v[6] = fmaxf(v[6], fmaxf(best[k] + qq[k], 0.f));
                 v[7] = fmaxf(v[7], qabs[k]);
             }
-    #pragma unroll
+#pragma unroll
             for (int c = 0; c < 3; ++c) v[c] = -warp_maxf(-v[c]);
-    #pragma unroll
+#pragma unroll
             for (int c = 3; c < 8; ++c) v[c] = warp_maxf(v[c]);
             if (lane == 0) {
-    #pragma unroll
+#pragma unroll
                 for (int c = 0; c < 8; ++c) red[warp][c] = v[c];
             }
             __syncthreads();
-    #pragma unroll
+#pragma unroll
             for (int w = 0; w < LIP_MAP_THREADS / 32; ++w) {
-    #pragma unroll
+#pragma unroll
                 for (int c = 0; c < 3; ++c) v[c] = fminf(v[c], red[w][c]);
-    #pragma unroll
+#pragma unroll
                 for (int c = 3; c < 8; ++c) v[c] = fmaxf(v[c], red[w][c]);
             }
             const float rmax2 = v[6], qabs_max = v[7];
@@ -1176,12 +1185,15 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                 if (tid < LIP_MAP_BOXBATCH) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
                     const int j = j0 + tid;
                     float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
-                    if (j < K && j != home && a.bin_off[bbt + j + 1] > a.bin_off[bbt + j]) {
+                    const int js = j < K ? a.bin_off[bbt + j] : 0, je = j < K ? a.bin_off[bbt + j + 1] : 0;
+                    S.sdesc[tid].start = js; S.sdesc[tid].end = je;
+                    if (j < K && j != home && je > js) {
                         const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
                         float bb2 = 0.f;
-    #pragma unroll
+#pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const float sh = (float)(lmt[3 * j + c] - (c == 0 ? C0 : c == 1 ? C1 : C2));
+                            S.sdesc[tid].sh[c] = sh;
                             lo[c] = bx[c] + sh; hi[c] = bx[3 + c] + sh;
                             mb = fmaxf(mb, fmaxf(fabsf(lo[c]), fabsf(hi[c])));
                             const float d = fmaxf(fmaxf(lo[c] - v[3 + c], v[c] - hi[c]), 0.f);
@@ -1205,11 +1217,11 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                     const int t = __ffsll((long long)cm) - 1;
                     cm &= cm - 1;
                     bool nd = false;
-    #pragma unroll
+#pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (!valid[k]) continue;
                         float bd2 = 0.f;
-    #pragma unroll
+#pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const float f = -0.5f * mq[k][c];
                             const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
@@ -1238,16 +1250,26 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
             while (fill < LIP_MAP_CHUNK) {
                 if (cur_p >= cur_e) {                        // next bin of this round (uniform)
                     int j = -1;
-                    if (round == 0) { if (pending_home) { j = home; pending_home = false; } }
-                    else {
-                        while (bits == 0u && wi < nwords) { bits = need[wi]; base = 32 * wi; ++wi; }
-                        if (bits) { j = base + __ffs(bits) - 1; bits &= bits - 1; }
+                    if (round == 0) {
+                        if (!pending_home) { more = false; break; }
+                        pending_home = false;
+                        cur_p = T.ts; cur_e = T.te; sh0 = sh1 = sh2 = 0.f;
+                        mabs = fmaxf(mabs, T.home_mabs);
+                        continue;
                     }
+                    while (bits == 0u && wi < nwords) { bits = need[wi]; base = 32 * wi; ++wi; }
+                    if (bits) { j = base + __ffs(bits) - 1; bits &= bits - 1; }
                     if (j < 0) { more = false; break; }
-                    cur_p = a.bin_off[bbt + j]; cur_e = a.bin_off[bbt + j + 1];
-                    if (cur_e > cur_p) {
-                        sh0 = (float)(lmt[3 * j] - C0); sh1 = (float)(lmt[3 * j + 1] - C1); sh2 = (float)(lmt[3 * j + 2] - C2);
-                        mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
+                    if (K <= LIP_MAP_BOXBATCH) {             // descriptors left in SMEM by the box pass
+                        cur_p = S.sdesc[j].start; cur_e = S.sdesc[j].end;
+                        sh0 = S.sdesc[j].sh[0]; sh1 = S.sdesc[j].sh[1]; sh2 = S.sdesc[j].sh[2];
+                        mabs = fmaxf(mabs, S.sbox[j][6]);
+                    } else {
+                        cur_p = a.bin_off[bbt + j]; cur_e = a.bin_off[bbt + j + 1];
+                        if (cur_e > cur_p) {
+                            sh0 = (float)(lmt[3 * j] - C0); sh1 = (float)(lmt[3 * j + 1] - C1); sh2 = (float)(lmt[3 * j + 2] - C2);
+                            mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
+                        }
                     }
                     continue;
                 }

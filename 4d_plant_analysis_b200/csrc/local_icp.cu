@@ -115,8 +115,8 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_cnt = take(8 * 8);
     const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
-    const size_t o_bxyz = take(n * 24), o_bq = take(n * 24);
-    const size_t o_mt = take(c->max_map_tiles * 8);
+    const size_t o_bxyz = take(n * 24), o_bq = take(n * 24), o_pb = take(n * 4), o_pn = take(n * 4), o_pd = take(n * 16);
+    const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile));
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
     LipArgs& a = c->args;
@@ -132,8 +132,9 @@ int carve_workspace(lip_ctx* c) {
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
     a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
-    a.map_tiles = (int*)(base + o_mt);
+    a.map_tiles = (MapTile*)(base + o_mt);
     a.bin_xyz = (double*)(base + o_bxyz); a.bin_q = (double*)(base + o_bq);
+    a.pos_bin = (int*)(base + o_pb); a.pos_nn1 = (int*)(base + o_pn); a.pos_d = (double*)(base + o_pd);
     return LIP_OK;
 }
 
@@ -240,6 +241,15 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     // otherwise the three ICP kernels and the grid build run as concurrent branches (their tails overlap).
     const bool serial = c->profiling;
     auto mark = [&]() { if (c->profiling) cudaEventRecord(c->ev[evi], st); ++evi; };
+    // LIP_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
+    static const bool debug_sync = getenv("LIP_DEBUG_SYNC") != nullptr;
+    auto check = [&](const char* what) -> int {
+        if (!debug_sync) return LIP_OK;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        return e == cudaSuccess ? LIP_OK : fail(c, LIP_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+#define LIP_CHECK(what) do { int rc_ = check(what); if (rc_) return rc_; } while (0)
     cudaStream_t s_big = serial ? st : c->side[0], s_grid = serial ? st : c->side[2];
     c->ev_valid = false;
     c->fill_done = false;
@@ -251,11 +261,13 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 3 + 1) * 4 + (size_t)c->maxK * 8 * 4;
         landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
         ++launches;
+        LIP_CHECK("landmark_partition_kernel");
     }
     mark();                                                  // 1: after partition
     bool forked_icp = false, forked_grid = false;
     if (stages & ST_ICP) {
         icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
+        LIP_CHECK("icp_schedule_kernel");
         mark();                                              // 2: after schedule
         if (!serial) {
             LIP_CUDA(c, cudaEventRecord(c->ev_fork, st));
@@ -278,6 +290,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
             mark(); mark();
         }
         launches += 3;
+        LIP_CHECK("icp_group_kernel / icp_big_kernel");
     } else { mark(); mark(); mark(); }
     mark();                                                  // 5: after big ICP
     const bool tiles = (stages & ST_BLEND) && c->map_mode == 0;      // final map on landmark-bin tiles: no grid needed
@@ -296,6 +309,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         if (tiles) {
             blend_kernel<<<(a.n_total + 255) / 256, 256, 0, st>>>(a);
             ++launches;
+            LIP_CHECK("blend_kernel");
             const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * c->map_blocks_per_sm);
             blend_tile_kernel<<<(unsigned)gm, LIP_MAP_THREADS, 0, st>>>(a);
         }
@@ -306,6 +320,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
+    LIP_CHECK("final map kernel");
     mark();                                                  // 7: after blend / query
     if ((stages & ST_BLEND) && !tiles && c->n_tiles > 0) {
         int gr = std::max(1, std::min(c->sm_count * 8, (a.n_total + 127) / 128));
