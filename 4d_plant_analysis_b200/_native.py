@@ -46,6 +46,7 @@ SIGNATURES = {
     "lip_set_profiling": (c_int, [c_void_p, c_int]),
     "lip_batch_get_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
     "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
+    "lip_batch_evaluate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, _D, _I64]),
     "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
     "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
     "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
@@ -202,6 +203,21 @@ class Context:
     def run_device(self, xyz1, xyz2, lm1, lm2, T21, T12, stream=0):
         """device addresses in/out, enqueued on `stream` (0 = the context's own stream); no sync."""
         self._check(self.lib.lip_batch_run_device(self.h, xyz1, xyz2, lm1, lm2, T21, T12, stream))
+
+    def evaluate(self, xyz1, xyz2, lm1, lm2, T21, T12=None, voxel_size=1.0, sample_proportion=0.1):
+        """scores (S,3) [continuity, landmark precision, cycle] and the integer counts (S,6) behind them"""
+        xyz1, xyz2, lm1, lm2 = _f64(xyz1), _f64(xyz2), _f64(lm1), _f64(lm2)
+        T21 = _i64(T21)
+        T12 = _i64(T12) if T12 is not None else None
+        if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(lm1) != self.sumK or len(lm2) != self.sumK or len(T21) != self.n2 \
+                or (T12 is not None and len(T12) != self.n1):
+            raise ValueError("array sizes do not match the planned batch")
+        scores, counts = np.empty((self.S, 3)), np.empty((self.S, 6), np.int64)
+        self._check(self.lib.lip_batch_evaluate_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, lm1.ctypes.data, lm2.ctypes.data,
+                                                     T21.ctypes.data, T12.ctypes.data if T12 is not None else None,
+                                                     float(voxel_size), float(sample_proportion), _ptr(scores, c_double),
+                                                     _ptr(counts, c_int64)))
+        return scores, counts
 
     def transforms(self, filled=True):
         K = self.sumK

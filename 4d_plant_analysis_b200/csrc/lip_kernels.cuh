@@ -1503,3 +1503,105 @@ __global__ void triangle_angles_kernel(const double* __restrict__ abc, int n, do
     out[3 * (size_t)i + 1] = acos((sc * sc + sa * sa - sb * sb) / (2 * sa * sc + eps));
     out[3 * (size_t)i + 2] = acos((sa * sa + sb * sb - sc * sc) / (2 * sa * sb + eps));
 }
+
+// =============================================================================================
+// evaluate_p2p_matching (p2p_matching_in_organ/p2p_matching_evaluation.py:8-88) for a batch of segment pairs.
+// All three scores are ratios of integer counts, so the kernels return the counts and the host divides:
+// given equal maps the scores equal the reference's bit for bit.
+//   cnt[6*s + 0..5] = landmark pairs within 2*threshold, landmarks, continuity passes, continuity samples,
+//                     cycle passes, vertices of mesh2
+// =============================================================================================
+// get_mesh_landmarks (landmark_utils.py:5-9): nearest mesh vertex of every skeleton landmark, float64 brute force,
+// one warp per landmark (lowest index on an exact tie).  lm_idx[b] for the unified landmark index b.
+__global__ void __launch_bounds__(128) eval_landmark_nn_kernel(LipArgs a, int* __restrict__ lm_idx) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= a.B) return;
+    const int m = a.bin_mesh[b];
+    const int n = a.mesh_ubase[m + 1] - a.mesh_ubase[m];
+    const double* __restrict__ xyz = mesh_xyz(a, m);
+    const double* lm = mesh_lm(a, m) + 3 * (size_t)(b - a.mesh_bin[m]);
+    const double l0 = lm[0], l1 = lm[1], l2 = lm[2];
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < n; v += 32) {
+        const double d = rdist64(l0, l1, l2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+        if (d < bd) { bd = d; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(LIP_FULL, bd, o);
+        const int oi = __shfl_xor_sync(LIP_FULL, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) lm_idx[b] = bi;
+}
+
+__device__ __forceinline__ double norm3(const double* __restrict__ p, const double* __restrict__ q) {
+    const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+// one CTA per segment pair; T21 / T12 are the caller's maps in batch order (local indices)
+__global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* __restrict__ lm_idx,
+                                                          const long long* __restrict__ T21, const long long* __restrict__ T12,
+                                                          double threshold, int sample_step, long long* __restrict__ cnt) {
+    __shared__ int s_cnt[3];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m1 = s, m2 = a.S + s;
+    const int u1 = a.mesh_ubase[m1], u2 = a.mesh_ubase[m2] - a.n1_total;       // offsets into xyz1 / xyz2 and T12 / T21
+    const int n2 = a.mesh_ubase[m2 + 1] - a.mesh_ubase[m2];
+    const int K = a.mesh_bin[m1 + 1] - a.mesh_bin[m1];
+    const double* __restrict__ v1 = a.xyz1 + 3 * (size_t)u1;
+    const double* __restrict__ v2 = a.xyz2 + 3 * (size_t)u2;
+    const long long* __restrict__ t21 = T21 + u2;
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    // landmark precision (:35-37): |v1[T21[lm2]] - v1[lm1]| < 2 * threshold
+    int c_lm = 0;
+    for (int k = tid; k < K; k += 256) {
+        const int i1 = lm_idx[a.mesh_bin[m1] + k], i2 = lm_idx[a.mesh_bin[m2] + k];
+        if (norm3(v1 + 3 * (size_t)t21[i2], v1 + 3 * (size_t)i1) < 2.0 * threshold) ++c_lm;
+    }
+    // continuity (:41-57): every sample_step-th vertex of mesh2, its two nearest vertices of mesh2 (KDTree k = 2,
+    // the first is the vertex itself), one warp per sample, float64 brute force with (distance, index) order
+    int c_cont = 0, n_samp = 0;
+    for (int i = warp * sample_step; i < n2; i += 8 * sample_step) {
+        const double q0 = v2[3 * (size_t)i], q1 = v2[3 * (size_t)i + 1], q2 = v2[3 * (size_t)i + 2];
+        double d0 = INFINITY, d1 = INFINITY;
+        int i0 = 0x7fffffff, i1 = 0x7fffffff;
+        for (int v = lane; v < n2; v += 32) {
+            const double d = rdist64(q0, q1, q2, v2[3 * (size_t)v], v2[3 * (size_t)v + 1], v2[3 * (size_t)v + 2]);
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = v; }
+            else if (d < d1) { d1 = d; i1 = v; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {                     // merge two sorted pairs, (distance, index) lexicographic
+            const double e0 = __shfl_xor_sync(LIP_FULL, d0, o), e1 = __shfl_xor_sync(LIP_FULL, d1, o);
+            const int j0 = __shfl_xor_sync(LIP_FULL, i0, o), j1 = __shfl_xor_sync(LIP_FULL, i1, o);
+            const bool mine = d0 < e0 || (d0 == e0 && i0 < j0);
+            const double w0 = mine ? d0 : e0, x0 = mine ? e0 : d0, x1 = mine ? d1 : e1;
+            const int wi = mine ? i0 : j0, xi0 = mine ? j0 : i0, xi1 = mine ? i1 : j1;
+            const bool second = x0 < x1 || (x0 == x1 && xi0 < xi1);      // runner-up: loser's best or winner's second
+            d0 = w0; i0 = wi; d1 = second ? x0 : x1; i1 = second ? xi0 : xi1;
+        }
+        if (lane == 0) {
+            ++n_samp;
+            const long long ma = t21[i0], mb = (n2 > 1) ? t21[i1] : ma;
+            if (ma != mb && norm3(v1 + 3 * (size_t)ma, v1 + 3 * (size_t)mb) < threshold) ++c_cont;
+        }
+    }
+    // cycle consistency (:59-68): |v2[T12[T21[i]]] - v2[i]| < threshold
+    int c_cyc = 0;
+    if (T12) {
+        const long long* __restrict__ t12 = T12 + u1;
+        for (int i = tid; i < n2; i += 256)
+            if (norm3(v2 + 3 * (size_t)t12[t21[i]], v2 + 3 * (size_t)i) < threshold) ++c_cyc;
+    }
+    atomicAdd(&s_cnt[0], c_lm); atomicAdd(&s_cnt[1], c_cont); atomicAdd(&s_cnt[2], c_cyc);
+    __syncthreads();
+    if (tid == 0) {
+        long long* c = cnt + 6 * (size_t)s;
+        c[0] = s_cnt[0]; c[1] = K; c[2] = s_cnt[1]; c[3] = (n2 + sample_step - 1) / sample_step; c[4] = s_cnt[2]; c[5] = n2;
+    }
+    (void)n_samp;
+}

@@ -670,6 +670,51 @@ int lip_batch_get_bin_offsets(lip_ctx* c, int32_t* bin_off) {
     return LIP_OK;
 }
 
+int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                            const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
+                            double* scores, int64_t* counts) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
+    if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !scores) return fail(c, LIP_EINVAL, "evaluate: null pointer");
+    if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "evaluate: sample_proportion must be > 0");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24, S = (size_t)c->S;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    const size_t o_cnt = align_up((size_t)c->B * 4);
+    LIP_CUDA(c, c->misc.ensure(o_cnt + S * 48));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, (size_t)c->n2 * 8, cudaMemcpyHostToDevice, st));
+    if (T12) LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, (size_t)c->n1 * 8, cudaMemcpyHostToDevice, st));
+    LipArgs a = c->args;
+    a.xyz1 = c->in_xyz1.as<double>(); a.xyz2 = c->in_xyz2.as<double>();
+    a.lm1 = c->in_lm1.as<double>(); a.lm2 = c->in_lm2.as<double>();
+    int* lm_idx = c->misc.as<int>();
+    long long* cnt = (long long*)(c->misc.as<char>() + o_cnt);
+    const int step = std::max((int)(1.0 / sample_proportion), 1);              // p2p_matching_evaluation.py:40
+    eval_landmark_nn_kernel<<<(c->B + 3) / 4, 128, 0, st>>>(a, lm_idx);
+    eval_scores_kernel<<<(unsigned)S, 256, 0, st>>>(a, lm_idx, c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr,
+                                                   2.0 * voxel_size, step, cnt);
+    LIP_CUDA(c, cudaGetLastError());
+    std::vector<long long> h(S * 6);
+    LIP_CUDA(c, cudaMemcpyAsync(h.data(), cnt, S * 48, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    for (size_t s = 0; s < S; ++s) {
+        const long long* k = &h[6 * s];
+        scores[3 * s] = (double)k[2] / (double)k[3];                            // continuity
+        scores[3 * s + 1] = (double)k[0] / (double)k[1];                        // landmark precision
+        scores[3 * s + 2] = T12 ? (double)k[4] / (double)k[5] : std::numeric_limits<double>::quiet_NaN();   // cycle
+        if (counts) for (int i = 0; i < 6; ++i) counts[6 * s + i] = k[i];
+    }
+    c->last_launches = 2;
+    return LIP_OK;
+}
+
 int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_off, const double* tgt,
                  const int64_t* tgt_off, double* R, double* t, int32_t* iters, int32_t* status) {
     if (!c) return LIP_EINVAL;

@@ -44,6 +44,14 @@ def install(verbose: bool = False):
             done.append((seg.__name__, n))
         seg.my_icp = _reg.my_icp                       # imported by name at p2p_matching_seg_icp.py:24
         done.append((seg.__name__, "my_icp"))
+    ev = _module("p2p_matching_in_organ.p2p_matching_evaluation")
+    if ev is not None:
+        from . import p2p_matching_evaluation as _ev
+        ev.evaluate_p2p_matching = _ev.evaluate_p2p_matching
+        done.append((ev.__name__, "evaluate_p2p_matching"))
+        if seg is not None and hasattr(seg, "evaluate_p2p_matching"):   # imported by name into the driver module
+            seg.evaluate_p2p_matching = _ev.evaluate_p2p_matching
+            done.append((seg.__name__, "evaluate_p2p_matching"))
     if verbose:
         for m, n in done:
             print(f"local_icp_b200: patched {m}.{n}")

@@ -126,6 +126,16 @@ int lip_batch_get_stage_ms(lip_ctx* ctx, float ms[LIP_N_STAGES]);
  * its mesh whose nearest landmark it is number bin_off[b+1] - bin_off[b]. */
 int lip_batch_get_bin_offsets(lip_ctx* ctx, int32_t* bin_off);
 
+/* ---- scores of the maps (the "score outputs" the driver returns, p2p_matching_seg_icp.py:184-189) ----------------
+ * evaluate_p2p_matching (p2p_matching_in_organ/p2p_matching_evaluation.py:8-88, with get_mesh_landmarks of
+ * landmark_utils.py:5-9) for every segment pair of the planned batch and the caller's maps T21 (off2[S]) / T12
+ * (off1[S], may be NULL):  scores (S,3) = continuity, landmark precision, cycle consistency (NaN without T12), each a
+ * ratio of integer counts; counts (S,6), optional = landmark pairs within 2*threshold, landmarks, continuity passes,
+ * continuity samples, cycle passes, vertices of mesh2.  threshold = 2 * voxel_size (:32). */
+int lip_batch_evaluate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                            const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
+                            double* scores, int64_t* counts);
+
 /* ---- the three registration_icp.py functions on their own ----------------------------------- */
 /* my_icp for P independent (src, tgt) problems in CSR form (registration_icp.py:60-98):
  * src (src_off[P],3), tgt (tgt_off[P],3) -> R (P,3,3), t (P,3) with x -> R x + t, iters (P). */

@@ -306,3 +306,23 @@ def test_pipelined_host_path_equals_single_pass(L, monkeypatch):
     for k in ("R21", "t21", "iters21", "status21", "R12", "t12", "iters12", "status12"):
         np.testing.assert_array_equal(res["1"][2][k], res["8"][2][k])
     assert res["1"][3]["small_icps"] + res["1"][3]["big_icps"] == res["8"][3]["small_icps"] + res["8"][3]["big_icps"]
+
+
+@pytest.mark.parametrize("case", ["c1_small", "c3_small", "c5_small"])
+def test_evaluate_p2p_matching_scores_match_reference(L, case):
+    """the score triple of p2p_matching_evaluation.py:8-88 on the reference's own maps (raw and
+    refined), recorded from the unmodified reference by tests/golden/make_golden.py.  Ratios of integer counts: exact."""
+    g = load_golden(case)
+    b = _batch_from_golden(L, g)
+    for maps, key in (((g["T21"], g["T12"]), "score_raw"), ((g["T21r"], g["T12r"]), "score")):
+        scores = L.evaluate_batch(b, maps[0], maps[1], voxel_size=1.0, sample_proportion=0.5)
+        np.testing.assert_allclose(scores, g[key], rtol=0, atol=1e-12)
+    # the drop-in signature, one segment pair, with and without T12 / landmarks
+    s, x1, x2, l1, l2 = next(golden_segments(g))
+    T21, T12 = g["T21"][g["off2"][s]:g["off2"][s + 1]], g["T12"][g["off1"][s]:g["off1"][s + 1]]
+    res = L.evaluate_p2p_matching(_Mesh(x1), _Mesh(x2), l1, l2, T21, T12, sample_proportion=0.5, verbose=False)
+    np.testing.assert_allclose(res, g["score_raw"][s], rtol=0, atol=1e-12)
+    res2 = L.evaluate_p2p_matching(_Mesh(x1), _Mesh(x2), l1, l2, T21, sample_proportion=0.5, verbose=False)
+    assert len(res2) == 2 and res2 == res[:2]
+    res1 = L.evaluate_p2p_matching(_Mesh(x1), _Mesh(x2), np.zeros((0, 3)), np.zeros((0, 3)), T21, T12, sample_proportion=0.5, verbose=False)
+    assert len(res1) == 2 and res1[0] == res[0] and res1[1] == res[2]
