@@ -326,3 +326,45 @@ def test_evaluate_p2p_matching_scores_match_reference(L, case):
     assert len(res2) == 2 and res2 == res[:2]
     res1 = L.evaluate_p2p_matching(_Mesh(x1), _Mesh(x2), np.zeros((0, 3)), np.zeros((0, 3)), T21, T12, sample_proportion=0.5, verbose=False)
     assert len(res1) == 2 and res1[0] == res[0] and res1[1] == res[2]
+
+
+def _tube(rng, n, L, r=1.2, jitter=0.05):
+    s = np.sort(rng.uniform(0, L, n))
+    th = rng.uniform(0, 2 * np.pi, n)
+    rr = r + rng.normal(0, jitter, n)
+    return np.stack([s + rng.normal(0, jitter, n), rr * np.cos(th) + 0.02 * s * s / L, rr * np.sin(th)], 1)
+
+
+@pytest.mark.parametrize("n_src,n_tgt", [(100, 600), (600, 100), (3000, 2500), (40, 2300), (1, 300), (300, 1)])
+def test_my_icp_chunked_target_paths(L, n_src, n_tgt):
+    """targets that stream through the SMEM tile in several chunks (warp kernel: > 256 points, CTA kernel: > 1,024)"""
+    rng = np.random.default_rng(n_src * 7 + n_tgt)
+    tgt = _tube(rng, n_tgt, 30.0) + 50.0
+    c, s_ = np.cos(0.05), np.sin(0.05)
+    Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+    src = (_tube(rng, n_src, 30.0) + 50.0) @ Rz.T + [0.4, -0.3, 0.2]
+    info = {}
+    _, R_ref, t_ref = O.icp(src, tgt, nn="brute", info=info)
+    ctx = L.default_context()
+    R, t, it, st = ctx.icp(src, [0, n_src], tgt, [0, n_tgt])
+    if st[0] == 1:
+        assert it[0] == info["iters"]
+        np.testing.assert_allclose(R[0], R_ref, rtol=0, atol=RT_TOL)
+        np.testing.assert_allclose(t[0], t_ref[:, 0], rtol=0, atol=RT_TOL)
+    else:
+        assert min(n_src, n_tgt) <= 2                         # only degenerate problems may be flagged
+
+
+def test_many_landmarks_segment(L):
+    """a long segment with 150 landmarks: the final map's box pass runs in several batches of 64 bins"""
+    rng = np.random.default_rng(21)
+    Lx, K = 420.0, 150
+    x1 = _tube(rng, 9000, Lx)
+    x2 = _tube(rng, 9400, Lx) * [1.03, 1.0, 1.0] + [0.5, 0.2, -0.1]
+    lm1 = np.stack([np.linspace(1.0, Lx - 1.0, K), np.zeros(K), np.zeros(K)], 1)
+    lm2 = lm1 * [1.03, 1.0, 1.0] + [0.5, 0.2, -0.1]
+    res = L.local_icp_batch([(x1, x2, lm1, lm2)], details=True)
+    for (xt, xs, lt, ls, T) in ((x1, x2, lm1, lm2, res.T21), (x2, x1, lm2, lm1, res.T12)):
+        det = {}
+        T_or = O.segment_map(xt, xs, lt, ls, nn="brute", details=det)
+        _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, "K=150")
