@@ -46,11 +46,12 @@ struct LipArgs {
     int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
     int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
+    float4* bin_tmp;         // [n_total] the same in vertex order inside each bin (scratch of the partition kernel)
     double* bin_xyz;         // [3 * n_total] the same vertices in float64, planes x | y | z in part_vid order
     double* bin_q;           // [3 * n_total] blended positions of the source vertices (blend_kernel), same layout
     int *pos_bin, *pos_nn1;  // [n_total] bin and second-nearest landmark of every slot (bin order)
     double* pos_d;           // [2 * n_total] distances to the nearest / second-nearest landmark, planes, bin order
-    float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, unused
+    float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, sort axis (-1: not sorted)
     MapTile* map_tiles;      // [n_total / LIP_MAP_TILE + B] final-map tiles; count in sched[20]
     double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number
     double* mesh_sum;        // [M*4] sum of the vertices of every mesh (x, y, z) and the vertex count

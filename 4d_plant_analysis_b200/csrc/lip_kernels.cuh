@@ -26,7 +26,7 @@
 //     replaces KDTree(lm).query(xyz, k=2) and the boolean masks NN_skel[:,0]==i
 //     (p2p_matching_in_organ/p2p_matching_seg_icp.py:388-392, 413-414).  One CTA per mesh.
 // =============================================================================================
-__global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
+__global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
     extern __shared__ double smem_d[];
     __shared__ double msum[8][3];
     const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
             for (int w = 0; w < warp; ++w) pos += wcnt[w * K + bin];
             const float fx = (float)(xyz[3 * (size_t)v] - lmS[3 * bin]), fy = (float)(xyz[3 * (size_t)v + 1] - lmS[3 * bin + 1]),
                         fz = (float)(xyz[3 * (size_t)v + 2] - lmS[3 * bin + 2]);
-            a.part_vid[pos] = v;
-            a.bin_pts[pos] = make_float4(fx, fy, fz, __int_as_float(v));
+            a.bin_tmp[pos] = make_float4(fx, fy, fz, __int_as_float(v));
         }
         __syncthreads();
         if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the chunk
@@ -113,36 +112,131 @@ __global__ void __launch_bounds__(256) landmark_partition_kernel(LipArgs a) {
         }
         __syncthreads();
     }
-    // per bin: bounding box of the fp32 offsets and the float64 mean of the vertices, in member order
-    // (the means give my_icp's initial translation, registration_icp.py:70, and the centre of the ICP frame)
+    // per bin (one warp): bounding box of the fp32 offsets, float64 mean of the vertices (in member order: the means
+    // give my_icp's initial translation, registration_icp.py:70, and the centre of the ICP frame), and the FINAL
+    // order of the bin: members sorted along the axis of the box's largest extent (stable counting sort by an
+    // 8-bit key = position along the axis in 1/256 of the extent), so that every search can be restricted to a
+    // window of the list around the query.  Windows are certified from exact per-block bounds, so the order only
+    // has to be approximately monotone; ties are always decided by vertex id.  Bins of up to 256 members (the
+    // usual case) are held in registers across the passes and permuted through SMEM: every global store coalesced.
+    unsigned* skey = (unsigned*)(wcnt + nwarps * K) + warp * 256;                    // 256 bucket counters per warp
+    float4* sdat = (float4*)(((size_t)((unsigned*)(wcnt + nwarps * K) + nwarps * 256) + 15) & ~(size_t)15) + warp * 256;   // the bin in sorted order
+    const size_t N = (size_t)a.n_total;
     for (int i = warp; i < K; i += nwarps) {
-        const int s0 = ub + excl[i], e0 = ub + excl[i + 1];
+        const int s0 = ub + excl[i], e0 = ub + excl[i + 1], nb = e0 - s0;
+        const bool fast = nb <= 256;
+        float4 tt[8];
         float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
         double bx0 = 0, bx1 = 0, bx2 = 0;
-        for (int p = s0 + lane; p < e0; p += 32) {
-            const float4 t = a.bin_pts[p];
-            lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
-            hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
-            const size_t v = (size_t)__float_as_int(t.w), N = (size_t)a.n_total;
-            const double x = xyz[3 * v], y = xyz[3 * v + 1], z = xyz[3 * v + 2];
-            bx0 += x; bx1 += y; bx2 += z;
-            // the bin-ordered float64 copies: coalesced stores here, gathers from what this CTA has just written
-            a.bin_xyz[p] = x; a.bin_xyz[N + p] = y; a.bin_xyz[2 * N + p] = z;
-            a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
-            a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int e = lane + 32 * k; if (e < nb) tt[k] = a.bin_tmp[s0 + e]; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (lane + 32 * k >= nb) continue;
+                const float4 t = tt[k];
+                lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
+                hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
+                const size_t v = (size_t)__float_as_int(t.w);
+                bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
+            }
+        } else {
+            for (int p = s0 + lane; p < e0; p += 32) {
+                const float4 t = a.bin_tmp[p];
+                lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
+                hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
+                const size_t v = (size_t)__float_as_int(t.w);
+                bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
+            }
         }
         lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
         hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
         bx0 = warp_sum(bx0); bx1 = warp_sum(bx1); bx2 = warp_sum(bx2);
+        const float ex0 = hi0 - lo0, ex1 = hi1 - lo1, ex2 = hi2 - lo2;
+        const int axis = (ex0 >= ex1 && ex0 >= ex2) ? 0 : (ex1 >= ex2) ? 1 : 2;
         if (lane == 0) {
             float* bx = a.bin_box + 8 * (size_t)(bb + i);
             bx[0] = lo0; bx[1] = lo1; bx[2] = lo2; bx[3] = hi0; bx[4] = hi1; bx[5] = hi2;
             bx[6] = fmaxf(fmaxf(fmaxf(fabsf(lo0), fabsf(hi0)), fmaxf(fabsf(lo1), fabsf(hi1))), fmaxf(fabsf(lo2), fabsf(hi2)));
-            bx[7] = 0.f;
+            bx[7] = (float)axis;
             double* bs = a.bin_sum + 4 * (size_t)(bb + i);
-            const double cnt = (double)(e0 - s0);
+            const double cnt = (double)nb;
             bs[0] = bx0 / cnt; bs[1] = bx1 / cnt; bs[2] = bx2 / cnt; bs[3] = cnt;     // (NaN for an empty bin: never read)
         }
+        const float alo = axis == 0 ? lo0 : axis == 1 ? lo1 : lo2, aex = axis == 0 ? ex0 : axis == 1 ? ex1 : ex2;
+        const float scale = 255.999f / fmaxf(aex, 1e-30f);
+        auto bucket_of = [&](const float4& t) {
+            const float c = axis == 0 ? t.x : axis == 1 ? t.y : t.z;
+            return (int)fminf(fmaxf((c - alo) * scale, 0.f), 255.f);
+        };
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) skey[lane + 32 * k] = 0u;
+        __syncwarp();
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (lane + 32 * k < nb) atomicAdd(&skey[bucket_of(tt[k])], 1u);
+        } else {
+            for (int e = lane; e < nb; e += 32) atomicAdd(&skey[bucket_of(a.bin_tmp[s0 + e])], 1u);
+        }
+        __syncwarp();
+        {                                                    // exclusive scan of the 256 counts: lane l owns buckets 8l .. 8l+7
+            unsigned c8[8], tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { c8[k] = skey[8 * lane + k]; tot += c8[k]; }
+            unsigned inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
+            unsigned run = inc - tot;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { skey[8 * lane + k] = run; run += c8[k]; }
+        }
+        __syncwarp();
+        // placement, chunk by chunk in member order: rank among the chunk's members of the same bucket + bucket cursor
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (32 * k >= nb) break;                     // uniform
+                const int e = lane + 32 * k;
+                const int bucket = e < nb ? bucket_of(tt[k]) : -1;
+                const unsigned peers = __match_any_sync(LIP_FULL, bucket);
+                const int rk = __popc(peers & ((1u << lane) - 1));
+                if (e < nb) sdat[(int)skey[bucket] + rk] = tt[k];
+                __syncwarp();
+                if (e < nb && rk == 0) skey[bucket] += __popc(peers);
+                __syncwarp();
+            }
+            for (int pr = lane; pr < nb; pr += 32) {         // coalesced stores of everything that is kept in bin order
+                const float4 t = sdat[pr];
+                const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + pr;
+                a.part_vid[p] = (int)v;
+                a.bin_pts[p] = t;
+                a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
+                a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
+                a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
+            }
+        } else {
+            for (int base = 0; base < nb; base += 32) {
+                const int e = base + lane;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                int bucket = -1;
+                if (e < nb) { t = a.bin_tmp[s0 + e]; bucket = bucket_of(t); }
+                const unsigned peers = __match_any_sync(LIP_FULL, bucket);
+                const int rk = __popc(peers & ((1u << lane) - 1));
+                if (e < nb) {
+                    const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + skey[bucket] + rk;
+                    a.part_vid[p] = (int)v;
+                    a.bin_pts[p] = t;
+                    a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
+                    a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
+                    a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
+                }
+                __syncwarp();
+                if (e < nb && rk == 0) skey[bucket] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -400,16 +494,19 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
                 const double p0 = __shfl_sync(LIP_FULL, pq[k][0], src), p1 = __shfl_sync(LIP_FULL, pq[k][1], src),
                              p2 = __shfl_sync(LIP_FULL, pq[k][2], src);
                 double bd = INFINITY;
-                int bj = 0x7fffffff;
+                int bj = 0, bv = 0x7fffffff;                 // position and vertex id: the lowest vertex id wins an exact tie
                 for (int j = tid & 31; j < nt; j += 32) {
                     const double d = rdist64(p0, p1, p2, tx[j] - c0, tx[N + j] - c1, tx[2 * N + j] - c2);
-                    if (d < bd) { bd = d; bj = j; }          // ascending j per lane: the lowest index is kept
+                    if (d <= bd) {
+                        const int vj = a.part_vid[to + j];
+                        if (d < bd || vj < bv) { bd = d; bj = j; bv = vj; }
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const double od = __shfl_xor_sync(LIP_FULL, bd, o);
-                    const int oj = __shfl_xor_sync(LIP_FULL, bj, o);
-                    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                    const int oj = __shfl_xor_sync(LIP_FULL, bj, o), ov = __shfl_xor_sync(LIP_FULL, bv, o);
+                    if (od < bd || (od == bd && ov < bv)) { bd = od; bj = oj; bv = ov; }
                 }
                 if ((tid & 31) == src) idx[k] = bj;
             }

@@ -16,6 +16,7 @@
 #define LIP_ARCH 100
 #endif
 #define LIP_PIPELINE_CHUNKS 8             // sub-batches of the pipelined host path
+#define LIP_PIPELINE_RAMP 1.0
 #define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
 namespace {
@@ -116,7 +117,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
     const size_t o_bxyz = take(n * 24), o_bq = take(n * 24), o_pb = take(n * 4), o_pn = take(n * 4), o_pd = take(n * 16);
-    const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile));
+    const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile)), o_btmp = take(n * 16);
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
     LipArgs& a = c->args;
@@ -132,7 +133,7 @@ int carve_workspace(lip_ctx* c) {
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
     a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
-    a.map_tiles = (MapTile*)(base + o_mt);
+    a.map_tiles = (MapTile*)(base + o_mt); a.bin_tmp = (float4*)(base + o_btmp);
     a.bin_xyz = (double*)(base + o_bxyz); a.bin_q = (double*)(base + o_bq);
     a.pos_bin = (int*)(base + o_pb); a.pos_nn1 = (int*)(base + o_pn); a.pos_d = (double*)(base + o_pd);
     return LIP_OK;
@@ -258,7 +259,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
     if (stages & ST_PARTITION) {
-        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 3 + 1) * 4 + (size_t)c->maxK * 8 * 4;
+        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 3 + 1) * 4 + (size_t)c->maxK * 8 * 4 + 8 * 256 * 4 + 8 * 256 * 16 + 16;
         landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
         ++launches;
         LIP_CHECK("landmark_partition_kernel");
@@ -417,7 +418,7 @@ int lip_create(lip_ctx** out, int device) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
     cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         LIP_MAX_LANDMARKS * 68 + 64);
+                         LIP_MAX_LANDMARKS * 68 + 64 + 8 * 256 * 4 + 8 * 256 * 16 + 16);
     memset(&c->args, 0, sizeof(c->args));
     *out = c;
     return LIP_OK;
@@ -466,11 +467,15 @@ static int plan_kids(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* 
     const int64_t n = off1[S] + off2[S];
     int chunks = LIP_PIPELINE_CHUNKS;
     if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    // sub-batch sizes grow like (k / chunks)^ramp: a small first sub-batch starts the kernels early, large later ones
+    // keep them efficient
+    double ramp = LIP_PIPELINE_RAMP;
+    if (const char* e = getenv("LIP_PIPELINE_RAMP")) ramp = std::max(1.0, std::min(4.0, atof(e)));
     int want = (int)std::min<int64_t>(chunks, S);
     if (n < LIP_PIPELINE_MIN_VERTICES || want < 2) return LIP_OK;
     c->kid_seg.assign(1, 0);
     for (int k = 1; k < want; ++k) {                         // cut where the running vertex count passes k/want of the total
-        const int64_t target = n * k / want;
+        const int64_t target = (int64_t)((double)n * std::pow((double)k / want, ramp));
         int64_t s = c->kid_seg.back() + 1;
         while (s < S && off1[s] + off2[s] < target) ++s;
         if (s >= S) break;
