@@ -43,6 +43,7 @@ SIGNATURES = {
     "lip_batch_get_transforms": (c_int, [c_void_p, c_int, _D, _D, _I32, _I32, _D, _D, _I32, _I32]),
     "lip_batch_get_landmark_nn": (c_int, [c_void_p, c_int, _I32, _D]),
     "lip_batch_get_counters": (c_int, [c_void_p, _I64]),
+    "lip_batch_get_pair_counts": (c_int, [c_void_p, _I64]),
     "lip_set_profiling": (c_int, [c_void_p, c_int]),
     "lip_batch_get_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
     "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
@@ -244,6 +245,11 @@ class Context:
 
     STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_group_kernel", "unused",
               "icp_big_kernel", "grid_build_kernel", "final_map_kernel", "retry_nn_kernel", "far_nn_kernel")
+
+    def pair_counts(self):
+        c = np.zeros(3, np.int64)
+        self._check(self.lib.lip_batch_get_pair_counts(self.h, _ptr(c, c_int64)))
+        return dict(icp_group_kernel=int(c[0]), icp_big_kernel=int(c[1]), final_map_kernel=int(c[2]))
 
     def set_profiling(self, on=True):
         self._check(self.lib.lip_set_profiling(self.h, int(bool(on))))

@@ -453,6 +453,7 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
     const float sc = DOT ? -2.0f : 1.0f;
     const bool one_chunk = nt <= CHUNK;
     if (one_chunk) { coop_sync<NT>(); icp_stage<DOT, NT>(a, tf, to, 0, nt, tid, sh0, sh1, sh2); coop_sync<NT>(); }
+    unsigned long long scanned = 0;
     for (int q0 = 0; q0 < ns; q0 += 2 * NT) {
         const bool two = ns - q0 > NT;                       // uniform
         const int qi[2] = {q0 + tid, q0 + tid + NT};
@@ -475,6 +476,7 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
             else tile_scan<1, DOT>(tf, npad, m, best, sec, blk);
             if (best[0] < prev0) idx[0] = t0 + tile_recover<DOT>(tf, blk[0], best[0], m[0], sec_in[0]);
             if (best[1] < prev1) idx[1] = t0 + tile_recover<DOT>(tf, blk[1], best[1], m[1], sec_in[1]);
+            scanned += (unsigned long long)npad * (two ? 64 : 32);
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -513,6 +515,7 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
             if (qi[k] < ns) nn_idx[qi[k]] = idx[k];
         }
     }
+    if (a.profile && (tid & 31) == 0) atomicAdd(&a.counters[NT == 32 ? 4 : 5], scanned);   // candidate pairs evaluated (incl. padding)
     // ---- sums of get_best_fit_transform + cost over the (source, winner) pairs, float64 ----
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = 0.0;

@@ -646,6 +646,26 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     return LIP_OK;
 }
 
+int lip_batch_get_pair_counts(lip_ctx* c, int64_t pairs[3]) {
+    if (!c || !c->planned || !pairs) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    cudaSetDevice(c->device);
+    pairs[0] = pairs[1] = pairs[2] = 0;
+    if (c->last_run_split) {
+        for (int k = 0; k < c->n_kids; ++k) {
+            int64_t part[3];
+            int rc = lip_batch_get_pair_counts(c->kids[k], part);
+            if (rc) return fail(c, rc, c->kids[k]->err);
+            for (int i = 0; i < 3; ++i) pairs[i] += part[i];
+        }
+        return LIP_OK;
+    }
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    unsigned long long h[8];
+    LIP_CUDA(c, cudaMemcpy(h, c->args.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    pairs[0] = (int64_t)h[4]; pairs[1] = (int64_t)h[5]; pairs[2] = (int64_t)h[7];
+    return LIP_OK;
+}
+
 int lip_set_profiling(lip_ctx* c, int on) {
     if (!c) return LIP_EINVAL;
     cudaSetDevice(c->device);

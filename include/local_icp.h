@@ -113,6 +113,10 @@ int lip_batch_get_landmark_nn(lip_ctx* ctx, int side, int32_t* nn, double* dist)
  * ring 1 of the final map (only counted while profiling is on) */
 int lip_batch_get_counters(lip_ctx* ctx, int64_t counters[8]);
 
+/* (source, candidate) pairs actually evaluated by the last run — the work figure of the FP32 roofline (8 flop per
+ * pair): [0] icp_group_kernel, [1] icp_big_kernel, [2] final map.  Counted only while profiling is on. */
+int lip_batch_get_pair_counts(lip_ctx* ctx, int64_t pairs[3]);
+
 /* Per-kernel device times of the last run, measured with CUDA events on the stream the kernels were
  * launched on.  Enable with lip_set_profiling before the run; while it is on, the kernels run back to
  * back on one stream (normally the ICP kernels and the grid build run as concurrent branches).
