@@ -4,15 +4,17 @@
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
-A step = one pass of the whole hot path (landmark partition, all partition ICPs, hashed grid, fill,
-blend + final map, both directions) over one batch: F maize-sized frame pairs (BASELINE configs[1]:
-~50k points per frame, 12 long ribbon segments each).  F = 64 by default so that the float64 inputs
-(~150 MB) exceed the 126 MB L2 and successive steps cannot reuse them from cache.
+A step = one pass of the whole hot path (landmark partition + bin sort, all partition ICPs, fill, blend, final
+map, both directions) over one batch: F maize-sized frame pairs (BASELINE configs[1]: ~50k points per frame,
+12 long ribbon segments each).  F = 64 by default so that the float64 inputs (~150 MB) exceed the 126 MB L2 and
+successive steps cannot reuse them from cache.
 
-`value`   device-resident throughput: inputs already in HBM, CUDA events on the launching stream.
-`e2e`     the same metric through the C-ABI call with HOST buffers (pinned), H2D and D2H inside.
-`roofline` the dominant kernel against the FP32 pipe (NN kernels are FP32-bound, 8 flop
-          per evaluated source/candidate pair); `roofline_hbm` the whole step against measured HBM.
+`value`    device-resident throughput: inputs already in HBM, CUDA events on the launching stream.
+`e2e`      the same metric through the C-ABI call with HOST buffers (pinned): H2D, kernels and D2H inside, pipelined
+           over 8 sub-batches by liblocalicp.
+`roofline` the dominant kernel against the FP32 pipe (NN kernels are FP32-bound, 8 flop per
+           evaluated source/candidate pair; `traffic` = its DRAM bytes per launch from the committed ncu capture);
+           `roofline_hbm` the whole step against measured HBM with the algorithmic bytes of SURVEY.md section 8d.
 Under torchrun every rank runs its own F frame pairs (weak scaling, no data-path collective).
 """
 import argparse
@@ -315,8 +317,18 @@ def run_b200(args):
     dom = max(pairs, key=lambda k: stage[k])
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12       # TFLOP/s, FP32 FMA pipe at the max SM clock
     achieved = 8.0 * pairs[dom] / (stage[dom] / 1e3) / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath) and args.config == 2 and args.frame_pairs == 64:       # captured on the default workload only
+        tj = json.load(open(tpath))
+        kmap = {"final_map_kernel": ("blend_kernel", "blend_tile_kernel")}
+        names = kmap.get(dom, (dom,))
+        if all(n in tj["kernels"] for n in names):
+            traffic = sum(tj["kernels"][n]["dram_bytes_per_launch"] for n in names)
+            traffic_src = "profiles/" + tj["source"].replace("prof_r1d", "r1d_step_kernels")
     roof = {"kernel": dom, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp32_peak, "traffic": None, "kernel_ms": stage[dom],
+            "frac": achieved / fp32_peak, "traffic": traffic, "traffic_unit": "dram bytes per launch (ncu --set full)",
+            "traffic_source": traffic_src, "kernel_ms": stage[dom],
             "pairs_per_launch": pairs[dom], "flop_per_pair": 8, "brute_force_pairs": brute,
             "peak_source": f"148 SM x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz ({peak_src})",
             "per_kernel": {k: {"ms": stage[k], "tflops": 8.0 * pairs[k] / (stage[k] / 1e3) / 1e12 if stage[k] > 0 else 0.0,
