@@ -368,3 +368,50 @@ def test_many_landmarks_segment(L):
         det = {}
         T_or = O.segment_map(xt, xs, lt, ls, nn="brute", details=det)
         _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, "K=150")
+
+
+def test_fuzz_small_random_segments(L):
+    """300 random small segment pairs in one batch (1..60 points, K = 1..6, clustered / duplicated / collinear points,
+    vertices sitting exactly on landmarks): the batch must run, and every segment whose ICPs are all non-degenerate
+    must reproduce the oracle's map up to exact ties."""
+    rng = np.random.default_rng(2024)
+    segs = []
+    for i in range(300):
+        n1, n2, K = int(rng.integers(1, 61)), int(rng.integers(1, 61)), int(rng.integers(1, 7))
+        Lx = 3.0 * K
+        lm = np.stack([np.linspace(0.5, Lx - 0.5, K) if K > 1 else np.array([Lx / 2]), np.zeros(K), np.zeros(K)], 1)
+        mk = lambda n: np.stack([rng.uniform(0, Lx, n), rng.normal(0, 0.8, n), rng.normal(0, 0.8, n)], 1)
+        x1, x2 = mk(n1), mk(n2)
+        kind = i % 6
+        if kind == 1 and n1 > 3:
+            x1[1] = x1[0]; x1[3] = x1[0]                       # duplicated target points
+        if kind == 2:
+            x2[:, 1:] = 0.0                                    # collinear source, on the landmark polyline
+        if kind == 3 and n2 > 2:
+            x2[0] = lm[0]; x2[-1] = lm[-1]                     # vertices exactly on landmarks
+        if kind == 4:
+            x1 = np.round(x1 * 2) / 2; x2 = np.round(x2 * 2) / 2   # lattice points: many exact distance ties
+        off = rng.uniform(-80, 80, 3)
+        segs.append((x1 + off, x2 + off + rng.normal(0, 0.2, 3), lm + off, lm + off))
+    res = L.local_icp_batch(segs, details=True)
+    raw = res.transforms["raw"]
+    n_checked = n_iter_diff = 0
+    for s, (x1, x2, l1, l2) in enumerate(segs):
+        e, f = res.lm_off[s], res.lm_off[s + 1]
+        T21, T12 = res.maps(s)
+        assert T21.min() >= 0 and T21.max() < len(x1) and T12.min() >= 0 and T12.max() < len(x2)
+        for (xt, xs, lt, ls, T, d) in ((x1, x2, l1, l2, T21, "21"), (x2, x1, l2, l1, T12, "12")):
+            st = raw["status" + d][e:f]
+            if not (st == 1).all():
+                continue                                        # a rank-deficient solve or an empty partition: R is not unique
+            det = {}
+            try:
+                T_or = O.segment_map(xt, xs, lt, ls, nn="brute", details=det)
+            except Exception:
+                continue
+            if not np.array_equal(det["iters"][det["valid"]], raw["iters" + d][e:f][det["valid"]]):
+                n_iter_diff += 1                                # a stop decision exactly on a threshold
+                continue
+            _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, f"fuzz seg {s} T{d}")
+            n_checked += 1
+    assert n_checked > 150 and n_iter_diff <= 0.02 * n_checked, (n_checked, n_iter_diff)
