@@ -8,12 +8,14 @@ Reference-shaped API (same names and signatures as the reference's functions):
     my_icp, get_best_fit_transform, get_NN_in_target                 (registration/registration_icp.py)
     get_triangle_angles, get_p2p_mapping_from_segments_using_icp     (p2p_matching_in_organ/p2p_matching_seg_icp.py)
     evaluate_p2p_matching                                            (p2p_matching_in_organ/p2p_matching_evaluation.py)
-Batched API: local_icp_batch, evaluate_batch.  Wiring into a reference checkout: install().
+    double_direction_refinement                                      (p2p_matching_in_organ/p2p_matching_fm.py)
+Batched API: local_icp_batch, refine_batch, evaluate_batch.  Wiring into a reference checkout: install().
 """
 from ._native import DIR_BOTH, DIR_T12, DIR_T21, Context, NativeError, build, default_context, load  # noqa: F401
 from .batch import LocalICPResult, local_icp_batch  # noqa: F401
 from .install import install  # noqa: F401
 from .p2p_matching_evaluation import evaluate_batch, evaluate_p2p_matching  # noqa: F401
+from .p2p_matching_fm import double_direction_refinement, refine_batch  # noqa: F401
 from .p2p_matching_seg_icp import get_p2p_mapping_from_segments_using_icp, get_triangle_angles  # noqa: F401
 from .registration_icp import get_best_fit_transform, get_NN_in_target, my_icp  # noqa: F401
 from .synthetic import SegmentPairBatch, batch_from_segments, make_config  # noqa: F401

@@ -48,6 +48,7 @@ SIGNATURES = {
     "lip_batch_get_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
     "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
     "lip_batch_evaluate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, _D, _I64]),
+    "lip_batch_refine_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
     "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
     "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
@@ -219,6 +220,16 @@ class Context:
                                                      float(voxel_size), float(sample_proportion), _ptr(scores, c_double),
                                                      _ptr(counts, c_int64)))
         return scores, counts
+
+    def refine(self, xyz1, xyz2, T21, T12):
+        """double_direction_refinement of the planned batch: returns the refined copy of T21 (int64)"""
+        xyz1, xyz2 = _f64(xyz1), _f64(xyz2)
+        out = np.array(T21, dtype=np.int64, copy=True)
+        T12 = _i64(T12)
+        if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(out) != self.n2 or len(T12) != self.n1:
+            raise ValueError("array sizes do not match the planned batch")
+        self._check(self.lib.lip_batch_refine_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, out.ctypes.data, T12.ctypes.data))
+        return out
 
     def transforms(self, filled=True):
         K = self.sumK

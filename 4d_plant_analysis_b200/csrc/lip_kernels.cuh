@@ -1705,3 +1705,156 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
     }
     (void)n_samp;
 }
+
+// =============================================================================================
+// double_direction_refinement (p2p_matching_in_organ/p2p_matching_fm.py:75-132) for a batch of
+// segment pairs.  The reference rewrites T21 in place while it iterates (np.unique / np.where are re-evaluated
+// inside the loops), so the result depends on the visiting order: the kernel keeps that order — one warp per
+// segment pair, lane 0 walking the targets in ascending order over inverse-index lists held in SMEM.
+// =============================================================================================
+// KDTree(vertices1).query(vertices1, k=5) (:78-79): for every vertex of mesh1 its five nearest vertices of mesh1 in
+// (distance, index) order; entries 1..4 (the reference's NN_mesh1[t, 1:]) are stored.  float64 brute force, one warp
+// per query.  nn4[4*u + k] = local index, or -1 when the mesh has fewer points.
+__global__ void __launch_bounds__(256) knn5_self_kernel(LipArgs a, int* __restrict__ nn4) {
+    const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const double* __restrict__ xyz = a.xyz1 + 3 * (size_t)ub;
+    for (int q = blockIdx.y * 8 + warp; q < n; q += 8 * gridDim.y) {
+        const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
+        double d[5];
+        int id[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { d[k] = INFINITY; id[k] = 0x7fffffff; }
+        for (int v = lane; v < n; v += 32) {                 // ascending v per lane: an equal distance never displaces an earlier index
+            const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+            if (dn < d[4]) {
+                d[4] = dn; id[4] = v;
+#pragma unroll
+                for (int k = 4; k > 0; --k)
+                    if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+            }
+        }
+        int out = -1;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {                        // five rounds of a warp-wide argmin over the lanes' list heads
+            double bd = d[0];
+            int bi = id[0], bl = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(LIP_FULL, bd, o);
+                const int oi = __shfl_xor_sync(LIP_FULL, bi, o), ol = __shfl_xor_sync(LIP_FULL, bl, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bl = ol; }
+            }
+            if (lane == bl) {                                // the winner pops its head
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { d[k] = d[k + 1]; id[k] = id[k + 1]; }
+                d[4] = INFINITY; id[4] = 0x7fffffff;
+            }
+            if (r >= 1 && lane == r - 1) out = (bd < INFINITY) ? bi : -1;
+        }
+        if (lane < 4) nn4[4 * (size_t)(ub + q) + lane] = out;
+    }
+}
+
+struct RefineView {                                          // per-segment tables (SMEM when they fit, global scratch otherwise)
+    int *t21, *next21, *head21, *head12, *next12, *t12;
+    double* v2;                                              // 3 * n2, interleaved
+};
+__device__ __forceinline__ double refine_norm(const double* __restrict__ p, const double* __restrict__ q) {
+    const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+// the source of target t to keep: smallest |v2[ind] - v2[T12[t]]|, first on ties (:88-96, :113-121)
+__device__ __forceinline__ int refine_keep(const RefineView& w, int t) {
+    const double* ref = w.v2 + 3 * (size_t)w.t12[t];
+    double best = 10000.0;
+    int keep = w.head21[t];
+    for (int ind = w.head21[t]; ind >= 0; ind = w.next21[ind]) {
+        const double d = refine_norm(w.v2 + 3 * (size_t)ind, ref);
+        if (d < best) { best = d; keep = ind; }
+    }
+    return keep;
+}
+// move source ind from the list of t_from to its place (ascending) in the list of t_to
+__device__ __forceinline__ void refine_move(const RefineView& w, int ind, int t_from, int t_to) {
+    int* link = &w.head21[t_from];
+    while (*link != ind) link = &w.next21[*link];
+    *link = w.next21[ind];
+    link = &w.head21[t_to];
+    while (*link >= 0 && *link < ind) link = &w.next21[*link];
+    w.next21[ind] = *link;
+    *link = ind;
+    w.t21[ind] = t_to;
+}
+
+__global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn4, long long* __restrict__ T21,
+                                                    const long long* __restrict__ T12, int* __restrict__ scratch, int smem_ints_cap) {
+    extern __shared__ double smem_ref[];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
+    const int u2g = a.mesh_ubase[a.S + s], n2 = a.mesh_ubase[a.S + s + 1] - u2g, u2 = u2g - a.n1_total;
+    long long* __restrict__ t21g = T21 + u2;
+    const long long* __restrict__ t12g = T12 + u1;
+    const double* __restrict__ v2g = a.xyz2 + 3 * (size_t)u2;
+    const int* __restrict__ nn = nn4 + 4 * (size_t)u1;
+    // tables: 3 n2 + 3 n1 ints (+ n1 snapshot flags packed into the sign... kept as a separate n1 ints) and 3 n2 doubles
+    const size_t need_ints = 3 * (size_t)n2 + 4 * (size_t)n1;
+    const bool in_smem = (size_t)6 * n2 + need_ints <= (size_t)smem_ints_cap;       // doubles count as two ints
+    RefineView w;
+    int* base;
+    if (in_smem) { w.v2 = smem_ref; base = (int*)(smem_ref + 3 * (size_t)n2); }
+    else { w.v2 = const_cast<double*>(v2g); base = scratch + 3 * (size_t)u2 + 4 * (size_t)u1; }      // too large for SMEM: global tables
+    w.t21 = base; w.next21 = base + n2; w.head12 = base + 2 * n2;
+    w.head21 = base + 3 * n2; w.next12 = w.head21 + n1; w.t12 = w.next12 + n1;
+    int* snap = w.t12 + n1;
+    for (int i = lane; i < n2; i += 32) {
+        w.t21[i] = (int)t21g[i]; w.head12[i] = -1;
+        if (in_smem) {
+            w.v2[3 * (size_t)i] = v2g[3 * (size_t)i]; w.v2[3 * (size_t)i + 1] = v2g[3 * (size_t)i + 1]; w.v2[3 * (size_t)i + 2] = v2g[3 * (size_t)i + 2];
+        }
+    }
+    for (int t = lane; t < n1; t += 32) { w.head21[t] = -1; w.t12[t] = (int)t12g[t]; }
+    __syncwarp();
+    if (lane == 0) {
+        // inverse lists, ascending: np.where(T21 == t)[0] and np.where(T12 == ind)[0]
+        for (int i = n2 - 1; i >= 0; --i) { const int t = w.t21[i]; w.next21[i] = w.head21[t]; w.head21[t] = i; }
+        for (int t = n1 - 1; t >= 0; --t) { const int i = w.t12[t]; w.next12[t] = w.head12[i]; w.head12[i] = t; }
+        for (int t = 0; t < n1; ++t) snap[t] = w.head21[t] >= 0;                  // np.unique(T21), taken once (:85)
+        for (int t = 0; t < n1; ++t) {
+            if (!snap[t] || w.head21[t] < 0 || w.next21[w.head21[t]] < 0) continue;   // a single source: nothing to do
+            const int keep = refine_keep(w, t);
+            int ind = w.head21[t];
+            while (ind >= 0) {
+                const int nxt = w.next21[ind];               // the reference iterates over the list as it was
+                if (ind != keep) {
+                    int t_keep = -1;
+                    if (w.head12[ind] >= 0) {                // targets whose T12 points at this source (:100-101)
+                        t_keep = w.head12[ind];
+                        for (int c = w.head12[ind]; c >= 0; c = w.next12[c]) if (w.head21[c] < 0) t_keep = c;
+                    } else {                                 // the four nearest neighbours of the target (:102-103)
+                        t_keep = nn[4 * (size_t)t];
+                        for (int k = 0; k < 4; ++k) { const int c = nn[4 * (size_t)t + k]; if (c >= 0 && w.head21[c] < 0) t_keep = c; }
+                    }
+                    if (t_keep >= 0 && t_keep != t) refine_move(w, ind, t, t_keep);
+                }
+                ind = nxt;
+            }
+        }
+        for (int t = 0; t < n1; ++t) {                       // targets nobody maps to take sources from their neighbours (:111-130)
+            if (w.head21[t] >= 0) continue;
+            for (int k = 0; k < 4; ++k) {
+                const int nb = nn[4 * (size_t)t + k];
+                if (nb < 0 || w.head21[nb] < 0 || nb == t) continue;
+                const int keep = refine_keep(w, nb);
+                int ind = w.head21[nb];
+                while (ind >= 0) {
+                    const int nxt = w.next21[ind];
+                    if (ind != keep) refine_move(w, ind, nb, t);
+                    ind = nxt;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < n2; i += 32) t21g[i] = w.t21[i];
+}

@@ -740,6 +740,56 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
     return LIP_OK;
 }
 
+int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "refine: no batch planned");
+    if (!xyz1 || !xyz2 || !T21 || !T12) return fail(c, LIP_EINVAL, "refine: null pointer");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
+    for (size_t i = 0; i < n2; ++i) {                         // the maps are used as indices on the device: validate them here
+        // (segment of entry i is found lazily below; a cheap global bound first)
+        if (T21[i] < 0) return fail(c, LIP_EINVAL, "refine: negative entry in T21");
+    }
+    size_t max_ints = 0;
+    for (size_t s = 0; s < S; ++s) {
+        const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
+        for (int64_t i = c->h_off2[s]; i < c->h_off2[s + 1]; ++i)
+            if (T21[i] >= a1) return fail(c, LIP_EINVAL, "refine: T21 entry out of range for its segment pair");
+        for (int64_t i = c->h_off1[s]; i < c->h_off1[s + 1]; ++i)
+            if (T12[i] < 0 || T12[i] >= a2) return fail(c, LIP_EINVAL, "refine: T12 entry out of range for its segment pair");
+        max_ints = std::max(max_ints, (size_t)(9 * a2 + 4 * a1));      // 3 n2 doubles + 3 n2 + 4 n1 ints
+    }
+    int smem_cap = 0;
+    LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    smem_cap -= 1024;
+    const size_t smem = std::min<size_t>((size_t)smem_cap, max_ints * 4 + 16);
+    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LIP_CUDA(c, c->in_xyz1.ensure(n1 * 24)); LIP_CUDA(c, c->in_xyz2.ensure(n2 * 24));
+    LIP_CUDA(c, c->out_T21.ensure(n2 * 8)); LIP_CUDA(c, c->out_T12.ensure(n1 * 8));
+    const size_t o_scratch = align_up(n1 * 16);
+    const bool need_scratch = max_ints * 4 + 16 > smem;
+    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * 4 : 16)));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, n1 * 24, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, n2 * 24, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, n2 * 8, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, n1 * 8, cudaMemcpyHostToDevice, st));
+    LipArgs a = c->args;
+    a.xyz1 = c->in_xyz1.as<double>(); a.xyz2 = c->in_xyz2.as<double>();
+    int* nn4 = c->misc.as<int>();
+    int* scratch = (int*)(c->misc.as<char>() + o_scratch);
+    int64_t max_n1 = 0;
+    for (size_t s = 0; s < S; ++s) max_n1 = std::max<int64_t>(max_n1, c->h_off1[s + 1] - c->h_off1[s]);
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(1024, (max_n1 + 63) / 64));
+    knn5_self_kernel<<<dim3((unsigned)S, gy), 256, 0, st>>>(a, nn4);
+    refine_kernel<<<(unsigned)S, 32, smem, st>>>(a, nn4, c->out_T21.as<long long>(), c->out_T12.as<long long>(), scratch, (int)(smem / 4));
+    LIP_CUDA(c, cudaGetLastError());
+    LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, n2 * 8, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    c->last_launches = 2;
+    return LIP_OK;
+}
+
 int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_off, const double* tgt,
                  const int64_t* tgt_off, double* R, double* t, int32_t* iters, int32_t* status) {
     if (!c) return LIP_EINVAL;

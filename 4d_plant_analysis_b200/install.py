@@ -52,6 +52,14 @@ def install(verbose: bool = False):
         if seg is not None and hasattr(seg, "evaluate_p2p_matching"):   # imported by name into the driver module
             seg.evaluate_p2p_matching = _ev.evaluate_p2p_matching
             done.append((seg.__name__, "evaluate_p2p_matching"))
+    fm = _module("p2p_matching_in_organ.p2p_matching_fm")
+    if fm is not None:
+        from . import p2p_matching_fm as _fm
+        fm.double_direction_refinement = _fm.double_direction_refinement
+        done.append((fm.__name__, "double_direction_refinement"))
+        if seg is not None and hasattr(seg, "double_direction_refinement"):   # imported by name into the driver module
+            seg.double_direction_refinement = _fm.double_direction_refinement
+            done.append((seg.__name__, "double_direction_refinement"))
     if verbose:
         for m, n in done:
             print(f"local_icp_b200: patched {m}.{n}")

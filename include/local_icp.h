@@ -140,6 +140,13 @@ int lip_batch_evaluate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2
                             const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
                             double* scores, int64_t* counts);
 
+/* double_direction_refinement (p2p_matching_in_organ/p2p_matching_fm.py:75-132, called right after the hot path at
+ * p2p_matching_seg_icp.py:181-182) for every segment pair of the planned batch: T21 (off2[S]) is refined IN PLACE with
+ * the reference's visiting order (it makes the map closer to injective using the cycle error |v2[i] - v2[T12[T21[i]]]|
+ * and the 4 nearest neighbours of each target); T12 (off1[S]) is read only, as in the reference.  Every mesh1 needs at
+ * least 5 vertices (KDTree.query(k=5), :79). */
+int lip_batch_refine_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12);
+
 /* ---- the three registration_icp.py functions on their own ----------------------------------- */
 /* my_icp for P independent (src, tgt) problems in CSR form (registration_icp.py:60-98):
  * src (src_off[P],3), tgt (tgt_off[P],3) -> R (P,3,3), t (P,3) with x -> R x + t, iters (P). */

@@ -247,3 +247,67 @@ def segment_pair_maps(xyz1, xyz2, lm1, lm2, nn="kdtree", loop=False):
     T21 = segment_map(xyz1, xyz2, lm1, lm2, nn, loop)
     T12 = segment_map(xyz2, xyz1, lm2, lm1, nn, loop)
     return T21, T12
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processing of the dense maps: p2p_matching_fm.py:75-132
+# ------------------------------------------------------------------------------------------------
+def double_direction_refinement(xyz1, xyz2, T21, T12, nn="kdtree"):
+    """p2p_matching_in_organ/p2p_matching_fm.py:75-132, restated with inverse-index tables instead of the
+    reference's np.unique / np.where inside the loops (same visiting order, same in-place semantics).
+    Returns the refined copy of T21 (T12 is not modified by the reference either)."""
+    v2 = np.asarray(xyz2, np.float64)
+    T21 = np.array(T21, np.int64)
+    T12 = np.asarray(T12, np.int64)
+    n1, n2 = len(xyz1), len(T21)
+    _, nn5 = knn(xyz1, xyz1, min(5, n1), nn)                      # :78-79 (row = [self, 4 nearest])
+    # sources of every target, ascending (what np.where(T21 == t)[0] returns), as sorted python lists
+    src_of = [[] for _ in range(n1)]
+    for i in range(n2):
+        src_of[T21[i]].append(i)
+    tgt_of = [[] for _ in range(n2)]                              # np.where(T12 == ind)[0]
+    for t in range(n1):
+        tgt_of[T12[t]].append(t)
+
+    def keep_of(t):                                               # :88-96 / :113-121: smallest cycle error, first on ties
+        best, keep = 10 ** 4, src_of[t][0]
+        ref = v2[T12[t]]
+        for ind in src_of[t]:
+            d = np.linalg.norm(v2[ind] - ref)
+            if d < best:
+                best, keep = d, ind
+        return keep
+
+    def move(ind, t_from, t_to):
+        src_of[t_from].remove(ind)
+        lst = src_of[t_to]
+        k = 0
+        while k < len(lst) and lst[k] < ind:
+            k += 1
+        lst.insert(k, ind)
+        T21[ind] = t_to
+
+    for t in [t for t in range(n1) if src_of[t]]:                 # np.unique(T21) taken once, :85
+        if len(src_of[t]) == 1:
+            continue
+        keep = keep_of(t)
+        for ind in list(src_of[t]):
+            if ind == keep:
+                continue
+            cand = tgt_of[ind] if tgt_of[ind] else list(nn5[t, 1:])   # :100-103
+            t_keep = cand[0]
+            for c in cand:                                        # the LAST candidate no source maps to, :105-107
+                if not src_of[c]:
+                    t_keep = c
+            move(ind, t, t_keep)
+    for t in range(n1):                                           # :111-130
+        if src_of[t]:
+            continue
+        for nb in nn5[t, 1:]:
+            if not src_of[nb]:
+                continue
+            keep = keep_of(nb)
+            for ind in list(src_of[nb]):
+                if ind != keep:
+                    move(ind, nb, t)
+    return T21

@@ -415,3 +415,35 @@ def test_fuzz_small_random_segments(L):
             _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, f"fuzz seg {s} T{d}")
             n_checked += 1
     assert n_checked > 150 and n_iter_diff <= 0.02 * n_checked, (n_checked, n_iter_diff)
+
+
+@pytest.mark.parametrize("case", ["c1_small", "c3_small", "c5_small"])
+def test_double_direction_refinement_matches_reference(L, case):
+    """p2p_matching_fm.py:75-132 on the reference's own raw maps against the refined maps the
+    unmodified reference produced (tests/golden/make_golden.py).  Integer work: bit-exact."""
+    g = load_golden(case)
+    b = _batch_from_golden(L, g)
+    T21r = L.refine_batch(b, g["T21"], g["T12"])
+    np.testing.assert_array_equal(T21r, g["T21r"])
+    # drop-in signature: in-place on the caller's array, (T21, T12) returned
+    s, x1, x2, l1, l2 = next(golden_segments(g))
+    a, bb_, c, d = g["off1"][s], g["off1"][s + 1], g["off2"][s], g["off2"][s + 1]
+    T21, T12 = g["T21"][c:d].copy(), g["T12"][a:bb_].copy()
+    r21, r12 = L.double_direction_refinement(_Mesh(x1), _Mesh(x2), T21, T12, None, None)
+    assert r21 is T21 and r12 is T12
+    np.testing.assert_array_equal(T21, g["T21r"][c:d])
+    np.testing.assert_array_equal(T12, g["T12r"][a:bb_])
+
+
+def test_refinement_full_pipeline_matches_oracle(L):
+    """hot path -> refinement -> evaluation on the GPU against the same chain of the oracle (maize-sized segments:
+    the tables of a segment fill most of an SM's shared memory)"""
+    b = L.make_config(2, scale=0.17)                         # two maize-sized segment pairs
+    res = L.local_icp_batch(b)
+    T21r = L.refine_batch(b, res.T21, res.T12)
+    for s in range(b.n_segments):
+        x1, x2, l1, l2 = b.segment(s)
+        T21, T12 = res.maps(s)
+        ref = O.double_direction_refinement(x1, x2, T21, T12, nn="brute")
+        np.testing.assert_array_equal(T21r[b.off2[s]:b.off2[s + 1]], ref)
+    assert (T21r != res.T21).mean() > 0.05                   # the refinement did something

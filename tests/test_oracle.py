@@ -81,3 +81,15 @@ def test_fill_order():
     np.testing.assert_array_equal(R[1], np.eye(3))          # 1: takes the already filled 0
     np.testing.assert_array_equal(R[3], I2)
     np.testing.assert_array_equal(R[4], I2)
+
+
+@pytest.mark.parametrize("case", ["c1_small", "c3_small", "c5_small"])
+def test_double_direction_refinement_matches_reference(case):
+    """the restatement with inverse-index tables reproduces the reference's refined maps"""
+    g = load_golden(case)
+    for s, x1, x2, l1, l2 in golden_segments(g):
+        a, b = g["off1"][s], g["off1"][s + 1]
+        c, d = g["off2"][s], g["off2"][s + 1]
+        T = O.double_direction_refinement(x1, x2, g["T21"][c:d], g["T12"][a:b], nn="kdtree")
+        np.testing.assert_array_equal(T, g["T21r"][c:d])
+        np.testing.assert_array_equal(g["T12"][a:b], g["T12r"][a:b])
