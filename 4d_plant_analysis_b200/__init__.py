@@ -9,10 +9,12 @@ Reference-shaped API (same names and signatures as the reference's functions):
     get_triangle_angles, get_p2p_mapping_from_segments_using_icp     (p2p_matching_in_organ/p2p_matching_seg_icp.py)
     evaluate_p2p_matching                                            (p2p_matching_in_organ/p2p_matching_evaluation.py)
     double_direction_refinement                                      (p2p_matching_in_organ/p2p_matching_fm.py)
-Batched API: local_icp_batch, refine_batch, evaluate_batch.  Wiring into a reference checkout: install().
+Batched API: local_icp_batch, refine_batch, evaluate_batch, match_segments_batch (the whole per-segment body of the
+reference's driver), save_segment_results (its on-disk format).  Wiring into a reference checkout: install().
 """
 from ._native import DIR_BOTH, DIR_T12, DIR_T21, Context, NativeError, build, default_context, load  # noqa: F401
-from .batch import LocalICPResult, local_icp_batch  # noqa: F401
+from .batch import (LocalICPResult, SegmentMatchResult, local_icp_batch, match_segments_batch,  # noqa: F401
+                    save_segment_results)
 from .install import install  # noqa: F401
 from .p2p_matching_evaluation import evaluate_batch, evaluate_p2p_matching  # noqa: F401
 from .p2p_matching_fm import double_direction_refinement, refine_batch  # noqa: F401

@@ -63,3 +63,54 @@ def local_icp_batch(segments, *, directions: int = _native.DIR_BOTH, details: bo
         res.transforms["raw"] = ctx.transforms(filled=False)
         res.counters = ctx.counters()
     return res
+
+
+@dataclass
+class SegmentMatchResult:
+    """What the reference's per-segment body (p2p_matching_seg_icp.py:152-196) accumulates for one frame pair."""
+
+    T21s: List[np.ndarray]            # per matched segment pair, after the refinement if requested
+    T12s: List[np.ndarray]
+    scores: np.ndarray                # (S, 3): continuity, landmark precision, cycle consistency  (score.csv)
+    score_weights: np.ndarray         # (S,): vertices of mesh1 (:189)
+    segments: SegmentPairBatch
+
+    @property
+    def score(self) -> np.ndarray:    # what get_p2p_mapping_organ_collection returns (:244)
+        return np.average(self.scores, axis=0, weights=self.score_weights)
+
+
+def match_segments_batch(segments, *, apply_double_direction_refinement: bool = True, voxel_size: float = 1.0,
+                         sample_proportion: float = 0.5, ctx: Optional[_native.Context] = None) -> SegmentMatchResult:
+    """The whole per-segment body of get_p2p_mapping_organ_collection for all matched segment pairs at once, on the GPU:
+    T21 / T12 (p2p_matching_seg_icp.py:173-176), double_direction_refinement (:181-182), evaluate_p2p_matching with the
+    driver's arguments (:184-185: default voxel_size = 1.0, sample_proportion = 0.5) and the score weights (:189)."""
+    from .p2p_matching_evaluation import evaluate_batch
+    from .p2p_matching_fm import refine_batch
+    b = _as_batch(segments)
+    ctx = ctx or _native.default_context()
+    res = local_icp_batch(b, ctx=ctx)
+    T21, T12 = res.T21, res.T12
+    if apply_double_direction_refinement:
+        T21 = refine_batch(b, T21, T12, ctx=ctx)
+    scores = evaluate_batch(b, T21, T12, voxel_size=voxel_size, sample_proportion=sample_proportion, ctx=ctx)
+    S = b.n_segments
+    return SegmentMatchResult([T21[b.off2[s]:b.off2[s + 1]] for s in range(S)], [T12[b.off1[s]:b.off1[s + 1]] for s in range(S)],
+                              scores, np.diff(b.off1).astype(np.float64), b)
+
+
+def save_segment_results(result: SegmentMatchResult, directory: str, day1: str, day2: str) -> None:
+    """The on-disk format the reference's driver writes (p2p_matching_seg_icp.py:210-242) and its consumers read
+    (interpolation/interpolation_pcd.py:15-55, visualize_p2p.py:34-74): per matched segment pair i
+    ``{day1}_{i}.csv`` / ``{day2}_{i}.csv`` (vertices, np.savetxt default format), ``T21_{i}.csv`` / ``T12_{i}.csv``
+    (one float per line) and ``score.csv``."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    b = result.segments
+    for i in range(b.n_segments):
+        x1, x2, _, _ = b.segment(i)
+        np.savetxt(os.path.join(directory, f"{day1}_{i}.csv"), x1)
+        np.savetxt(os.path.join(directory, f"{day2}_{i}.csv"), x2)
+        np.savetxt(os.path.join(directory, f"T21_{i}.csv"), result.T21s[i])
+        np.savetxt(os.path.join(directory, f"T12_{i}.csv"), result.T12s[i])
+    np.savetxt(os.path.join(directory, "score.csv"), np.vstack(result.scores))

@@ -447,3 +447,14 @@ def test_refinement_full_pipeline_matches_oracle(L):
         ref = O.double_direction_refinement(x1, x2, T21, T12, nn="brute")
         np.testing.assert_array_equal(T21r[b.off2[s]:b.off2[s + 1]], ref)
     assert (T21r != res.T21).mean() > 0.05                   # the refinement did something
+
+
+def test_match_segments_batch_reproduces_the_reference_body(L):
+    """hot path + refinement + evaluation for all segment pairs at once == the reference's recorded per-segment results
+    (refined maps and score.csv rows of tests/golden/c1_small.npz, produced with the driver's own arguments)"""
+    g = load_golden("c1_small")
+    r = L.match_segments_batch(_batch_from_golden(L, g))
+    np.testing.assert_array_equal(np.concatenate(r.T21s), g["T21r"])
+    np.testing.assert_array_equal(np.concatenate(r.T12s), g["T12r"])
+    np.testing.assert_allclose(r.scores, g["score"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(r.score, np.average(g["score"], axis=0, weights=np.diff(g["off1"])), rtol=0, atol=1e-12)

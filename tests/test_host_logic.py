@@ -111,3 +111,25 @@ def test_world_size_2_gather_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_result_files_are_what_the_consumers_read(tmp_path, syn):
+    """the on-disk format of p2p_matching_seg_icp.py:210-242 round-trips through the reader
+    logic of interpolation/interpolation_pcd.py:15-55 (np.loadtxt of {day}_{i}.csv, T21_{i}.csv, T12_{i}.csv)."""
+    B = importlib.import_module("4d_plant_analysis_b200.batch")
+    b = syn.make_config(1, scale=0.1)
+    rng = np.random.default_rng(0)
+    T21s = [rng.integers(0, b.off1[s + 1] - b.off1[s], b.off2[s + 1] - b.off2[s]) for s in range(b.n_segments)]
+    T12s = [rng.integers(0, b.off2[s + 1] - b.off2[s], b.off1[s + 1] - b.off1[s]) for s in range(b.n_segments)]
+    res = B.SegmentMatchResult(T21s, T12s, rng.random((b.n_segments, 3)), np.diff(b.off1).astype(float), b)
+    B.save_segment_results(res, str(tmp_path), "03-22_AM", "03-23_AM")
+    i = 0
+    while os.path.exists(tmp_path / f"03-22_AM_{i}.csv"):                  # the reader's loop
+        x1 = np.loadtxt(tmp_path / f"03-22_AM_{i}.csv"); x2 = np.loadtxt(tmp_path / f"03-23_AM_{i}.csv")
+        t21 = np.loadtxt(tmp_path / f"T21_{i}.csv"); t12 = np.loadtxt(tmp_path / f"T12_{i}.csv")
+        np.testing.assert_array_equal(x1, b.segment(i)[0]); np.testing.assert_array_equal(x2, b.segment(i)[1])
+        np.testing.assert_array_equal(t21.astype(int), T21s[i]); np.testing.assert_array_equal(t12.astype(int), T12s[i])
+        i += 1
+    assert i == b.n_segments
+    np.testing.assert_allclose(np.loadtxt(tmp_path / "score.csv"), res.scores)
+    np.testing.assert_allclose(res.score, np.average(res.scores, axis=0, weights=np.diff(b.off1)))
