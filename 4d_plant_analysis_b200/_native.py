@@ -49,6 +49,7 @@ SIGNATURES = {
     "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
     "lip_batch_evaluate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, _D, _I64]),
     "lip_batch_refine_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lip_batch_match_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, _D]),
     "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
     "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
     "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
@@ -220,6 +221,17 @@ class Context:
                                                      float(voxel_size), float(sample_proportion), _ptr(scores, c_double),
                                                      _ptr(counts, c_int64)))
         return scores, counts
+
+    def match(self, xyz1, xyz2, lm1, lm2, refine=True, voxel_size=1.0, sample_proportion=0.5):
+        """hot path + refinement + evaluation of the planned batch in one call: (T21, T12, scores (S,3))"""
+        xyz1, xyz2, lm1, lm2 = _f64(xyz1), _f64(xyz2), _f64(lm1), _f64(lm2)
+        if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(lm1) != self.sumK or len(lm2) != self.sumK:
+            raise ValueError("array sizes do not match the planned batch")
+        T21, T12, scores = np.empty(self.n2, np.int64), np.empty(self.n1, np.int64), np.empty((self.S, 3))
+        self._check(self.lib.lip_batch_match_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, lm1.ctypes.data, lm2.ctypes.data,
+                                                  int(bool(refine)), float(voxel_size), float(sample_proportion),
+                                                  T21.ctypes.data, T12.ctypes.data, _ptr(scores, c_double)))
+        return T21, T12, scores
 
     def refine(self, xyz1, xyz2, T21, T12):
         """double_direction_refinement of the planned batch: returns the refined copy of T21 (int64)"""

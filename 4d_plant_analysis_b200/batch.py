@@ -85,15 +85,13 @@ def match_segments_batch(segments, *, apply_double_direction_refinement: bool = 
     """The whole per-segment body of get_p2p_mapping_organ_collection for all matched segment pairs at once, on the GPU:
     T21 / T12 (p2p_matching_seg_icp.py:173-176), double_direction_refinement (:181-182), evaluate_p2p_matching with the
     driver's arguments (:184-185: default voxel_size = 1.0, sample_proportion = 0.5) and the score weights (:189)."""
-    from .p2p_matching_evaluation import evaluate_batch
-    from .p2p_matching_fm import refine_batch
     b = _as_batch(segments)
+    for arr in (b.xyz1, b.xyz2, b.lm1, b.lm2):
+        if not np.isfinite(arr).all():
+            raise ValueError("Input contains NaN or infinity.")
     ctx = ctx or _native.default_context()
-    res = local_icp_batch(b, ctx=ctx)
-    T21, T12 = res.T21, res.T12
-    if apply_double_direction_refinement:
-        T21 = refine_batch(b, T21, T12, ctx=ctx)
-    scores = evaluate_batch(b, T21, T12, voxel_size=voxel_size, sample_proportion=sample_proportion, ctx=ctx)
+    ctx.plan(b.off1, b.off2, b.lm_off)
+    T21, T12, scores = ctx.match(b.xyz1, b.xyz2, b.lm1, b.lm2, apply_double_direction_refinement, voxel_size, sample_proportion)
     S = b.n_segments
     return SegmentMatchResult([T21[b.off2[s]:b.off2[s + 1]] for s in range(S)], [T12[b.off1[s]:b.off1[s + 1]] for s in range(S)],
                               scores, np.diff(b.off1).astype(np.float64), b)

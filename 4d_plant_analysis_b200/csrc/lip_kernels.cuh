@@ -1604,6 +1604,51 @@ __global__ void triangle_angles_kernel(const double* __restrict__ abc, int n, do
     out[3 * (size_t)i + 2] = acos((sa * sa + sb * sb - sc * sc) / (2 * sa * sb + eps));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact k nearest vertices of the same mesh in (distance, index) order, float64 (sklearn KDTree(x).query(x, k)):
+// one THREAD per query, the mesh staged in shared memory as three float64 planes and read by all lanes at once
+// (broadcast), candidates visited in ascending index so that a strict '<' keeps the lowest index on exact ties.
+// side 0: mesh1 (xyz1), side 1: mesh2 (xyz2).  Query i of mesh m is its local vertex i * step.
+// out[KNN * (qbase[m] + i) + k] = local index of the k-th neighbour (k = 0 is the vertex itself unless duplicated),
+// -1 beyond the mesh size.  grid = (meshes, query blocks), dynamic SMEM = 24 * smem_pts bytes (0: read global).
+// ---------------------------------------------------------------------------------------------
+template <int KNN>
+__global__ void __launch_bounds__(256) self_knn_kernel(LipArgs a, int side, int step, const int* __restrict__ qbase,
+                                                       int* __restrict__ out, int smem_pts) {
+    extern __shared__ double smem_knn[];
+    const int mi = blockIdx.x, m = side ? a.S + mi : mi;
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const double* __restrict__ xyz = side ? a.xyz2 + 3 * (size_t)(ub - a.n1_total) : a.xyz1 + 3 * (size_t)ub;
+    const int nq = (n + step - 1) / step;
+    if ((int)blockIdx.y * 256 >= nq) return;
+    const bool staged = n <= smem_pts;
+    if (staged) {
+        for (int i = threadIdx.x; i < 3 * n; i += 256) { const int v = i / 3, c = i - 3 * v; smem_knn[(size_t)c * n + v] = xyz[i]; }
+        __syncthreads();
+    }
+    for (int qi = blockIdx.y * 256 + threadIdx.x; qi < nq; qi += 256 * gridDim.y) {
+        const int q = qi * step;
+        const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
+        double d[KNN];
+        int id[KNN];
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) { d[k] = INFINITY; id[k] = -1; }
+        for (int v = 0; v < n; ++v) {
+            const double dn = staged ? rdist64(q0, q1, q2, smem_knn[v], smem_knn[(size_t)n + v], smem_knn[2 * (size_t)n + v])
+                                     : rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+            if (dn < d[KNN - 1]) {
+                d[KNN - 1] = dn; id[KNN - 1] = v;
+#pragma unroll
+                for (int k = KNN - 1; k > 0; --k)
+                    if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+            }
+        }
+        int* o = out + (size_t)KNN * (qbase[mi] + qi);
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) o[k] = id[k];
+    }
+}
+
 // =============================================================================================
 // evaluate_p2p_matching (p2p_matching_in_organ/p2p_matching_evaluation.py:8-88) for a batch of segment pairs.
 // All three scores are ratios of integer counts, so the kernels return the counts and the host divides:
@@ -1642,11 +1687,12 @@ __device__ __forceinline__ double norm3(const double* __restrict__ p, const doub
 }
 
 // one CTA per segment pair; T21 / T12 are the caller's maps in batch order (local indices)
-__global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* __restrict__ lm_idx,
+__global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* __restrict__ lm_idx, const int* __restrict__ nn2,
+                                                          const int* __restrict__ nn2_base,
                                                           const long long* __restrict__ T21, const long long* __restrict__ T12,
                                                           double threshold, int sample_step, long long* __restrict__ cnt) {
     __shared__ int s_cnt[3];
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x, tid = threadIdx.x;
     const int m1 = s, m2 = a.S + s;
     const int u1 = a.mesh_ubase[m1], u2 = a.mesh_ubase[m2] - a.n1_total;       // offsets into xyz1 / xyz2 and T12 / T21
     const int n2 = a.mesh_ubase[m2 + 1] - a.mesh_ubase[m2];
@@ -1662,33 +1708,15 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
         const int i1 = lm_idx[a.mesh_bin[m1] + k], i2 = lm_idx[a.mesh_bin[m2] + k];
         if (norm3(v1 + 3 * (size_t)t21[i2], v1 + 3 * (size_t)i1) < 2.0 * threshold) ++c_lm;
     }
-    // continuity (:41-57): every sample_step-th vertex of mesh2, its two nearest vertices of mesh2 (KDTree k = 2,
-    // the first is the vertex itself), one warp per sample, float64 brute force with (distance, index) order
-    int c_cont = 0, n_samp = 0;
-    for (int i = warp * sample_step; i < n2; i += 8 * sample_step) {
-        const double q0 = v2[3 * (size_t)i], q1 = v2[3 * (size_t)i + 1], q2 = v2[3 * (size_t)i + 2];
-        double d0 = INFINITY, d1 = INFINITY;
-        int i0 = 0x7fffffff, i1 = 0x7fffffff;
-        for (int v = lane; v < n2; v += 32) {
-            const double d = rdist64(q0, q1, q2, v2[3 * (size_t)v], v2[3 * (size_t)v + 1], v2[3 * (size_t)v + 2]);
-            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = v; }
-            else if (d < d1) { d1 = d; i1 = v; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {                     // merge two sorted pairs, (distance, index) lexicographic
-            const double e0 = __shfl_xor_sync(LIP_FULL, d0, o), e1 = __shfl_xor_sync(LIP_FULL, d1, o);
-            const int j0 = __shfl_xor_sync(LIP_FULL, i0, o), j1 = __shfl_xor_sync(LIP_FULL, i1, o);
-            const bool mine = d0 < e0 || (d0 == e0 && i0 < j0);
-            const double w0 = mine ? d0 : e0, x0 = mine ? e0 : d0, x1 = mine ? d1 : e1;
-            const int wi = mine ? i0 : j0, xi0 = mine ? j0 : i0, xi1 = mine ? i1 : j1;
-            const bool second = x0 < x1 || (x0 == x1 && xi0 < xi1);      // runner-up: loser's best or winner's second
-            d0 = w0; i0 = wi; d1 = second ? x0 : x1; i1 = second ? xi0 : xi1;
-        }
-        if (lane == 0) {
-            ++n_samp;
-            const long long ma = t21[i0], mb = (n2 > 1) ? t21[i1] : ma;
-            if (ma != mb && norm3(v1 + 3 * (size_t)ma, v1 + 3 * (size_t)mb) < threshold) ++c_cont;
-        }
+    // continuity (:41-57): every sample_step-th vertex of mesh2 and its two nearest vertices of mesh2 (KDTree k = 2,
+    // self_knn_kernel<2>; the first is the vertex itself)
+    int c_cont = 0;
+    const int nsamp = (n2 + sample_step - 1) / sample_step;
+    const int* __restrict__ nn = nn2 + 2 * (size_t)nn2_base[s];
+    for (int i = tid; i < nsamp; i += 256) {
+        const int i0 = nn[2 * (size_t)i], i1 = nn[2 * (size_t)i + 1];
+        const long long ma = t21[i0], mb = (i1 >= 0) ? t21[i1] : ma;
+        if (ma != mb && norm3(v1 + 3 * (size_t)ma, v1 + 3 * (size_t)mb) < threshold) ++c_cont;
     }
     // cycle consistency (:59-68): |v2[T12[T21[i]]] - v2[i]| < threshold
     int c_cyc = 0;
@@ -1703,7 +1731,6 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
         long long* c = cnt + 6 * (size_t)s;
         c[0] = s_cnt[0]; c[1] = K; c[2] = s_cnt[1]; c[3] = (n2 + sample_step - 1) / sample_step; c[4] = s_cnt[2]; c[5] = n2;
     }
-    (void)n_samp;
 }
 
 // =============================================================================================
@@ -1712,50 +1739,7 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
 // inside the loops), so the result depends on the visiting order: the kernel keeps that order — one warp per
 // segment pair, lane 0 walking the targets in ascending order over inverse-index lists held in SMEM.
 // =============================================================================================
-// KDTree(vertices1).query(vertices1, k=5) (:78-79): for every vertex of mesh1 its five nearest vertices of mesh1 in
-// (distance, index) order; entries 1..4 (the reference's NN_mesh1[t, 1:]) are stored.  float64 brute force, one warp
-// per query.  nn4[4*u + k] = local index, or -1 when the mesh has fewer points.
-__global__ void __launch_bounds__(256) knn5_self_kernel(LipArgs a, int* __restrict__ nn4) {
-    const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
-    const double* __restrict__ xyz = a.xyz1 + 3 * (size_t)ub;
-    for (int q = blockIdx.y * 8 + warp; q < n; q += 8 * gridDim.y) {
-        const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
-        double d[5];
-        int id[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { d[k] = INFINITY; id[k] = 0x7fffffff; }
-        for (int v = lane; v < n; v += 32) {                 // ascending v per lane: an equal distance never displaces an earlier index
-            const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
-            if (dn < d[4]) {
-                d[4] = dn; id[4] = v;
-#pragma unroll
-                for (int k = 4; k > 0; --k)
-                    if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
-            }
-        }
-        int out = -1;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {                        // five rounds of a warp-wide argmin over the lanes' list heads
-            double bd = d[0];
-            int bi = id[0], bl = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(LIP_FULL, bd, o);
-                const int oi = __shfl_xor_sync(LIP_FULL, bi, o), ol = __shfl_xor_sync(LIP_FULL, bl, o);
-                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bl = ol; }
-            }
-            if (lane == bl) {                                // the winner pops its head
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { d[k] = d[k + 1]; id[k] = id[k + 1]; }
-                d[4] = INFINITY; id[4] = 0x7fffffff;
-            }
-            if (r >= 1 && lane == r - 1) out = (bd < INFINITY) ? bi : -1;
-        }
-        if (lane < 4) nn4[4 * (size_t)(ub + q) + lane] = out;
-    }
-}
-
+// (the 5-NN self query of :78-79 is self_knn_kernel<5>; entries 1..4 of a row are the reference's NN_mesh1[t, 1:])
 struct RefineView {                                          // per-segment tables (SMEM when they fit, global scratch otherwise)
     int *t21, *next21, *head21, *head12, *next12, *t12;
     double* v2;                                              // 3 * n2, interleaved
@@ -1787,7 +1771,7 @@ __device__ __forceinline__ void refine_move(const RefineView& w, int ind, int t_
     w.t21[ind] = t_to;
 }
 
-__global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn4, long long* __restrict__ T21,
+__global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn5, long long* __restrict__ T21,
                                                     const long long* __restrict__ T12, int* __restrict__ scratch, int smem_ints_cap) {
     extern __shared__ double smem_ref[];
     const int s = blockIdx.x, lane = threadIdx.x;
@@ -1796,7 +1780,7 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
     long long* __restrict__ t21g = T21 + u2;
     const long long* __restrict__ t12g = T12 + u1;
     const double* __restrict__ v2g = a.xyz2 + 3 * (size_t)u2;
-    const int* __restrict__ nn = nn4 + 4 * (size_t)u1;
+    const int* __restrict__ nn = nn5 + 5 * (size_t)u1 + 1;          // entries 1..4 of every row: NN_mesh1[t, 1:]
     // tables: 3 n2 + 3 n1 ints (+ n1 snapshot flags packed into the sign... kept as a separate n1 ints) and 3 n2 doubles
     const size_t need_ints = 3 * (size_t)n2 + 4 * (size_t)n1;
     const bool in_smem = (size_t)6 * n2 + need_ints <= (size_t)smem_ints_cap;       // doubles count as two ints
@@ -1832,27 +1816,38 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
                         t_keep = w.head12[ind];
                         for (int c = w.head12[ind]; c >= 0; c = w.next12[c]) if (w.head21[c] < 0) t_keep = c;
                     } else {                                 // the four nearest neighbours of the target (:102-103)
-                        t_keep = nn[4 * (size_t)t];
-                        for (int k = 0; k < 4; ++k) { const int c = nn[4 * (size_t)t + k]; if (c >= 0 && w.head21[c] < 0) t_keep = c; }
+                        t_keep = nn[5 * (size_t)t];
+                        for (int k = 0; k < 4; ++k) { const int c = nn[5 * (size_t)t + k]; if (c >= 0 && w.head21[c] < 0) t_keep = c; }
                     }
                     if (t_keep >= 0 && t_keep != t) refine_move(w, ind, t, t_keep);
                 }
                 ind = nxt;
             }
         }
-        for (int t = 0; t < n1; ++t) {                       // targets nobody maps to take sources from their neighbours (:111-130)
-            if (w.head21[t] >= 0) continue;
-            for (int k = 0; k < 4; ++k) {
-                const int nb = nn[4 * (size_t)t + k];
-                if (nb < 0 || w.head21[nb] < 0 || nb == t) continue;
-                const int keep = refine_keep(w, nb);
-                int ind = w.head21[nb];
+    }
+    __syncwarp();
+    // targets nobody maps to take sources from their neighbours (:111-130).  The four neighbours of a target are
+    // distinct, and moving the sources of one of them to the target does not touch the lists of the others, so the
+    // four "which source stays" decisions are taken by four lanes at once; the moves stay in the reference's order.
+    for (int t = 0; t < n1; ++t) {
+        if (w.head21[t] >= 0) continue;                      // uniform
+        int nb = -1, keep = -1;
+        if (lane < 4) {
+            nb = nn[5 * (size_t)t + lane];
+            if (nb >= 0 && nb != t && w.head21[nb] >= 0) keep = refine_keep(w, nb); else nb = -1;
+        }
+        __syncwarp();
+        for (int k = 0; k < 4; ++k) {
+            const int nbk = __shfl_sync(LIP_FULL, nb, k), keepk = __shfl_sync(LIP_FULL, keep, k);
+            if (lane == 0 && nbk >= 0) {
+                int ind = w.head21[nbk];
                 while (ind >= 0) {
                     const int nxt = w.next21[ind];
-                    if (ind != keep) refine_move(w, ind, nb, t);
+                    if (ind != keepk) refine_move(w, ind, nbk, t);
                     ind = nxt;
                 }
             }
+            __syncwarp();
         }
     }
     __syncwarp();

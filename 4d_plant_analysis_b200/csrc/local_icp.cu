@@ -59,6 +59,7 @@ struct lip_ctx {
     std::vector<lip_ctx*> kids;
     std::vector<int64_t> kid_seg;       // first segment pair of each kid, and S at the end
     std::vector<int64_t> h_off1, h_off2, h_lm_off;   // the planned CSR (for slicing the host arrays)
+    std::vector<int> h_qbase_eval, h_qbase_ref;      // first query of every mesh (self_knn_kernel), uploaded asynchronously
     int n_kids = 0;                     // kids in use by the current plan (0: no split)
     bool last_run_split = false;
     bool is_kid = false;
@@ -76,7 +77,7 @@ struct lip_ctx {
     DevBuf ws;
     LipArgs args;
     // device copies of host-API inputs / outputs
-    DevBuf in_xyz1, in_xyz2, in_lm1, in_lm2, out_T21, out_T12, misc;
+    DevBuf in_xyz1, in_xyz2, in_lm1, in_lm2, out_T21, out_T12, misc, misc2;
     int64_t last_launches = 0;
     // optional per-stage CUDA-event timing (lip_set_profiling)
     bool profiling = false;
@@ -434,7 +435,7 @@ void lip_destroy(lip_ctx* c) {
     for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc})
+    for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc, &c->misc2})
         b->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -695,48 +696,126 @@ int lip_batch_get_bin_offsets(lip_ctx* c, int32_t* bin_off) {
     return LIP_OK;
 }
 
+// launch self_knn_kernel<KNN> for side (0: mesh1, 1: mesh2), every step-th vertex; qbase (device) = first query of each mesh
+extern "C++" {
+template <int KNN>
+static int launch_self_knn(lip_ctx* c, const LipArgs& a, int side, int step, const int* d_qbase, int* d_out, int64_t max_n, cudaStream_t st) {
+    int smem_cap = 0;
+    LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    int smem_pts = (int)std::min<int64_t>(max_n, (smem_cap - 1024) / 24 / 2);        // two CTAs per SM
+    const size_t smem = (size_t)smem_pts * 24;
+    LIP_CUDA(c, cudaFuncSetAttribute(self_knn_kernel<KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t max_q = (max_n + step - 1) / step;
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(65535, (max_q + 255) / 256));
+    self_knn_kernel<KNN><<<dim3((unsigned)c->S, gy), 256, smem, st>>>(a, side, step, d_qbase, d_out, smem_pts);
+    LIP_CUDA(c, cudaGetLastError());
+    return LIP_OK;
+}
+}  // extern "C++"
+
+// evaluate_p2p_matching on device-resident inputs and maps: enqueues the kernels and the copy of the counts
+static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
+                           const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
+                           cudaStream_t st, std::vector<long long>& h_counts) {
+    const size_t S = (size_t)c->S;
+    const int step = std::max((int)(1.0 / sample_proportion), 1);              // p2p_matching_evaluation.py:40
+    std::vector<int>& qbase = c->h_qbase_eval;                 // kept in the context: the upload below is asynchronous
+    qbase.assign(S + 1, 0);
+    int64_t max_n2 = 0;
+    for (size_t s = 0; s < S; ++s) {
+        const int64_t n2s = c->h_off2[s + 1] - c->h_off2[s];
+        qbase[s + 1] = qbase[s] + (int)((n2s + step - 1) / step);
+        max_n2 = std::max(max_n2, n2s);
+    }
+    const size_t o_cnt = align_up((size_t)c->B * 4), o_qb = o_cnt + align_up(S * 48), o_nn = o_qb + align_up((S + 1) * 4);
+    LIP_CUDA(c, c->misc2.ensure(o_nn + (size_t)qbase[S] * 8 + 16));
+    LipArgs a = c->args;
+    a.xyz1 = d_xyz1; a.xyz2 = d_xyz2; a.lm1 = d_lm1; a.lm2 = d_lm2;
+    int* lm_idx = c->misc2.as<int>();
+    long long* cnt = (long long*)(c->misc2.as<char>() + o_cnt);
+    int* d_qbase = (int*)(c->misc2.as<char>() + o_qb);
+    int* d_nn2 = (int*)(c->misc2.as<char>() + o_nn);
+    LIP_CUDA(c, cudaMemcpyAsync(d_qbase, qbase.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
+    eval_landmark_nn_kernel<<<(c->B + 3) / 4, 128, 0, st>>>(a, lm_idx);
+    int rc = launch_self_knn<2>(c, a, 1, step, d_qbase, d_nn2, max_n2, st);
+    if (rc) return rc;
+    eval_scores_kernel<<<(unsigned)S, 256, 0, st>>>(a, lm_idx, d_nn2, d_qbase, d_T21, d_T12, 2.0 * voxel_size, step, cnt);
+    LIP_CUDA(c, cudaGetLastError());
+    h_counts.resize(S * 6);
+    LIP_CUDA(c, cudaMemcpyAsync(h_counts.data(), cnt, S * 48, cudaMemcpyDeviceToHost, st));
+    return LIP_OK;
+}
+static void scores_from_counts(const std::vector<long long>& h, size_t S, bool with_T12, double* scores, int64_t* counts) {
+    for (size_t s = 0; s < S; ++s) {
+        const long long* k = &h[6 * s];
+        scores[3 * s] = (double)k[2] / (double)k[3];                            // continuity
+        scores[3 * s + 1] = (double)k[0] / (double)k[1];                        // landmark precision
+        scores[3 * s + 2] = with_T12 ? (double)k[4] / (double)k[5] : std::numeric_limits<double>::quiet_NaN();   // cycle
+        if (counts) for (int i = 0; i < 6; ++i) counts[6 * s + i] = k[i];
+    }
+}
+
 int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                             const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
                             double* scores, int64_t* counts) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
+    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !scores) return fail(c, LIP_EINVAL, "evaluate: null pointer");
     if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "evaluate: sample_proportion must be > 0");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
-    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24, S = (size_t)c->S;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
     LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
     LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
-    const size_t o_cnt = align_up((size_t)c->B * 4);
-    LIP_CUDA(c, c->misc.ensure(o_cnt + S * 48));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, (size_t)c->n2 * 8, cudaMemcpyHostToDevice, st));
     if (T12) LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, (size_t)c->n1 * 8, cudaMemcpyHostToDevice, st));
-    LipArgs a = c->args;
-    a.xyz1 = c->in_xyz1.as<double>(); a.xyz2 = c->in_xyz2.as<double>();
-    a.lm1 = c->in_lm1.as<double>(); a.lm2 = c->in_lm2.as<double>();
-    int* lm_idx = c->misc.as<int>();
-    long long* cnt = (long long*)(c->misc.as<char>() + o_cnt);
-    const int step = std::max((int)(1.0 / sample_proportion), 1);              // p2p_matching_evaluation.py:40
-    eval_landmark_nn_kernel<<<(c->B + 3) / 4, 128, 0, st>>>(a, lm_idx);
-    eval_scores_kernel<<<(unsigned)S, 256, 0, st>>>(a, lm_idx, c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr,
-                                                   2.0 * voxel_size, step, cnt);
-    LIP_CUDA(c, cudaGetLastError());
-    std::vector<long long> h(S * 6);
-    LIP_CUDA(c, cudaMemcpyAsync(h.data(), cnt, S * 48, cudaMemcpyDeviceToHost, st));
+    std::vector<long long> h;
+    int rc = evaluate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
+                             c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, voxel_size, sample_proportion, st, h);
+    if (rc) return rc;
     LIP_CUDA(c, cudaStreamSynchronize(st));
-    for (size_t s = 0; s < S; ++s) {
-        const long long* k = &h[6 * s];
-        scores[3 * s] = (double)k[2] / (double)k[3];                            // continuity
-        scores[3 * s + 1] = (double)k[0] / (double)k[1];                        // landmark precision
-        scores[3 * s + 2] = T12 ? (double)k[4] / (double)k[5] : std::numeric_limits<double>::quiet_NaN();   // cycle
-        if (counts) for (int i = 0; i < 6; ++i) counts[6 * s + i] = k[i];
-    }
+    scores_from_counts(h, (size_t)c->S, T12 != nullptr, scores, counts);
     c->last_launches = 2;
+    return LIP_OK;
+}
+
+// double_direction_refinement on device-resident coordinates and maps (d_T21 rewritten in place)
+static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12,
+                         cudaStream_t st) {
+    const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
+    size_t max_ints = 0;
+    int64_t max_n1 = 0;
+    for (size_t s = 0; s < S; ++s) {
+        const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
+        max_ints = std::max(max_ints, (size_t)(9 * a2 + 4 * a1));      // 3 n2 doubles + 3 n2 + 4 n1 ints
+        max_n1 = std::max(max_n1, a1);
+    }
+    int smem_cap = 0;
+    LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    smem_cap -= 1024;
+    const size_t smem = std::min<size_t>((size_t)smem_cap, max_ints * 4 + 16);
+    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t o_qb = align_up(n1 * 20), o_scratch = o_qb + align_up((S + 1) * 4);
+    const bool need_scratch = max_ints * 4 + 16 > smem;
+    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * 4 : 16)));
+    LipArgs a = c->args;
+    a.xyz1 = d_xyz1; a.xyz2 = d_xyz2;
+    int* nn4 = c->misc.as<int>();                            // 5 neighbours per vertex of mesh1, row = [self, 4 nearest]
+    int* d_qbase = (int*)(c->misc.as<char>() + o_qb);
+    int* scratch = (int*)(c->misc.as<char>() + o_scratch);
+    std::vector<int>& qbase = c->h_qbase_ref;
+    qbase.resize(S + 1);
+    for (size_t s = 0; s <= S; ++s) qbase[s] = (int)c->h_off1[s];
+    LIP_CUDA(c, cudaMemcpyAsync(d_qbase, qbase.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
+    int rc5 = launch_self_knn<5>(c, a, 0, 1, d_qbase, nn4, max_n1, st);
+    if (rc5) return rc5;
+    refine_kernel<<<(unsigned)S, 32, smem, st>>>(a, nn4, d_T21, d_T12, scratch, (int)(smem / 4));
+    LIP_CUDA(c, cudaGetLastError());
     return LIP_OK;
 }
 
@@ -747,46 +826,62 @@ int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, in
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
-    for (size_t i = 0; i < n2; ++i) {                         // the maps are used as indices on the device: validate them here
-        // (segment of entry i is found lazily below; a cheap global bound first)
-        if (T21[i] < 0) return fail(c, LIP_EINVAL, "refine: negative entry in T21");
-    }
-    size_t max_ints = 0;
-    for (size_t s = 0; s < S; ++s) {
+    for (size_t s = 0; s < S; ++s) {                          // the maps are used as indices on the device: validate them here
         const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
+        if (a1 < 5) return fail(c, LIP_EINVAL, "refine: every mesh1 needs at least 5 vertices (KDTree.query(k=5))");
         for (int64_t i = c->h_off2[s]; i < c->h_off2[s + 1]; ++i)
-            if (T21[i] >= a1) return fail(c, LIP_EINVAL, "refine: T21 entry out of range for its segment pair");
+            if (T21[i] < 0 || T21[i] >= a1) return fail(c, LIP_EINVAL, "refine: T21 entry out of range for its segment pair");
         for (int64_t i = c->h_off1[s]; i < c->h_off1[s + 1]; ++i)
             if (T12[i] < 0 || T12[i] >= a2) return fail(c, LIP_EINVAL, "refine: T12 entry out of range for its segment pair");
-        max_ints = std::max(max_ints, (size_t)(9 * a2 + 4 * a1));      // 3 n2 doubles + 3 n2 + 4 n1 ints
     }
-    int smem_cap = 0;
-    LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    smem_cap -= 1024;
-    const size_t smem = std::min<size_t>((size_t)smem_cap, max_ints * 4 + 16);
-    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LIP_CUDA(c, c->in_xyz1.ensure(n1 * 24)); LIP_CUDA(c, c->in_xyz2.ensure(n2 * 24));
     LIP_CUDA(c, c->out_T21.ensure(n2 * 8)); LIP_CUDA(c, c->out_T12.ensure(n1 * 8));
-    const size_t o_scratch = align_up(n1 * 16);
-    const bool need_scratch = max_ints * 4 + 16 > smem;
-    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * 4 : 16)));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, n1 * 24, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, n2 * 24, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, n2 * 8, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, n1 * 8, cudaMemcpyHostToDevice, st));
-    LipArgs a = c->args;
-    a.xyz1 = c->in_xyz1.as<double>(); a.xyz2 = c->in_xyz2.as<double>();
-    int* nn4 = c->misc.as<int>();
-    int* scratch = (int*)(c->misc.as<char>() + o_scratch);
-    int64_t max_n1 = 0;
-    for (size_t s = 0; s < S; ++s) max_n1 = std::max<int64_t>(max_n1, c->h_off1[s + 1] - c->h_off1[s]);
-    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(1024, (max_n1 + 63) / 64));
-    knn5_self_kernel<<<dim3((unsigned)S, gy), 256, 0, st>>>(a, nn4);
-    refine_kernel<<<(unsigned)S, 32, smem, st>>>(a, nn4, c->out_T21.as<long long>(), c->out_T12.as<long long>(), scratch, (int)(smem / 4));
-    LIP_CUDA(c, cudaGetLastError());
+    int rc = refine_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(), c->out_T12.as<long long>(), st);
+    if (rc) return rc;
     LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, n2 * 8, cudaMemcpyDeviceToHost, st));
     LIP_CUDA(c, cudaStreamSynchronize(st));
     c->last_launches = 2;
+    return LIP_OK;
+}
+
+int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                         int refine, double voxel_size, double sample_proportion, int64_t* T21, int64_t* T12, double* scores) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "match: no batch planned");
+    if (c->directions != LIP_DIR_BOTH) return fail(c, LIP_EINVAL, "match: the batch must be planned for both directions");
+    if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !T12 || !scores) return fail(c, LIP_EINVAL, "match: null pointer");
+    if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "match: sample_proportion must be > 0");
+    if (refine)
+        for (int64_t s = 0; s < c->S; ++s)
+            if (c->h_off1[s + 1] - c->h_off1[s] < 5) return fail(c, LIP_EINVAL, "match: refinement needs at least 5 vertices in every mesh1");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
+    const double *dx1 = c->in_xyz1.as<double>(), *dx2 = c->in_xyz2.as<double>(), *dl1 = c->in_lm1.as<double>(), *dl2 = c->in_lm2.as<double>();
+    long long *d21 = c->out_T21.as<long long>(), *d12 = c->out_T12.as<long long>();
+    c->last_run_split = false;
+    int rc = run_stages(c, dx1, dx2, dl1, dl2, d21, d12, nullptr, kFullPipeline, st);      // maps stay on the device
+    if (rc) return rc;
+    const int64_t hot_launches = c->last_launches;
+    if (refine && (rc = refine_device(c, dx1, dx2, d21, d12, st)) != LIP_OK) return rc;
+    std::vector<long long> h;
+    if ((rc = evaluate_device(c, dx1, dx2, dl1, dl2, d21, d12, voxel_size, sample_proportion, st, h)) != LIP_OK) return rc;
+    LIP_CUDA(c, cudaMemcpyAsync(T21, d21, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaMemcpyAsync(T12, d12, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    scores_from_counts(h, (size_t)c->S, true, scores, nullptr);
+    c->last_launches = hot_launches + (refine ? 2 : 0) + 2;
     return LIP_OK;
 }
 

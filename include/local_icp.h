@@ -147,6 +147,13 @@ int lip_batch_evaluate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2
  * least 5 vertices (KDTree.query(k=5), :79). */
 int lip_batch_refine_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12);
 
+/* The whole per-segment body of get_p2p_mapping_organ_collection (p2p_matching_seg_icp.py:173-189) for the planned batch
+ * in one call, everything between the upload of the inputs and the download of the results staying on the device:
+ * T21 / T12 (:173-176), double_direction_refinement if `refine` != 0 (:181-182), evaluate_p2p_matching (:184-185).
+ * T21 (off2[S]), T12 (off1[S]), scores (S,3) as in lip_batch_evaluate_host.  The batch must be planned LIP_DIR_BOTH. */
+int lip_batch_match_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                         int refine, double voxel_size, double sample_proportion, int64_t* T21, int64_t* T12, double* scores);
+
 /* ---- the three registration_icp.py functions on their own ----------------------------------- */
 /* my_icp for P independent (src, tgt) problems in CSR form (registration_icp.py:60-98):
  * src (src_off[P],3), tgt (tgt_off[P],3) -> R (P,3,3), t (P,3) with x -> R x + t, iters (P). */

@@ -15,9 +15,11 @@ def timed(f, n=3):
         t = time.perf_counter(); r = f(); best = min(best, time.perf_counter() - t)
     return r, best
 res, t_map = timed(lambda: L.local_icp_batch(b, validate=False))
+_, t_all = timed(lambda: L.match_segments_batch(b))
 T21r, t_ref = timed(lambda: L.refine_batch(b, res.T21, res.T12))
 sc, t_ev = timed(lambda: L.evaluate_batch(b, T21r, res.T12, voxel_size=0.8, sample_proportion=0.1))
 print(f"config {cfg} x {fp}: {b.n_segments} segment pairs, {b.n_correspondences} correspondences (host numpy in -> numpy out)")
 print(f"  hot path (local_icp_batch)        {1e3 * t_map:8.2f} ms")
 print(f"  double_direction_refinement       {1e3 * t_ref:8.2f} ms   changed {100 * (T21r != res.T21).mean():.1f}% of T21")
+print(f"  all three in one call (match_segments_batch) {1e3 * t_all:8.2f} ms")
 print(f"  evaluate_p2p_matching             {1e3 * t_ev:8.2f} ms   mean scores {sc.mean(0).round(4)}")
