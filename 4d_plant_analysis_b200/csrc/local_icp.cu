@@ -17,6 +17,7 @@
 #endif
 #define LIP_PIPELINE_CHUNKS 8             // sub-batches of the pipelined host path
 #define LIP_PIPELINE_RAMP 1.0
+#define LIP_DEVICE_CHUNKS 2               // sub-batches of the device-resident entry point
 #define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
 namespace {
@@ -56,8 +57,10 @@ struct lip_ctx {
     size_t max_map_tiles = 0;
     // host-path pipeline: the batch split into sub-batches, each on its own child context (own stream and
     // workspace), so that H2D of one, kernels of another and D2H of a third overlap (lip_batch_run_host)
-    std::vector<lip_ctx*> kids;
-    std::vector<int64_t> kid_seg;       // first segment pair of each kid, and S at the end
+    std::vector<lip_ctx*> kids, dkids;  // sub-batches of the host path (LIP_PIPELINE_CHUNKS) / of the device path (LIP_DEVICE_CHUNKS)
+    std::vector<int64_t> kid_seg, dkid_seg;   // first segment pair of each kid, and S at the end
+    int n_dkids = 0;
+    bool last_run_dsplit = false;
     std::vector<int64_t> h_off1, h_off2, h_lm_off;   // the planned CSR (for slicing the host arrays)
     std::vector<int> h_qbase_eval, h_qbase_ref;      // first query of every mesh (self_knn_kernel), uploaded asynchronously
     int n_kids = 0;                     // kids in use by the current plan (0: no split)
@@ -344,6 +347,11 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
 
 const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // the fill is resolved inside blend_nn_kernel
 
+// the sub-batch set the last run used (host pipeline or device split)
+std::vector<lip_ctx*>& split_kids(lip_ctx* c) { return c->last_run_dsplit ? c->dkids : c->kids; }
+std::vector<int64_t>& split_seg(lip_ctx* c) { return c->last_run_dsplit ? c->dkid_seg : c->kid_seg; }
+int split_n(lip_ctx* c) { return c->last_run_dsplit ? c->n_dkids : c->n_kids; }
+
 // H2D of one (sub-)batch, the whole pipeline and D2H, all enqueued on the context's stream; no synchronisation
 int host_run_async(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                    int64_t* T21, int64_t* T12) {
@@ -429,6 +437,8 @@ void lip_destroy(lip_ctx* c) {
     if (!c) return;
     for (lip_ctx* k : c->kids) lip_destroy(k);
     c->kids.clear();
+    for (lip_ctx* k : c->dkids) lip_destroy(k);
+    c->dkids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -462,49 +472,49 @@ int lip_host_alloc(void** p, uint64_t bytes) {
 }
 int lip_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LIP_OK : LIP_ECUDA; }
 
-// split the planned batch into sub-batches of about equal vertex count for the pipelined host path
-static int plan_kids(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
-    c->n_kids = 0;
+// split the planned batch into `chunks` sub-batches of about equal vertex count, each planned on its own child context
+struct KidSet { std::vector<lip_ctx*>* kids; std::vector<int64_t>* seg; int* n; };
+static int plan_kids(lip_ctx* c, KidSet ks, int chunks, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off,
+                     int directions) {
+    *ks.n = 0;
     const int64_t n = off1[S] + off2[S];
-    int chunks = LIP_PIPELINE_CHUNKS;
-    if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
-    // sub-batch sizes grow like (k / chunks)^ramp: a small first sub-batch starts the kernels early, large later ones
-    // keep them efficient
     double ramp = LIP_PIPELINE_RAMP;
     if (const char* e = getenv("LIP_PIPELINE_RAMP")) ramp = std::max(1.0, std::min(4.0, atof(e)));
     int want = (int)std::min<int64_t>(chunks, S);
     if (n < LIP_PIPELINE_MIN_VERTICES || want < 2) return LIP_OK;
-    c->kid_seg.assign(1, 0);
-    for (int k = 1; k < want; ++k) {                         // cut where the running vertex count passes k/want of the total
+    std::vector<int64_t>& seg = *ks.seg;
+    seg.assign(1, 0);
+    for (int k = 1; k < want; ++k) {                         // cut where the running vertex count passes (k/want)^ramp of the total
         const int64_t target = (int64_t)((double)n * std::pow((double)k / want, ramp));
-        int64_t s = c->kid_seg.back() + 1;
+        int64_t s = seg.back() + 1;
         while (s < S && off1[s] + off2[s] < target) ++s;
         if (s >= S) break;
-        c->kid_seg.push_back(s);
+        seg.push_back(s);
     }
-    c->kid_seg.push_back(S);
-    const int nk = (int)c->kid_seg.size() - 1;
+    seg.push_back(S);
+    const int nk = (int)seg.size() - 1;
     if (nk < 2) return LIP_OK;
-    while ((int)c->kids.size() < nk) {
+    std::vector<lip_ctx*>& kids = *ks.kids;
+    while ((int)kids.size() < nk) {
         lip_ctx* k = nullptr;
         int rc = lip_create(&k, c->device);
         if (rc) return fail(c, rc, std::string("pipeline context: ") + lip_last_error(nullptr));
         k->is_kid = true;
-        c->kids.push_back(k);
+        kids.push_back(k);
     }
     std::vector<int64_t> o1, o2, ol;
     for (int k = 0; k < nk; ++k) {
-        const int64_t s0 = c->kid_seg[k], s1 = c->kid_seg[k + 1];
+        const int64_t s0 = seg[k], s1 = seg[k + 1];
         o1.assign(off1 + s0, off1 + s1 + 1); o2.assign(off2 + s0, off2 + s1 + 1); ol.assign(lm_off + s0, lm_off + s1 + 1);
         for (auto& x : o1) x -= off1[s0];
         for (auto& x : o2) x -= off2[s0];
         for (auto& x : ol) x -= lm_off[s0];
-        lip_ctx* kc = c->kids[k];
+        lip_ctx* kc = kids[k];
         kc->params = c->params; kc->map_mode = c->map_mode;
         int rc = plan_impl(kc, s1 - s0, o1.data(), o2.data(), ol.data(), directions);
         if (rc) return fail(c, rc, "pipeline plan: " + kc->err);
     }
-    c->n_kids = nk;
+    *ks.n = nk;
     return LIP_OK;
 }
 
@@ -515,7 +525,15 @@ int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* of
     if (rc) return rc;
     c->h_off1.assign(off1, off1 + S + 1); c->h_off2.assign(off2, off2 + S + 1); c->h_lm_off.assign(lm_off, lm_off + S + 1);
     c->last_run_split = false;
-    return plan_kids(c, S, off1, off2, lm_off, directions);
+    int chunks = LIP_PIPELINE_CHUNKS;
+    if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    rc = plan_kids(c, KidSet{&c->kids, &c->kid_seg, &c->n_kids}, chunks, S, off1, off2, lm_off, directions);
+    if (rc) return rc;
+    // the device-resident entry point runs the batch as LIP_DEVICE_CHUNKS sub-batches on their own streams: the
+    // latency-bound kernels of one (partition, the tails of the ICP kernels) overlap the scans of the other
+    int dchunks = LIP_DEVICE_CHUNKS;
+    if (const char* e = getenv("LIP_DEVICE_CHUNKS")) dchunks = std::max(1, std::min(16, atoi(e)));
+    return plan_kids(c, KidSet{&c->dkids, &c->dkid_seg, &c->n_dkids}, dchunks, S, off1, off2, lm_off, directions);
 }
 
 int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
@@ -524,9 +542,27 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
-    c->last_run_split = false;
-    return run_stages(c, xyz1, xyz2, lm1, lm2, (long long*)T21, (long long*)T12, nullptr, kFullPipeline,
-                      stream ? (cudaStream_t)stream : c->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (c->n_dkids >= 2 && !c->profiling) {
+        // sub-batches on the child contexts' streams, fork / join on the caller's stream
+        LIP_CUDA(c, cudaEventRecord(c->ev_fork, st));
+        for (int k = 0; k < c->n_dkids; ++k) {
+            lip_ctx* kc = c->dkids[k];
+            const int64_t s0 = c->dkid_seg[k];
+            kc->params = c->params;
+            LIP_CUDA(c, cudaStreamWaitEvent(kc->stream, c->ev_fork, 0));
+            int rc = run_stages(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
+                                T21 ? (long long*)T21 + c->h_off2[s0] : nullptr, T12 ? (long long*)T12 + c->h_off1[s0] : nullptr,
+                                nullptr, kFullPipeline, kc->stream);
+            if (rc) return fail(c, rc, "device split: " + kc->err);
+            LIP_CUDA(c, cudaEventRecord(kc->ev_begin, kc->stream));      // (ev_begin is free again once run_stages has forked)
+            LIP_CUDA(c, cudaStreamWaitEvent(st, kc->ev_begin, 0));
+        }
+        c->last_run_split = true; c->last_run_dsplit = true;
+        return LIP_OK;
+    }
+    c->last_run_split = false; c->last_run_dsplit = false;
+    return run_stages(c, xyz1, xyz2, lm1, lm2, (long long*)T21, (long long*)T12, nullptr, kFullPipeline, st);
 }
 
 int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
@@ -547,10 +583,10 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
             if (rc) return fail(c, rc, "pipeline run: " + kc->err);
         }
         for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
-        c->last_run_split = true;
+        c->last_run_split = true; c->last_run_dsplit = false;
         return LIP_OK;
     }
-    c->last_run_split = false;
+    c->last_run_split = false; c->last_run_dsplit = false;
     int rc = host_run_async(c, xyz1, xyz2, lm1, lm2, T21, T12);
     if (rc) return rc;
     LIP_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -562,13 +598,13 @@ int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, i
     if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
     if (c->last_run_split) {                                 // the last run was pipelined: collect from the sub-batches
-        for (int k = 0; k < c->n_kids; ++k) {
-            const size_t o = (size_t)c->h_lm_off[c->kid_seg[k]];
-            int rc = lip_batch_get_transforms(c->kids[k], filled, R21 ? R21 + 9 * o : nullptr, t21 ? t21 + 3 * o : nullptr,
+        for (int k = 0; k < split_n(c); ++k) {
+            const size_t o = (size_t)c->h_lm_off[split_seg(c)[k]];
+            int rc = lip_batch_get_transforms(split_kids(c)[k], filled, R21 ? R21 + 9 * o : nullptr, t21 ? t21 + 3 * o : nullptr,
                                               iters21 ? iters21 + o : nullptr, status21 ? status21 + o : nullptr,
                                               R12 ? R12 + 9 * o : nullptr, t12 ? t12 + 3 * o : nullptr,
                                               iters12 ? iters12 + o : nullptr, status12 ? status12 + o : nullptr);
-            if (rc) return fail(c, rc, c->kids[k]->err);
+            if (rc) return fail(c, rc, split_kids(c)[k]->err);
         }
         return LIP_OK;
     }
@@ -600,10 +636,10 @@ int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
     if (side != 1 && side != 2) return fail(c, LIP_EINVAL, "side must be 1 or 2");
     cudaSetDevice(c->device);
     if (c->last_run_split) {
-        for (int k = 0; k < c->n_kids; ++k) {
-            const size_t o = (size_t)(side == 1 ? c->h_off1 : c->h_off2)[c->kid_seg[k]];
-            int rc = lip_batch_get_landmark_nn(c->kids[k], side, nn ? nn + 2 * o : nullptr, dist ? dist + 2 * o : nullptr);
-            if (rc) return fail(c, rc, c->kids[k]->err);
+        for (int k = 0; k < split_n(c); ++k) {
+            const size_t o = (size_t)(side == 1 ? c->h_off1 : c->h_off2)[split_seg(c)[k]];
+            int rc = lip_batch_get_landmark_nn(split_kids(c)[k], side, nn ? nn + 2 * o : nullptr, dist ? dist + 2 * o : nullptr);
+            if (rc) return fail(c, rc, split_kids(c)[k]->err);
         }
         return LIP_OK;
     }
@@ -628,10 +664,10 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
     cudaSetDevice(c->device);
     if (c->last_run_split) {
         for (int i = 0; i < 8; ++i) counters[i] = 0;
-        for (int k = 0; k < c->n_kids; ++k) {
+        for (int k = 0; k < split_n(c); ++k) {
             int64_t part[8];
-            int rc = lip_batch_get_counters(c->kids[k], part);
-            if (rc) return fail(c, rc, c->kids[k]->err);
+            int rc = lip_batch_get_counters(split_kids(c)[k], part);
+            if (rc) return fail(c, rc, split_kids(c)[k]->err);
             for (int i = 0; i < 8; ++i) counters[i] += part[i];
         }
         return LIP_OK;
@@ -652,10 +688,10 @@ int lip_batch_get_pair_counts(lip_ctx* c, int64_t pairs[3]) {
     cudaSetDevice(c->device);
     pairs[0] = pairs[1] = pairs[2] = 0;
     if (c->last_run_split) {
-        for (int k = 0; k < c->n_kids; ++k) {
+        for (int k = 0; k < split_n(c); ++k) {
             int64_t part[3];
-            int rc = lip_batch_get_pair_counts(c->kids[k], part);
-            if (rc) return fail(c, rc, c->kids[k]->err);
+            int rc = lip_batch_get_pair_counts(split_kids(c)[k], part);
+            if (rc) return fail(c, rc, split_kids(c)[k]->err);
             for (int i = 0; i < 3; ++i) pairs[i] += part[i];
         }
         return LIP_OK;
