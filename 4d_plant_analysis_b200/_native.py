@@ -266,8 +266,8 @@ class Context:
         return dict(small_icps=int(c[0]), big_icps=int(c[1]), icp_f64_rescans=int(c[2]), map_f64_rescans=int(c[3]),
                     map_retry=int(c[4]), map_far=int(c[5]), launches=int(c[6]), map_ring1_pairs=int(c[7]))
 
-    STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_group_kernel", "unused",
-              "icp_big_kernel", "grid_build_kernel", "final_map_kernel", "retry_nn_kernel", "far_nn_kernel")
+    STAGES = ("landmark_partition_kernel", "icp_schedule_kernel", "icp_group_kernel", "icp_big_kernel", "grid_build_kernel",
+              "blend_kernel", "final_map_kernel", "retry_nn_kernel", "far_nn_kernel")
 
     def pair_counts(self):
         c = np.zeros(3, np.int64)

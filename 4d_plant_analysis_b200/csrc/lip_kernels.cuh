@@ -3,7 +3,6 @@
 #pragma once
 #include "lip_device.cuh"
 
-#define LIP_WARP_CAP 256      // (sizing of launch grids only)
 #ifndef LIP_WARP_WORK
 #define LIP_WARP_WORK 65536    // partitions with n_src * n_tgt <= this: icp_group_kernel (a warp per partition), else CTA
 #endif

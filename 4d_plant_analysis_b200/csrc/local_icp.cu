@@ -40,7 +40,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_FILL = 8, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
+enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
 
 }  // namespace
 
@@ -49,11 +49,10 @@ struct lip_ctx {
     int sm_count = 0;
     int group_blocks_per_sm = 1, big_blocks_per_sm = 1, map_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: big ICP, (unused), grid build
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: [0] CTA ICP kernel, [2] grid build
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool fill_done = false;
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
-    int plan_tile = LIP_TILE;
     size_t max_map_tiles = 0;
     // host-path pipeline: the batch split into sub-batches, each on its own child context (own stream and
     // workspace), so that H2D of one, kernels of another and D2H of a third overlap (lip_batch_run_host)
@@ -155,8 +154,8 @@ void set_param_args(lip_ctx* c) {
     a.map_mode = c->map_mode;
 }
 
-int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions,
-              int tile = LIP_TILE) {
+int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+    const int tile = LIP_TILE;                               // tiles of the grid-mode kernels (blend_nn_kernel, nn_query_kernel)
     if (!c) return LIP_EINVAL;
     c->planned = false;
     if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
@@ -206,7 +205,6 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
         for (int f = 0; f < n; f += tile) { c->h_tile_mesh.push_back(m); c->h_tile_first.push_back(f); }
     }
     c->n_tiles = (int)c->h_tile_mesh.size();
-    c->plan_tile = tile;
     // upload
     size_t off = 0;
     auto take = [&](size_t cnt) { size_t o = off; off = align_up(off + cnt * 4); return o; };
@@ -243,7 +241,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     int64_t launches = 0;
     int evi = 0;
     // While profiling, everything runs back to back on `st` so that the events bracket one kernel each;
-    // otherwise the three ICP kernels and the grid build run as concurrent branches (their tails overlap).
+    // otherwise the CTA ICP kernel (and the grid build of map mode 1) run as concurrent branches.
     const bool serial = c->profiling;
     auto mark = [&]() { if (c->profiling) cudaEventRecord(c->ev[evi], st); ++evi; };
     // LIP_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
@@ -280,24 +278,23 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
             forked_icp = true;
         }
         // the CTA-per-partition kernel (few, long tasks) runs as a concurrent branch of the group kernel
-        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / LIP_WARP_CAP + 1);
+        int64_t bound = std::min<int64_t>(c->B, 2 * (int64_t)a.n_total / 256 + 1);     // heavy partitions hold > 256 points
         int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
         int gs = c->sm_count * c->group_blocks_per_sm;
         gs = std::max(1, std::min(gs, (c->B + LIP_ICP_WARPS - 1) / LIP_ICP_WARPS));
         if (serial) {
             icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
             mark();                                          // 3: after the group kernel
-            mark();                                          // 4: (unused)
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
         } else {
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, s_big>>>(a);
             icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
-            mark(); mark();
+            mark();
         }
         launches += 3;
         LIP_CHECK("icp_group_kernel / icp_big_kernel");
-    } else { mark(); mark(); mark(); }
-    mark();                                                  // 5: after big ICP
+    } else { mark(); mark(); }
+    mark();                                                  // 4: after the CTA ICP kernel
     const bool tiles = (stages & ST_BLEND) && c->map_mode == 0;      // final map on landmark-bin tiles: no grid needed
     if ((stages & (ST_GRID | ST_GRID_ALL)) && !tiles) {
         if (!serial) { LIP_CUDA(c, cudaStreamWaitEvent(s_grid, c->ev_begin, 0)); forked_grid = true; }
@@ -305,7 +302,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         grid_build_kernel<<<c->M, 256, 0, s_grid>>>(a, (stages & ST_GRID_ALL) ? 1 : 0);
         ++launches;
     }
-    mark();                                                  // 6: after grid build
+    mark();                                                  // 5: after grid build
     if (forked_icp) {
         LIP_CUDA(c, cudaEventRecord(c->ev_join[0], s_big)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
     }
@@ -315,18 +312,19 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
             blend_kernel<<<(a.n_total + 255) / 256, 256, 0, st>>>(a);
             ++launches;
             LIP_CHECK("blend_kernel");
+            mark();                                          // 6: after the blend kernel
             const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * c->map_blocks_per_sm);
             blend_tile_kernel<<<(unsigned)gm, LIP_MAP_THREADS, 0, st>>>(a);
         }
-        else blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
+        else { mark(); blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a); }
         ++launches;
-    }
+    } else mark();
     if ((stages & ST_QUERY) && c->n_tiles > 0) {
         nn_query_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a);
         ++launches;
     }
     LIP_CHECK("final map kernel");
-    mark();                                                  // 7: after blend / query
+    mark();                                                  // 7: after the final-map search / query kernel
     if ((stages & ST_BLEND) && !tiles && c->n_tiles > 0) {
         int gr = std::max(1, std::min(c->sm_count * 8, (a.n_total + 127) / 128));
         retry_nn_kernel<<<gr, 128, 0, st>>>(a);
@@ -345,7 +343,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     return LIP_OK;
 }
 
-const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // the fill is resolved inside blend_nn_kernel
+const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // (the grid is only built in map mode 1; the fill is resolved on the fly)
 
 // the sub-batch set the last run used (host pipeline or device split)
 std::vector<lip_ctx*>& split_kids(lip_ctx* c) { return c->last_run_dsplit ? c->dkids : c->kids; }

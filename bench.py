@@ -337,9 +337,9 @@ def run_b200(args):
     achieved = 8.0 * pairs[dom] / (stage[dom] / 1e3) / 1e12
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.exists(tpath) and args.config == 2 and args.frame_pairs == 64:       # captured on the default workload only
+    if os.path.exists(tpath) and args.config == 2 and args.frame_pairs == 64 and args.map_mode == 0:   # captured on the default workload only
         tj = json.load(open(tpath))
-        kmap = {"final_map_kernel": ("blend_kernel", "blend_tile_kernel")}
+        kmap = {"final_map_kernel": ("blend_tile_kernel",)}
         names = kmap.get(dom, (dom,))
         if all(n in tj["kernels"] for n in names):
             traffic = sum(tj["kernels"][n]["dram_bytes_per_launch"] for n in names)

@@ -121,8 +121,9 @@ int lip_batch_get_pair_counts(lip_ctx* ctx, int64_t pairs[3]);
  * launched on.  Enable with lip_set_profiling before the run; while it is on, the kernels run back to
  * back on one stream (normally the ICP kernels and the grid build run as concurrent branches).
  * ms[0] landmark_partition_kernel, [1] icp_schedule_kernel, [2] icp_group_kernel (warp per partition),
- * [3] unused (0), [4] icp_big_kernel (CTA per partition), [5] grid_build_kernel (+ its table memset),
- * [6] blend_nn_kernel / nn_query_kernel, [7] retry_nn_kernel, [8] far_nn_kernel. */
+ * [3] icp_big_kernel (CTA per partition), [4] grid_build_kernel (+ its table memset; 0 in map mode 0),
+ * [5] blend_kernel (map mode 0), [6] blend_tile_kernel (map mode 0) / blend_nn_kernel (mode 1) / nn_query_kernel,
+ * [7] retry_nn_kernel, [8] far_nn_kernel (both 0 in map mode 0). */
 #define LIP_N_STAGES 9
 int lip_set_profiling(lip_ctx* ctx, int on);
 int lip_batch_get_stage_ms(lip_ctx* ctx, float ms[LIP_N_STAGES]);
