@@ -49,7 +49,7 @@ struct lip_ctx {
     int sm_count = 0;
     int group_blocks_per_sm = 1, big_blocks_per_sm = 1, map_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: [0] CTA ICP kernel, [2] grid build
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: [0] CTA ICP kernel, [1] uploads of the host pipeline, [2] grid build
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool fill_done = false;
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
@@ -85,6 +85,7 @@ struct lip_ctx {
     bool profiling = false;
     cudaEvent_t ev[LIP_N_STAGES + 1] = {};
     bool ev_valid = false;
+    cudaEvent_t tr[4] = {};       // LIP_TRACE_PIPELINE: H2D start / end, kernels end, D2H end of the last host run
 };
 
 namespace {
@@ -350,23 +351,39 @@ std::vector<lip_ctx*>& split_kids(lip_ctx* c) { return c->last_run_dsplit ? c->d
 std::vector<int64_t>& split_seg(lip_ctx* c) { return c->last_run_dsplit ? c->dkid_seg : c->kid_seg; }
 int split_n(lip_ctx* c) { return c->last_run_dsplit ? c->n_dkids : c->n_kids; }
 
-// H2D of one (sub-)batch, the whole pipeline and D2H, all enqueued on the context's stream; no synchronisation
-int host_run_async(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                   int64_t* T21, int64_t* T12) {
-    cudaStream_t st = c->stream;
+// H2D of one (sub-)batch, enqueued on `up` (the context's own stream, or the parent's upload stream: then the context's
+// stream waits for it); no synchronisation
+int host_upload_async(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2, cudaStream_t up = nullptr) {
+    cudaStream_t st = up ? up : c->stream;
     const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
     LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
     LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    static const bool trace = getenv("LIP_TRACE_PIPELINE") != nullptr;     // per-sub-batch timeline (lip_batch_run_host prints it)
+    if (trace && !c->tr[0]) for (auto& e : c->tr) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(c->tr[0], st);
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
+    if (trace) cudaEventRecord(c->tr[1], st);
+    if (up) {
+        LIP_CUDA(c, cudaEventRecord(c->ev_fork, up));        // (ev_fork is re-recorded later by run_stages, after this wait is enqueued)
+        LIP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+    }
+    return LIP_OK;
+}
+// the whole pipeline on the uploaded (sub-)batch and D2H of the maps, enqueued on the context's stream
+int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12) {
+    cudaStream_t st = c->stream;
+    static const bool trace = getenv("LIP_TRACE_PIPELINE") != nullptr;
     int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
                         c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
     if (rc) return rc;
+    if (trace) cudaEventRecord(c->tr[2], st);
     if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
     if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
+    if (trace) cudaEventRecord(c->tr[3], st);
     return LIP_OK;
 }
 
@@ -571,21 +588,38 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
     if (c->n_kids >= 2) {
-        // pipelined: every sub-batch on its own stream — copies in, kernels and copies out of different sub-batches overlap
+        // pipelined: every sub-batch on its own stream — copies in, kernels and copies out of different sub-batches overlap.
+        // All uploads are enqueued first, on ONE stream: issuing the kernels of a sub-batch takes the host longer than its
+        // upload takes the copy engine (which must never wait for the host), and in-order uploads give every sub-batch its
+        // data as early as possible.
         for (int k = 0; k < c->n_kids; ++k) {
             lip_ctx* kc = c->kids[k];
             const int64_t s0 = c->kid_seg[k];
             kc->params = c->params;
-            int rc = host_run_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0],
-                                    lm2 + 3 * c->h_lm_off[s0], T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr);
+            int rc = host_upload_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
+                                       c->side[1]);         // one upload stream: the sub-batches arrive in order, each as early as possible
+            if (rc) return fail(c, rc, "pipeline upload: " + kc->err);
+        }
+        for (int k = 0; k < c->n_kids; ++k) {
+            lip_ctx* kc = c->kids[k];
+            const int64_t s0 = c->kid_seg[k];
+            int rc = host_compute_async(kc, T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr);
             if (rc) return fail(c, rc, "pipeline run: " + kc->err);
         }
         for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
+        if (getenv("LIP_TRACE_PIPELINE") && c->kids[0]->tr[0]) {
+            for (int k = 0; k < c->n_kids; ++k) {
+                float t[4];
+                for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->kids[0]->tr[0], c->kids[k]->tr[i]);
+                fprintf(stderr, "[lip pipeline] sub-batch %d: H2D %.3f-%.3f ms, kernels end %.3f, D2H end %.3f\n", k, t[0], t[1], t[2], t[3]);
+            }
+        }
         c->last_run_split = true; c->last_run_dsplit = false;
         return LIP_OK;
     }
     c->last_run_split = false; c->last_run_dsplit = false;
-    int rc = host_run_async(c, xyz1, xyz2, lm1, lm2, T21, T12);
+    int rc = host_upload_async(c, xyz1, xyz2, lm1, lm2);
+    if (rc == LIP_OK) rc = host_compute_async(c, T21, T12);
     if (rc) return rc;
     LIP_CUDA(c, cudaStreamSynchronize(c->stream));
     return LIP_OK;
