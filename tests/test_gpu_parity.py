@@ -458,3 +458,29 @@ def test_match_segments_batch_reproduces_the_reference_body(L):
     np.testing.assert_array_equal(np.concatenate(r.T12s), g["T12r"])
     np.testing.assert_allclose(r.scores, g["score"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(r.score, np.average(g["score"], axis=0, weights=np.diff(g["off1"])), rtol=0, atol=1e-12)
+
+
+def test_c_abi_error_behaviour(L):
+    """status codes of include/local_icp.h surface as exceptions: LIP_ENOPLAN / LIP_ECUDA -> NativeError, LIP_EINVAL -> ValueError"""
+    ctx = L.Context(0)
+    x = np.random.default_rng(1).normal(size=(50, 3))
+    with pytest.raises(L.NativeError):                       # run before plan
+        ctx.lib.lip_batch_run_host.restype                   # (symbol exists)
+        ctx._check(ctx.lib.lip_batch_run_host(ctx.h, x.ctypes.data, x.ctypes.data, x.ctypes.data, x.ctypes.data, None, None))
+    with pytest.raises(ValueError):                          # more landmarks than LIP_MAX_LANDMARKS in one segment
+        ctx.plan([0, 50], [0, 50], [0, 4096])
+    with pytest.raises(ValueError):                          # empty mesh
+        ctx.plan([0, 0], [0, 50], [0, 2])
+    with pytest.raises(ValueError):                          # directions must name T21 and/or T12
+        ctx.plan([0, 50], [0, 50], [0, 2], directions=0)
+    ctx.plan([0, 50], [0, 50], [0, 2], directions=L.DIR_T21)
+    T21, T12 = ctx.run_host(x, x + 0.01, x[:2], x[:2])
+    assert T12 is None and T21.shape == (50,)
+    with pytest.raises(ValueError):                          # the whole per-segment body needs both directions
+        ctx.match(x, x, x[:2], x[:2])
+    with pytest.raises(ValueError):                          # wrong array sizes for the planned batch
+        ctx.run_host(x[:10], x, x[:2], x[:2])
+    ctx.plan([0, 4], [0, 50], [0, 2])
+    with pytest.raises(ValueError):                          # refinement needs >= 5 vertices in mesh1 (KDTree.query(k=5))
+        ctx.refine(x[:4], x, np.zeros(50, np.int64), np.zeros(4, np.int64))
+    ctx.close()
