@@ -73,6 +73,7 @@ struct LipArgs {
     double* q_dist;          // raw-query mode: distance output over xyz2 (or nullptr)
     unsigned long long* counters;  // [8]
     int max_iter, profile;   // profile != 0: count evaluated candidate pairs (counters[7])
+    int icp_tasks_per_warp, icp_class_shift;   // group sizes of icp_group_kernel (tuning knobs)
     int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };

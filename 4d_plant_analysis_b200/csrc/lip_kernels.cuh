@@ -8,6 +8,12 @@
 #endif
 #define LIP_ICP_WARPS 4       // warps per CTA of icp_group_kernel
 #define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp
+#ifndef LIP_ICP_TASKS_PER_WARP
+#define LIP_ICP_TASKS_PER_WARP 1   // group size cap: at least this many tasks per resident warp
+#endif
+#ifndef LIP_ICP_CLASS_SHIFT
+#define LIP_ICP_CLASS_SHIFT 4       // work classes up to this one use groups of LIP_ICP_GMAX, each heavier class half as many
+#endif
 #define LIP_ICP_GMAX 8        // partitions per warp task: their 3x3 solves run SIMT, one lane per partition
 #define LIP_BIG_CHUNK 1024    // tgt tile (float4) of the CTA-per-partition variant
 #define LIP_BIG_THREADS 128
@@ -565,8 +571,8 @@ struct IcpGroupSmem {
     IcpState st[LIP_ICP_GMAX];
     double acc[LIP_ICP_GMAX][17];
 };
-// partitions per task of work class c (n_src * n_tgt in [512 * 2^c, 1024 * 2^c)): heavy classes go one by one
-__device__ __forceinline__ int icp_class_group(int c, int gcap) { return max(1, min(gcap, LIP_ICP_GMAX >> max(c - 3, 0))); }
+// partitions per task of work class c (n_src * n_tgt in [512 * 2^c, 1024 * 2^c)): 8 up to 16k pairs, then 4, 2, 1
+__device__ __forceinline__ int icp_class_group(int c, int gcap, int shift) { return max(1, min(gcap, LIP_ICP_GMAX >> max(c - shift, 0))); }
 
 __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_group_kernel(LipArgs a) {
     __shared__ IcpGroupSmem sm_all[LIP_ICP_WARPS];
@@ -574,17 +580,18 @@ __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_gr
     const int lane = threadIdx.x & 31;
     const int n_items = a.sched[0];
     // group size cap: as large as leaves every resident warp a few tasks
-    const int gcap = max(1, min(n_items / (int)(gridDim.x * LIP_ICP_WARPS * 3), LIP_ICP_GMAX));
+    const int gcap = max(1, min(n_items / (int)(gridDim.x * LIP_ICP_WARPS * a.icp_tasks_per_warp), LIP_ICP_GMAX));
+    const int gshift = a.icp_class_shift;
     int n_tasks = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { const int G = icp_class_group(c, gcap); n_tasks += (a.sched[24 + c] + G - 1) / G; }
+    for (int c = 0; c < 8; ++c) { const int G = icp_class_group(c, gcap, gshift); n_tasks += (a.sched[24 + c] + G - 1) / G; }
     for (;;) {                                              // persistent warps, dynamic task queue, heaviest class first
         int w = 0;
         if (lane == 0) w = atomicAdd(&a.sched[2], 1);
         w = __shfl_sync(LIP_FULL, w, 0);
         if (w >= n_tasks) break;
-        int c = 7, G = icp_class_group(7, gcap), tc = (a.sched[24 + 7] + G - 1) / G;
-        while (c > 0 && w >= tc) { w -= tc; --c; G = icp_class_group(c, gcap); tc = (a.sched[24 + c] + G - 1) / G; }
+        int c = 7, G = icp_class_group(7, gcap, gshift), tc = (a.sched[24 + 7] + G - 1) / G;
+        while (c > 0 && w >= tc) { w -= tc; --c; G = icp_class_group(c, gcap, gshift); tc = (a.sched[24 + c] + G - 1) / G; }
         const int first = w * G, g = min(G, a.sched[24 + c] - first);
         // ---- lane p < g owns partition p of the task -------------------------------------------------------
         int b = 0, own_ns = 1, iters = 0, status = 1;
