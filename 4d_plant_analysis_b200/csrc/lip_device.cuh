@@ -74,6 +74,7 @@ struct LipArgs {
     unsigned long long* counters;  // [8]
     int max_iter, profile;   // profile != 0: count evaluated candidate pairs (counters[7])
     int icp_tasks_per_warp, icp_class_shift;   // group sizes of icp_group_kernel (tuning knobs)
+    long long warp_work;     // partitions with n_src * n_tgt <= this go to icp_group_kernel, heavier ones to icp_big_kernel
     int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };

@@ -272,7 +272,7 @@ __global__ void icp_schedule_kernel(LipArgs a) {
     }
     if (ns == 0 || nt == 0) return;
     const long long w = (long long)ns * nt;
-    if (w <= LIP_WARP_WORK) {
+    if (w <= a.warp_work) {
         // eight work classes (factor 2 apart); the persistent warps take groups of partitions heaviest class first
         int cls = 0;
         for (long long t = 1024; t <= w && cls < 7; t <<= 1) ++cls;
