@@ -4,7 +4,9 @@
 #include "lip_device.cuh"
 
 #ifndef LIP_WARP_WORK
-#define LIP_WARP_WORK 65536    // partitions with n_src * n_tgt <= this: icp_group_kernel (a warp per partition), else CTA
+#define LIP_WARP_WORK 32768         // partitions with n_src * n_tgt <= this: icp_group_kernel (a warp per partition), else CTA ...
+#define LIP_WARP_WORK_LARGE 98304   // ... in batches of at least LIP_WARP_WORK_BINS landmark bins this much (measured, profiles/README.md)
+#define LIP_WARP_WORK_BINS 12000
 #endif
 #define LIP_ICP_WARPS 4       // warps per CTA of icp_group_kernel
 #define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp

@@ -156,8 +156,10 @@ void set_param_args(lip_ctx* c) {
     static const int tpw = getenv("LIP_ICP_TASKS_PER_WARP") ? std::max(1, atoi(getenv("LIP_ICP_TASKS_PER_WARP"))) : LIP_ICP_TASKS_PER_WARP;
     static const int csh = getenv("LIP_ICP_CLASS_SHIFT") ? atoi(getenv("LIP_ICP_CLASS_SHIFT")) : LIP_ICP_CLASS_SHIFT;
     a.icp_tasks_per_warp = tpw; a.icp_class_shift = csh;
-    static const long long ww = getenv("LIP_WARP_WORK") ? atoll(getenv("LIP_WARP_WORK")) : LIP_WARP_WORK;
-    a.warp_work = ww;
+    // warp / CTA split of the ICP partitions: large batches keep the (more efficient) warp kernel busy with up to 96 k pairs
+    // per partition, small ones (the sub-batches of the host pipeline) hand more to the CTA kernel, whose tails are shorter
+    static const long long ww = getenv("LIP_WARP_WORK") ? atoll(getenv("LIP_WARP_WORK")) : 0;
+    a.warp_work = ww > 0 ? ww : (c->B >= LIP_WARP_WORK_BINS ? LIP_WARP_WORK_LARGE : LIP_WARP_WORK);
 }
 
 int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {

@@ -323,12 +323,13 @@ def run_b200(args):
     iters = np.concatenate([tr["iters21"], tr["iters12"]]).astype(np.float64)
     mx = np.maximum(ns, nt)
     w = iters * ns * nt                                        # evaluated (source, candidate) pairs per partition
-    brute = {"icp_group_kernel": float(w[ns * nt <= 65536].sum()),          # n_src * n_tgt * passes: what a brute-force scan evaluates
-             "icp_big_kernel": float(w[ns * nt > 65536].sum())}
+    split = 98304 if 2 * sumK >= 12000 else 32768               # LIP_WARP_WORK_LARGE / LIP_WARP_WORK of the (unsplit) profiled run
+    brute = {"icp_group_kernel": float(w[ns * nt <= split].sum()),          # n_src * n_tgt * passes: what a brute-force scan evaluates
+             "icp_big_kernel": float(w[ns * nt > split].sum())}
     # algorithmic pair counts: brute force inside a partition for the ICP kernels (padding excluded), the candidates the
     # final map actually evaluates (box-pruned bins, windowed along the sort axis)
     pairs = dict(brute, final_map_kernel=float(pair_counts["final_map_kernel"]))
-    big = ns * nt > 65536
+    big = ns * nt > split
     it_stats = {"group": {"n": int((~big & (iters > 0)).sum()), "mean": float(iters[~big & (iters > 0)].mean()), "p99": float(np.percentile(iters[~big & (iters > 0)], 99)), "max": float(iters[~big].max())},
                 "big": {"n": int((big & (iters > 0)).sum()), "mean": float(iters[big & (iters > 0)].mean()) if (big & (iters > 0)).any() else 0.0,
                         "p99": float(np.percentile(iters[big & (iters > 0)], 99)) if (big & (iters > 0)).any() else 0.0, "max": float(iters[big].max()) if big.any() else 0.0}}
