@@ -17,7 +17,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "liblocalicp.so")
+LIB_PATH = os.environ.get("LIP_LIBRARY") or os.path.join(PKG_DIR, "liblocalicp.so")   # (LIP_LIBRARY: tuning variants)
 SOURCES = ["local_icp.cu", "lip_kernels.cuh", "lip_device.cuh"]
 HEADER = os.path.join(ROOT, "include", "local_icp.h")
 

@@ -8,21 +8,33 @@
 #define LIP_WARP_WORK_LARGE 98304   // ... in batches of at least LIP_WARP_WORK_BINS landmark bins this much (measured, profiles/README.md)
 #define LIP_WARP_WORK_BINS 12000
 #endif
+#ifndef LIP_ICP_WARPS
 #define LIP_ICP_WARPS 4       // warps per CTA of icp_group_kernel
+#endif
+#ifndef LIP_ICP_CHUNK
 #define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp
+#endif
 #ifndef LIP_ICP_TASKS_PER_WARP
 #define LIP_ICP_TASKS_PER_WARP 1   // group size cap: at least this many tasks per resident warp
 #endif
 #ifndef LIP_ICP_CLASS_SHIFT
 #define LIP_ICP_CLASS_SHIFT 4       // work classes up to this one use groups of LIP_ICP_GMAX, each heavier class half as many
 #endif
+#ifndef LIP_ICP_GMAX
 #define LIP_ICP_GMAX 8        // partitions per warp task: their 3x3 solves run SIMT, one lane per partition
+#endif
+#ifndef LIP_BIG_CHUNK
 #define LIP_BIG_CHUNK 1024    // tgt tile (float4) of the CTA-per-partition variant
+#endif
+#ifndef LIP_BIG_THREADS
 #define LIP_BIG_THREADS 128
+#endif
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
 #define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA, two queries per thread
 #define LIP_MAP_TILE (2 * LIP_MAP_THREADS)
+#ifndef LIP_MAP_CHUNK
 #define LIP_MAP_CHUNK 512    // candidates staged per scan
+#endif
 #define LIP_MAP_BOXBATCH 64
 #ifndef LIP_WARP_MINBLOCKS
 #define LIP_WARP_MINBLOCKS 5   // CTAs per SM the warp-per-partition kernels are compiled for (register cap 96)
