@@ -159,7 +159,7 @@ def test_nn_duplicate_targets_lowest_index(L):
     assert (i == 7).all()
 
 
-@pytest.mark.parametrize("config,scale", [(1, 1.0), (2, 0.34), (3, 0.3), (5, 0.02)])
+@pytest.mark.parametrize("config,scale", [(1, 1.0), (2, 0.34), (3, 0.3), (4, 0.07), (5, 0.02)])
 def test_configs_against_oracle(L, config, scale):
     """seeded BASELINE configs at sizes the oracle finishes in seconds; both directions, whole batch"""
     b = L.make_config(config, scale=scale)
