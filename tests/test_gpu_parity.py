@@ -484,3 +484,29 @@ def test_c_abi_error_behaviour(L):
     with pytest.raises(ValueError):                          # refinement needs >= 5 vertices in mesh1 (KDTree.query(k=5))
         ctx.refine(x[:4], x, np.zeros(50, np.int64), np.zeros(4, np.int64))
     ctx.close()
+
+
+def test_max_landmarks_segment(L):
+    """LIP_MAX_LANDMARKS (2,048) landmarks in one segment: largest dynamic shared-memory footprint of the partition
+    kernel, 32 batches of 64 bins in the final map's box pass; one landmark more is rejected"""
+    rng = np.random.default_rng(33)
+    K, n = 2048, 40000
+    Lx = 3.0 * K
+    x1 = _tube(rng, n, Lx)
+    x2 = _tube(rng, n + 500, Lx) + [0.3, 0.1, -0.1]
+    lm1 = np.stack([np.linspace(1.0, Lx - 1.0, K), np.zeros(K), np.zeros(K)], 1)
+    lm2 = lm1 + [0.3, 0.1, -0.1]
+    res = L.local_icp_batch([(x1, x2, lm1, lm2)], details=True)
+    det = {}
+    T_or = O.segment_map(x1, x2, lm1, lm2, nn="brute", details=det)
+    st = res.transforms["raw"]["status21"]
+    np.testing.assert_array_equal(st != 0, det["valid"])
+    ok = st == 1
+    same = res.transforms["raw"]["iters21"][ok] == det["iters"][ok]
+    assert same.mean() > 0.995
+    np.testing.assert_allclose(res.transforms["R21"][ok][same], det["R"][ok][same], rtol=0, atol=RT_TOL)
+    bad = np.nonzero(res.T21 != T_or)[0]
+    assert len(bad) <= 0.002 * len(T_or)                      # only points fed by the few partitions with another stop decision
+    with pytest.raises(ValueError):
+        lm3 = np.vstack([lm1, lm1[-1:] + 1.0])
+        L.local_icp_batch([(x1, x2, lm3, lm3)])
