@@ -14,6 +14,12 @@
 #ifndef LIP_ICP_CHUNK
 #define LIP_ICP_CHUNK 256     // target points per SMEM tile of a warp
 #endif
+#ifndef LIP_ICP_SUM17
+#define LIP_ICP_SUM17 1       // 1: the 17 float64 sums of a pass are reduced through an SMEM transpose (the dead search tile), 0: 17 butterflies
+#endif
+#ifndef LIP_ICP_QCAP
+#define LIP_ICP_QCAP 512      // queries of a partition whose winner is kept in SMEM (one byte each; the rest go through nn_idx)
+#endif
 #ifndef LIP_ICP_TASKS_PER_WARP
 #define LIP_ICP_TASKS_PER_WARP 1   // group size cap: at least this many tasks per resident warp
 #endif
@@ -37,7 +43,7 @@
 #endif
 #define LIP_MAP_BOXBATCH 64
 #ifndef LIP_WARP_MINBLOCKS
-#define LIP_WARP_MINBLOCKS 5   // CTAs per SM the warp-per-partition kernels are compiled for (register cap 96)
+#define LIP_WARP_MINBLOCKS 5   // CTAs per SM icp_group_kernel is compiled for (register cap 96)
 #endif
 
 // =============================================================================================
@@ -461,16 +467,17 @@ __device__ __forceinline__ void icp_stage(const LipArgs& a, float4* tf, int to, 
 // source bin at so/ns, target bin at to/nt; frame centred on c (the target centroid); the tile points are the
 // stored offsets shifted by sh = landmark - c.  Returns this thread's partial sums in acc[17]:
 // 0 sum dist | 1..3 sum p | 4..6 sum b | 7..15 sum p_i b_j | 16 pairs kept.
-template <bool DOT, int NT, int CHUNK>
-__device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const IcpState* st, int tid, int so, int ns, int to, int nt,
-                                         double c0, double c1, double c2, float sh0, float sh1, float sh2, float mabs,
-                                         double (&acc)[17]) {
+template <bool DOT, int NT, int CHUNK, bool TS>
+__device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, unsigned char* nns, const IcpState* st, int tid,
+                                         int so, int ns, int to, int nt, double c0, double c1, double c2,
+                                         float sh0, float sh1, float sh2, float mabs, double* __restrict__ out17) {
     const size_t N = (size_t)a.n_total;
     const double* __restrict__ sx = a.bin_xyz + so;
     const double* __restrict__ tx = a.bin_xyz + to;
     int* __restrict__ nn_idx = a.nn_idx + so;
     const float sc = DOT ? -2.0f : 1.0f;
     const bool one_chunk = nt <= CHUNK;
+    const bool staged = TS && one_chunk;                     // winners fit one byte: they stay in SMEM between the two phases
     if (one_chunk) { coop_sync<NT>(); icp_stage<DOT, NT>(a, tf, to, 0, nt, tid, sh0, sh1, sh2); coop_sync<NT>(); }
     unsigned long long scanned = 0;
     for (int q0 = 0; q0 < ns; q0 += 2 * NT) {
@@ -531,16 +538,20 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
                 }
                 if ((tid & 31) == src) idx[k] = bj;
             }
-            if (qi[k] < ns) nn_idx[qi[k]] = idx[k];
+            if (qi[k] < ns) {
+                if (staged && qi[k] < LIP_ICP_QCAP) nns[qi[k]] = (unsigned char)idx[k];
+                else nn_idx[qi[k]] = idx[k];
+            }
         }
     }
     if (a.profile && (tid & 31) == 0) atomicAdd(&a.counters[NT == 32 ? 4 : 5], scanned);   // candidate pairs evaluated (incl. padding)
     // ---- sums of get_best_fit_transform + cost over the (source, winner) pairs, float64 ----
+    double acc[17];
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = 0.0;
     const double reject = a.reject_dist;
     for (int q = tid; q < ns; q += NT) {
-        const int w = nn_idx[q];
+        const int w = (staged && q < LIP_ICP_QCAP) ? (int)nns[q] : nn_idx[q];     // written by this very lane
         double px, py, pz;
         mat3_vec(st->R, sx[q] - c0, sx[N + q] - c1, sx[2 * N + q] - c2, px, py, pz);
         px += st->t[0]; py += st->t[1]; pz += st->t[2];
@@ -556,11 +567,43 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, const Icp
             acc[16] += 1.0;
         }
     }
+    // ---- the warp's 17 sums -> out17[0..16] ----
+    const int lane = tid & 31;
+#if LIP_ICP_SUM17
+    // reduce-scatter through SMEM instead of 17 butterflies: the search tile is dead by now and serves as scratch, 16 rows
+    // (sums 1..16) of 32 doubles per warp, column l of row i stored at l ^ i (conflict-free both ways); lane (r, h) adds
+    // half h of row r, one shuffle joins the halves.  Sum 0 (the cost) takes the butterfly.
+    coop_sync<NT>();
+    double* scr = reinterpret_cast<double*>(tf) + (size_t)(tid >> 5) * (16 * 32);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) scr[i * 32 + (lane ^ i)] = acc[i + 1];
+    __syncwarp();
+    {
+        const int r = lane & 15, h = lane & 16;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += scr[r * 32 + ((h + k) ^ r)];
+        s += __shfl_xor_sync(LIP_FULL, s, 16);
+        if (lane < 16) out17[1 + r] = s;
+    }
+    const double s0 = warp_sum(acc[0]);
+    if (lane == 0) out17[0] = s0;
+    __syncwarp();
+#else
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) out17[i] = acc[i];
+    }
+#endif
 }
 
 // frame of one ICP: centre = target centroid, tile shift = target landmark - centre, bound on |tile coordinate|
+#if LIP_ICP_SUM17
+static_assert((LIP_ICP_CHUNK + 8) * 16 >= 16 * 32 * 8 && (LIP_BIG_CHUNK + 8) * 16 >= (LIP_BIG_THREADS / 32) * 16 * 32 * 8,
+              "the search tile doubles as the scratch of the 17-sum reduction: 4 KB per warp");
+#endif
 struct IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; };
 __device__ __forceinline__ IcpFrame icp_frame(const LipArgs& a, int b) {
     IcpFrame f;
@@ -584,13 +627,14 @@ struct IcpGroupSmem {
     float4 tf[LIP_ICP_CHUNK + 8];                         // fp32 search tile
     IcpState st[LIP_ICP_GMAX];
     double acc[LIP_ICP_GMAX][17];
+    unsigned char nn[LIP_ICP_QCAP ? LIP_ICP_QCAP : 1];                       // winner of every query of the current pass
 };
 // partitions per task of work class c (n_src * n_tgt in [512 * 2^c, 1024 * 2^c)): 8 up to 16k pairs, then 4, 2, 1
 __device__ __forceinline__ int icp_class_group(int c, int gcap, int shift) { return max(1, min(gcap, LIP_ICP_GMAX >> max(c - shift, 0))); }
 
 __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_group_kernel(LipArgs a) {
-    __shared__ IcpGroupSmem sm_all[LIP_ICP_WARPS];
-    IcpGroupSmem& sm = sm_all[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char icp_group_smem[];
+    IcpGroupSmem& sm = reinterpret_cast<IcpGroupSmem*>(icp_group_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int n_items = a.sched[0];
     // group size cap: as large as leaves every resident warp a few tasks
@@ -629,14 +673,9 @@ __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_gr
                 const int p = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const IcpFrame f = icp_frame(a, __shfl_sync(LIP_FULL, b, p));
-                double acc[17];
                 // dot-form scores only while the cancellation error stays far below the point spacing
-                if (f.mabs <= 24.0f) icp_pass<true, 32, LIP_ICP_CHUNK>(a, sm.tf, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
-                else icp_pass<false, 32, LIP_ICP_CHUNK>(a, sm.tf, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
-                if (lane == 0) {
-#pragma unroll
-                    for (int i = 0; i < 17; ++i) sm.acc[p][i] = acc[i];
-                }
+                if (f.mabs <= 24.0f) icp_pass<true, 32, LIP_ICP_CHUNK, true>(a, sm.tf, sm.nn, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, sm.acc[p]);
+                else icp_pass<false, 32, LIP_ICP_CHUNK, true>(a, sm.tf, sm.nn, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, sm.acc[p]);
             }
             __syncwarp();
             if (active) {                                       // SIMT over the task's partitions
@@ -704,13 +743,8 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS, 4) icp_big_kernel(LipArgs a) 
             if (!s_go) break;
             if (warp == 0) icp_state_accumulate(st);
             __syncthreads();
-            double acc[17];
-            if (f.mabs <= 24.0f) icp_pass<true, LIP_BIG_THREADS, LIP_BIG_CHUNK>(a, tf, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
-            else icp_pass<false, LIP_BIG_THREADS, LIP_BIG_CHUNK>(a, tf, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, acc);
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 17; ++i) red17[warp][i] = acc[i];
-            }
+            if (f.mabs <= 24.0f) icp_pass<true, LIP_BIG_THREADS, LIP_BIG_CHUNK, false>(a, tf, nullptr, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, red17[warp]);
+            else icp_pass<false, LIP_BIG_THREADS, LIP_BIG_CHUNK, false>(a, tf, nullptr, st, tid, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, red17[warp]);
             __syncthreads();
             if (warp == 0) {                                 // serial part: all lanes of warp 0 identically
                 if (lane < 17) {

@@ -22,6 +22,9 @@
 
 namespace {
 
+constexpr size_t kGroupSmem = sizeof(IcpGroupSmem) * LIP_ICP_WARPS;     // dynamic SMEM of icp_group_kernel (> 48 KB: opt-in)
+static_assert(LIP_ICP_CHUNK <= 256, "winners of a staged partition are stored as one byte");
+
 std::string g_startup_error;
 
 struct DevBuf {
@@ -291,12 +294,12 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         int gs = c->sm_count * c->group_blocks_per_sm;
         gs = std::max(1, std::min(gs, (c->B + LIP_ICP_WARPS - 1) / LIP_ICP_WARPS));
         if (serial) {
-            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
+            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, kGroupSmem, st>>>(a);
             mark();                                          // 3: after the group kernel
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
         } else {
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, s_big>>>(a);
-            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, 0, st>>>(a);
+            icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, kGroupSmem, st>>>(a);
             mark();
         }
         launches += 3;
@@ -442,7 +445,8 @@ int lip_create(lip_ctx** out, int device) {
     cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_group_kernel, LIP_ICP_WARPS * 32, 0) == cudaSuccess && nb > 0)
+    cudaFuncSetAttribute(icp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_group_kernel, LIP_ICP_WARPS * 32, kGroupSmem) == cudaSuccess && nb > 0)
         c->group_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, blend_tile_kernel, LIP_MAP_THREADS, 0) == cudaSuccess && nb > 0)
         c->map_blocks_per_sm = nb;
