@@ -50,6 +50,8 @@ SIGNATURES = {
     "lip_batch_evaluate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, _D, _I64]),
     "lip_batch_refine_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lip_batch_match_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, _D]),
+    "lip_batch_interpolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
+    "lip_batch_interpolate_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
     "lip_icp_host": (c_int, [c_void_p, c_int64, _D, _I64, _D, _I64, _D, _D, _I32, _I32]),
     "lip_nn_host": (c_int, [c_void_p, _D, c_int64, _D, c_int64, _D, _I64]),
     "lip_kabsch_host": (c_int, [c_void_p, _D, _D, c_int64, _D, _D, _I32]),
@@ -242,6 +244,21 @@ class Context:
             raise ValueError("array sizes do not match the planned batch")
         self._check(self.lib.lip_batch_refine_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, out.ctypes.data, T12.ctypes.data))
         return out
+
+    def interpolate(self, xyz1, xyz2, T21, T12, alpha):
+        """interpolation_segment_level of the planned batch: (n1 + n2, 3) float64, per segment pair the n2 rows
+        (1 - alpha) * xyz1[T21] + alpha * xyz2 followed by the n1 rows (1 - alpha) * xyz1 + alpha * xyz2[T12]"""
+        xyz1, xyz2, T21, T12 = _f64(xyz1), _f64(xyz2), _i64(T21), _i64(T12)
+        if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(T21) != self.n2 or len(T12) != self.n1:
+            raise ValueError("array sizes do not match the planned batch")
+        out = np.empty((self.n1 + self.n2, 3), np.float64)
+        self._check(self.lib.lip_batch_interpolate_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, T21.ctypes.data, T12.ctypes.data,
+                                                        float(alpha), out.ctypes.data))
+        return out
+
+    def interpolate_device(self, d_xyz1, d_xyz2, d_T21, d_T12, alpha, d_out, stream=0):
+        """the same on device pointers (ints), enqueued on `stream`; no synchronisation"""
+        self._check(self.lib.lip_batch_interpolate_device(self.h, d_xyz1, d_xyz2, d_T21, d_T12, float(alpha), d_out, stream))
 
     def transforms(self, filled=True):
         K = self.sumK

@@ -1907,3 +1907,31 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
     __syncwarp();
     for (int i = lane; i < n2; i += 32) t21g[i] = w.t21[i];
 }
+
+
+// =============================================================================================
+// interpolation_segment_level (interpolation/interpolation_pcd.py:122-134): for every segment pair the rows
+//   (1 - alpha) * xyz1[T21] + alpha * xyz2        (n2 rows, mesh2 pulled back onto its matches)
+//   (1 - alpha) * xyz1      + alpha * xyz2[T12]   (n1 rows, mesh1 pushed towards its matches)
+// stacked in that order.  numpy evaluates the two products and the sum separately (no contraction): so do we.
+// A negative map entry counts from the end, as numpy's fancy indexing does; anything else out of range sets err.
+// =============================================================================================
+__global__ void __launch_bounds__(256) interpolate_kernel(LipArgs a, const long long* __restrict__ T21, const long long* __restrict__ T12,
+                                                          double alpha, double* __restrict__ out, int* __restrict__ err) {
+    const int s = blockIdx.x;
+    const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
+    const int u2 = a.mesh_ubase[a.S + s] - a.n1_total, n2 = a.mesh_ubase[a.S + s + 1] - a.n1_total - u2;
+    const double* __restrict__ x1 = a.xyz1 + 3 * (size_t)u1;
+    const double* __restrict__ x2 = a.xyz2 + 3 * (size_t)u2;
+    double* __restrict__ o = out + 3 * ((size_t)u1 + (size_t)u2);
+    const double w1 = 1.0 - alpha;
+    for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < n1 + n2; r += gridDim.y * blockDim.x) {
+        long long i, j;
+        if (r < n2) { j = r; i = T21[u2 + r]; if (i < 0) i += n1; }
+        else { i = r - n2; j = T12[u1 + (r - n2)]; if (j < 0) j += n2; }
+        if (i < 0 || i >= n1 || j < 0 || j >= n2) { atomicExch(err, 1); continue; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            o[3 * (size_t)r + k] = __dadd_rn(__dmul_rn(w1, x1[3 * (size_t)i + k]), __dmul_rn(alpha, x2[3 * (size_t)j + k]));
+    }
+}

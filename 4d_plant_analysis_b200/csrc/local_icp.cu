@@ -964,6 +964,61 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
     return LIP_OK;
 }
 
+// interpolation_segment_level for the planned batch on device-resident arrays; d_err: one int, zeroed here
+static int interpolate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const long long* d_T21, const long long* d_T12,
+                              double alpha, double* d_out, int* d_err, cudaStream_t st) {
+    LipArgs a = c->args;
+    a.xyz1 = d_xyz1; a.xyz2 = d_xyz2;
+    int64_t max_rows = 1;
+    for (size_t s = 0; s < (size_t)c->S; ++s)
+        max_rows = std::max(max_rows, (c->h_off1[s + 1] - c->h_off1[s]) + (c->h_off2[s + 1] - c->h_off2[s]));
+    LIP_CUDA(c, cudaMemsetAsync(d_err, 0, 4, st));
+    // rows of one segment pair over blockIdx.y: enough CTAs for a full wave, at most one per 256 rows
+    const int64_t want = (4 * (int64_t)c->sm_count + c->S - 1) / c->S;
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>((max_rows + 255) / 256, std::max<int64_t>(want, 1)));
+    interpolate_kernel<<<dim3((unsigned)c->S, gy), 256, 0, st>>>(a, d_T21, d_T12, alpha, d_out, d_err);
+    LIP_CUDA(c, cudaGetLastError());
+    c->last_launches = 1;
+    return LIP_OK;
+}
+
+int lip_batch_interpolate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const int64_t* d_T21, const int64_t* d_T12,
+                                 double alpha, double* d_out, void* stream) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
+    if (!d_xyz1 || !d_xyz2 || !d_T21 || !d_T12 || !d_out) return fail(c, LIP_EINVAL, "interpolate: null pointer");
+    cudaSetDevice(c->device);
+    LIP_CUDA(c, c->misc2.ensure(16));
+    return interpolate_device(c, d_xyz1, d_xyz2, (const long long*)d_T21, (const long long*)d_T12, alpha, d_out,
+                              c->misc2.as<int>(), (cudaStream_t)stream);
+}
+
+int lip_batch_interpolate_host(lip_ctx* c, const double* xyz1, const double* xyz2, const int64_t* T21, const int64_t* T12,
+                               double alpha, double* out) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
+    if (!xyz1 || !xyz2 || !T21 || !T12 || !out) return fail(c, LIP_EINVAL, "interpolate: null pointer");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24;
+    LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
+    LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
+    LIP_CUDA(c, c->misc.ensure(b1 + b2)); LIP_CUDA(c, c->misc2.ensure(16));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, (size_t)c->n2 * 8, cudaMemcpyHostToDevice, st));
+    LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, (size_t)c->n1 * 8, cudaMemcpyHostToDevice, st));
+    int rc = interpolate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(),
+                                c->out_T12.as<long long>(), alpha, c->misc.as<double>(), c->misc2.as<int>(), st);
+    if (rc) return rc;
+    int h_err = 0;
+    LIP_CUDA(c, cudaMemcpyAsync(out, c->misc.p, b1 + b2, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaMemcpyAsync(&h_err, c->misc2.p, 4, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaStreamSynchronize(st));
+    if (h_err) return fail(c, LIP_EINVAL, "interpolate: map entry out of range");
+    return LIP_OK;
+}
+
 int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_off, const double* tgt,
                  const int64_t* tgt_off, double* R, double* t, int32_t* iters, int32_t* status) {
     if (!c) return LIP_EINVAL;

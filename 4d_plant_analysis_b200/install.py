@@ -60,6 +60,11 @@ def install(verbose: bool = False):
         if seg is not None and hasattr(seg, "double_direction_refinement"):   # imported by name into the driver module
             seg.double_direction_refinement = _fm.double_direction_refinement
             done.append((seg.__name__, "double_direction_refinement"))
+    ip = sys.modules.get("interpolation.interpolation_pcd")     # only if the caller imported it (it needs open3d, imageio)
+    if ip is not None:
+        from . import interpolation_pcd as _ip
+        ip.interpolation_segment_level = _ip.interpolation_segment_level
+        done.append((ip.__name__, "interpolation_segment_level"))
     if verbose:
         for m, n in done:
             print(f"local_icp_b200: patched {m}.{n}")

@@ -155,6 +155,19 @@ int lip_batch_refine_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, 
 int lip_batch_match_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                          int refine, double voxel_size, double sample_proportion, int64_t* T21, int64_t* T12, double* scores);
 
+/* interpolation_segment_level (interpolation/interpolation_pcd.py:122-134, the consumer of the saved maps:
+ * interpolation_plant_level :71-76) for every segment pair of the planned batch.  out holds, per segment pair s and
+ * starting at row off1[s] + off2[s], the n2 rows (1 - alpha) * xyz1[T21] + alpha * xyz2 followed by the n1 rows
+ * (1 - alpha) * xyz1 + alpha * xyz2[T12] — the reference's np.vstack([xyz_inter_0, xyz_inter_1]); (off1[S] + off2[S], 3)
+ * float64 in all.  Products and sum are rounded separately, as numpy does: the rows equal the reference's bit for bit.
+ * Map entries are segment-local; a negative entry counts from the end (numpy indexing), anything else out of range is
+ * LIP_EINVAL.  lip_batch_interpolate_device: the same on device-resident arrays, enqueued on `stream` (a cudaStream_t),
+ * no synchronisation; rows whose map entry is out of range are left unwritten. */
+int lip_batch_interpolate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, const int64_t* T21, const int64_t* T12,
+                               double alpha, double* out);
+int lip_batch_interpolate_device(lip_ctx* ctx, const double* d_xyz1, const double* d_xyz2, const int64_t* d_T21,
+                                 const int64_t* d_T12, double alpha, double* d_out, void* stream);
+
 /* ---- the three registration_icp.py functions on their own ----------------------------------- */
 /* my_icp for P independent (src, tgt) problems in CSR form (registration_icp.py:60-98):
  * src (src_off[P],3), tgt (tgt_off[P],3) -> R (P,3,3), t (P,3) with x -> R x + t, iters (P). */

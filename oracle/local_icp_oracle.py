@@ -16,6 +16,11 @@ Reference functions restated (paths relative to the reference root):
   triangle_angles      <- p2p_matching_in_organ/p2p_matching_seg_icp.py:27-34
   segment_map          <- p2p_matching_in_organ/p2p_matching_seg_icp.py:383-489
                           (get_p2p_mapping_from_segments_using_icp)
+  double_direction_refinement <- p2p_matching_in_organ/p2p_matching_fm.py:75-132
+  interpolation_segment_level <- interpolation/interpolation_pcd.py:122-134
+  label_points_by_skeleton    <- segment_matching/segment_matching_utils.py:130-137
+  skeleton_landmarks          <- segment_matching/segment_matching_ml.py:210-239
+                          (the last three pinned by tests/golden/next.npz, written by make_golden_next.py)
 
 Third-party arithmetic on the path that is not in the reference tree:
   * scikit-learn ``sklearn.neighbors.KDTree`` (reference pins scikit-learn~=0.24.2, requirements.txt:11;
@@ -311,3 +316,41 @@ def double_direction_refinement(xyz1, xyz2, T21, T12, nn="kdtree"):
                 if ind != keep:
                     move(ind, nb, t)
     return T21
+
+
+def interpolation_segment_level(xyz1, xyz2, T21, T12, alpha):
+    """interpolation/interpolation_pcd.py:122-134: mesh2 pulled back onto its matches in mesh1, then mesh1 pushed towards
+    its matches in mesh2; rows stacked in that order."""
+    xyz1, xyz2 = np.asarray(xyz1, np.float64), np.asarray(xyz2, np.float64)
+    inter_0 = (1 - alpha) * xyz1[np.asarray(T21).astype(int)] + alpha * xyz2        # :128-129
+    inter_1 = (1 - alpha) * xyz1 + alpha * xyz2[np.asarray(T12).astype(int)]        # :131-132
+    return np.vstack([inter_0, inter_1])
+
+
+def label_points_by_skeleton(xyz_pcd, xyz_skeleton, nn="kdtree"):
+    """segment_matching/segment_matching_utils.py:130-137: segment id (4th column) of the nearest skeleton node."""
+    xyz_skeleton = np.asarray(xyz_skeleton, np.float64)
+    seg_skeleton, nodes = xyz_skeleton[:, 3], xyz_skeleton[:, :3]
+    _, idx = knn(np.asarray(xyz_pcd, np.float64), nodes, 1, nn)
+    idx = idx.reshape(-1)
+    return seg_skeleton[idx], idx
+
+
+def skeleton_landmarks(skel_1, skel_2, voxel_size, sample_method="end"):
+    """segment_matching/segment_matching_ml.py:210-239: thin both polylines to a spacing of 2 * voxel_size, then pair
+    landmarks either by truncating to the shorter and keeping every second node plus the last ("end"), or by striding."""
+    def thin(sk):
+        kept = [sk[0]]
+        for x in sk:                                          # :212-215 / :217-220
+            if np.linalg.norm(kept[-1] - x) > 2 * voxel_size:
+                kept.append(x)
+        return np.vstack(kept)
+    a, b = thin(np.asarray(skel_1, np.float64)), thin(np.asarray(skel_2, np.float64))
+    if sample_method == "end":                                # :225-230
+        n = min(len(a), len(b))
+        a, b = a[:n], b[:n]
+        return np.vstack([a[0:len(a) - 1:2], a[-1]]), np.vstack([b[0:len(b) - 1:2], b[-1]])
+    half = min(len(a), len(b)) / 2                            # :232-239
+    a, b = a[0:len(a):int(len(a) / half) + 1], b[0:len(b):int(len(b) / half) + 1]
+    n = min(len(a), len(b))
+    return a[:n], b[:n]

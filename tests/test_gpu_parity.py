@@ -510,3 +510,58 @@ def test_max_landmarks_segment(L):
     with pytest.raises(ValueError):
         lm3 = np.vstack([lm1, lm1[-1:] + 1.0])
         L.local_icp_batch([(x1, x2, lm3, lm3)])
+
+
+# ---- rows either side of the hot path ---------------------------------------------------------
+def test_interpolation_segment_level_matches_reference(L):
+    """bit for bit against rows recorded from the unmodified interpolation/interpolation_pcd.py:122-134"""
+    g, nx = load_golden("c1_small"), load_golden("next")
+    for k, s in enumerate(nx["interp_segments"]):
+        a1, b1, a2, b2 = g["off1"][s], g["off1"][s + 1], g["off2"][s], g["off2"][s + 1]
+        x1, x2, T21, T12 = g["xyz1"][a1:b1], g["xyz2"][a2:b2], g["T21r"][a2:b2], g["T12r"][a1:b1]
+        for alpha in (0.3, 0.5, 1.0):
+            got = L.interpolation_segment_level(x1, x2, T21.astype(float), T12.astype(float), alpha)   # np.loadtxt columns
+            assert got.dtype == np.float64 and got.shape == (len(x1) + len(x2), 3)
+            np.testing.assert_array_equal(got, nx[f"interp_{k}_{alpha}"])
+    # numpy's negative indices count from the end; anything else out of range is an IndexError as in the reference
+    T21n = T21.copy(); T21n[:5] -= len(x1)
+    np.testing.assert_array_equal(L.interpolation_segment_level(x1, x2, T21n, T12, 0.25), O.interpolation_segment_level(x1, x2, T21, T12, 0.25))
+    T21n[0] = len(x1)
+    with pytest.raises(IndexError):
+        L.interpolation_segment_level(x1, x2, T21n, T12, 0.25)
+
+
+def test_interpolate_batch_and_saved_result(L, tmp_path):
+    """whole batch in one call == the oracle per segment pair, also through the files the driver writes"""
+    b = L.make_config(3, scale=0.05)
+    r = L.match_segments_batch(b)
+    alpha = 0.37
+    got = L.interpolate_batch(b, np.concatenate(r.T21s), np.concatenate(r.T12s), alpha)
+    assert got.shape == (b.off1[-1] + b.off2[-1], 3)
+    for s in range(b.n_segments):
+        x1, x2, _, _ = b.segment(s)
+        o = b.off1[s] + b.off2[s]
+        np.testing.assert_array_equal(got[o:o + len(x1) + len(x2)], O.interpolation_segment_level(x1, x2, r.T21s[s], r.T12s[s], alpha))
+    L.save_segment_results(r, str(tmp_path), "d1", "d2")
+    np.testing.assert_array_equal(L.interpolate_saved_result(str(tmp_path), "d1", "d2", alpha), got)
+
+
+def test_label_points_by_skeleton_matches_reference(L):
+    """the vertex -> skeleton-node labelling of segment_matching_utils.py:130-137 on the NN kernels (f4)"""
+    nx = load_golden("next")
+    seg, idx = L.label_points_by_skeleton(nx["label_pts"], nx["label_skeleton"])
+    diff = np.nonzero(idx != nx["label_nn"])[0]
+    d_got = np.linalg.norm(nx["label_pts"] - nx["label_skeleton"][idx, :3], axis=1)
+    d_ref = np.linalg.norm(nx["label_pts"] - nx["label_skeleton"][nx["label_nn"], :3], axis=1)
+    assert (np.abs(d_got - d_ref)[diff] <= TIE_RTOL * d_ref[diff]).all() and len(diff) <= 40     # the 40 exact midpoints
+    keep = np.setdiff1d(np.arange(len(idx)), diff)
+    np.testing.assert_array_equal(seg[keep], nx["label_seg"][keep])
+    parts = L.split_by_label(nx["label_pts"], seg, np.unique(nx["label_skeleton"][:, 3]))
+    assert sum(len(p) for p in parts.values()) == len(idx)
+    # frame scale: every point of a 60k-point frame against 3,000 nodes equals the float64 brute force
+    rng = np.random.default_rng(3)
+    nodes = np.column_stack([rng.uniform(-80, 80, (3000, 3)), rng.integers(0, 40, 3000)])
+    pts = rng.uniform(-80, 80, (60000, 3))
+    seg, idx = L.label_points_by_skeleton(pts, nodes)
+    _, want = O.knn(pts, nodes[:, :3], 1, "brute")
+    np.testing.assert_array_equal(idx, want.reshape(-1))

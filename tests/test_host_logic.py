@@ -133,3 +133,16 @@ def test_result_files_are_what_the_consumers_read(tmp_path, syn):
     assert i == b.n_segments
     np.testing.assert_allclose(np.loadtxt(tmp_path / "score.csv"), res.scores)
     np.testing.assert_allclose(res.score, np.average(res.scores, axis=0, weights=np.diff(b.off1)))
+
+
+def test_skeleton_landmarks_match_reference():
+    """SURVEY.md section 8 f4 (host logic): the landmark sampling of segment_matching_ml.py:210-239 against values produced
+    by those very source lines (tests/golden/make_golden_next.py)."""
+    from conftest import load_golden
+    S = importlib.import_module("4d_plant_analysis_b200.segment_matching_utils")
+    nx = load_golden("next")
+    for ci in nx["lm_cases"]:
+        vox, method = nx[f"lm_{ci}_par"]
+        lm1, lm2 = S.skeleton_landmarks(nx[f"lm_{ci}_skel1"], nx[f"lm_{ci}_skel2"], vox, "end" if method == 0 else "uniform")
+        np.testing.assert_array_equal(lm1, nx[f"lm_{ci}_lm1"])
+        np.testing.assert_array_equal(lm2, nx[f"lm_{ci}_lm2"])

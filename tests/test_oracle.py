@@ -93,3 +93,44 @@ def test_double_direction_refinement_matches_reference(case):
         T = O.double_direction_refinement(x1, x2, g["T21"][c:d], g["T12"][a:b], nn="kdtree")
         np.testing.assert_array_equal(T, g["T21r"][c:d])
         np.testing.assert_array_equal(g["T12"][a:b], g["T12r"][a:b])
+
+
+# ---- rows either side of the hot path, pinned by tests/golden/next.npz -----------------------
+def _interp_cases():
+    g, nx = load_golden("c1_small"), load_golden("next")
+    for k, s in enumerate(nx["interp_segments"]):
+        a1, b1, a2, b2 = g["off1"][s], g["off1"][s + 1], g["off2"][s], g["off2"][s + 1]
+        for alpha in (0.3, 0.5, 1.0):
+            yield g["xyz1"][a1:b1], g["xyz2"][a2:b2], g["T21r"][a2:b2], g["T12r"][a1:b1], alpha, nx[f"interp_{k}_{alpha}"]
+
+
+def test_interpolation_segment_level_matches_reference():
+    n = 0
+    for x1, x2, T21, T12, alpha, want in _interp_cases():
+        got = O.interpolation_segment_level(x1, x2, T21.astype(float), T12, alpha)      # float maps: what np.loadtxt yields
+        assert got.shape == (len(x1) + len(x2), 3)
+        np.testing.assert_array_equal(got, want)
+        n += 1
+    assert n == 6
+
+
+@pytest.mark.parametrize("nn", ["kdtree", "brute"])
+def test_label_points_by_skeleton_matches_reference(nn):
+    nx = load_golden("next")
+    seg, idx = O.label_points_by_skeleton(nx["label_pts"], nx["label_skeleton"], nn=nn)
+    d_got = np.linalg.norm(nx["label_pts"] - nx["label_skeleton"][idx, :3], axis=1)
+    d_ref = np.linalg.norm(nx["label_pts"] - nx["label_skeleton"][nx["label_nn"], :3], axis=1)
+    diff = idx != nx["label_nn"]
+    assert (np.abs(d_got - d_ref)[diff] <= 1e-12 * d_ref[diff]).all()                    # only exact-tie midpoints may differ
+    assert diff.sum() <= 40
+    np.testing.assert_array_equal(seg[~diff], nx["label_seg"][~diff])
+
+
+def test_skeleton_landmarks_match_reference():
+    nx = load_golden("next")
+    for ci in nx["lm_cases"]:
+        vox, method = nx[f"lm_{ci}_par"]
+        lm1, lm2 = O.skeleton_landmarks(nx[f"lm_{ci}_skel1"], nx[f"lm_{ci}_skel2"], vox, "end" if method == 0 else "uniform")
+        np.testing.assert_array_equal(lm1, nx[f"lm_{ci}_lm1"])
+        np.testing.assert_array_equal(lm2, nx[f"lm_{ci}_lm2"])
+        assert len(lm1) == len(lm2)

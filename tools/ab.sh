@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for rep in 1 2; do
   for v in "$@"; do
     name=${v%%=*}; lib=${v#*=}
-    LIP_LIBRARY=$lib python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_${name}_$rep.json 2> gpurun_out/ab_${name}_$rep.err
+    LIP_LIBRARY=$lib python bench.py --steps 10 --warmup 3 --no-cpu-baseline $AB_ARGS > gpurun_out/ab_${name}_$rep.json 2> gpurun_out/ab_${name}_$rep.err
     python - "$name" "$rep" gpurun_out/ab_${name}_$rep.json <<'PY'
 import json, sys
 try:

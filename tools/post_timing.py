@@ -18,8 +18,10 @@ res, t_map = timed(lambda: L.local_icp_batch(b, validate=False))
 _, t_all = timed(lambda: L.match_segments_batch(b))
 T21r, t_ref = timed(lambda: L.refine_batch(b, res.T21, res.T12))
 sc, t_ev = timed(lambda: L.evaluate_batch(b, T21r, res.T12, voxel_size=0.8, sample_proportion=0.1))
+xi, t_int = timed(lambda: L.interpolate_batch(b, T21r, res.T12, 0.5))
 print(f"config {cfg} x {fp}: {b.n_segments} segment pairs, {b.n_correspondences} correspondences (host numpy in -> numpy out)")
 print(f"  hot path (local_icp_batch)        {1e3 * t_map:8.2f} ms")
 print(f"  double_direction_refinement       {1e3 * t_ref:8.2f} ms   changed {100 * (T21r != res.T21).mean():.1f}% of T21")
 print(f"  all three in one call (match_segments_batch) {1e3 * t_all:8.2f} ms")
 print(f"  evaluate_p2p_matching             {1e3 * t_ev:8.2f} ms   mean scores {sc.mean(0).round(4)}")
+print(f"  interpolation_segment_level       {1e3 * t_int:8.2f} ms   {xi.nbytes / 1e6:.0f} MB out, {(b.xyz1.nbytes + b.xyz2.nbytes + 16 * len(xi)) / 1e6:.0f} MB in (PCIe-bound)")
