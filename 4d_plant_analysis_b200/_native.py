@@ -36,6 +36,7 @@ SIGNATURES = {
     "lip_set_params": (c_int, [c_void_p, c_void_p]),
     "lip_set_map_mode": (c_int, [c_void_p, c_int]),
     "lip_host_alloc": (c_int, [POINTER(c_void_p), c_uint64]),
+    "lip_set_input_validation": (c_int, [c_void_p, c_int]),
     "lip_host_free": (c_int, [c_void_p]),
     "lip_batch_plan": (c_int, [c_void_p, c_int64, _I64, _I64, _I64, c_int]),
     "lip_batch_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -178,6 +179,10 @@ class Context:
         self._check(self.lib.lip_set_map_mode(self.h, int(mode)))
 
     # ---- batch --------------------------------------------------------------------------------
+    def set_input_validation(self, on: bool):
+        """run_host raises ValueError on NaN / infinity in the inputs (checked on the library's copy threads)"""
+        self._check(self.lib.lip_set_input_validation(self.h, int(bool(on))))
+
     def plan(self, off1, off2, lm_off, directions=DIR_BOTH):
         off1, off2, lm_off = _i64(off1), _i64(off2), _i64(lm_off)
         S = len(off1) - 1

@@ -50,13 +50,13 @@ def local_icp_batch(segments, *, directions: int = _native.DIR_BOTH, details: bo
                     ) -> LocalICPResult:
     """segments: a SegmentPairBatch or a list of (xyz1, xyz2, lm1, lm2).  Host numpy in, host numpy out."""
     b = _as_batch(segments)
-    if validate:
-        for a in (b.xyz1, b.xyz2, b.lm1, b.lm2):
-            if not np.isfinite(a).all():
-                raise ValueError("Input contains NaN or infinity.")
     ctx = ctx or _native.default_context(device)
+    ctx.set_input_validation(validate)       # NaN / infinity -> ValueError, checked by the library while it stages the arrays
     ctx.plan(b.off1, b.off2, b.lm_off, directions)
-    T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+    try:
+        T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+    finally:
+        ctx.set_input_validation(False)
     res = LocalICPResult(T21, T12, b.off1, b.off2, b.lm_off)
     if details:
         res.transforms = ctx.transforms(filled=True)
@@ -86,12 +86,13 @@ def match_segments_batch(segments, *, apply_double_direction_refinement: bool = 
     T21 / T12 (p2p_matching_seg_icp.py:173-176), double_direction_refinement (:181-182), evaluate_p2p_matching with the
     driver's arguments (:184-185: default voxel_size = 1.0, sample_proportion = 0.5) and the score weights (:189)."""
     b = _as_batch(segments)
-    for arr in (b.xyz1, b.xyz2, b.lm1, b.lm2):
-        if not np.isfinite(arr).all():
-            raise ValueError("Input contains NaN or infinity.")
     ctx = ctx or _native.default_context()
+    ctx.set_input_validation(True)
     ctx.plan(b.off1, b.off2, b.lm_off)
-    T21, T12, scores = ctx.match(b.xyz1, b.xyz2, b.lm1, b.lm2, apply_double_direction_refinement, voxel_size, sample_proportion)
+    try:
+        T21, T12, scores = ctx.match(b.xyz1, b.xyz2, b.lm1, b.lm2, apply_double_direction_refinement, voxel_size, sample_proportion)
+    finally:
+        ctx.set_input_validation(False)
     S = b.n_segments
     return SegmentMatchResult([T21[b.off2[s]:b.off2[s + 1]] for s in range(S)], [T12[b.off1[s]:b.off1[s + 1]] for s in range(S)],
                               scores, np.diff(b.off1).astype(np.float64), b)

@@ -4,7 +4,13 @@
 #include "lip_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +47,77 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return (T*)p; }
+};
+
+// pinned host buffer, grow-only (staging of pageable caller arrays)
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// A few host threads that copy between the caller's pageable arrays and pinned staging buffers, so that the copy engines
+// are fed at PCIe speed while the caller passes ordinary numpy arrays (a cudaMemcpyAsync from pageable memory is staged
+// by the driver on the calling thread at a fraction of that).  Jobs are (dst, src, bytes) slices counted per group.
+struct StagePool {
+    struct Job { void* dst; const void* src; size_t bytes; std::atomic<int>* left; std::atomic<int>* bad; };
+    // any NaN / infinity among n doubles (exponent bits all ones)
+    static bool nonfinite(const void* src, size_t bytes) {
+        const uint64_t* p = (const uint64_t*)src;
+        uint64_t hit = 0;
+        for (size_t i = 0; i < bytes / 8; ++i) hit |= (uint64_t)((p[i] & 0x7ff0000000000000ull) == 0x7ff0000000000000ull);
+        return hit != 0;
+    }
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::deque<Job> q;
+    bool stop = false;
+    void start(int n) {
+        for (int i = (int)th.size(); i < n; ++i) th.emplace_back([this] { run(); });
+    }
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                j = q.front(); q.pop_front();
+            }
+            if (j.dst) memcpy(j.dst, j.src, j.bytes);
+            if (j.bad && nonfinite(j.dst ? j.dst : j.src, j.bytes)) j.bad->store(1, std::memory_order_relaxed);
+            if (j.left->fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(m); cv_done.notify_all(); }
+        }
+    }
+    // slices of at most `slice` bytes; *left must already count them (slices_of)
+    static int slices_of(size_t bytes, size_t slice) { return (int)((bytes + slice - 1) / slice); }
+    // dst == nullptr: no copy (check only); bad != nullptr: set to 1 if the slice (of doubles) holds a NaN or an infinity
+    void submit(void* dst, const void* src, size_t bytes, size_t slice, std::atomic<int>* left, std::atomic<int>* bad = nullptr) {
+        std::lock_guard<std::mutex> lk(m);
+        for (size_t o = 0; o < bytes; o += slice)
+            q.push_back({dst ? (char*)dst + o : nullptr, (const char*)src + o, std::min(slice, bytes - o), left, bad});
+        cv.notify_all();
+    }
+    bool done(const std::atomic<int>& left) const { return left.load(std::memory_order_acquire) == 0; }
+    void wait(const std::atomic<int>& left) {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return left.load(std::memory_order_acquire) == 0; });
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; q.clear(); }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
 };
 
 enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_BLEND = 16, ST_QUERY = 32, ST_GRID_ALL = 64 };
@@ -89,6 +166,10 @@ struct lip_ctx {
     cudaEvent_t ev[LIP_N_STAGES + 1] = {};
     bool ev_valid = false;
     cudaEvent_t tr[4] = {};       // LIP_TRACE_PIPELINE: H2D start / end, kernels end, D2H end of the last host run
+    // staging of pageable caller arrays (host pipeline): per sub-batch pinned buffers, a small pool of copy threads
+    HostBuf st_in, st_out;
+    StagePool* pool = nullptr;
+    bool validate_inputs = false;   // lip_set_input_validation
 };
 
 namespace {
@@ -397,6 +478,107 @@ int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12) {
     return LIP_OK;
 }
 
+// ---- pageable caller arrays: the pipeline fed through pinned staging buffers --------------------------------------
+bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+int staging_threads() {
+    static const int n = [] {
+        if (const char* e = getenv("LIP_STAGING_THREADS")) return std::max(0, atoi(e));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(6u, hw / 2));
+    }();
+    return n;
+}
+// lip_set_input_validation: the check sklearn's check_array makes at every KDTree construction of the reference
+// (registration_icp.py:51), here once per call and on all copy threads
+int check_finite(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2) {
+    const size_t slice = (size_t)1 << 20;
+    const size_t b[4] = {(size_t)c->n1 * 24, (size_t)c->n2 * 24, (size_t)c->sumK * 24, (size_t)c->sumK * 24};
+    const double* src[4] = {xyz1, xyz2, lm1, lm2};
+    std::atomic<int> bad(0), left(0);
+    if (b[0] + b[1] < ((size_t)1 << 21) || staging_threads() == 0) {
+        for (int i = 0; i < 4; ++i) if (StagePool::nonfinite(src[i], b[i])) bad.store(1);
+    } else {
+        if (!c->pool) c->pool = new StagePool();
+        c->pool->start(staging_threads());
+        int n = 0;
+        for (int i = 0; i < 4; ++i) n += StagePool::slices_of(b[i], slice);
+        left.store(n);
+        for (int i = 0; i < 4; ++i) c->pool->submit(nullptr, src[i], b[i], slice, &left, &bad);
+        c->pool->wait(left);
+    }
+    return bad.load() ? fail(c, LIP_EINVAL, "Input contains NaN or infinity.") : LIP_OK;
+}
+
+// Same pipeline as lip_batch_run_host's, with a host stage in front and behind: copy threads fill the pinned input buffer
+// of sub-batch k (in order), the calling thread enqueues its upload as soon as it is full and the kernels + download of the
+// sub-batches already uploaded in between; finished maps go from the pinned output buffers to the caller's arrays.
+int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                    int64_t* T21, int64_t* T12) {
+    const int nk = c->n_kids;
+    if (!c->pool) c->pool = new StagePool();
+    c->pool->start(staging_threads());
+    StagePool& pool = *c->pool;
+    const size_t slice = (size_t)1 << 20;
+    std::vector<std::atomic<int>> in_left(nk), out_left(nk);
+    std::atomic<int> bad(0);
+    std::atomic<int>* chk = c->validate_inputs ? &bad : nullptr;
+    struct Part { size_t b1, b2, bl; char* in; int64_t *o21, *o12; };
+    std::vector<Part> part(nk);
+    for (int k = 0; k < nk; ++k) {
+        lip_ctx* kc = c->kids[k];
+        Part& p = part[k];
+        p.b1 = (size_t)kc->n1 * 24; p.b2 = (size_t)kc->n2 * 24; p.bl = (size_t)kc->sumK * 24;
+        LIP_CUDA(c, kc->st_in.ensure(p.b1 + p.b2 + 2 * p.bl));
+        LIP_CUDA(c, kc->st_out.ensure(((size_t)kc->n1 + (size_t)kc->n2) * 8));
+        p.in = (char*)kc->st_in.p;
+        p.o21 = (int64_t*)kc->st_out.p; p.o12 = p.o21 + kc->n2;
+        const int64_t s0 = c->kid_seg[k];
+        in_left[k].store(StagePool::slices_of(p.b1, slice) + StagePool::slices_of(p.b2, slice) + 2 * StagePool::slices_of(p.bl, slice));
+        pool.submit(p.in, xyz1 + 3 * c->h_off1[s0], p.b1, slice, &in_left[k], chk);
+        pool.submit(p.in + p.b1, xyz2 + 3 * c->h_off2[s0], p.b2, slice, &in_left[k], chk);
+        pool.submit(p.in + p.b1 + p.b2, lm1 + 3 * c->h_lm_off[s0], p.bl, slice, &in_left[k], chk);
+        pool.submit(p.in + p.b1 + p.b2 + p.bl, lm2 + 3 * c->h_lm_off[s0], p.bl, slice, &in_left[k], chk);
+    }
+    int rc = LIP_OK, up = 0, cp = 0;
+    while (cp < nk && rc == LIP_OK) {
+        if (up < nk && (pool.done(in_left[up]) || cp == up)) {
+            pool.wait(in_left[up]);
+            if (bad.load()) { rc = fail(c, LIP_EINVAL, "Input contains NaN or infinity."); break; }   // nothing of it was uploaded
+            lip_ctx* kc = c->kids[up];
+            const Part& p = part[up];
+            kc->params = c->params;
+            rc = host_upload_async(kc, (const double*)p.in, (const double*)(p.in + p.b1), (const double*)(p.in + p.b1 + p.b2),
+                                   (const double*)(p.in + p.b1 + p.b2 + p.bl), c->side[1]);
+            if (rc) c->err = "pipeline upload: " + kc->err;
+            ++up;
+        } else {
+            lip_ctx* kc = c->kids[cp];
+            rc = host_compute_async(kc, T21 ? part[cp].o21 : nullptr, T12 ? part[cp].o12 : nullptr);
+            if (rc) c->err = "pipeline run: " + kc->err;
+            ++cp;
+        }
+    }
+    for (int k = 0; k < nk; ++k) {
+        cudaError_t e = cudaStreamSynchronize(c->kids[k]->stream);
+        if (e != cudaSuccess && rc == LIP_OK) rc = fail(c, LIP_ECUDA, std::string("pipeline sync: ") + cudaGetErrorString(e));
+        out_left[k].store(0);
+        if (rc != LIP_OK || k >= cp) continue;
+        const int64_t s0 = c->kid_seg[k];
+        const size_t o1 = T12 ? (size_t)c->kids[k]->n1 * 8 : 0, o2 = T21 ? (size_t)c->kids[k]->n2 * 8 : 0;
+        out_left[k].store(StagePool::slices_of(o1, slice) + StagePool::slices_of(o2, slice));
+        if (o2) pool.submit(T21 + c->h_off2[s0], part[k].o21, o2, slice, &out_left[k]);
+        if (o1) pool.submit(T12 + c->h_off1[s0], part[k].o12, o1, slice, &out_left[k]);
+    }
+    for (int k = 0; k < nk; ++k) { pool.wait(in_left[k]); pool.wait(out_left[k]); }   // nothing of this call left in the queue
+    if (rc != LIP_OK) return rc;
+    c->last_run_split = true; c->last_run_dsplit = false;
+    return LIP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -473,6 +655,8 @@ void lip_destroy(lip_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc, &c->misc2})
         b->release();
+    delete c->pool;
+    c->st_in.release(); c->st_out.release();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -481,6 +665,12 @@ int lip_set_params(lip_ctx* c, const lip_params* p) {
     if (!c || !p) return LIP_EINVAL;
     if (p->max_iter < 1) return fail(c, LIP_EINVAL, "max_iter must be >= 1");
     c->params = *p;
+    return LIP_OK;
+}
+
+int lip_set_input_validation(lip_ctx* c, int on) {
+    if (!c) return LIP_EINVAL;
+    c->validate_inputs = on != 0;
     return LIP_OK;
 }
 
@@ -598,6 +788,13 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
+    if (c->n_kids >= 2 && staging_threads() > 0 &&
+        (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12))))
+        return run_host_staged(c, xyz1, xyz2, lm1, lm2, T21, T12);
+    if (c->validate_inputs) {
+        int rc = check_finite(c, xyz1, xyz2, lm1, lm2);
+        if (rc) return rc;
+    }
     if (c->n_kids >= 2) {
         // pipelined: every sub-batch on its own stream — copies in, kernels and copies out of different sub-batches overlap.
         // All uploads are enqueued first, on ONE stream: issuing the kernels of a sub-batch takes the host longer than its
@@ -938,6 +1135,10 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
         for (int64_t s = 0; s < c->S; ++s)
             if (c->h_off1[s + 1] - c->h_off1[s] < 5) return fail(c, LIP_EINVAL, "match: refinement needs at least 5 vertices in every mesh1");
     cudaSetDevice(c->device);
+    if (c->validate_inputs) {
+        int vrc = check_finite(c, xyz1, xyz2, lm1, lm2);
+        if (vrc) return vrc;
+    }
     cudaStream_t st = c->stream;
     const size_t b1 = (size_t)c->n1 * 24, b2 = (size_t)c->n2 * 24, bl = (size_t)c->sumK * 24;
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));

@@ -63,9 +63,16 @@ int  lip_set_params(lip_ctx* ctx, const lip_params* p);
  * landmark-bin tiles (blend_tile_kernel), 1 = exact search in a hashed uniform grid (grid_build_kernel +
  * blend_nn_kernel + retry/far passes).  Same results; call before lip_batch_plan. */
 int  lip_set_map_mode(lip_ctx* ctx, int mode);
-/* pinned host memory for the *_host entry points (optional; any host pointer works) */
+/* pinned host memory for the *_host entry points.  Optional: lip_batch_run_host stages ordinary (pageable) arrays through
+ * pinned buffers of its own with a few copy threads (environment LIP_STAGING_THREADS, default min(6, cores / 2); 0 = leave
+ * it to the driver), which costs about a quarter more time than pinned caller buffers instead of five times more. */
 int  lip_host_alloc(void** p, uint64_t bytes);
 int  lip_host_free(void* p);
+
+/* on != 0: lip_batch_run_host rejects inputs holding a NaN or an infinity with LIP_EINVAL before anything is uploaded —
+ * the ValueError sklearn's check_array raises at every KDTree construction of the reference (registration_icp.py:51,
+ * p2p_matching_seg_icp.py:388-391).  The check runs on the copy threads.  Off by default. */
+int  lip_set_input_validation(lip_ctx* ctx, int on);
 
 /* ---- batched segment-pair maps --------------------------------------------------------------
  * Replaces, for S matched segment pairs at once, the pair of calls

@@ -565,3 +565,49 @@ def test_label_points_by_skeleton_matches_reference(L):
     seg, idx = L.label_points_by_skeleton(pts, nodes)
     _, want = O.knn(pts, nodes[:, :3], 1, "brute")
     np.testing.assert_array_equal(idx, want.reshape(-1))
+
+
+def test_pageable_and_pinned_host_buffers_give_the_same_maps(L, monkeypatch):
+    """lip_batch_run_host stages pageable arrays through pinned buffers on copy threads (large batches); pinned caller
+    buffers go straight to the copy engine.  Same maps either way, with and without the copy threads; a NaN anywhere in a
+    large batch is rejected before anything is computed (input validation runs on the same threads)."""
+    import ctypes
+    native = importlib.import_module("4d_plant_analysis_b200._native")
+    b = L.make_config(2, frame_pairs=8)
+    lib = native.load()
+    ctx = L.Context(0)
+    ctx.plan(b.off1, b.off2, b.lm_off)
+    T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)                       # pageable numpy: staged
+    bufs = []
+
+    def pinned(a):
+        p = ctypes.c_void_p()
+        assert lib.lip_host_alloc(ctypes.byref(p), a.nbytes) == 0
+        ctypes.memmove(p, np.ascontiguousarray(a).ctypes.data, a.nbytes)
+        bufs.append(p)
+        return p.value
+    o21, o12 = pinned(np.zeros_like(T21)), pinned(np.zeros_like(T12))
+    ctx.run_host_ptr(pinned(b.xyz1), pinned(b.xyz2), pinned(b.lm1), pinned(b.lm2), o21, o12)
+    np.testing.assert_array_equal(np.ctypeslib.as_array((ctypes.c_int64 * len(T21)).from_address(o21)), T21)
+    np.testing.assert_array_equal(np.ctypeslib.as_array((ctypes.c_int64 * len(T12)).from_address(o12)), T12)
+    for p in bufs:
+        lib.lip_host_free(p)
+    bad = b.xyz2.copy()
+    bad[-7, 2] = np.inf                                                           # in the last sub-batch
+    ctx.set_input_validation(True)
+    with pytest.raises(ValueError, match="NaN or infinity"):
+        ctx.run_host(b.xyz1, bad, b.lm1, b.lm2)
+    T21b, T12b = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)                      # the context is usable afterwards
+    np.testing.assert_array_equal(T21b, T21)
+    ctx.close()
+    monkeypatch.setenv("LIP_PIPELINE_CHUNKS", "1")                               # one piece: validation without the pipeline
+    ctx = L.Context(0)
+    ctx.plan(b.off1, b.off2, b.lm_off)
+    ctx.set_input_validation(True)
+    with pytest.raises(ValueError, match="NaN or infinity"):
+        ctx.run_host(b.xyz1, bad, b.lm1, b.lm2)
+    T21c, T12c = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+    np.testing.assert_array_equal(T21c, T21); np.testing.assert_array_equal(T12c, T12)
+    ctx.close()
+    with pytest.raises(ValueError, match="NaN or infinity"):
+        L.match_segments_batch(L.SegmentPairBatch(b.xyz1, bad, b.off1, b.off2, b.lm1, b.lm2, b.lm_off, np.zeros(b.n_segments, np.int32)))
