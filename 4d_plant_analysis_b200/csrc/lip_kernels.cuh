@@ -1660,25 +1660,51 @@ __global__ void triangle_angles_kernel(const double* __restrict__ abc, int n, do
 
 // ---------------------------------------------------------------------------------------------
 // Exact k nearest vertices of the same mesh in (distance, index) order, float64 (sklearn KDTree(x).query(x, k)):
-// one THREAD per query, the mesh staged in shared memory as three float64 planes and read by all lanes at once
-// (broadcast), candidates visited in ascending index so that a strict '<' keeps the lowest index on exact ties.
+// one THREAD per query, candidates visited in ascending index so that a strict '<' keeps the lowest index on exact ties.
+// The mesh is staged in shared memory as fp32 points relative to its first vertex and read by all lanes at once
+// (broadcast): a candidate whose fp32 squared distance exceeds the current k-th best float64 distance by more than a
+// rigorous bound on the fp32 error (d2_err) cannot enter the list and is skipped after 6 FP32 instructions; the few that
+// pass (and everything while the list is not full) are evaluated in float64 from global memory with sklearn's
+// operation order.  Meshes larger than the tile take the plain float64 loop.
 // side 0: mesh1 (xyz1), side 1: mesh2 (xyz2).  Query i of mesh m is its local vertex i * step.
 // out[KNN * (qbase[m] + i) + k] = local index of the k-th neighbour (k = 0 is the vertex itself unless duplicated),
-// -1 beyond the mesh size.  grid = (meshes, query blocks), dynamic SMEM = 24 * smem_pts bytes (0: read global).
+// -1 beyond the mesh size.  grid = (meshes, query blocks), dynamic SMEM = 16 * smem_pts bytes.
 // ---------------------------------------------------------------------------------------------
+template <int KNN>
+__device__ __forceinline__ void knn_insert(double dn, int v, double (&d)[KNN], int (&id)[KNN]) {
+    d[KNN - 1] = dn; id[KNN - 1] = v;
+#pragma unroll
+    for (int k = KNN - 1; k > 0; --k)
+        if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+}
 template <int KNN>
 __global__ void __launch_bounds__(256) self_knn_kernel(LipArgs a, int side, int step, const int* __restrict__ qbase,
                                                        int* __restrict__ out, int smem_pts) {
-    extern __shared__ double smem_knn[];
+    extern __shared__ float4 smem_knn[];
+    __shared__ float s_rad[8];
     const int mi = blockIdx.x, m = side ? a.S + mi : mi;
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
     const double* __restrict__ xyz = side ? a.xyz2 + 3 * (size_t)(ub - a.n1_total) : a.xyz1 + 3 * (size_t)ub;
     const int nq = (n + step - 1) / step;
     if ((int)blockIdx.y * 256 >= nq) return;
     const bool staged = n <= smem_pts;
+    const double c0 = xyz[0], c1 = xyz[1], c2 = xyz[2];
+    float e = 0.f;
     if (staged) {
-        for (int i = threadIdx.x; i < 3 * n; i += 256) { const int v = i / 3, c = i - 3 * v; smem_knn[(size_t)c * n + v] = xyz[i]; }
+        float rad = 0.f;
+        for (int v = threadIdx.x; v < n; v += 256) {
+            const float4 f = make_float4((float)(xyz[3 * (size_t)v] - c0), (float)(xyz[3 * (size_t)v + 1] - c1), (float)(xyz[3 * (size_t)v + 2] - c2), 0.f);
+            smem_knn[v] = f;
+            rad = fmaxf(rad, fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fabsf(f.z)));
+        }
+        rad = warp_maxf(rad);
+        if ((threadIdx.x & 31) == 0) s_rad[threadIdx.x >> 5] = rad;
         __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) rad = fmaxf(rad, s_rad[w]);
+        // per-coordinate error of an fp32 difference: both operands rounded from float64 (2^-24 |x| each) and the
+        // subtraction (2^-24 |dx|), |x|, |dx| / 2 <= rad: 4 * 2^-24 * rad, times 1.5
+        e = 3.6e-7f * rad;
     }
     for (int qi = blockIdx.y * 256 + threadIdx.x; qi < nq; qi += 256 * gridDim.y) {
         const int q = qi * step;
@@ -1687,14 +1713,40 @@ __global__ void __launch_bounds__(256) self_knn_kernel(LipArgs a, int side, int 
         int id[KNN];
 #pragma unroll
         for (int k = 0; k < KNN; ++k) { d[k] = INFINITY; id[k] = -1; }
-        for (int v = 0; v < n; ++v) {
-            const double dn = staged ? rdist64(q0, q1, q2, smem_knn[v], smem_knn[(size_t)n + v], smem_knn[2 * (size_t)n + v])
-                                     : rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
-            if (dn < d[KNN - 1]) {
-                d[KNN - 1] = dn; id[KNN - 1] = v;
+        if (staged) {
+            const float4 fq = smem_knn[q];
+            float thr = INFINITY;                             // fp32 distances above it cannot enter the list
+            auto consider = [&](int v) {
+                const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (dn < d[KNN - 1]) {
+                    knn_insert<KNN>(dn, v, d, id);
+                    const float dk = __double2float_ru(d[KNN - 1]);
+                    thr = fmaf(dk + d2_err(dk, e), 1.000001f, 1e-30f);
+                }
+            };
+            int v = 0;
+            for (; v + 4 <= n; v += 4) {
+                float f[4];
 #pragma unroll
-                for (int k = KNN - 1; k > 0; --k)
-                    if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = smem_knn[v + u];
+                    const float dx = fq.x - t.x, dy = fq.y - t.y, dz = fq.z - t.z;
+                    f[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                }
+                if (fminf(fminf(f[0], f[1]), fminf(f[2], f[3])) <= thr) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (f[u] <= thr) consider(v + u);
+                }
+            }
+            for (; v < n; ++v) {
+                const float4 t = smem_knn[v];
+                const float dx = fq.x - t.x, dy = fq.y - t.y, dz = fq.z - t.z;
+                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) consider(v);
+            }
+        } else {
+            for (int v = 0; v < n; ++v) {
+                const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (dn < d[KNN - 1]) knn_insert<KNN>(dn, v, d, id);
             }
         }
         int* o = out + (size_t)KNN * (qbase[mi] + qi);
@@ -1794,84 +1846,93 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
 // segment pair, lane 0 walking the targets in ascending order over inverse-index lists held in SMEM.
 // =============================================================================================
 // (the 5-NN self query of :78-79 is self_knn_kernel<5>; entries 1..4 of a row are the reference's NN_mesh1[t, 1:])
+// The tables are 16-bit when every mesh of the batch has fewer than 65,535 vertices (IT = unsigned short, 0xFFFF = none):
+// 2 * (3 n2 + 4 n1) bytes per segment pair, so that three maize-sized pairs share an SM instead of one; the mesh2
+// coordinates stay in global memory (read only where two sources compete for a target).
+template <typename IT>
 struct RefineView {                                          // per-segment tables (SMEM when they fit, global scratch otherwise)
-    int *t21, *next21, *head21, *head12, *next12, *t12;
-    double* v2;                                              // 3 * n2, interleaved
+    IT *t21, *next21, *head21, *head12, *next12, *t12;
+    const double* v2;                                        // 3 * n2, interleaved
+    static constexpr IT NONE = (IT)~(IT)0;                   // -1 for int
 };
 __device__ __forceinline__ double refine_norm(const double* __restrict__ p, const double* __restrict__ q) {
     const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
     return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
 }
 // the source of target t to keep: smallest |v2[ind] - v2[T12[t]]|, first on ties (:88-96, :113-121)
-__device__ __forceinline__ int refine_keep(const RefineView& w, int t) {
+template <typename IT>
+__device__ __forceinline__ IT refine_keep(const RefineView<IT>& w, int t) {
     const double* ref = w.v2 + 3 * (size_t)w.t12[t];
     double best = 10000.0;
-    int keep = w.head21[t];
-    for (int ind = w.head21[t]; ind >= 0; ind = w.next21[ind]) {
+    IT keep = w.head21[t];
+    for (IT ind = w.head21[t]; ind != RefineView<IT>::NONE; ind = w.next21[ind]) {
         const double d = refine_norm(w.v2 + 3 * (size_t)ind, ref);
         if (d < best) { best = d; keep = ind; }
     }
     return keep;
 }
 // move source ind from the list of t_from to its place (ascending) in the list of t_to
-__device__ __forceinline__ void refine_move(const RefineView& w, int ind, int t_from, int t_to) {
-    int* link = &w.head21[t_from];
+template <typename IT>
+__device__ __forceinline__ void refine_move(const RefineView<IT>& w, IT ind, int t_from, int t_to) {
+    IT* link = &w.head21[t_from];
     while (*link != ind) link = &w.next21[*link];
     *link = w.next21[ind];
     link = &w.head21[t_to];
-    while (*link >= 0 && *link < ind) link = &w.next21[*link];
+    while (*link != RefineView<IT>::NONE && *link < ind) link = &w.next21[*link];
     w.next21[ind] = *link;
     *link = ind;
-    w.t21[ind] = t_to;
+    w.t21[ind] = (IT)t_to;
 }
 
+template <typename IT>
 __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn5, long long* __restrict__ T21,
-                                                    const long long* __restrict__ T12, int* __restrict__ scratch, int smem_ints_cap) {
+                                                    const long long* __restrict__ T12, IT* __restrict__ scratch, int smem_entries_cap) {
     extern __shared__ double smem_ref[];
+    constexpr IT NONE = RefineView<IT>::NONE;
     const int s = blockIdx.x, lane = threadIdx.x;
     const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
     const int u2g = a.mesh_ubase[a.S + s], n2 = a.mesh_ubase[a.S + s + 1] - u2g, u2 = u2g - a.n1_total;
     long long* __restrict__ t21g = T21 + u2;
     const long long* __restrict__ t12g = T12 + u1;
-    const double* __restrict__ v2g = a.xyz2 + 3 * (size_t)u2;
     const int* __restrict__ nn = nn5 + 5 * (size_t)u1 + 1;          // entries 1..4 of every row: NN_mesh1[t, 1:]
-    // tables: 3 n2 + 3 n1 ints (+ n1 snapshot flags packed into the sign... kept as a separate n1 ints) and 3 n2 doubles
-    const size_t need_ints = 3 * (size_t)n2 + 4 * (size_t)n1;
-    const bool in_smem = (size_t)6 * n2 + need_ints <= (size_t)smem_ints_cap;       // doubles count as two ints
-    RefineView w;
-    int* base;
-    if (in_smem) { w.v2 = smem_ref; base = (int*)(smem_ref + 3 * (size_t)n2); }
-    else { w.v2 = const_cast<double*>(v2g); base = scratch + 3 * (size_t)u2 + 4 * (size_t)u1; }      // too large for SMEM: global tables
+    // tables: 3 n2 + 4 n1 entries (the last n1: the snapshot of which targets had a source at the start)
+    const size_t need = 3 * (size_t)n2 + 4 * (size_t)n1;
+    RefineView<IT> w;
+    IT* base = (need <= (size_t)smem_entries_cap) ? reinterpret_cast<IT*>(smem_ref) : scratch + 3 * (size_t)u2 + 4 * (size_t)u1;
+    w.v2 = a.xyz2 + 3 * (size_t)u2;
     w.t21 = base; w.next21 = base + n2; w.head12 = base + 2 * n2;
     w.head21 = base + 3 * n2; w.next12 = w.head21 + n1; w.t12 = w.next12 + n1;
-    int* snap = w.t12 + n1;
-    for (int i = lane; i < n2; i += 32) {
-        w.t21[i] = (int)t21g[i]; w.head12[i] = -1;
-        if (in_smem) {
-            w.v2[3 * (size_t)i] = v2g[3 * (size_t)i]; w.v2[3 * (size_t)i + 1] = v2g[3 * (size_t)i + 1]; w.v2[3 * (size_t)i + 2] = v2g[3 * (size_t)i + 2];
-        }
-    }
-    for (int t = lane; t < n1; t += 32) { w.head21[t] = -1; w.t12[t] = (int)t12g[t]; }
+    IT* snap = w.t12 + n1;
+    for (int i = lane; i < n2; i += 32) { w.t21[i] = (IT)t21g[i]; w.head12[i] = NONE; }
+    for (int t = lane; t < n1; t += 32) { w.head21[t] = NONE; w.t12[t] = (IT)t12g[t]; }
     __syncwarp();
     if (lane == 0) {
         // inverse lists, ascending: np.where(T21 == t)[0] and np.where(T12 == ind)[0]
-        for (int i = n2 - 1; i >= 0; --i) { const int t = w.t21[i]; w.next21[i] = w.head21[t]; w.head21[t] = i; }
-        for (int t = n1 - 1; t >= 0; --t) { const int i = w.t12[t]; w.next12[t] = w.head12[i]; w.head12[i] = t; }
-        for (int t = 0; t < n1; ++t) snap[t] = w.head21[t] >= 0;                  // np.unique(T21), taken once (:85)
+        for (int i = n2 - 1; i >= 0; --i) { const int t = w.t21[i]; w.next21[i] = w.head21[t]; w.head21[t] = (IT)i; }
+        for (int t = n1 - 1; t >= 0; --t) { const int i = w.t12[t]; w.next12[t] = w.head12[i]; w.head12[i] = (IT)t; }
+    }
+    __syncwarp();
+    for (int t = lane; t < n1; t += 32) snap[t] = (IT)(w.head21[t] != NONE);      // np.unique(T21), taken once (:85)
+    __syncwarp();
+    if (lane == 0) {
         for (int t = 0; t < n1; ++t) {
-            if (!snap[t] || w.head21[t] < 0 || w.next21[w.head21[t]] < 0) continue;   // a single source: nothing to do
-            const int keep = refine_keep(w, t);
-            int ind = w.head21[t];
-            while (ind >= 0) {
-                const int nxt = w.next21[ind];               // the reference iterates over the list as it was
+            if (!snap[t] || w.head21[t] == NONE || w.next21[w.head21[t]] == NONE) continue;   // a single source: nothing to do
+            const IT keep = refine_keep(w, t);
+            IT ind = w.head21[t];
+            while (ind != NONE) {
+                const IT nxt = w.next21[ind];                // the reference iterates over the list as it was
                 if (ind != keep) {
                     int t_keep = -1;
-                    if (w.head12[ind] >= 0) {                // targets whose T12 points at this source (:100-101)
+                    if (w.head12[ind] != NONE) {             // targets whose T12 points at this source (:100-101)
                         t_keep = w.head12[ind];
-                        for (int c = w.head12[ind]; c >= 0; c = w.next12[c]) if (w.head21[c] < 0) t_keep = c;
+                        for (IT c = w.head12[ind]; c != NONE; c = w.next12[c]) if (w.head21[c] == NONE) t_keep = c;
                     } else {                                 // the four nearest neighbours of the target (:102-103)
-                        t_keep = nn[5 * (size_t)t];
-                        for (int k = 0; k < 4; ++k) { const int c = nn[5 * (size_t)t + k]; if (c >= 0 && w.head21[c] < 0) t_keep = c; }
+                        const int c0 = nn[5 * (size_t)t], c1 = nn[5 * (size_t)t + 1], c2 = nn[5 * (size_t)t + 2], c3 = nn[5 * (size_t)t + 3];
+                        t_keep = c0;
+                        if (c0 >= 0 && w.head21[c0] == NONE) t_keep = c0;
+                        if (c1 >= 0 && w.head21[c1] == NONE) t_keep = c1;
+                        if (c2 >= 0 && w.head21[c2] == NONE) t_keep = c2;
+                        if (c3 >= 0 && w.head21[c3] == NONE) t_keep = c3;
                     }
                     if (t_keep >= 0 && t_keep != t) refine_move(w, ind, t, t_keep);
                 }
@@ -1883,29 +1944,35 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
     // targets nobody maps to take sources from their neighbours (:111-130).  The four neighbours of a target are
     // distinct, and moving the sources of one of them to the target does not touch the lists of the others, so the
     // four "which source stays" decisions are taken by four lanes at once; the moves stay in the reference's order.
-    for (int t = 0; t < n1; ++t) {
-        if (w.head21[t] >= 0) continue;                      // uniform
-        int nb = -1, keep = -1;
-        if (lane < 4) {
-            nb = nn[5 * (size_t)t + lane];
-            if (nb >= 0 && nb != t && w.head21[nb] >= 0) keep = refine_keep(w, nb); else nb = -1;
-        }
-        __syncwarp();
-        for (int k = 0; k < 4; ++k) {
-            const int nbk = __shfl_sync(LIP_FULL, nb, k), keepk = __shfl_sync(LIP_FULL, keep, k);
-            if (lane == 0 && nbk >= 0) {
-                int ind = w.head21[nbk];
-                while (ind >= 0) {
-                    const int nxt = w.next21[ind];
-                    if (ind != keepk) refine_move(w, ind, nbk, t);
-                    ind = nxt;
-                }
-            }
+    // The neighbour rows of eight targets are fetched with one coalesced load (lane l: entry l % 4 of target t0 + l / 4).
+    for (int t0 = 0; t0 < n1; t0 += 8) {
+        const int tr = t0 + (lane >> 2);
+        const int row = (tr < n1) ? nn[5 * (size_t)tr + (lane & 3)] : -1;
+        const int jn = min(8, n1 - t0);
+        for (int j = 0; j < jn; ++j) {
+            const int t = t0 + j;
+            if (w.head21[t] != NONE) continue;               // uniform
+            int nb = __shfl_sync(LIP_FULL, row, 4 * j + (lane & 3));
+            IT keep = NONE;
+            if (lane < 4 && nb >= 0 && nb != t && w.head21[nb] != NONE) keep = refine_keep(w, nb); else nb = -1;
             __syncwarp();
+            for (int k = 0; k < 4; ++k) {
+                const int nbk = __shfl_sync(LIP_FULL, nb, k);
+                const IT keepk = (IT)__shfl_sync(LIP_FULL, (int)keep, k);
+                if (lane == 0 && nbk >= 0) {
+                    IT ind = w.head21[nbk];
+                    while (ind != NONE) {
+                        const IT nxt = w.next21[ind];
+                        if (ind != keepk) refine_move(w, ind, nbk, t);
+                        ind = nxt;
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
     __syncwarp();
-    for (int i = lane; i < n2; i += 32) t21g[i] = w.t21[i];
+    for (int i = lane; i < n2; i += 32) t21g[i] = (long long)w.t21[i];
 }
 
 

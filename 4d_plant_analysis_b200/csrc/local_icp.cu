@@ -170,6 +170,7 @@ struct lip_ctx {
     HostBuf st_in, st_out;
     StagePool* pool = nullptr;
     bool validate_inputs = false;   // lip_set_input_validation
+    std::vector<cudaEvent_t> stage_events;   // per-chunk download events of StageCall
 };
 
 namespace {
@@ -579,6 +580,87 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
     return LIP_OK;
 }
 
+// The staged transfers of ONE call of a *_host entry point that is not pipelined over sub-batches (evaluate, refine, match,
+// interpolate): large pageable arrays go through the context's pinned buffers in 8 MB chunks — the copy threads fill chunk
+// i + 1 while chunk i is on the bus; downloads land in the pinned output buffer chunk by chunk (an event each) and are
+// copied out by the threads in finish().  Small or pinned arrays take plain cudaMemcpyAsync.
+struct StageCall {
+    lip_ctx* c;
+    size_t in_off = 0, out_off = 0;
+    std::deque<std::atomic<int>> counters;                   // stable addresses
+    struct Out { void* h_dst; const void* pinned; size_t bytes; cudaEvent_t ev; };
+    std::vector<Out> outs;
+    size_t n_ev = 0;
+    static constexpr size_t kChunk = (size_t)8 << 20, kSlice = (size_t)1 << 20;
+    explicit StageCall(lip_ctx* ctx) : c(ctx) {}
+    static bool wanted(const void* h, size_t bytes) { return bytes >= ((size_t)1 << 20) && staging_threads() > 0 && is_pageable(h); }
+    // capacity for everything this call will stage (the buffers must not move once in use)
+    int begin(size_t in_bytes, size_t out_bytes) {
+        if (in_bytes) LIP_CUDA(c, c->st_in.ensure(in_bytes + 4096));
+        if (out_bytes) LIP_CUDA(c, c->st_out.ensure(out_bytes + 4096));
+        if ((in_bytes || out_bytes) && !c->pool) c->pool = new StagePool();
+        if (c->pool) c->pool->start(staging_threads());
+        return LIP_OK;
+    }
+    int h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+        if (!bytes) return LIP_OK;
+        if (!wanted(h_src, bytes) || in_off + bytes > c->st_in.cap) {
+            LIP_CUDA(c, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+            return LIP_OK;
+        }
+        char* pin = (char*)c->st_in.p + in_off;
+        in_off += (bytes + 255) & ~(size_t)255;
+        const size_t first = counters.size();
+        for (size_t o = 0; o < bytes; o += kChunk) {
+            const size_t b = std::min(kChunk, bytes - o);
+            counters.emplace_back(StagePool::slices_of(b, kSlice));
+            c->pool->submit(pin + o, (const char*)h_src + o, b, kSlice, &counters.back());
+        }
+        size_t k = first;
+        for (size_t o = 0; o < bytes; o += kChunk, ++k) {
+            c->pool->wait(counters[k]);
+            LIP_CUDA(c, cudaMemcpyAsync((char*)d_dst + o, pin + o, std::min(kChunk, bytes - o), cudaMemcpyHostToDevice, st));
+        }
+        return LIP_OK;
+    }
+    int d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+        if (!bytes) return LIP_OK;
+        if (!wanted(h_dst, bytes) || out_off + bytes > c->st_out.cap) {
+            LIP_CUDA(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+            return LIP_OK;
+        }
+        char* pin = (char*)c->st_out.p + out_off;
+        out_off += (bytes + 255) & ~(size_t)255;
+        for (size_t o = 0; o < bytes; o += kChunk) {
+            const size_t b = std::min(kChunk, bytes - o);
+            if (n_ev == c->stage_events.size()) {
+                cudaEvent_t e;
+                LIP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c->stage_events.push_back(e);
+            }
+            LIP_CUDA(c, cudaMemcpyAsync(pin + o, (const char*)d_src + o, b, cudaMemcpyDeviceToHost, st));
+            LIP_CUDA(c, cudaEventRecord(c->stage_events[n_ev], st));
+            outs.push_back({(char*)h_dst + o, pin + o, b, c->stage_events[n_ev++]});
+        }
+        return LIP_OK;
+    }
+    // everything enqueued on st is complete and every staged download has reached the caller's arrays on return
+    int finish(cudaStream_t st) {
+        cudaError_t err = cudaSuccess;
+        for (const Out& o : outs) {
+            cudaError_t e = cudaEventSynchronize(o.ev);
+            if (e != cudaSuccess) { err = e; break; }
+            counters.emplace_back(StagePool::slices_of(o.bytes, kSlice));
+            c->pool->submit(o.h_dst, o.pinned, o.bytes, kSlice, &counters.back());
+        }
+        for (auto& k : counters) c->pool->wait(k);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) return fail(c, LIP_ECUDA, std::string("staged transfer: ") + cudaGetErrorString(err));
+        return LIP_OK;
+    }
+    ~StageCall() { if (c->pool) for (auto& k : counters) c->pool->wait(k); }     // no job may outlive the counters
+};
+
 }  // namespace
 
 extern "C" {
@@ -657,6 +739,7 @@ void lip_destroy(lip_ctx* c) {
         b->release();
     delete c->pool;
     c->st_in.release(); c->st_out.release();
+    for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -978,8 +1061,8 @@ template <int KNN>
 static int launch_self_knn(lip_ctx* c, const LipArgs& a, int side, int step, const int* d_qbase, int* d_out, int64_t max_n, cudaStream_t st) {
     int smem_cap = 0;
     LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int smem_pts = (int)std::min<int64_t>(max_n, (smem_cap - 1024) / 24 / 2);        // two CTAs per SM
-    const size_t smem = (size_t)smem_pts * 24;
+    int smem_pts = (int)std::min<int64_t>(max_n, (smem_cap - 2048) / 16);            // fp32 tile of the whole mesh
+    const size_t smem = (size_t)smem_pts * 16;
     LIP_CUDA(c, cudaFuncSetAttribute(self_knn_kernel<KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t max_q = (max_n + step - 1) / step;
     const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(65535, (max_q + 255) / 256));
@@ -1044,12 +1127,14 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
     LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
     LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    StageCall sc(c);
+    int src = sc.begin(b1 + b2 + ((size_t)c->n1 + (size_t)c->n2) * 8 + 2048, 0);
+    if (src) return src;
+    if ((src = sc.h2d(c->in_xyz1.p, xyz1, b1, st)) || (src = sc.h2d(c->in_xyz2.p, xyz2, b2, st))) return src;
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, (size_t)c->n2 * 8, cudaMemcpyHostToDevice, st));
-    if (T12) LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, (size_t)c->n1 * 8, cudaMemcpyHostToDevice, st));
+    if ((src = sc.h2d(c->out_T21.p, T21, (size_t)c->n2 * 8, st))) return src;
+    if (T12 && (src = sc.h2d(c->out_T12.p, T12, (size_t)c->n1 * 8, st))) return src;
     std::vector<long long> h;
     int rc = evaluate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
                              c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, voxel_size, sample_proportion, st, h);
@@ -1061,38 +1146,49 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
 }
 
 // double_direction_refinement on device-resident coordinates and maps (d_T21 rewritten in place)
-static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12,
-                         cudaStream_t st) {
-    const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
-    size_t max_ints = 0;
-    int64_t max_n1 = 0;
-    for (size_t s = 0; s < S; ++s) {
-        const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
-        max_ints = std::max(max_ints, (size_t)(9 * a2 + 4 * a1));      // 3 n2 doubles + 3 n2 + 4 n1 ints
-        max_n1 = std::max(max_n1, a1);
-    }
+extern "C++" {
+template <typename IT>
+static int launch_refine(lip_ctx* c, const LipArgs& a, const int* nn5, long long* d_T21, const long long* d_T12, IT* scratch,
+                         size_t max_entries, cudaStream_t st) {
     int smem_cap = 0;
     LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     smem_cap -= 1024;
-    const size_t smem = std::min<size_t>((size_t)smem_cap, max_ints * 4 + 16);
-    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = std::min<size_t>((size_t)smem_cap, max_entries * sizeof(IT) + 16);
+    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_kernel<IT><<<(unsigned)c->S, 32, smem, st>>>(a, nn5, d_T21, d_T12, scratch, (int)(smem / sizeof(IT)));
+    LIP_CUDA(c, cudaGetLastError());
+    return LIP_OK;
+}
+}  // extern "C++"
+static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12,
+                         cudaStream_t st) {
+    const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
+    size_t max_entries = 0;
+    int64_t max_n1 = 0, max_n = 0;
+    for (size_t s = 0; s < S; ++s) {
+        const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
+        max_entries = std::max(max_entries, (size_t)(3 * a2 + 4 * a1));
+        max_n1 = std::max(max_n1, a1);
+        max_n = std::max(max_n, std::max(a1, a2));
+    }
+    const bool narrow = max_n < 65535;                       // 16-bit tables: 0xFFFF = none
+    const size_t esz = narrow ? 2 : 4;
     const size_t o_qb = align_up(n1 * 20), o_scratch = o_qb + align_up((S + 1) * 4);
-    const bool need_scratch = max_ints * 4 + 16 > smem;
-    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * 4 : 16)));
+    const bool need_scratch = max_entries * esz + 16 > (size_t)(227 * 1024 - 1024);
+    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * esz : 16)));
     LipArgs a = c->args;
     a.xyz1 = d_xyz1; a.xyz2 = d_xyz2;
     int* nn4 = c->misc.as<int>();                            // 5 neighbours per vertex of mesh1, row = [self, 4 nearest]
     int* d_qbase = (int*)(c->misc.as<char>() + o_qb);
-    int* scratch = (int*)(c->misc.as<char>() + o_scratch);
+    void* scratch = c->misc.as<char>() + o_scratch;
     std::vector<int>& qbase = c->h_qbase_ref;
     qbase.resize(S + 1);
     for (size_t s = 0; s <= S; ++s) qbase[s] = (int)c->h_off1[s];
     LIP_CUDA(c, cudaMemcpyAsync(d_qbase, qbase.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
     int rc5 = launch_self_knn<5>(c, a, 0, 1, d_qbase, nn4, max_n1, st);
     if (rc5) return rc5;
-    refine_kernel<<<(unsigned)S, 32, smem, st>>>(a, nn4, d_T21, d_T12, scratch, (int)(smem / 4));
-    LIP_CUDA(c, cudaGetLastError());
-    return LIP_OK;
+    return narrow ? launch_refine<unsigned short>(c, a, nn4, d_T21, d_T12, (unsigned short*)scratch, max_entries, st)
+                  : launch_refine<int>(c, a, nn4, d_T21, d_T12, (int*)scratch, max_entries, st);
 }
 
 int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12) {
@@ -1112,14 +1208,14 @@ int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, in
     }
     LIP_CUDA(c, c->in_xyz1.ensure(n1 * 24)); LIP_CUDA(c, c->in_xyz2.ensure(n2 * 24));
     LIP_CUDA(c, c->out_T21.ensure(n2 * 8)); LIP_CUDA(c, c->out_T12.ensure(n1 * 8));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, n1 * 24, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, n2 * 24, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, n2 * 8, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, n1 * 8, cudaMemcpyHostToDevice, st));
-    int rc = refine_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(), c->out_T12.as<long long>(), st);
+    StageCall sc(c);
+    int rc = sc.begin((n1 + n2) * 32 + 2048, n2 * 8);
     if (rc) return rc;
-    LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, n2 * 8, cudaMemcpyDeviceToHost, st));
-    LIP_CUDA(c, cudaStreamSynchronize(st));
+    if ((rc = sc.h2d(c->in_xyz1.p, xyz1, n1 * 24, st)) || (rc = sc.h2d(c->in_xyz2.p, xyz2, n2 * 24, st)) ||
+        (rc = sc.h2d(c->out_T21.p, T21, n2 * 8, st)) || (rc = sc.h2d(c->out_T12.p, T12, n1 * 8, st))) return rc;
+    rc = refine_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(), c->out_T12.as<long long>(), st);
+    if (rc) return rc;
+    if ((rc = sc.d2h(T21, c->out_T21.p, n2 * 8, st)) || (rc = sc.finish(st))) return rc;
     c->last_launches = 2;
     return LIP_OK;
 }
@@ -1144,8 +1240,10 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
     LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
     LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
+    StageCall sc(c);
+    int src = sc.begin(b1 + b2 + 1024, ((size_t)c->n1 + (size_t)c->n2) * 8 + 1024);
+    if (src) return src;
+    if ((src = sc.h2d(c->in_xyz1.p, xyz1, b1, st)) || (src = sc.h2d(c->in_xyz2.p, xyz2, b2, st))) return src;
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
     const double *dx1 = c->in_xyz1.as<double>(), *dx2 = c->in_xyz2.as<double>(), *dl1 = c->in_lm1.as<double>(), *dl2 = c->in_lm2.as<double>();
@@ -1157,9 +1255,7 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
     if (refine && (rc = refine_device(c, dx1, dx2, d21, d12, st)) != LIP_OK) return rc;
     std::vector<long long> h;
     if ((rc = evaluate_device(c, dx1, dx2, dl1, dl2, d21, d12, voxel_size, sample_proportion, st, h)) != LIP_OK) return rc;
-    LIP_CUDA(c, cudaMemcpyAsync(T21, d21, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
-    LIP_CUDA(c, cudaMemcpyAsync(T12, d12, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
-    LIP_CUDA(c, cudaStreamSynchronize(st));
+    if ((rc = sc.d2h(T21, d21, (size_t)c->n2 * 8, st)) || (rc = sc.d2h(T12, d12, (size_t)c->n1 * 8, st)) || (rc = sc.finish(st))) return rc;
     scores_from_counts(h, (size_t)c->S, true, scores, nullptr);
     c->last_launches = hot_launches + (refine ? 2 : 0) + 2;
     return LIP_OK;
@@ -1205,17 +1301,18 @@ int lip_batch_interpolate_host(lip_ctx* c, const double* xyz1, const double* xyz
     LIP_CUDA(c, c->in_xyz1.ensure(b1)); LIP_CUDA(c, c->in_xyz2.ensure(b2));
     LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8));
     LIP_CUDA(c, c->misc.ensure(b1 + b2)); LIP_CUDA(c, c->misc2.ensure(16));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz1.p, xyz1, b1, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->in_xyz2.p, xyz2, b2, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->out_T21.p, T21, (size_t)c->n2 * 8, cudaMemcpyHostToDevice, st));
-    LIP_CUDA(c, cudaMemcpyAsync(c->out_T12.p, T12, (size_t)c->n1 * 8, cudaMemcpyHostToDevice, st));
-    int rc = interpolate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(),
+    StageCall sc(c);
+    int rc = sc.begin(b1 + b2 + ((size_t)c->n1 + (size_t)c->n2) * 8 + 2048, b1 + b2 + 1024);
+    if (rc) return rc;
+    if ((rc = sc.h2d(c->in_xyz1.p, xyz1, b1, st)) || (rc = sc.h2d(c->in_xyz2.p, xyz2, b2, st)) ||
+        (rc = sc.h2d(c->out_T21.p, T21, (size_t)c->n2 * 8, st)) || (rc = sc.h2d(c->out_T12.p, T12, (size_t)c->n1 * 8, st))) return rc;
+    rc = interpolate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(),
                                 c->out_T12.as<long long>(), alpha, c->misc.as<double>(), c->misc2.as<int>(), st);
     if (rc) return rc;
     int h_err = 0;
-    LIP_CUDA(c, cudaMemcpyAsync(out, c->misc.p, b1 + b2, cudaMemcpyDeviceToHost, st));
+    if ((rc = sc.d2h(out, c->misc.p, b1 + b2, st))) return rc;
     LIP_CUDA(c, cudaMemcpyAsync(&h_err, c->misc2.p, 4, cudaMemcpyDeviceToHost, st));
-    LIP_CUDA(c, cudaStreamSynchronize(st));
+    if ((rc = sc.finish(st))) return rc;
     if (h_err) return fail(c, LIP_EINVAL, "interpolate: map entry out of range");
     return LIP_OK;
 }
