@@ -66,8 +66,12 @@ __global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
     for (int i = tid; i < K; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     double sx = 0, sy = 0, sz = 0;
+    double nx = 0, ny = 0, nz = 0;                           // the next vertex of this thread: its load is in flight during the scan
+    if (tid < n) { nx = xyz[3 * (size_t)tid]; ny = xyz[3 * (size_t)tid + 1]; nz = xyz[3 * (size_t)tid + 2]; }
     for (int v = tid; v < n; v += blockDim.x) {
-        const double x = xyz[3 * (size_t)v], y = xyz[3 * (size_t)v + 1], z = xyz[3 * (size_t)v + 2];
+        const double x = nx, y = ny, z = nz;
+        const int vn = v + blockDim.x;
+        if (vn < n) { nx = xyz[3 * (size_t)vn]; ny = xyz[3 * (size_t)vn + 1]; nz = xyz[3 * (size_t)vn + 2]; }
         sx += x; sy += y; sz += z;
         double best = INFINITY, sec = INFINITY;
         int i0 = 0, i1 = 0;
@@ -116,9 +120,18 @@ __global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
     for (int i = tid; i < K; i += blockDim.x) running[i] = excl[i];
     for (int i = tid; i < nwarps * K; i += blockDim.x) wcnt[i] = 0;
     __syncthreads();
+    int bin_n = -1;                                          // this thread's vertex of the NEXT chunk: loads in flight across the barriers
+    double px = 0, py = 0, pz = 0;
+    if (tid < n) { bin_n = a.nn0[ub + tid]; px = xyz[3 * (size_t)tid]; py = xyz[3 * (size_t)tid + 1]; pz = xyz[3 * (size_t)tid + 2]; }
     for (int base = 0; base < n; base += blockDim.x) {
         const int v = base + tid;
-        const int bin = (v < n) ? a.nn0[ub + v] : -1;
+        const int bin = bin_n;
+        const double vx = px, vy = py, vz = pz;
+        {
+            const int vn = v + blockDim.x;
+            bin_n = -1;
+            if (vn < n) { bin_n = a.nn0[ub + vn]; px = xyz[3 * (size_t)vn]; py = xyz[3 * (size_t)vn + 1]; pz = xyz[3 * (size_t)vn + 2]; }
+        }
         const unsigned peers = __match_any_sync(LIP_FULL, bin);
         const int rank = __popc(peers & ((1u << lane) - 1));
         if (bin >= 0 && rank == 0) wcnt[warp * K + bin] = __popc(peers);
@@ -126,8 +139,7 @@ __global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
         if (bin >= 0) {
             int pos = ub + running[bin] + rank;
             for (int w = 0; w < warp; ++w) pos += wcnt[w * K + bin];
-            const float fx = (float)(xyz[3 * (size_t)v] - lmS[3 * bin]), fy = (float)(xyz[3 * (size_t)v + 1] - lmS[3 * bin + 1]),
-                        fz = (float)(xyz[3 * (size_t)v + 2] - lmS[3 * bin + 2]);
+            const float fx = (float)(vx - lmS[3 * bin]), fy = (float)(vy - lmS[3 * bin + 1]), fz = (float)(vz - lmS[3 * bin + 2]);
             a.bin_tmp[pos] = make_float4(fx, fy, fz, __int_as_float(v));
         }
         __syncthreads();
