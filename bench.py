@@ -344,7 +344,7 @@ def run_b200(args):
         names = kmap.get(dom, (dom,))
         if all(n in tj["kernels"] for n in names):
             traffic = sum(tj["kernels"][n]["dram_bytes_per_launch"] for n in names)
-            traffic_src = "profiles/" + tj["source"].replace("prof_r1e", "r1e_step_kernels")
+            traffic_src = "profiles/" + tj["source"]
     roof = {"kernel": dom, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved / fp32_peak, "traffic": traffic, "traffic_unit": "dram bytes per launch (ncu --set full)",
             "traffic_source": traffic_src, "kernel_ms": stage[dom],
