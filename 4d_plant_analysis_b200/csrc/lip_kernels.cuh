@@ -1671,99 +1671,174 @@ __global__ void triangle_angles_kernel(const double* __restrict__ abc, int n, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact k nearest vertices of the same mesh in (distance, index) order, float64 (sklearn KDTree(x).query(x, k)):
-// one THREAD per query, candidates visited in ascending index so that a strict '<' keeps the lowest index on exact ties.
-// The mesh is staged in shared memory as fp32 points relative to its first vertex and read by all lanes at once
-// (broadcast): a candidate whose fp32 squared distance exceeds the current k-th best float64 distance by more than a
-// rigorous bound on the fp32 error (d2_err) cannot enter the list and is skipped after 6 FP32 instructions; the few that
-// pass (and everything while the list is not full) are evaluated in float64 from global memory with sklearn's
-// operation order.  Meshes larger than the tile take the plain float64 loop.
+// Exact k nearest vertices of the same mesh in (distance, index) order, float64 (sklearn KDTree(x).query(x, k)).
+// One CTA stages the mesh in shared memory as fp32 points relative to its first vertex, counting-sorted into buckets
+// along the axis of its largest extent (a one-dimensional cell list, about 8 points per bucket); one THREAD per query
+// then scans the query's own bucket and grows the range one bucket to the left / right for as long as a point beyond the
+// scanned range could still enter the list: every unscanned point on the left lies strictly left of every scanned one
+// (bucket index is a monotone function of the fp32 coordinate), so its distance exceeds the gap between the query and the
+// leftmost scanned coordinate, minus the fp32 coordinate error.  A candidate whose fp32 squared distance exceeds the
+// current k-th best float64 distance by more than a rigorous bound on the fp32 error (d2_err) is skipped; the others are
+// evaluated in float64 from global memory with sklearn's operation order and ranked by (distance, index), so the result
+// does not depend on the visiting order.  Meshes larger than the tile take the plain float64 loop in index order.
 // side 0: mesh1 (xyz1), side 1: mesh2 (xyz2).  Query i of mesh m is its local vertex i * step.
 // out[KNN * (qbase[m] + i) + k] = local index of the k-th neighbour (k = 0 is the vertex itself unless duplicated),
-// -1 beyond the mesh size.  grid = (meshes, query blocks), dynamic SMEM = 16 * smem_pts bytes.
+// -1 beyond the mesh size.  grid = (meshes, query blocks), dynamic SMEM = 16 * smem_pts + 4 * (LIP_KNN_BUCKETS + 1) bytes.
 // ---------------------------------------------------------------------------------------------
+#define LIP_KNN_BUCKETS 1024
+// (d, v) ranks before (d2, v2)
+__device__ __forceinline__ bool knn_before(double d, int v, double d2, int v2) { return d < d2 || (d == d2 && v < v2); }
 template <int KNN>
 __device__ __forceinline__ void knn_insert(double dn, int v, double (&d)[KNN], int (&id)[KNN]) {
     d[KNN - 1] = dn; id[KNN - 1] = v;
 #pragma unroll
     for (int k = KNN - 1; k > 0; --k)
-        if (d[k] < d[k - 1]) { const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+        if (knn_before(d[k], id[k], d[k - 1], id[k - 1])) {
+            const double td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti;
+        }
 }
 template <int KNN>
 __global__ void __launch_bounds__(256) self_knn_kernel(LipArgs a, int side, int step, const int* __restrict__ qbase,
                                                        int* __restrict__ out, int smem_pts) {
     extern __shared__ float4 smem_knn[];
-    __shared__ float s_rad[8];
+    __shared__ float s_red[8][7];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mi = blockIdx.x, m = side ? a.S + mi : mi;
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
     const double* __restrict__ xyz = side ? a.xyz2 + 3 * (size_t)(ub - a.n1_total) : a.xyz1 + 3 * (size_t)ub;
     const int nq = (n + step - 1) / step;
-    if ((int)blockIdx.y * 256 >= nq) return;
-    const bool staged = n <= smem_pts;
-    const double c0 = xyz[0], c1 = xyz[1], c2 = xyz[2];
-    float e = 0.f;
-    if (staged) {
-        float rad = 0.f;
-        for (int v = threadIdx.x; v < n; v += 256) {
-            const float4 f = make_float4((float)(xyz[3 * (size_t)v] - c0), (float)(xyz[3 * (size_t)v + 1] - c1), (float)(xyz[3 * (size_t)v + 2] - c2), 0.f);
-            smem_knn[v] = f;
-            rad = fmaxf(rad, fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fabsf(f.z)));
-        }
-        rad = warp_maxf(rad);
-        if ((threadIdx.x & 31) == 0) s_rad[threadIdx.x >> 5] = rad;
-        __syncthreads();
+    int* o_base = out + (size_t)KNN * qbase[mi];
+    if (n > smem_pts) {                                      // too large for the tile: float64 brute force, index order
+        for (int qi = blockIdx.y * 256 + tid; qi < nq; qi += 256 * gridDim.y) {
+            const int q = qi * step;
+            const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
+            double d[KNN];
+            int id[KNN];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) rad = fmaxf(rad, s_rad[w]);
-        // per-coordinate error of an fp32 difference: both operands rounded from float64 (2^-24 |x| each) and the
-        // subtraction (2^-24 |dx|), |x|, |dx| / 2 <= rad: 4 * 2^-24 * rad, times 1.5
-        e = 3.6e-7f * rad;
-    }
-    for (int qi = blockIdx.y * 256 + threadIdx.x; qi < nq; qi += 256 * gridDim.y) {
-        const int q = qi * step;
-        const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
-        double d[KNN];
-        int id[KNN];
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) { d[k] = INFINITY; id[k] = -1; }
-        if (staged) {
-            const float4 fq = smem_knn[q];
-            float thr = INFINITY;                             // fp32 distances above it cannot enter the list
-            auto consider = [&](int v) {
-                const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
-                if (dn < d[KNN - 1]) {
-                    knn_insert<KNN>(dn, v, d, id);
-                    const float dk = __double2float_ru(d[KNN - 1]);
-                    thr = fmaf(dk + d2_err(dk, e), 1.000001f, 1e-30f);
-                }
-            };
-            int v = 0;
-            for (; v + 4 <= n; v += 4) {
-                float f[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 t = smem_knn[v + u];
-                    const float dx = fq.x - t.x, dy = fq.y - t.y, dz = fq.z - t.z;
-                    f[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                }
-                if (fminf(fminf(f[0], f[1]), fminf(f[2], f[3])) <= thr) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (f[u] <= thr) consider(v + u);
-                }
-            }
-            for (; v < n; ++v) {
-                const float4 t = smem_knn[v];
-                const float dx = fq.x - t.x, dy = fq.y - t.y, dz = fq.z - t.z;
-                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) consider(v);
-            }
-        } else {
+            for (int k = 0; k < KNN; ++k) { d[k] = INFINITY; id[k] = -1; }
             for (int v = 0; v < n; ++v) {
                 const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
                 if (dn < d[KNN - 1]) knn_insert<KNN>(dn, v, d, id);
             }
-        }
-        int* o = out + (size_t)KNN * (qbase[mi] + qi);
 #pragma unroll
-        for (int k = 0; k < KNN; ++k) o[k] = id[k];
+            for (int k = 0; k < KNN; ++k) o_base[(size_t)KNN * qi + k] = id[k];
+        }
+        return;
+    }
+    int* bstart = reinterpret_cast<int*>(smem_knn + smem_pts);            // LIP_KNN_BUCKETS + 1 bucket starts / cursors
+    const double c0 = xyz[0], c1 = xyz[1], c2 = xyz[2];
+    // ---- pass 1: box of the mesh -> axis, bucket scale, coordinate error -------------------------------------------
+    float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int v = tid; v < n; v += 256) {
+        const float f[3] = {(float)(xyz[3 * (size_t)v] - c0), (float)(xyz[3 * (size_t)v + 1] - c1), (float)(xyz[3 * (size_t)v + 2] - c2)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { bl[c] = fminf(bl[c], f[c]); bh[c] = fmaxf(bh[c], f[c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { bl[c] = -warp_maxf(-bl[c]); bh[c] = warp_maxf(bh[c]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s_red[warp][c] = bl[c]; s_red[warp][3 + c] = bh[c]; }
+    }
+    const int NB = max(1, min(LIP_KNN_BUCKETS, n / 8));
+    for (int b = tid; b <= NB; b += 256) bstart[b] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { bl[c] = fminf(bl[c], s_red[w][c]); bh[c] = fmaxf(bh[c], s_red[w][3 + c]); }
+    }
+    const float ex[3] = {bh[0] - bl[0], bh[1] - bl[1], bh[2] - bl[2]};
+    const int axis = (ex[0] >= ex[1] && ex[0] >= ex[2]) ? 0 : (ex[1] >= ex[2]) ? 1 : 2;
+    const float alo = axis == 0 ? bl[0] : axis == 1 ? bl[1] : bl[2];
+    const float scale = (float)NB * 0.99999f / fmaxf(axis == 0 ? ex[0] : axis == 1 ? ex[1] : ex[2], 1e-30f);
+    float rad = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rad = fmaxf(rad, fmaxf(fabsf(bl[c]), fabsf(bh[c])));
+    // per-coordinate error of an fp32 difference: both operands rounded from float64 (2^-24 |x| each) and the
+    // subtraction (2^-24 |dx|), |x|, |dx| / 2 <= rad: 4 * 2^-24 * rad, times 1.5
+    const float e = 3.6e-7f * rad;
+    auto bucket_of = [&](float xa) { return min(NB - 1, max(0, (int)((xa - alo) * scale))); };   // monotone in xa
+    // ---- pass 2: counts, starts, scatter (the order inside a bucket is arbitrary: the ranking below does not depend on it)
+    for (int v = tid; v < n; v += 256) {
+        const float xa = (float)(xyz[3 * (size_t)v + axis] - (axis == 0 ? c0 : axis == 1 ? c1 : c2));
+        atomicAdd(&bstart[bucket_of(xa)], 1);
+    }
+    __syncthreads();
+    {                                                        // exclusive scan of NB <= 1024 counts: 4 per thread
+        int c4[4], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int b = 4 * tid + k; c4[k] = b < NB ? bstart[b] : 0; tot += c4[k]; }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_red[warp][6] = __int_as_float(inc);
+        __syncthreads();
+        int run = inc - tot;
+        for (int w = 0; w < warp; ++w) run += __float_as_int(s_red[w][6]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int b = 4 * tid + k; if (b < NB) bstart[b] = run; run += c4[k]; }
+        if (tid == 255) bstart[NB] = run;
+    }
+    __syncthreads();
+    for (int v = tid; v < n; v += 256) {
+        const float4 f = make_float4((float)(xyz[3 * (size_t)v] - c0), (float)(xyz[3 * (size_t)v + 1] - c1), (float)(xyz[3 * (size_t)v + 2] - c2),
+                                     __int_as_float(v));
+        const int pos = atomicAdd(&bstart[bucket_of(axis == 0 ? f.x : axis == 1 ? f.y : f.z)], 1);
+        smem_knn[pos] = f;
+    }
+    __syncthreads();
+    // the cursors now hold the bucket ENDS: start of bucket b = end of bucket b - 1.
+    // This CTA answers the queries of a contiguous range of BUCKETS (every CTA of a mesh sorts it for itself and the order
+    // inside a bucket differs from CTA to CTA, bucket membership does not); queries are taken in sorted order, so the lanes
+    // of a warp are neighbours in space.
+    const int b_lo = (int)((long long)NB * blockIdx.y / gridDim.y), b_hi = (int)((long long)NB * (blockIdx.y + 1) / gridDim.y);
+    const int p_lo = b_lo ? bstart[b_lo - 1] : 0, p_hi = b_hi ? bstart[b_hi - 1] : 0;
+    // ---- queries ----------------------------------------------------------------------------------------------------
+    for (int p = p_lo + tid; p < p_hi; p += 256) {
+        const float4 fq = smem_knn[p];
+        const int q = __float_as_int(fq.w);
+        if (q % step) continue;
+        const double q0 = xyz[3 * (size_t)q], q1 = xyz[3 * (size_t)q + 1], q2 = xyz[3 * (size_t)q + 2];
+        const float xq = axis == 0 ? fq.x : axis == 1 ? fq.y : fq.z;
+        double d[KNN];
+        int id[KNN];
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) { d[k] = INFINITY; id[k] = -1; }
+        float thr = INFINITY;                                 // fp32 distances above it cannot enter the list
+        float xmin = xq, xmax = xq;                           // extent of everything scanned so far along the axis
+        auto scan = [&](int b) {
+            const int s = b ? bstart[b - 1] : 0, t = bstart[b];
+            for (int i = s; i < t; ++i) {
+                const float4 c = smem_knn[i];
+                const float xa = axis == 0 ? c.x : axis == 1 ? c.y : c.z;
+                xmin = fminf(xmin, xa); xmax = fmaxf(xmax, xa);
+                const float dx = fq.x - c.x, dy = fq.y - c.y, dz = fq.z - c.z;
+                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > thr) continue;
+                const int v = __float_as_int(c.w);
+                const double dn = rdist64(q0, q1, q2, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]);
+                if (knn_before(dn, v, d[KNN - 1], id[KNN - 1]) || id[KNN - 1] < 0) {
+                    knn_insert<KNN>(dn, v, d, id);
+                    const float dk = __double2float_ru(d[KNN - 1]);
+                    thr = fmaf(dk + d2_err(dk, e), 1.000001f, 1e-30f);
+                }
+            }
+        };
+        int bl_ = bucket_of(xq), br_ = bl_;
+        scan(bl_);
+        for (;;) {
+            // could a point left of / right of the scanned range still enter?  its |dx| exceeds the gap (minus the error)
+            const float dkf = __double2float_ru(d[KNN - 1]);
+            const float gl = fmaxf(xq - xmin - e, 0.f), gr = fmaxf(xmax - xq - e, 0.f);
+            const bool goL = bl_ > 0 && !(gl * gl * 0.999999f > dkf);
+            const bool goR = br_ < NB - 1 && !(gr * gr * 0.999999f > dkf);
+            if (!goL && !goR) break;
+            if (goL) scan(--bl_);
+            if (goR) scan(++br_);
+        }
+        const int qi = q / step;
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) o_base[(size_t)KNN * qi + k] = id[k];
     }
 }
 

@@ -1061,11 +1061,13 @@ template <int KNN>
 static int launch_self_knn(lip_ctx* c, const LipArgs& a, int side, int step, const int* d_qbase, int* d_out, int64_t max_n, cudaStream_t st) {
     int smem_cap = 0;
     LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int smem_pts = (int)std::min<int64_t>(max_n, (smem_cap - 2048) / 16);            // fp32 tile of the whole mesh
-    const size_t smem = (size_t)smem_pts * 16;
+    const size_t bucket_bytes = (LIP_KNN_BUCKETS + 1) * 4;
+    int smem_pts = (int)std::min<int64_t>(max_n, (smem_cap - 2048 - (int)bucket_bytes) / 16);   // fp32 tile of the whole mesh
+    if (getenv("LIP_KNN_BRUTE")) smem_pts = 0;               // debugging aid: the float64 brute-force path for every mesh
+    const size_t smem = (size_t)smem_pts * 16 + bucket_bytes;
     LIP_CUDA(c, cudaFuncSetAttribute(self_knn_kernel<KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t max_q = (max_n + step - 1) / step;
-    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(65535, (max_q + 255) / 256));
+    // every CTA of a mesh sorts it again: a few CTAs per mesh only (about 1,024 sorted positions each)
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(65535, (max_n + 1023) / 1024));
     self_knn_kernel<KNN><<<dim3((unsigned)c->S, gy), 256, smem, st>>>(a, side, step, d_qbase, d_out, smem_pts);
     LIP_CUDA(c, cudaGetLastError());
     return LIP_OK;

@@ -611,3 +611,39 @@ def test_pageable_and_pinned_host_buffers_give_the_same_maps(L, monkeypatch):
     ctx.close()
     with pytest.raises(ValueError, match="NaN or infinity"):
         L.match_segments_batch(L.SegmentPairBatch(b.xyz1, bad, b.off1, b.off2, b.lm1, b.lm2, b.lm_off, np.zeros(b.n_segments, np.int32)))
+
+
+def test_bucketed_self_knn_equals_float64_brute_force(L, monkeypatch):
+    """self_knn_kernel answers the k-NN self queries of the refinement (k = 5) and of the scores (k = 2) from a
+    one-dimensional cell list with an fp32 skip test; LIP_KNN_BRUTE=1 forces its float64 brute-force path.  Same
+    results on a lattice (exact distance ties everywhere: (distance, index) order decides), on meshes spanning
+    several CTAs, with duplicated points and with a degenerate (all points on a line across the sort axis) mesh."""
+    rng = np.random.default_rng(12)
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(12.0), np.arange(12.0), indexing="ij"), -1).reshape(-1, 3)
+    lattice = g[rng.permutation(len(g))] + 30.0
+    long_box = rng.uniform(0, 1, (5000, 3)) * [120.0, 6.0, 2.0] - 40.0
+    dup = rng.normal(size=(700, 3)) * [8.0, 1.0, 1.0]
+    dup[600:650] = dup[100:150]
+    line = np.zeros((300, 3)); line[:, 1] = np.repeat(np.arange(100.0), 3); line[:, 0] = 1e-9 * np.arange(300)
+    segs = []
+    for x in (lattice, long_box, dup, line):
+        y = x + rng.normal(0, 0.05, x.shape)
+        segs.append((x, y[rng.permutation(len(y))][: len(y) - 7], x[:1], y[:1]))
+    b = L.batch_from_segments(segs)
+    T21 = np.concatenate([rng.integers(0, len(s[0]), len(s[1])) for s in segs])
+    T12 = np.concatenate([rng.integers(0, len(s[1]), len(s[0])) for s in segs])
+    res = {}
+    for mode in ("bucket", "brute"):
+        if mode == "brute":
+            monkeypatch.setenv("LIP_KNN_BRUTE", "1")
+        res[mode] = (L.refine_batch(b, T21, T12), L.evaluate_batch(b, T21, T12, voxel_size=0.8, sample_proportion=0.5),
+                     L.evaluate_batch(b, T21, T12, voxel_size=0.8, sample_proportion=1.0))
+    monkeypatch.delenv("LIP_KNN_BRUTE")
+    for a, c in zip(res["bucket"], res["brute"]):
+        np.testing.assert_array_equal(a, c)
+    assert (res["bucket"][0] != T21).any()
+    # and both equal the oracle's refinement (KD-tree ties aside: the lattice is left out)
+    for s in (1, 2):
+        x1, x2, _, _ = segs[s]
+        want = O.double_direction_refinement(x1, x2, T21[b.off2[s]:b.off2[s + 1]], T12[b.off1[s]:b.off1[s + 1]], nn="brute")
+        np.testing.assert_array_equal(res["bucket"][0][b.off2[s]:b.off2[s + 1]], want)
