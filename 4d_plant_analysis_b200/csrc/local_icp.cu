@@ -171,6 +171,7 @@ struct lip_ctx {
     StagePool* pool = nullptr;
     bool validate_inputs = false;   // lip_set_input_validation
     std::vector<cudaEvent_t> stage_events;   // per-chunk download events of StageCall
+    HostBuf h_counts;                        // score counts of this (sub-)batch, pinned: their download must not block the host
 };
 
 namespace {
@@ -443,6 +444,17 @@ std::vector<lip_ctx*>& split_kids(lip_ctx* c) { return c->last_run_dsplit ? c->d
 std::vector<int64_t>& split_seg(lip_ctx* c) { return c->last_run_dsplit ? c->dkid_seg : c->kid_seg; }
 int split_n(lip_ctx* c) { return c->last_run_dsplit ? c->n_dkids : c->n_kids; }
 
+// what lip_batch_match_host runs after the maps of a (sub-)batch: refinement (optional) and the score counts
+struct MatchOpts { int refine; double voxel_size, sample_proportion; };
+}  // namespace
+extern "C" {
+static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12, cudaStream_t st);
+static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
+                           const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
+                           cudaStream_t st);
+}
+namespace {
+
 // H2D of one (sub-)batch, enqueued on `up` (the context's own stream, or the parent's upload stream: then the context's
 // stream waits for it); no synchronisation
 int host_upload_async(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2, cudaStream_t up = nullptr) {
@@ -466,12 +478,21 @@ int host_upload_async(lip_ctx* c, const double* xyz1, const double* xyz2, const 
     return LIP_OK;
 }
 // the whole pipeline on the uploaded (sub-)batch and D2H of the maps, enqueued on the context's stream
-int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12) {
+int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12, const MatchOpts* mo = nullptr) {
     cudaStream_t st = c->stream;
     static const bool trace = getenv("LIP_TRACE_PIPELINE") != nullptr;
     int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
                         c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
     if (rc) return rc;
+    if (mo) {                                                // the rest of the per-segment body, maps still on the device
+        const int64_t hot = c->last_launches;
+        if (mo->refine && (rc = refine_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(),
+                                              c->out_T12.as<long long>(), st)) != LIP_OK) return rc;
+        if ((rc = evaluate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
+                                  c->out_T21.as<long long>(), c->out_T12.as<long long>(), mo->voxel_size, mo->sample_proportion,
+                                  st)) != LIP_OK) return rc;
+        c->last_launches = hot + (mo->refine ? 2 : 0) + 2;
+    }
     if (trace) cudaEventRecord(c->tr[2], st);
     if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
     if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
@@ -518,7 +539,7 @@ int check_finite(lip_ctx* c, const double* xyz1, const double* xyz2, const doubl
 // of sub-batch k (in order), the calling thread enqueues its upload as soon as it is full and the kernels + download of the
 // sub-batches already uploaded in between; finished maps go from the pinned output buffers to the caller's arrays.
 int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                    int64_t* T21, int64_t* T12) {
+                    int64_t* T21, int64_t* T12, const MatchOpts* mo) {
     const int nk = c->n_kids;
     if (!c->pool) c->pool = new StagePool();
     c->pool->start(staging_threads());
@@ -558,7 +579,7 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
             ++up;
         } else {
             lip_ctx* kc = c->kids[cp];
-            rc = host_compute_async(kc, T21 ? part[cp].o21 : nullptr, T12 ? part[cp].o12 : nullptr);
+            rc = host_compute_async(kc, T21 ? part[cp].o21 : nullptr, T12 ? part[cp].o12 : nullptr, mo);
             if (rc) c->err = "pipeline run: " + kc->err;
             ++cp;
         }
@@ -576,6 +597,47 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
     }
     for (int k = 0; k < nk; ++k) { pool.wait(in_left[k]); pool.wait(out_left[k]); }   // nothing of this call left in the queue
     if (rc != LIP_OK) return rc;
+    c->last_run_split = true; c->last_run_dsplit = false;
+    return LIP_OK;
+}
+
+// The planned batch as a pipeline of its sub-batches (n_kids >= 2), every sub-batch on its own stream: copies in, kernels
+// and copies out of different sub-batches overlap.  mo != nullptr: the whole per-segment body (lip_batch_match_host), the
+// score counts of sub-batch k are left in kids[k]->h_counts.
+int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+                   int64_t* T21, int64_t* T12, const MatchOpts* mo) {
+    if (staging_threads() > 0 &&
+        (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12))))
+        return run_host_staged(c, xyz1, xyz2, lm1, lm2, T21, T12, mo);
+    if (c->validate_inputs) {
+        int rc = check_finite(c, xyz1, xyz2, lm1, lm2);
+        if (rc) return rc;
+    }
+    // All uploads are enqueued first, on ONE stream: issuing the kernels of a sub-batch takes the host longer than its
+    // upload takes the copy engine (which must never wait for the host), and in-order uploads give every sub-batch its
+    // data as early as possible.
+    for (int k = 0; k < c->n_kids; ++k) {
+        lip_ctx* kc = c->kids[k];
+        const int64_t s0 = c->kid_seg[k];
+        kc->params = c->params;
+        int rc = host_upload_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
+                                   c->side[1]);             // one upload stream: the sub-batches arrive in order, each as early as possible
+        if (rc) return fail(c, rc, "pipeline upload: " + kc->err);
+    }
+    for (int k = 0; k < c->n_kids; ++k) {
+        lip_ctx* kc = c->kids[k];
+        const int64_t s0 = c->kid_seg[k];
+        int rc = host_compute_async(kc, T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr, mo);
+        if (rc) return fail(c, rc, "pipeline run: " + kc->err);
+    }
+    for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
+    if (getenv("LIP_TRACE_PIPELINE") && c->kids[0]->tr[0]) {
+        for (int k = 0; k < c->n_kids; ++k) {
+            float t[4];
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->kids[0]->tr[0], c->kids[k]->tr[i]);
+            fprintf(stderr, "[lip pipeline] sub-batch %d: H2D %.3f-%.3f ms, kernels end %.3f, D2H end %.3f\n", k, t[0], t[1], t[2], t[3]);
+        }
+    }
     c->last_run_split = true; c->last_run_dsplit = false;
     return LIP_OK;
 }
@@ -738,7 +800,7 @@ void lip_destroy(lip_ctx* c) {
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc, &c->misc2})
         b->release();
     delete c->pool;
-    c->st_in.release(); c->st_out.release();
+    c->st_in.release(); c->st_out.release(); c->h_counts.release();
     for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -812,6 +874,7 @@ static int plan_kids(lip_ctx* c, KidSet ks, int chunks, int64_t S, const int64_t
         kc->params = c->params; kc->map_mode = c->map_mode;
         int rc = plan_impl(kc, s1 - s0, o1.data(), o2.data(), ol.data(), directions);
         if (rc) return fail(c, rc, "pipeline plan: " + kc->err);
+        kc->h_off1 = o1; kc->h_off2 = o2; kc->h_lm_off = ol;   // the refinement and the scores of a sub-batch slice by segment pair
     }
     *ks.n = nk;
     return LIP_OK;
@@ -871,42 +934,10 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
-    if (c->n_kids >= 2 && staging_threads() > 0 &&
-        (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12))))
-        return run_host_staged(c, xyz1, xyz2, lm1, lm2, T21, T12);
+    if (c->n_kids >= 2) return run_host_split(c, xyz1, xyz2, lm1, lm2, T21, T12, nullptr);
     if (c->validate_inputs) {
         int rc = check_finite(c, xyz1, xyz2, lm1, lm2);
         if (rc) return rc;
-    }
-    if (c->n_kids >= 2) {
-        // pipelined: every sub-batch on its own stream — copies in, kernels and copies out of different sub-batches overlap.
-        // All uploads are enqueued first, on ONE stream: issuing the kernels of a sub-batch takes the host longer than its
-        // upload takes the copy engine (which must never wait for the host), and in-order uploads give every sub-batch its
-        // data as early as possible.
-        for (int k = 0; k < c->n_kids; ++k) {
-            lip_ctx* kc = c->kids[k];
-            const int64_t s0 = c->kid_seg[k];
-            kc->params = c->params;
-            int rc = host_upload_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
-                                       c->side[1]);         // one upload stream: the sub-batches arrive in order, each as early as possible
-            if (rc) return fail(c, rc, "pipeline upload: " + kc->err);
-        }
-        for (int k = 0; k < c->n_kids; ++k) {
-            lip_ctx* kc = c->kids[k];
-            const int64_t s0 = c->kid_seg[k];
-            int rc = host_compute_async(kc, T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr);
-            if (rc) return fail(c, rc, "pipeline run: " + kc->err);
-        }
-        for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
-        if (getenv("LIP_TRACE_PIPELINE") && c->kids[0]->tr[0]) {
-            for (int k = 0; k < c->n_kids; ++k) {
-                float t[4];
-                for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->kids[0]->tr[0], c->kids[k]->tr[i]);
-                fprintf(stderr, "[lip pipeline] sub-batch %d: H2D %.3f-%.3f ms, kernels end %.3f, D2H end %.3f\n", k, t[0], t[1], t[2], t[3]);
-            }
-        }
-        c->last_run_split = true; c->last_run_dsplit = false;
-        return LIP_OK;
     }
     c->last_run_split = false; c->last_run_dsplit = false;
     int rc = host_upload_async(c, xyz1, xyz2, lm1, lm2);
@@ -1077,7 +1108,7 @@ static int launch_self_knn(lip_ctx* c, const LipArgs& a, int side, int step, con
 // evaluate_p2p_matching on device-resident inputs and maps: enqueues the kernels and the copy of the counts
 static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
                            const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
-                           cudaStream_t st, std::vector<long long>& h_counts) {
+                           cudaStream_t st) {
     const size_t S = (size_t)c->S;
     const int step = std::max((int)(1.0 / sample_proportion), 1);              // p2p_matching_evaluation.py:40
     std::vector<int>& qbase = c->h_qbase_eval;                 // kept in the context: the upload below is asynchronous
@@ -1102,11 +1133,11 @@ static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz
     if (rc) return rc;
     eval_scores_kernel<<<(unsigned)S, 256, 0, st>>>(a, lm_idx, d_nn2, d_qbase, d_T21, d_T12, 2.0 * voxel_size, step, cnt);
     LIP_CUDA(c, cudaGetLastError());
-    h_counts.resize(S * 6);
-    LIP_CUDA(c, cudaMemcpyAsync(h_counts.data(), cnt, S * 48, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, c->h_counts.ensure(S * 48));                 // (valid after the stream has been synchronised)
+    LIP_CUDA(c, cudaMemcpyAsync(c->h_counts.p, cnt, S * 48, cudaMemcpyDeviceToHost, st));
     return LIP_OK;
 }
-static void scores_from_counts(const std::vector<long long>& h, size_t S, bool with_T12, double* scores, int64_t* counts) {
+static void scores_from_counts(const long long* h, size_t S, bool with_T12, double* scores, int64_t* counts) {
     for (size_t s = 0; s < S; ++s) {
         const long long* k = &h[6 * s];
         scores[3 * s] = (double)k[2] / (double)k[3];                            // continuity
@@ -1137,12 +1168,11 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
     if ((src = sc.h2d(c->out_T21.p, T21, (size_t)c->n2 * 8, st))) return src;
     if (T12 && (src = sc.h2d(c->out_T12.p, T12, (size_t)c->n1 * 8, st))) return src;
-    std::vector<long long> h;
     int rc = evaluate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
-                             c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, voxel_size, sample_proportion, st, h);
+                             c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, voxel_size, sample_proportion, st);
     if (rc) return rc;
     LIP_CUDA(c, cudaStreamSynchronize(st));
-    scores_from_counts(h, (size_t)c->S, T12 != nullptr, scores, counts);
+    scores_from_counts((const long long*)c->h_counts.p, (size_t)c->S, T12 != nullptr, scores, counts);
     c->last_launches = 2;
     return LIP_OK;
 }
@@ -1233,6 +1263,19 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
         for (int64_t s = 0; s < c->S; ++s)
             if (c->h_off1[s + 1] - c->h_off1[s] < 5) return fail(c, LIP_EINVAL, "match: refinement needs at least 5 vertices in every mesh1");
     cudaSetDevice(c->device);
+    if (c->n_kids >= 2) {                                    // large batch: sub-batches pipelined like the hot path alone
+        const MatchOpts mo{refine, voxel_size, sample_proportion};
+        int prc = run_host_split(c, xyz1, xyz2, lm1, lm2, T21, T12, &mo);
+        if (prc) return prc;
+        int64_t launches = 0;
+        for (int k = 0; k < c->n_kids; ++k) {
+            lip_ctx* kc = c->kids[k];
+            scores_from_counts((const long long*)kc->h_counts.p, (size_t)kc->S, true, scores + 3 * c->kid_seg[k], nullptr);
+            launches += kc->last_launches;
+        }
+        c->last_launches = launches;
+        return LIP_OK;
+    }
     if (c->validate_inputs) {
         int vrc = check_finite(c, xyz1, xyz2, lm1, lm2);
         if (vrc) return vrc;
@@ -1255,10 +1298,9 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
     if (rc) return rc;
     const int64_t hot_launches = c->last_launches;
     if (refine && (rc = refine_device(c, dx1, dx2, d21, d12, st)) != LIP_OK) return rc;
-    std::vector<long long> h;
-    if ((rc = evaluate_device(c, dx1, dx2, dl1, dl2, d21, d12, voxel_size, sample_proportion, st, h)) != LIP_OK) return rc;
+    if ((rc = evaluate_device(c, dx1, dx2, dl1, dl2, d21, d12, voxel_size, sample_proportion, st)) != LIP_OK) return rc;
     if ((rc = sc.d2h(T21, d21, (size_t)c->n2 * 8, st)) || (rc = sc.d2h(T12, d12, (size_t)c->n1 * 8, st)) || (rc = sc.finish(st))) return rc;
-    scores_from_counts(h, (size_t)c->S, true, scores, nullptr);
+    scores_from_counts((const long long*)c->h_counts.p, (size_t)c->S, true, scores, nullptr);
     c->last_launches = hot_launches + (refine ? 2 : 0) + 2;
     return LIP_OK;
 }

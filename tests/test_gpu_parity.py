@@ -647,3 +647,20 @@ def test_bucketed_self_knn_equals_float64_brute_force(L, monkeypatch):
         x1, x2, _, _ = segs[s]
         want = O.double_direction_refinement(x1, x2, T21[b.off2[s]:b.off2[s + 1]], T12[b.off1[s]:b.off1[s + 1]], nn="brute")
         np.testing.assert_array_equal(res["bucket"][0][b.off2[s]:b.off2[s + 1]], want)
+
+
+def test_pipelined_match_equals_single_pass(L, monkeypatch):
+    """lip_batch_match_host runs a large batch as a pipeline of sub-batches (maps, refinement and scores per sub-batch on
+    its own stream); segment pairs are independent, so maps and scores equal those of the batch run in one piece"""
+    b = L.make_config(2, frame_pairs=8)
+    res = {}
+    for chunks in ("1", "8"):
+        monkeypatch.setenv("LIP_PIPELINE_CHUNKS", chunks)
+        ctx = L.Context(0)
+        r = L.match_segments_batch(b, ctx=ctx)
+        res[chunks] = (np.concatenate(r.T21s), np.concatenate(r.T12s), r.scores.copy(), ctx.counters())
+        ctx.close()
+    for k in range(3):
+        np.testing.assert_array_equal(res["1"][k], res["8"][k])
+    assert res["8"][3]["launches"] > res["1"][3]["launches"]      # really ran as sub-batches
+    assert (res["8"][2] > 0).all() and (res["8"][2] <= 1).all()
