@@ -2089,3 +2089,18 @@ __global__ void __launch_bounds__(256) interpolate_kernel(LipArgs a, const long 
             o[3 * (size_t)r + k] = __dadd_rn(__dmul_rn(w1, x1[3 * (size_t)i + k]), __dmul_rn(alpha, x2[3 * (size_t)j + k]));
     }
 }
+
+// maps handed to the refinement / the scores are used as indices on the device: every entry of T21 (off2[S]) must address
+// a vertex of its segment pair's mesh1, every entry of T12 (optional) one of mesh2; *err = 1 otherwise
+__global__ void __launch_bounds__(256) map_check_kernel(LipArgs a, const long long* __restrict__ T21, const long long* __restrict__ T12,
+                                                        int* __restrict__ err) {
+    const int s = blockIdx.x;
+    const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
+    const int u2 = a.mesh_ubase[a.S + s] - a.n1_total, n2 = a.mesh_ubase[a.S + s + 1] - a.n1_total - u2;
+    bool bad = false;
+    for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < n1 + n2; r += gridDim.y * blockDim.x) {
+        if (r < n2) { const long long v = T21[u2 + r]; bad |= v < 0 || v >= n1; }
+        else if (T12) { const long long v = T12[u1 + (r - n2)]; bad |= v < 0 || v >= n2; }
+    }
+    if (bad) atomicExch(err, 1);
+}

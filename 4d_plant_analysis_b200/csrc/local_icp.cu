@@ -171,6 +171,7 @@ struct lip_ctx {
     StagePool* pool = nullptr;
     bool validate_inputs = false;   // lip_set_input_validation
     std::vector<cudaEvent_t> stage_events;   // per-chunk download events of StageCall
+    DevBuf d_err; HostBuf h_err; cudaEvent_t ev_chk = nullptr;   // map_check_kernel: flag, its pinned copy, "copy done"
     HostBuf h_counts;                        // score counts of this (sub-)batch, pinned: their download must not block the host
 };
 
@@ -800,7 +801,8 @@ void lip_destroy(lip_ctx* c) {
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc, &c->misc2})
         b->release();
     delete c->pool;
-    c->st_in.release(); c->st_out.release(); c->h_counts.release();
+    c->st_in.release(); c->st_out.release(); c->h_counts.release(); c->d_err.release(); c->h_err.release();
+    if (c->ev_chk) cudaEventDestroy(c->ev_chk);
     for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1105,6 +1107,32 @@ static int launch_self_knn(lip_ctx* c, const LipArgs& a, int side, int step, con
 }
 }  // extern "C++"
 
+// range check of uploaded maps (they index device arrays): enqueue, then wait for the verdict only
+static int check_maps_enqueue(lip_ctx* c, const long long* d_T21, const long long* d_T12, cudaStream_t st) {
+    LIP_CUDA(c, c->d_err.ensure(16)); LIP_CUDA(c, c->h_err.ensure(16));
+    if (!c->ev_chk) LIP_CUDA(c, cudaEventCreateWithFlags(&c->ev_chk, cudaEventDisableTiming));
+    LIP_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 4, st));
+    int64_t max_rows = 1;
+    for (size_t s = 0; s < (size_t)c->S; ++s)
+        max_rows = std::max(max_rows, (c->h_off1[s + 1] - c->h_off1[s]) + (c->h_off2[s + 1] - c->h_off2[s]));
+    const int64_t want = (4 * (int64_t)c->sm_count + c->S - 1) / c->S;
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>((max_rows + 255) / 256, want));
+    LipArgs a = c->args;
+    map_check_kernel<<<dim3((unsigned)c->S, gy), 256, 0, st>>>(a, d_T21, d_T12, c->d_err.as<int>());
+    LIP_CUDA(c, cudaGetLastError());
+    LIP_CUDA(c, cudaMemcpyAsync(c->h_err.p, c->d_err.p, 4, cudaMemcpyDeviceToHost, st));
+    LIP_CUDA(c, cudaEventRecord(c->ev_chk, st));
+    return LIP_OK;
+}
+static int check_maps_verdict(lip_ctx* c, cudaStream_t st, const char* who) {
+    LIP_CUDA(c, cudaEventSynchronize(c->ev_chk));
+    if (*(const int*)c->h_err.p) {
+        cudaStreamSynchronize(st);                           // nothing of this call may still be reading the caller's arrays
+        return fail(c, LIP_EINVAL, std::string(who) + ": map entry out of range for its segment pair");
+    }
+    return LIP_OK;
+}
+
 // evaluate_p2p_matching on device-resident inputs and maps: enqueues the kernels and the copy of the counts
 static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
                            const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
@@ -1163,11 +1191,13 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
     StageCall sc(c);
     int src = sc.begin(b1 + b2 + ((size_t)c->n1 + (size_t)c->n2) * 8 + 2048, 0);
     if (src) return src;
+    if ((src = sc.h2d(c->out_T21.p, T21, (size_t)c->n2 * 8, st))) return src;       // the maps first: they are checked on the
+    if (T12 && (src = sc.h2d(c->out_T12.p, T12, (size_t)c->n1 * 8, st))) return src;  // device while the coordinates travel
+    if ((src = check_maps_enqueue(c, c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, st))) return src;
     if ((src = sc.h2d(c->in_xyz1.p, xyz1, b1, st)) || (src = sc.h2d(c->in_xyz2.p, xyz2, b2, st))) return src;
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, st));
     LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, st));
-    if ((src = sc.h2d(c->out_T21.p, T21, (size_t)c->n2 * 8, st))) return src;
-    if (T12 && (src = sc.h2d(c->out_T12.p, T12, (size_t)c->n1 * 8, st))) return src;
+    if ((src = check_maps_verdict(c, st, "evaluate"))) return src;
     int rc = evaluate_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
                              c->out_T21.as<long long>(), T12 ? c->out_T12.as<long long>() : nullptr, voxel_size, sample_proportion, st);
     if (rc) return rc;
@@ -1230,21 +1260,18 @@ int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, in
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
-    for (size_t s = 0; s < S; ++s) {                          // the maps are used as indices on the device: validate them here
-        const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
-        if (a1 < 5) return fail(c, LIP_EINVAL, "refine: every mesh1 needs at least 5 vertices (KDTree.query(k=5))");
-        for (int64_t i = c->h_off2[s]; i < c->h_off2[s + 1]; ++i)
-            if (T21[i] < 0 || T21[i] >= a1) return fail(c, LIP_EINVAL, "refine: T21 entry out of range for its segment pair");
-        for (int64_t i = c->h_off1[s]; i < c->h_off1[s + 1]; ++i)
-            if (T12[i] < 0 || T12[i] >= a2) return fail(c, LIP_EINVAL, "refine: T12 entry out of range for its segment pair");
-    }
+    for (size_t s = 0; s < S; ++s)
+        if (c->h_off1[s + 1] - c->h_off1[s] < 5) return fail(c, LIP_EINVAL, "refine: every mesh1 needs at least 5 vertices (KDTree.query(k=5))");
     LIP_CUDA(c, c->in_xyz1.ensure(n1 * 24)); LIP_CUDA(c, c->in_xyz2.ensure(n2 * 24));
     LIP_CUDA(c, c->out_T21.ensure(n2 * 8)); LIP_CUDA(c, c->out_T12.ensure(n1 * 8));
     StageCall sc(c);
     int rc = sc.begin((n1 + n2) * 32 + 2048, n2 * 8);
     if (rc) return rc;
-    if ((rc = sc.h2d(c->in_xyz1.p, xyz1, n1 * 24, st)) || (rc = sc.h2d(c->in_xyz2.p, xyz2, n2 * 24, st)) ||
-        (rc = sc.h2d(c->out_T21.p, T21, n2 * 8, st)) || (rc = sc.h2d(c->out_T12.p, T12, n1 * 8, st))) return rc;
+    // the maps are used as indices on the device: they go first and are range-checked there while the coordinates travel
+    if ((rc = sc.h2d(c->out_T21.p, T21, n2 * 8, st)) || (rc = sc.h2d(c->out_T12.p, T12, n1 * 8, st)) ||
+        (rc = check_maps_enqueue(c, c->out_T21.as<long long>(), c->out_T12.as<long long>(), st)) ||
+        (rc = sc.h2d(c->in_xyz1.p, xyz1, n1 * 24, st)) || (rc = sc.h2d(c->in_xyz2.p, xyz2, n2 * 24, st)) ||
+        (rc = check_maps_verdict(c, st, "refine"))) return rc;
     rc = refine_device(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->out_T21.as<long long>(), c->out_T12.as<long long>(), st);
     if (rc) return rc;
     if ((rc = sc.d2h(T21, c->out_T21.p, n2 * 8, st)) || (rc = sc.finish(st))) return rc;

@@ -152,7 +152,9 @@ int lip_batch_evaluate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2
  * p2p_matching_seg_icp.py:181-182) for every segment pair of the planned batch: T21 (off2[S]) is refined IN PLACE with
  * the reference's visiting order (it makes the map closer to injective using the cycle error |v2[i] - v2[T12[T21[i]]]|
  * and the 4 nearest neighbours of each target); T12 (off1[S]) is read only, as in the reference.  Every mesh1 needs at
- * least 5 vertices (KDTree.query(k=5), :79). */
+ * least 5 vertices (KDTree.query(k=5), :79).  Map entries are segment-local indices; they are range-checked on the
+ * device before anything dereferences them (LIP_EINVAL; the reference's numpy raises IndexError), also in
+ * lip_batch_evaluate_host. */
 int lip_batch_refine_host(lip_ctx* ctx, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12);
 
 /* The whole per-segment body of get_p2p_mapping_organ_collection (p2p_matching_seg_icp.py:173-189) for the planned batch

@@ -664,3 +664,19 @@ def test_pipelined_match_equals_single_pass(L, monkeypatch):
         np.testing.assert_array_equal(res["1"][k], res["8"][k])
     assert res["8"][3]["launches"] > res["1"][3]["launches"]      # really ran as sub-batches
     assert (res["8"][2] > 0).all() and (res["8"][2] <= 1).all()
+
+
+def test_out_of_range_maps_are_rejected(L):
+    """The maps handed to the refinement and to the scores index device arrays: a bad entry is found on the device before
+    anything dereferences it (ValueError; the reference raises IndexError from numpy), and the context stays usable."""
+    b = L.make_config(1, scale=0.2)
+    r = L.local_icp_batch(b)
+    good = L.refine_batch(b, r.T21, r.T12)
+    for which, val in (("T21", -1), ("T21", 10 ** 6), ("T12", -3), ("T12", 10 ** 7)):
+        T21, T12 = r.T21.copy(), r.T12.copy()
+        (T21 if which == "T21" else T12)[5] = val
+        with pytest.raises(ValueError, match="out of range"):
+            L.refine_batch(b, T21, T12)
+        with pytest.raises(ValueError, match="out of range"):
+            L.evaluate_batch(b, T21, T12)
+    np.testing.assert_array_equal(L.refine_batch(b, r.T21, r.T12), good)
