@@ -680,3 +680,28 @@ def test_out_of_range_maps_are_rejected(L):
         with pytest.raises(ValueError, match="out of range"):
             L.evaluate_batch(b, T21, T12)
     np.testing.assert_array_equal(L.refine_batch(b, r.T21, r.T12), good)
+
+
+def test_fuzz_refinement_small_random_segments(L):
+    """double_direction_refinement on 250 random small segment pairs in one batch (5..200 points, duplicated and lattice
+    points, maps with heavy collisions): bit-identical to the oracle's sequential restatement with lowest-index ties."""
+    rng = np.random.default_rng(77)
+    segs, maps = [], []
+    for i in range(250):
+        n1, n2 = int(rng.integers(5, 201)), int(rng.integers(1, 201))
+        x1 = rng.normal(size=(n1, 3)) * [6.0, 1.0, 1.0]
+        x2 = rng.normal(size=(n2, 3)) * [6.0, 1.0, 1.0]
+        if i % 5 == 1:
+            x1[n1 // 2] = x1[0]                                   # duplicated points: zero distances in the 5-NN rows
+        if i % 5 == 2:
+            x1 = np.round(x1); x2 = np.round(x2)                 # lattice: exact ties in the neighbour order and the cycle errors
+        off = rng.uniform(-50, 50, 3)
+        segs.append((x1 + off, x2 + off, x1[:1] + off, x2[:1] + off))
+        hot = max(1, n1 // int(rng.integers(1, 6)))               # sources crowd onto few targets
+        maps.append((rng.integers(0, hot, n2), rng.integers(0, n2, n1)))
+    b = L.batch_from_segments(segs)
+    T21 = np.concatenate([m[0] for m in maps]); T12 = np.concatenate([m[1] for m in maps])
+    got = L.refine_batch(b, T21, T12)
+    for s, (x1, x2, _, _) in enumerate(segs):
+        want = O.double_direction_refinement(x1, x2, maps[s][0], maps[s][1], nn="brute")
+        np.testing.assert_array_equal(got[b.off2[s]:b.off2[s + 1]], want, err_msg=f"segment pair {s}")
