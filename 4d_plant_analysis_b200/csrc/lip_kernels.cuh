@@ -36,7 +36,12 @@
 #define LIP_BIG_THREADS 128
 #endif
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
+#ifndef LIP_MAP_THREADS
 #define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA, two queries per thread
+#endif
+#ifndef LIP_MAP_MINBLOCKS
+#define LIP_MAP_MINBLOCKS 12 // CTAs per SM blend_tile_kernel is compiled for
+#endif
 #define LIP_MAP_TILE (2 * LIP_MAP_THREADS)
 #ifndef LIP_MAP_CHUNK
 #define LIP_MAP_CHUNK 512    // candidates staged per scan
@@ -1515,7 +1520,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     }
 }
 
-__global__ void __launch_bounds__(LIP_MAP_THREADS, 12) blend_tile_kernel(LipArgs a) {
+__global__ void __launch_bounds__(LIP_MAP_THREADS, LIP_MAP_MINBLOCKS) blend_tile_kernel(LipArgs a) {
     __shared__ MapSmem S;
     __shared__ int s_tile;
     const int n_tiles = a.sched[20];

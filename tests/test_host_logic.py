@@ -146,3 +146,33 @@ def test_skeleton_landmarks_match_reference():
         lm1, lm2 = S.skeleton_landmarks(nx[f"lm_{ci}_skel1"], nx[f"lm_{ci}_skel2"], vox, "end" if method == 0 else "uniform")
         np.testing.assert_array_equal(lm1, nx[f"lm_{ci}_lm1"])
         np.testing.assert_array_equal(lm2, nx[f"lm_{ci}_lm2"])
+
+
+def test_install_patches_every_reference_module(monkeypatch):
+    """install() replaces the functions of the path (and of the rows either side of it) in the reference's modules by name,
+    wherever the reference resolves them as module globals.  Stub modules stand in for the reference."""
+    import types
+    L = importlib.import_module("4d_plant_analysis_b200")
+    names = {
+        "registration.registration_icp": ["get_best_fit_transform", "get_NN_in_target", "my_icp"],
+        "p2p_matching_in_organ.p2p_matching_seg_icp": ["get_triangle_angles", "get_p2p_mapping_from_segments_using_icp", "my_icp",
+                                                       "evaluate_p2p_matching", "double_direction_refinement"],
+        "p2p_matching_in_organ.p2p_matching_evaluation": ["evaluate_p2p_matching"],
+        "p2p_matching_in_organ.p2p_matching_fm": ["double_direction_refinement"],
+        "interpolation.interpolation_pcd": ["interpolation_segment_level"],
+    }
+    for pkg in ("registration", "p2p_matching_in_organ", "interpolation"):
+        monkeypatch.setitem(sys.modules, pkg, types.ModuleType(pkg))
+    mods = {}
+    for name, fns in names.items():
+        m = types.ModuleType(name)
+        for f in fns:
+            setattr(m, f, lambda *a, **k: "reference")
+        monkeypatch.setitem(sys.modules, name, m)
+        mods[name] = m
+    done = L.install()
+    for name, fns in names.items():
+        for f in fns:
+            fn = getattr(mods[name], f)
+            assert fn.__module__.startswith("4d_plant_analysis_b200"), (name, f)
+            assert (name, f) in done
