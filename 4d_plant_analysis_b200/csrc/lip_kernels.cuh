@@ -1976,21 +1976,13 @@ __device__ __forceinline__ void refine_move(const RefineView<IT>& w, IT ind, int
     w.t21[ind] = (IT)t_to;
 }
 
+// the refinement of one segment pair on tables at `base` (called once with the shared-memory tables and once with the
+// global ones, so that the compiler emits shared-memory loads and stores for the usual case instead of generic ones)
 template <typename IT>
-__global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn5, long long* __restrict__ T21,
-                                                    const long long* __restrict__ T12, IT* __restrict__ scratch, int smem_entries_cap) {
-    extern __shared__ double smem_ref[];
+__device__ __forceinline__ void refine_pair(const LipArgs& a, IT* __restrict__ base, const int* __restrict__ nn, long long* __restrict__ t21g,
+                                            const long long* __restrict__ t12g, int u2, int n1, int n2, int lane) {
     constexpr IT NONE = RefineView<IT>::NONE;
-    const int s = blockIdx.x, lane = threadIdx.x;
-    const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
-    const int u2g = a.mesh_ubase[a.S + s], n2 = a.mesh_ubase[a.S + s + 1] - u2g, u2 = u2g - a.n1_total;
-    long long* __restrict__ t21g = T21 + u2;
-    const long long* __restrict__ t12g = T12 + u1;
-    const int* __restrict__ nn = nn5 + 5 * (size_t)u1 + 1;          // entries 1..4 of every row: NN_mesh1[t, 1:]
-    // tables: 3 n2 + 4 n1 entries (the last n1: the snapshot of which targets had a source at the start)
-    const size_t need = 3 * (size_t)n2 + 4 * (size_t)n1;
     RefineView<IT> w;
-    IT* base = (need <= (size_t)smem_entries_cap) ? reinterpret_cast<IT*>(smem_ref) : scratch + 3 * (size_t)u2 + 4 * (size_t)u1;
     w.v2 = a.xyz2 + 3 * (size_t)u2;
     w.t21 = base; w.next21 = base + n2; w.head12 = base + 2 * n2;
     w.head21 = base + 3 * n2; w.next12 = w.head21 + n1; w.t12 = w.next12 + n1;
@@ -2065,6 +2057,22 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
     }
     __syncwarp();
     for (int i = lane; i < n2; i += 32) t21g[i] = (long long)w.t21[i];
+}
+
+template <typename IT>
+__global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn5, long long* __restrict__ T21,
+                                                    const long long* __restrict__ T12, IT* __restrict__ scratch, int smem_entries_cap) {
+    extern __shared__ double smem_ref[];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int u1 = a.mesh_ubase[s], n1 = a.mesh_ubase[s + 1] - u1;
+    const int u2g = a.mesh_ubase[a.S + s], n2 = a.mesh_ubase[a.S + s + 1] - u2g, u2 = u2g - a.n1_total;
+    long long* __restrict__ t21g = T21 + u2;
+    const long long* __restrict__ t12g = T12 + u1;
+    const int* __restrict__ nn = nn5 + 5 * (size_t)u1 + 1;          // entries 1..4 of every row: NN_mesh1[t, 1:]
+    // tables: 3 n2 + 4 n1 entries (the last n1: the snapshot of which targets had a source at the start)
+    const size_t need = 3 * (size_t)n2 + 4 * (size_t)n1;
+    if (need <= (size_t)smem_entries_cap) refine_pair<IT>(a, reinterpret_cast<IT*>(smem_ref), nn, t21g, t12g, u2, n1, n2, lane);
+    else refine_pair<IT>(a, scratch + 3 * (size_t)u2 + 4 * (size_t)u1, nn, t21g, t12g, u2, n1, n2, lane);
 }
 
 
