@@ -608,8 +608,16 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
 int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                    int64_t* T21, int64_t* T12, const MatchOpts* mo) {
     if (staging_threads() > 0 &&
-        (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12))))
-        return run_host_staged(c, xyz1, xyz2, lm1, lm2, T21, T12, mo);
+        (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12)))) {
+        bool ready = true;                                   // pinned staging buffers for every sub-batch; if the host cannot pin
+        for (int k = 0; k < c->n_kids && ready; ++k) {       // that much memory the arrays go to the driver as they are
+            lip_ctx* kc = c->kids[k];
+            ready = kc->st_in.ensure(((size_t)kc->n1 + (size_t)kc->n2 + 2 * (size_t)kc->sumK) * 24) == cudaSuccess &&
+                    kc->st_out.ensure(((size_t)kc->n1 + (size_t)kc->n2) * 8) == cudaSuccess;
+        }
+        if (ready) return run_host_staged(c, xyz1, xyz2, lm1, lm2, T21, T12, mo);
+        cudaGetLastError();
+    }
     if (c->validate_inputs) {
         int rc = check_finite(c, xyz1, xyz2, lm1, lm2);
         if (rc) return rc;
@@ -659,8 +667,9 @@ struct StageCall {
     static bool wanted(const void* h, size_t bytes) { return bytes >= ((size_t)1 << 20) && staging_threads() > 0 && is_pageable(h); }
     // capacity for everything this call will stage (the buffers must not move once in use)
     int begin(size_t in_bytes, size_t out_bytes) {
-        if (in_bytes) LIP_CUDA(c, c->st_in.ensure(in_bytes + 4096));
-        if (out_bytes) LIP_CUDA(c, c->st_out.ensure(out_bytes + 4096));
+        // (if the host cannot pin that much memory the transfers below fall back to plain copies: capacity stays short)
+        if (in_bytes && c->st_in.ensure(in_bytes + 4096) != cudaSuccess) cudaGetLastError();
+        if (out_bytes && c->st_out.ensure(out_bytes + 4096) != cudaSuccess) cudaGetLastError();
         if ((in_bytes || out_bytes) && !c->pool) c->pool = new StagePool();
         if (c->pool) c->pool->start(staging_threads());
         return LIP_OK;
