@@ -170,6 +170,7 @@ struct lip_ctx {
     HostBuf st_in, st_out;
     StagePool* pool = nullptr;
     bool validate_inputs = false;   // lip_set_input_validation
+    int plan_chunks = 0, plan_dchunks = 0;   // sub-batch counts the current plan was made with
     std::vector<cudaEvent_t> stage_events;   // per-chunk download events of StageCall
     DevBuf d_err; HostBuf h_err; cudaEvent_t ev_chk = nullptr;   // map_check_kernel: flag, its pinned copy, "copy done"
     HostBuf h_counts;                        // score counts of this (sub-)batch, pinned: their download must not block the host
@@ -894,18 +895,25 @@ static int plan_kids(lip_ctx* c, KidSet ks, int chunks, int64_t S, const int64_t
 int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
     if (!c) return LIP_EINVAL;
     cudaSetDevice(c->device);
+    int chunks = LIP_PIPELINE_CHUNKS;
+    if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    int dchunks = LIP_DEVICE_CHUNKS;
+    if (const char* e = getenv("LIP_DEVICE_CHUNKS")) dchunks = std::max(1, std::min(16, atoi(e)));
+    // the same batch shape as the one already planned (a caller registering frame after frame of one layout): nothing to do
+    if (c->planned && S > 0 && off1 && off2 && lm_off && c->S == S && c->directions == directions && (int64_t)c->h_off1.size() == S + 1 &&
+        c->plan_chunks == chunks && c->plan_dchunks == dchunks &&
+        !memcmp(c->h_off1.data(), off1, (S + 1) * 8) && !memcmp(c->h_off2.data(), off2, (S + 1) * 8) &&
+        !memcmp(c->h_lm_off.data(), lm_off, (S + 1) * 8))
+        return LIP_OK;
     int rc = plan_impl(c, S, off1, off2, lm_off, directions);
     if (rc) return rc;
     c->h_off1.assign(off1, off1 + S + 1); c->h_off2.assign(off2, off2 + S + 1); c->h_lm_off.assign(lm_off, lm_off + S + 1);
     c->last_run_split = false;
-    int chunks = LIP_PIPELINE_CHUNKS;
-    if (const char* e = getenv("LIP_PIPELINE_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    c->plan_chunks = chunks; c->plan_dchunks = dchunks;
     rc = plan_kids(c, KidSet{&c->kids, &c->kid_seg, &c->n_kids}, chunks, S, off1, off2, lm_off, directions);
     if (rc) return rc;
     // the device-resident entry point runs the batch as LIP_DEVICE_CHUNKS sub-batches on their own streams: the
     // latency-bound kernels of one (partition, the tails of the ICP kernels) overlap the scans of the other
-    int dchunks = LIP_DEVICE_CHUNKS;
-    if (const char* e = getenv("LIP_DEVICE_CHUNKS")) dchunks = std::max(1, std::min(16, atoi(e)));
     return plan_kids(c, KidSet{&c->dkids, &c->dkid_seg, &c->n_dkids}, dchunks, S, off1, off2, lm_off, directions);
 }
 

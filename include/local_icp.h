@@ -82,7 +82,8 @@ int  lip_set_input_validation(lip_ctx* ctx, int on);
  * my_icp / get_best_fit_transform / get_NN_in_target (registration/registration_icp.py:8-98) and
  * the sklearn KDTree queries they make.
  *
- * lip_batch_plan: CSR description of the batch (host arrays, copied).
+ * lip_batch_plan: CSR description of the batch (host arrays, copied).  Planning the shape that is already planned
+ *   (same offsets and directions) returns at once, so a caller may plan before every run.
  *   off1, off2 : (S+1) vertex offsets of mesh1 / mesh2 of every pair;  lm_off : (S+1) landmark
  *   offsets (lm1 and lm2 of a pair have the same count, p2p_matching_seg_icp.py:408-416).
  * lip_batch_run_*:
