@@ -151,7 +151,7 @@ struct lip_ctx {
     bool planned = false;
     int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0;
     int M = 0, B = 0, n_tiles = 0, tab_total = 0, directions = 3;
-    std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first;
+    std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first, h_plan;
     DevBuf d_plan;      // all plan arrays in one allocation
     int *mesh_ubase = nullptr, *mesh_bin = nullptr, *mesh_tab = nullptr, *bin_mesh = nullptr, *tile_mesh = nullptr,
         *tile_first = nullptr;
@@ -309,13 +309,12 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     char* base = c->d_plan.as<char>();
     c->mesh_ubase = (int*)(base + o0); c->mesh_bin = (int*)(base + o1); c->mesh_tab = (int*)(base + o2);
     c->bin_mesh = (int*)(base + o3); c->tile_mesh = (int*)(base + o4); c->tile_first = (int*)(base + o5);
-    auto up = [&](int* d, const std::vector<int>& h) {
-        return h.empty() ? cudaSuccess : cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream);
-    };
-    LIP_CUDA(c, up(c->mesh_ubase, c->h_mesh_ubase)); LIP_CUDA(c, up(c->mesh_bin, c->h_mesh_bin));
-    LIP_CUDA(c, up(c->mesh_tab, c->h_mesh_tab)); LIP_CUDA(c, up(c->bin_mesh, c->h_bin_mesh));
-    LIP_CUDA(c, up(c->tile_mesh, c->h_tile_mesh)); LIP_CUDA(c, up(c->tile_first, c->h_tile_first));
-    LIP_CUDA(c, cudaStreamSynchronize(c->stream));           // host vectors may be rewritten by the next plan
+    // one upload for all six arrays; complete on return, whatever stream the kernels will run on
+    c->h_plan.assign(off / 4, 0);
+    auto put = [&](size_t o, const std::vector<int>& h) { if (!h.empty()) memcpy(c->h_plan.data() + o / 4, h.data(), h.size() * 4); };
+    put(o0, c->h_mesh_ubase); put(o1, c->h_mesh_bin); put(o2, c->h_mesh_tab); put(o3, c->h_bin_mesh); put(o4, c->h_tile_mesh); put(o5, c->h_tile_first);
+    LIP_CUDA(c, cudaMemcpyAsync(base, c->h_plan.data(), off, cudaMemcpyHostToDevice, c->stream));
+    LIP_CUDA(c, cudaStreamSynchronize(c->stream));
     int rc = carve_workspace(c);
     if (rc) return rc;
     LipArgs& a = c->args;
