@@ -58,6 +58,7 @@ struct LipArgs {
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
+    double* bin_desc;              // [B*16] per landmark bin, for blend_kernel: filled R (9), t (3), landmark (3), {first bin of the mesh, K} as two ints (K = 0: mesh not a source)
     int* sched;              // [32] [0] partitions of icp_group_kernel [1] n_big [2] group task cursor [3] n_far
                              //      [6] far cursor [7] n_retry [12..15] big class counts [24..31] group class counts
                              //      [16] big cursor [20] number of final-map tiles [21] their cursor

@@ -1155,21 +1155,76 @@ __device__ __forceinline__ void blend_query(const LipArgs& a, int m, int bb, int
                 q0, q1, q2);
 }
 
+// One thread per landmark bin, after the ICPs: everything blend_kernel needs of a bin in ONE 128-byte record — the
+// transform of the bin after the fill of p2p_matching_seg_icp.py:422-437 (an identity rotation with the mean shift as
+// translation when no ICP of the mesh ran), its landmark, the first bin and the landmark count of its mesh — so that a
+// vertex reaches its two transforms in two dependent loads instead of six.
+__global__ void __launch_bounds__(128) bin_desc_kernel(LipArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    double* D = a.bin_desc + 16 * (size_t)b;
+    const int m = a.bin_mesh[b];
+    int2 meta = make_int2(0, 0);
+    if (src_active(a, m)) {
+        const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+        const int src = fill_source(a, bb, K, b - bb);
+        if (src >= 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) D[i] = a.icp_R[9 * (size_t)src + i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) D[9 + i] = a.icp_t[3 * (size_t)src + i];
+        } else {                                             // identity, t = mean(target mesh) - mean(source mesh)
+            const double* hs = a.mesh_sum + 4 * (size_t)m;
+            const double* ht = a.mesh_sum + 4 * (size_t)pair_mesh(a, m);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) D[i] = (i % 4 == 0) ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) D[9 + i] = ht[i] / ht[3] - hs[i] / hs[3];
+        }
+        const double* lm = mesh_lm(a, m) + 3 * (size_t)(b - bb);
+        D[12] = lm[0]; D[13] = lm[1]; D[14] = lm[2];
+        meta = make_int2(bb, K);
+    }
+    *reinterpret_cast<int2*>(D + 15) = meta;
+}
+
 // One thread per source vertex (bin order): the blended position of p2p_matching_seg_icp.py:454-487 in float64,
 // written as planes x | y | z like bin_xyz.  Streaming and fully parallel, so that the latency of its dependent
-// loads and float64 divisions is not paid inside the search tiles.
+// loads and float64 divisions is not paid inside the search tiles.  Same arithmetic as blend_point, on the bin records.
 __global__ void __launch_bounds__(256) blend_kernel(LipArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_total) return;
-    const int b = a.pos_bin[p], m = a.bin_mesh[b];           // everything per vertex is read in bin order: coalesced
-    if (!src_active(a, m)) return;
-    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
-    const size_t N0 = (size_t)a.n_total;
-    double q0, q1, q2;
-    blend_point(a, m, bb, K, a.bin_xyz[p], a.bin_xyz[N0 + p], a.bin_xyz[2 * N0 + p], b - bb, a.pos_nn1[p], a.pos_d[p], a.pos_d[N0 + p],
-                q0, q1, q2);
+    const int b = a.pos_bin[p];                              // everything per vertex is read in bin order: coalesced
+    const double* __restrict__ Da = a.bin_desc + 16 * (size_t)b;
+    const int2 meta = *reinterpret_cast<const int2*>(Da + 15);
+    const int bb = meta.x, K = meta.y;
+    if (K == 0) return;                                      // not a source of a requested direction
     const size_t N = (size_t)a.n_total;
-    a.bin_q[p] = q0; a.bin_q[N + p] = q1; a.bin_q[2 * N + p] = q2;
+    const double x = a.bin_xyz[p], y = a.bin_xyz[N + p], z = a.bin_xyz[2 * N + p];
+    const int ia = b - bb, ib = a.pos_nn1[p];
+    const double da = a.pos_d[p], db = a.pos_d[N + p];
+    const double* __restrict__ Db = a.bin_desc + 16 * (size_t)(bb + ib);
+    double f0 = 0.5, f1 = 0.5;
+    if (K > 1) {
+        const double gx = Db[12] - Da[12], gy = Db[13] - Da[13], gz = Db[14] - Da[14];
+        const double g = sqrt(gx * gx + gy * gy + gz * gz);  // |lm[b] - lm[a]|            (:467)
+        // get_triangle_angles(g, da, db): B opposite da, C opposite db
+        double cosB = (db * db + g * g - da * da) / (2.0 * g * db + a.cos_den_eps);
+        double cosC = (g * g + da * da - db * db) / (2.0 * g * da + a.cos_den_eps);
+        cosB = fmin(fmax(cosB, -1.0), 1.0);
+        cosC = fmin(fmax(cosC, -1.0), 1.0);
+        if (cosC < a.obtuse_cos) { f0 = 1.0; f1 = 0.0; }     // C > pi/2 - 1e-5                (:471)
+        else {
+            const double cb = fabs(cosB), cc = fabs(cosC);
+            f0 = cb / (cb + cc); f1 = cc / (cb + cc);
+        }
+    }
+    double ax, ay, az, bx, by, bz;
+    mat3_vec(Da, x, y, z, ax, ay, az);
+    ax += Da[9]; ay += Da[10]; az += Da[11];
+    if (ib == ia) { bx = ax; by = ay; bz = az; }
+    else { mat3_vec(Db, x, y, z, bx, by, bz); bx += Db[9]; by += Db[10]; bz += Db[11]; }
+    a.bin_q[p] = f0 * ax + f1 * bx; a.bin_q[N + p] = f0 * ay + f1 * by; a.bin_q[2 * N + p] = f0 * az + f1 * bz;
 }
 
 // =============================================================================================
