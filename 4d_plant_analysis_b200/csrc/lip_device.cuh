@@ -31,6 +31,10 @@ struct MapTile {
     double C[3];                                        // tile origin: the target's landmark
 };
 
+// frame of one partition ICP: centre = target centroid, tile shift = target landmark - centre, bound on |tile coordinate|,
+// source / target ranges in bin order (written per landmark bin by icp_schedule_kernel, read once per pass)
+struct __align__(16) IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; int pad[2]; };
+
 struct LipArgs {
     int S, M, B, sumK, n1_total, n_total, dir_mask, n_tiles;
     const double *xyz1, *xyz2, *lm1, *lm2;
@@ -58,6 +62,7 @@ struct LipArgs {
     double *icp_R, *icp_t;   // [B*9], [B*3]
     int *icp_iters, *icp_status;   // [B]
     double *fill_R, *fill_t;       // [B*9], [B*3] after the fill step
+    IcpFrame* icp_frames;          // [B]
     double* bin_desc;              // [B*16] per landmark bin, for blend_kernel: filled R (9), t (3), landmark (3), {first bin of the mesh, K} as two ints (K = 0: mesh not a source)
     int* sched;              // [32] [0] partitions of icp_group_kernel [1] n_big [2] group task cursor [3] n_far
                              //      [6] far cursor [7] n_retry [12..15] big class counts [24..31] group class counts

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
 // =============================================================================================
 // ICP scheduling: one thread per bin; empty src or tgt -> "no ICP" (p2p_matching_seg_icp.py:415-419)
 // =============================================================================================
+__device__ __forceinline__ IcpFrame icp_frame(const LipArgs& a, int b);
 __global__ void icp_schedule_kernel(LipArgs a) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -308,6 +309,7 @@ __global__ void icp_schedule_kernel(LipArgs a) {
         for (int i = 0; i < nt_map; ++i) { t.first = i * LIP_MAP_TILE; t.nq = min(LIP_MAP_TILE, ns - t.first); a.map_tiles[slot + i] = t; }
     }
     if (ns == 0 || nt == 0) return;
+    a.icp_frames[b] = icp_frame(a, b);                       // one 64-byte record per ICP instead of a chain of look-ups per pass
     const long long w = (long long)ns * nt;
     if (w <= a.warp_work) {
         // eight work classes (factor 2 apart); the persistent warps take groups of partitions heaviest class first
@@ -621,7 +623,7 @@ __device__ __forceinline__ void icp_pass(const LipArgs& a, float4* tf, unsigned 
 static_assert((LIP_ICP_CHUNK + 8) * 16 >= 16 * 32 * 8 && (LIP_BIG_CHUNK + 8) * 16 >= (LIP_BIG_THREADS / 32) * 16 * 32 * 8,
               "the search tile doubles as the scratch of the 17-sum reduction: 4 KB per warp");
 #endif
-struct IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; };
+// (IcpFrame: lip_device.cuh) derived from the partition kernel's outputs
 __device__ __forceinline__ IcpFrame icp_frame(const LipArgs& a, int b) {
     IcpFrame f;
     const int pb = pair_bin(a, b), mt = pair_mesh(a, a.bin_mesh[b]);
@@ -689,7 +691,7 @@ __global__ void __launch_bounds__(LIP_ICP_WARPS * 32, LIP_WARP_MINBLOCKS) icp_gr
             while (todo) {                                      // NN pass + sums, one partition after the other
                 const int p = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const IcpFrame f = icp_frame(a, __shfl_sync(LIP_FULL, b, p));
+                const IcpFrame f = a.icp_frames[__shfl_sync(LIP_FULL, b, p)];
                 // dot-form scores only while the cancellation error stays far below the point spacing
                 if (f.mabs <= 24.0f) icp_pass<true, 32, LIP_ICP_CHUNK, true>(a, sm.tf, sm.nn, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, sm.acc[p]);
                 else icp_pass<false, 32, LIP_ICP_CHUNK, true>(a, sm.tf, sm.nn, &sm.st[p], lane, f.so, f.ns, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, sm.acc[p]);
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS, 4) icp_big_kernel(LipArgs a) 
         int cls = 3, ri = wi;
         while (cls > 0 && ri >= a.sched[12 + cls]) { ri -= a.sched[12 + cls]; --cls; }
         const int b = a.big_list[(size_t)cls * a.B + ri];
-        const IcpFrame f = icp_frame(a, b);
+        const IcpFrame f = a.icp_frames[b];
         if (warp == 0) {
             const double* ss = a.bin_sum + 4 * (size_t)b;
             const double* ts = a.bin_sum + 4 * (size_t)pair_bin(a, b);

@@ -201,7 +201,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_nn0 = take(n * 4), o_nn1 = take(n * 4), o_d0 = take(n * 8), o_d1 = take(n * 8);
     const size_t o_binoff = take((B + 1) * 4), o_vid = take(n * 4), o_nnidx = take(n * 4);
     const size_t o_R = take(B * 72), o_t = take(B * 24), o_it = take(B * 4), o_stat = take(B * 4);
-    const size_t o_fR = take(B * 72), o_ft = take(B * 24), o_bdesc = take(B * 128);
+    const size_t o_fR = take(B * 72), o_ft = take(B * 24), o_bdesc = take(B * 128), o_frames = take(B * sizeof(IcpFrame));
     const size_t o_sched = take(32 * 4), o_warp = take(8 * B * 4), o_big = take(4 * B * 4), o_bsum = take(B * 32);
     const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
@@ -218,7 +218,7 @@ int carve_workspace(lip_ctx* c) {
     a.bin_off = (int*)(base + o_binoff); a.part_vid = (int*)(base + o_vid); a.nn_idx = (int*)(base + o_nnidx);
     a.icp_R = (double*)(base + o_R); a.icp_t = (double*)(base + o_t);
     a.icp_iters = (int*)(base + o_it); a.icp_status = (int*)(base + o_stat);
-    a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft); a.bin_desc = (double*)(base + o_bdesc);
+    a.fill_R = (double*)(base + o_fR); a.fill_t = (double*)(base + o_ft); a.bin_desc = (double*)(base + o_bdesc); a.icp_frames = (IcpFrame*)(base + o_frames);
     a.sched = (int*)(base + o_sched); a.warp_list = (int*)(base + o_warp); a.bin_sum = (double*)(base + o_bsum);
     a.big_list = (int*)(base + o_big); a.far_list = (int*)(base + o_far); a.far_q = (double*)(base + o_farq);
     a.retry_list = (int*)(base + o_re); a.retry_q = (double*)(base + o_req);
