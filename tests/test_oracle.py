@@ -134,3 +134,25 @@ def test_skeleton_landmarks_match_reference():
         np.testing.assert_array_equal(lm1, nx[f"lm_{ci}_lm1"])
         np.testing.assert_array_equal(lm2, nx[f"lm_{ci}_lm2"])
         assert len(lm1) == len(lm2)
+
+
+def test_interpolation_and_landmark_sampling_properties():
+    """size-independent properties of the two restatements: alpha = 0 / 1 reproduce the matched / the original clouds,
+    the rows are affine in alpha; the sampled landmarks of a pair have equal counts, start at the first skeleton node and
+    are spaced by more than the thinning distance."""
+    rng = np.random.default_rng(9)
+    for n1, n2 in ((1, 1), (7, 40), (300, 280)):
+        x1, x2 = rng.normal(size=(n1, 3)), rng.normal(size=(n2, 3))
+        T21, T12 = rng.integers(0, n1, n2), rng.integers(0, n2, n1)
+        a0, a1 = O.interpolation_segment_level(x1, x2, T21, T12, 0.0), O.interpolation_segment_level(x1, x2, T21, T12, 1.0)
+        np.testing.assert_array_equal(a0, np.vstack([x1[T21], x1]))
+        np.testing.assert_array_equal(a1, np.vstack([x2, x2[T12]]))
+        np.testing.assert_allclose(O.interpolation_segment_level(x1, x2, T21, T12, 0.25), 0.75 * a0 + 0.25 * a1, rtol=0, atol=1e-15)
+    for n1, n2, vox, method in ((50, 70, 0.4, "end"), (9, 200, 0.3, "uniform"), (1, 5, 0.4, "end"), (40, 40, 2.0, "uniform")):
+        mk = lambda n: np.cumsum(np.abs(rng.normal(0.5, 0.2, (n, 3))), axis=0)
+        s1, s2 = mk(n1), mk(n2)
+        lm1, lm2 = O.skeleton_landmarks(s1, s2, vox, method)
+        assert len(lm1) == len(lm2) >= 1
+        np.testing.assert_array_equal(lm1[0], s1[0]); np.testing.assert_array_equal(lm2[0], s2[0])
+        if method == "uniform" and len(lm1) > 1:
+            assert (np.linalg.norm(np.diff(lm1, axis=0), axis=1) > 2 * vox).all()
