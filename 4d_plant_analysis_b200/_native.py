@@ -22,6 +22,7 @@ SOURCES = ["local_icp.cu", "lip_kernels.cuh", "lip_device.cuh"]
 HEADER = os.path.join(ROOT, "include", "local_icp.h")
 
 DIR_T21, DIR_T12, DIR_BOTH = 1, 2, 3
+ABI_VERSION = 2          # == LIP_ABI_VERSION of include/local_icp.h; bump both whenever a signature or struct layout changes
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC", "-DLIP_ARCH=100"]
@@ -95,7 +96,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 
 
 def load():
@@ -109,6 +110,10 @@ def load():
             raise NativeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(nvcc, sm_100a). There is no CPU fallback.")
         lib = ctypes.CDLL(LIB_PATH)
+        lib.lip_version.restype, lib.lip_version.argtypes = c_int, []
+        if lib.lip_version() != ABI_VERSION:     # an old binary against new prototypes would crash or, worse, return wrong maps
+            raise NativeError(f"{LIB_PATH} has ABI version {lib.lip_version()}, the Python layer expects {ABI_VERSION}: "
+                              "rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
@@ -132,9 +137,12 @@ def _i64(a):
 
 
 class Context:
-    """One lip_ctx: a CUDA stream plus grow-only device workspace on one GPU."""
+    """One lip_ctx: a CUDA stream plus grow-only device workspace on one GPU.  A context is single-threaded: plan, run and
+    the getters of one call sequence belong together.  Code that shares a context between threads (the drop-in functions
+    all use ``default_context()``) holds ``ctx.lock`` around the whole sequence."""
 
     def __init__(self, device: int = 0):
+        self.lock = threading.RLock()
         self.lib = load()
         h = c_void_p()
         rc = self.lib.lip_create(byref(h), int(device))
@@ -345,9 +353,11 @@ _default = {}
 
 
 def default_context(device: int | None = None) -> Context:
-    """process-wide context per device (device defaults to LOCAL_RANK, else 0)."""
+    """process-wide context per device (device defaults to LOCAL_RANK, else 0).  Shared by every drop-in function: hold
+    ``ctx.lock`` around plan + run + getters."""
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    if device not in _default:
-        _default[device] = Context(device)
-    return _default[device]
+    with _lock:
+        if device not in _default:
+            _default[device] = Context(device)
+        return _default[device]

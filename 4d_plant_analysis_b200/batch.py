@@ -51,17 +51,18 @@ def local_icp_batch(segments, *, directions: int = _native.DIR_BOTH, details: bo
     """segments: a SegmentPairBatch or a list of (xyz1, xyz2, lm1, lm2).  Host numpy in, host numpy out."""
     b = _as_batch(segments)
     ctx = ctx or _native.default_context(device)
-    ctx.set_input_validation(validate)       # NaN / infinity -> ValueError, checked by the library while it stages the arrays
-    ctx.plan(b.off1, b.off2, b.lm_off, directions)
-    try:
-        T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
-    finally:
-        ctx.set_input_validation(False)
-    res = LocalICPResult(T21, T12, b.off1, b.off2, b.lm_off)
-    if details:
-        res.transforms = ctx.transforms(filled=True)
-        res.transforms["raw"] = ctx.transforms(filled=False)
-        res.counters = ctx.counters()
+    with ctx.lock:
+        ctx.set_input_validation(validate)   # NaN / infinity -> ValueError, checked by the library while it stages the arrays
+        try:
+            ctx.plan(b.off1, b.off2, b.lm_off, directions)
+            T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+        finally:
+            ctx.set_input_validation(False)
+        res = LocalICPResult(T21, T12, b.off1, b.off2, b.lm_off)
+        if details:
+            res.transforms = ctx.transforms(filled=True)
+            res.transforms["raw"] = ctx.transforms(filled=False)
+            res.counters = ctx.counters()
     return res
 
 
@@ -87,12 +88,13 @@ def match_segments_batch(segments, *, apply_double_direction_refinement: bool = 
     driver's arguments (:184-185: default voxel_size = 1.0, sample_proportion = 0.5) and the score weights (:189)."""
     b = _as_batch(segments)
     ctx = ctx or _native.default_context()
-    ctx.set_input_validation(True)
-    ctx.plan(b.off1, b.off2, b.lm_off)
-    try:
-        T21, T12, scores = ctx.match(b.xyz1, b.xyz2, b.lm1, b.lm2, apply_double_direction_refinement, voxel_size, sample_proportion)
-    finally:
-        ctx.set_input_validation(False)
+    with ctx.lock:
+        ctx.set_input_validation(True)
+        try:
+            ctx.plan(b.off1, b.off2, b.lm_off)
+            T21, T12, scores = ctx.match(b.xyz1, b.xyz2, b.lm1, b.lm2, apply_double_direction_refinement, voxel_size, sample_proportion)
+        finally:
+            ctx.set_input_validation(False)
     S = b.n_segments
     return SegmentMatchResult([T21[b.off2[s]:b.off2[s + 1]] for s in range(S)], [T12[b.off1[s]:b.off1[s + 1]] for s in range(S)],
                               scores, np.diff(b.off1).astype(np.float64), b)

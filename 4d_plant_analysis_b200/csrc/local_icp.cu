@@ -147,8 +147,9 @@ struct lip_ctx {
     bool is_kid = false;
     lip_params params;
     std::string err;
-    // plan
-    bool planned = false;
+    // plan.  planned: the plan arrays / workspace describe SOME batch (plan_impl); user_plan: that batch is the caller's
+    // (lip_batch_plan) and not an internal one of lip_icp_host / lip_nn_host, which clear it before they do anything else
+    bool planned = false, user_plan = false;
     int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0;
     int M = 0, B = 0, n_tiles = 0, tab_total = 0, directions = 3;
     std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first, h_plan;
@@ -623,6 +624,8 @@ int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const dou
         int rc = check_finite(c, xyz1, xyz2, lm1, lm2);
         if (rc) return rc;
     }
+    // nothing enqueued by this call may still touch the caller's arrays when an error is returned
+    auto drain = [&] { cudaStreamSynchronize(c->side[1]); for (int k = 0; k < c->n_kids; ++k) cudaStreamSynchronize(c->kids[k]->stream); };
     // All uploads are enqueued first, on ONE stream: issuing the kernels of a sub-batch takes the host longer than its
     // upload takes the copy engine (which must never wait for the host), and in-order uploads give every sub-batch its
     // data as early as possible.
@@ -632,13 +635,13 @@ int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const dou
         kc->params = c->params;
         int rc = host_upload_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
                                    c->side[1]);             // one upload stream: the sub-batches arrive in order, each as early as possible
-        if (rc) return fail(c, rc, "pipeline upload: " + kc->err);
+        if (rc) { drain(); return fail(c, rc, "pipeline upload: " + kc->err); }
     }
     for (int k = 0; k < c->n_kids; ++k) {
         lip_ctx* kc = c->kids[k];
         const int64_t s0 = c->kid_seg[k];
         int rc = host_compute_async(kc, T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr, mo);
-        if (rc) return fail(c, rc, "pipeline run: " + kc->err);
+        if (rc) { drain(); return fail(c, rc, "pipeline run: " + kc->err); }
     }
     for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
     if (getenv("LIP_TRACE_PIPELINE") && c->kids[0]->tr[0]) {
@@ -738,7 +741,7 @@ struct StageCall {
 
 extern "C" {
 
-int lip_version(void) { return 1; }
+int lip_version(void) { return LIP_ABI_VERSION; }
 int lip_compiled_arch(void) { return LIP_ARCH; }
 
 void lip_default_params(lip_params* p) {
@@ -834,7 +837,9 @@ int lip_set_input_validation(lip_ctx* c, int on) {
 int lip_set_map_mode(lip_ctx* c, int mode) {
     if (!c) return LIP_EINVAL;
     if (mode != 0 && mode != 1) return fail(c, LIP_EINVAL, "map mode must be 0 (landmark-bin tiles) or 1 (hashed grid)");
-    if (mode != c->map_mode) c->planned = false;             // the tile list depends on the mode: plan again
+    if (mode != c->map_mode) {                               // the tile list depends on the mode: plan again (sub-batches too)
+        c->planned = false; c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;
+    }
     c->map_mode = mode;
     return LIP_OK;
 }
@@ -887,6 +892,7 @@ static int plan_kids(lip_ctx* c, KidSet ks, int chunks, int64_t S, const int64_t
         int rc = plan_impl(kc, s1 - s0, o1.data(), o2.data(), ol.data(), directions);
         if (rc) return fail(c, rc, "pipeline plan: " + kc->err);
         kc->h_off1 = o1; kc->h_off2 = o2; kc->h_lm_off = ol;   // the refinement and the scores of a sub-batch slice by segment pair
+        kc->user_plan = true;
     }
     *ks.n = nk;
     return LIP_OK;
@@ -900,26 +906,31 @@ int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* of
     int dchunks = LIP_DEVICE_CHUNKS;
     if (const char* e = getenv("LIP_DEVICE_CHUNKS")) dchunks = std::max(1, std::min(16, atoi(e)));
     // the same batch shape as the one already planned (a caller registering frame after frame of one layout): nothing to do
-    if (c->planned && S > 0 && off1 && off2 && lm_off && c->S == S && c->directions == directions && (int64_t)c->h_off1.size() == S + 1 &&
+    if (c->planned && c->user_plan && S > 0 && off1 && off2 && lm_off && c->S == S && c->directions == directions && (int64_t)c->h_off1.size() == S + 1 &&
         c->plan_chunks == chunks && c->plan_dchunks == dchunks &&
         !memcmp(c->h_off1.data(), off1, (S + 1) * 8) && !memcmp(c->h_off2.data(), off2, (S + 1) * 8) &&
         !memcmp(c->h_lm_off.data(), lm_off, (S + 1) * 8))
         return LIP_OK;
+    c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;
     int rc = plan_impl(c, S, off1, off2, lm_off, directions);
     if (rc) return rc;
     c->h_off1.assign(off1, off1 + S + 1); c->h_off2.assign(off2, off2 + S + 1); c->h_lm_off.assign(lm_off, lm_off + S + 1);
     c->last_run_split = false;
     c->plan_chunks = chunks; c->plan_dchunks = dchunks;
     rc = plan_kids(c, KidSet{&c->kids, &c->kid_seg, &c->n_kids}, chunks, S, off1, off2, lm_off, directions);
-    if (rc) return rc;
+    if (rc) { c->n_kids = 0; c->planned = false; return rc; }
     // the device-resident entry point runs the batch as LIP_DEVICE_CHUNKS sub-batches on their own streams: the
     // latency-bound kernels of one (partition, the tails of the ICP kernels) overlap the scans of the other
-    return plan_kids(c, KidSet{&c->dkids, &c->dkid_seg, &c->n_dkids}, dchunks, S, off1, off2, lm_off, directions);
+    rc = plan_kids(c, KidSet{&c->dkids, &c->dkid_seg, &c->n_dkids}, dchunks, S, off1, off2, lm_off, directions);
+    if (rc) { c->n_kids = 0; c->n_dkids = 0; c->planned = false; return rc; }
+    c->user_plan = true;
+    return LIP_OK;
 }
 
 int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                          int64_t* T21, int64_t* T12, void* stream) {
     if (!c) return LIP_EINVAL;
+    if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
@@ -949,7 +960,7 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
 int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                        int64_t* T21, int64_t* T12) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
+    if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
     if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "run: null output pointer");
     cudaSetDevice(c->device);
@@ -968,7 +979,7 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
 
 int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, int32_t* iters21, int32_t* status21,
                              double* R12, double* t12, int32_t* iters12, int32_t* status12) {
-    if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (!c || !c->planned || !c->user_plan) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
     if (c->last_run_split) {                                 // the last run was pipelined: collect from the sub-batches
         for (int k = 0; k < split_n(c); ++k) {
@@ -1005,7 +1016,7 @@ int lip_batch_get_transforms(lip_ctx* c, int filled, double* R21, double* t21, i
 }
 
 int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
-    if (!c || !c->planned) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (!c || !c->planned || !c->user_plan) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     if (side != 1 && side != 2) return fail(c, LIP_EINVAL, "side must be 1 or 2");
     cudaSetDevice(c->device);
     if (c->last_run_split) {
@@ -1033,7 +1044,7 @@ int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
 }
 
 int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
-    if (!c || !c->planned || !counters) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (!c || !c->planned || !c->user_plan || !counters) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
     if (c->last_run_split) {
         for (int i = 0; i < 8; ++i) counters[i] = 0;
@@ -1057,7 +1068,7 @@ int lip_batch_get_counters(lip_ctx* c, int64_t counters[8]) {
 }
 
 int lip_batch_get_pair_counts(lip_ctx* c, int64_t pairs[3]) {
-    if (!c || !c->planned || !pairs) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (!c || !c->planned || !c->user_plan || !pairs) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     cudaSetDevice(c->device);
     pairs[0] = pairs[1] = pairs[2] = 0;
     if (c->last_run_split) {
@@ -1097,7 +1108,7 @@ int lip_batch_get_stage_ms(lip_ctx* c, float ms[LIP_N_STAGES]) {
 }
 
 int lip_batch_get_bin_offsets(lip_ctx* c, int32_t* bin_off) {
-    if (!c || !c->planned || !bin_off) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
+    if (!c || !c->planned || !c->user_plan || !bin_off) return c ? fail(c, LIP_ENOPLAN, "no batch planned") : LIP_EINVAL;
     if (c->last_run_split) return fail(c, LIP_ENOPLAN, "bin offsets: the last run was a pipelined host run; use lip_batch_run_device");
     cudaSetDevice(c->device);
     LIP_CUDA(c, cudaDeviceSynchronize());
@@ -1196,7 +1207,7 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
                             const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
                             double* scores, int64_t* counts) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !scores) return fail(c, LIP_EINVAL, "evaluate: null pointer");
     if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "evaluate: sample_proportion must be > 0");
     cudaSetDevice(c->device);
@@ -1272,7 +1283,7 @@ static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2,
 
 int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "refine: no batch planned");
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "refine: no batch planned");
     if (!xyz1 || !xyz2 || !T21 || !T12) return fail(c, LIP_EINVAL, "refine: null pointer");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
@@ -1299,7 +1310,7 @@ int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, in
 int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                          int refine, double voxel_size, double sample_proportion, int64_t* T21, int64_t* T12, double* scores) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "match: no batch planned");
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "match: no batch planned");
     if (c->directions != LIP_DIR_BOTH) return fail(c, LIP_EINVAL, "match: the batch must be planned for both directions");
     if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !T12 || !scores) return fail(c, LIP_EINVAL, "match: null pointer");
     if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "match: sample_proportion must be > 0");
@@ -1370,7 +1381,7 @@ static int interpolate_device(lip_ctx* c, const double* d_xyz1, const double* d_
 int lip_batch_interpolate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const int64_t* d_T21, const int64_t* d_T12,
                                  double alpha, double* d_out, void* stream) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
     if (!d_xyz1 || !d_xyz2 || !d_T21 || !d_T12 || !d_out) return fail(c, LIP_EINVAL, "interpolate: null pointer");
     cudaSetDevice(c->device);
     LIP_CUDA(c, c->misc2.ensure(16));
@@ -1381,7 +1392,7 @@ int lip_batch_interpolate_device(lip_ctx* c, const double* d_xyz1, const double*
 int lip_batch_interpolate_host(lip_ctx* c, const double* xyz1, const double* xyz2, const int64_t* T21, const int64_t* T12,
                                double alpha, double* out) {
     if (!c) return LIP_EINVAL;
-    if (!c->planned || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "interpolate: no batch planned");
     if (!xyz1 || !xyz2 || !T21 || !T12 || !out) return fail(c, LIP_EINVAL, "interpolate: null pointer");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
@@ -1408,6 +1419,7 @@ int lip_batch_interpolate_host(lip_ctx* c, const double* xyz1, const double* xyz
 int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_off, const double* tgt,
                  const int64_t* tgt_off, double* R, double* t, int32_t* iters, int32_t* status) {
     if (!c) return LIP_EINVAL;
+    c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;      // whatever happens below, the caller's batch plan is gone
     if (P <= 0 || !src || !src_off || !tgt || !tgt_off) return fail(c, LIP_EINVAL, "icp: bad arguments");
     cudaSetDevice(c->device);
     std::vector<int64_t> lm_off(P + 1);
@@ -1437,6 +1449,7 @@ int lip_icp_host(lip_ctx* c, int64_t P, const double* src, const int64_t* src_of
 
 int lip_nn_host(lip_ctx* c, const double* src, int64_t n, const double* tgt, int64_t m, double* dist, int64_t* idx) {
     if (!c) return LIP_EINVAL;
+    c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;      // whatever happens below, the caller's batch plan is gone
     if (n <= 0 || m <= 0 || !src || !tgt || !idx) return fail(c, LIP_EINVAL, "nn: bad arguments");
     cudaSetDevice(c->device);
     const int64_t off1[2] = {0, m}, off2[2] = {0, n}, lmo[2] = {0, 1};

@@ -25,7 +25,7 @@ def _module(name):
         return sys.modules[name]
     try:
         return importlib.import_module(name)
-    except ImportError:
+    except Exception:        # ImportError, or an OSError / AttributeError from an eager open3d or pyFM import in the reference
         return None
 
 

@@ -41,8 +41,9 @@ def _maps(T, name):
 def interpolate_batch(batch, T21, T12, alpha, ctx=None):
     """(off1[S] + off2[S], 3) float64: per segment pair s, from row off1[s] + off2[s], its interpolation_segment_level rows."""
     ctx = ctx or _native.default_context()
-    ctx.plan(batch.off1, batch.off2, batch.lm_off)
-    return ctx.interpolate(batch.xyz1, batch.xyz2, _maps(T21, "T21"), _maps(T12, "T12"), alpha)
+    with ctx.lock:
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)
+        return ctx.interpolate(batch.xyz1, batch.xyz2, _maps(T21, "T21"), _maps(T12, "T12"), alpha)
 
 
 def interpolation_segment_level(xyz1, xyz2, T21, T12, alpha):
@@ -55,9 +56,10 @@ def interpolation_segment_level(xyz1, xyz2, T21, T12, alpha):
     if len(v1) == 0 or len(v2) == 0:
         raise IndexError("index 0 is out of bounds for axis 0 with size 0")
     ctx = _native.default_context()
-    ctx.plan([0, len(v1)], [0, len(v2)], [0, 1])
     try:
-        return ctx.interpolate(v1, v2, T21, T12, alpha)
+        with ctx.lock:
+            ctx.plan([0, len(v1)], [0, len(v2)], [0, 1])
+            return ctx.interpolate(v1, v2, T21, T12, alpha)
     except ValueError as e:                                  # numpy's exception type for a bad fancy index
         raise IndexError(str(e)) from None
 
@@ -81,5 +83,6 @@ def interpolate_saved_result(directory, day1, day2, alpha, ctx=None):
     off1 = np.concatenate([[0], np.cumsum([len(a) for a in x1])]).astype(np.int64)
     off2 = np.concatenate([[0], np.cumsum([len(a) for a in x2])]).astype(np.int64)
     ctx = ctx or _native.default_context()
-    ctx.plan(off1, off2, np.arange(len(x1) + 1, dtype=np.int64))
-    return ctx.interpolate(np.vstack(x1), np.vstack(x2), _maps(np.concatenate(t21), "T21"), _maps(np.concatenate(t12), "T12"), alpha)
+    with ctx.lock:
+        ctx.plan(off1, off2, np.arange(len(x1) + 1, dtype=np.int64))
+        return ctx.interpolate(np.vstack(x1), np.vstack(x2), _maps(np.concatenate(t21), "T21"), _maps(np.concatenate(t12), "T12"), alpha)

@@ -19,8 +19,9 @@ from .registration_icp import _points
 def evaluate_batch(batch, T21, T12=None, voxel_size=1.0, sample_proportion=0.1, ctx=None):
     """scores (S,3) float64 = [continuity, landmark precision, cycle] per segment pair of a SegmentPairBatch."""
     ctx = ctx or _native.default_context()
-    ctx.plan(batch.off1, batch.off2, batch.lm_off)
-    scores, _ = ctx.evaluate(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2, T21, T12, voxel_size, sample_proportion)
+    with ctx.lock:
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)
+        scores, _ = ctx.evaluate(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2, T21, T12, voxel_size, sample_proportion)
     return scores
 
 
@@ -36,9 +37,10 @@ def evaluate_p2p_matching(mesh1, mesh2, skel_landmarks1, skel_landmarks2, T21, T
     if not with_lm:                                              # a placeholder landmark; its score is dropped below
         l1, l2 = v1[:1], v2[:1]
     ctx = _native.default_context()
-    ctx.plan([0, len(v1)], [0, len(v2)], [0, len(l1)])
-    scores, _ = ctx.evaluate(v1, v2, l1, l2, np.asarray(T21), None if T12 is None else np.asarray(T12),
-                             voxel_size, sample_proportion)
+    with ctx.lock:
+        ctx.plan([0, len(v1)], [0, len(v2)], [0, len(l1)])
+        scores, _ = ctx.evaluate(v1, v2, l1, l2, np.asarray(T21), None if T12 is None else np.asarray(T12),
+                                 voxel_size, sample_proportion)
     continuity, lm_precision, cycle = (float(x) for x in scores[0])
     res = [continuity]
     if verbose:

@@ -14,8 +14,9 @@ def refine_batch(batch, T21, T12, ctx=None):
     ctx = ctx or _native.default_context()
     if (np.diff(batch.off1) < 5).any():
         raise ValueError("Expected n_neighbors <= n_samples_fit: every mesh1 needs at least 5 vertices (KDTree.query(k=5))")
-    ctx.plan(batch.off1, batch.off2, batch.lm_off)
-    return ctx.refine(batch.xyz1, batch.xyz2, T21, T12)
+    with ctx.lock:
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)
+        return ctx.refine(batch.xyz1, batch.xyz2, T21, T12)
 
 
 def double_direction_refinement(mesh1, mesh2, T21, T12, lm1=None, lm2=None):
@@ -24,8 +25,9 @@ def double_direction_refinement(mesh1, mesh2, T21, T12, lm1=None, lm2=None):
     if len(v1) < 5:
         raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = 5, n_samples_fit = {len(v1)}")
     ctx = _native.default_context()
-    ctx.plan([0, len(v1)], [0, len(v2)], [0, 1])
-    out = ctx.refine(v1, v2, T21, T12)
+    with ctx.lock:
+        ctx.plan([0, len(v1)], [0, len(v2)], [0, 1])
+        out = ctx.refine(v1, v2, T21, T12)
     if isinstance(T21, np.ndarray) and T21.shape == out.shape:
         T21[...] = out                                       # the reference rewrites the caller's array in place
         return T21, T12

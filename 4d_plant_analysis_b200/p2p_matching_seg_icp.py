@@ -19,7 +19,9 @@ from .registration_icp import _points
 
 def get_triangle_angles(a, b, c):
     assert a + b >= c and a + c >= b and b + c >= a
-    return _native.default_context().triangle_angles(np.array([[a, b, c]], dtype=np.float64))[0]
+    ctx = _native.default_context()
+    with ctx.lock:
+        return ctx.triangle_angles(np.array([[a, b, c]], dtype=np.float64))[0]
 
 
 def _vector3d(colors):
@@ -40,17 +42,18 @@ def get_p2p_mapping_from_segments_using_icp(mesh1, mesh2, lm1, lm2, voxel_size):
     if lm1.shape[0] != lm2.shape[0]:
         raise ValueError("lm1 and lm2 must hold the same number of landmarks")
     ctx = _native.default_context()
-    ctx.plan([0, len(xyz1)], [0, len(xyz2)], [0, len(lm1)], _native.DIR_T21)
-    T21, _ = ctx.run_host(xyz1, xyz2, lm1, lm2)
-    if lm1.shape[0] > 1:
-        # side effects of the reference (:394-398): one draw from the global numpy RNG, vertex colours
-        # by nearest landmark
-        color_setting = np.random.random((lm1.shape[0], 3))
-        try:
-            nn1, _ = ctx.landmark_nn(1)
-            nn2, _ = ctx.landmark_nn(2)
-            mesh1.vertex_colors = _vector3d(color_setting[nn1[:, 0]])
-            mesh2.vertex_colors = _vector3d(color_setting[nn2[:, 0]])
-        except AttributeError:
-            pass
+    with ctx.lock:                          # plan + run + getters of the shared context belong together
+        ctx.plan([0, len(xyz1)], [0, len(xyz2)], [0, len(lm1)], _native.DIR_T21)
+        T21, _ = ctx.run_host(xyz1, xyz2, lm1, lm2)
+        if lm1.shape[0] > 1:
+            # side effects of the reference (:394-398): one draw from the global numpy RNG, vertex colours
+            # by nearest landmark
+            color_setting = np.random.random((lm1.shape[0], 3))
+            try:
+                nn1, _ = ctx.landmark_nn(1)
+                nn2, _ = ctx.landmark_nn(2)
+                mesh1.vertex_colors = _vector3d(color_setting[nn1[:, 0]])
+                mesh2.vertex_colors = _vector3d(color_setting[nn2[:, 0]])
+            except AttributeError:
+                pass
     return T21

@@ -28,7 +28,9 @@ def get_best_fit_transform(A, B):
     row, as the reference builds it), R (3,3), t (3,)."""
     assert len(A) == len(B)
     A, B = _points(A, "A"), _points(B, "B")
-    R, t, _ = _native.default_context().kabsch(A, B)
+    ctx = _native.default_context()
+    with ctx.lock:
+        R, t, _ = ctx.kabsch(A, B)
     T = np.identity(4)
     T[0:3, 0:3] = R.T
     T[[3], 0:3] = t.T
@@ -38,7 +40,9 @@ def get_best_fit_transform(A, B):
 def get_NN_in_target(xyz1, xyz2):
     """Exact nearest neighbour in xyz2 of every point of xyz1: (distance (n,1) float64, indices (n,) int64)."""
     xyz1, xyz2 = _points(xyz1, "xyz1"), _points(xyz2, "xyz2")
-    d, i = _native.default_context().nn(xyz1, xyz2)
+    ctx = _native.default_context()
+    with ctx.lock:
+        d, i = ctx.nn(xyz1, xyz2)
     return d.reshape(-1, 1), i
 
 
@@ -46,7 +50,9 @@ def my_icp(xyz1, xyz2):
     """Point-to-point ICP of source xyz1 onto target xyz2.  Returns T (4x4, R top-left, t^T in row 3),
     R (3,3), t (3,1); callers apply it as ``x @ R.T + t.T``."""
     xyz1, xyz2 = _points(xyz1, "xyz1"), _points(xyz2, "xyz2")
-    R, t, _, _ = _native.default_context().icp(xyz1, [0, len(xyz1)], xyz2, [0, len(xyz2)])
+    ctx = _native.default_context()
+    with ctx.lock:
+        R, t, _, _ = ctx.icp(xyz1, [0, len(xyz1)], xyz2, [0, len(xyz2)])
     R, t = R[0], t[0].reshape(3, 1)
     T = np.identity(4)
     T[0:3, 0:3] = R

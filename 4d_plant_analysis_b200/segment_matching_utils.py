@@ -24,7 +24,8 @@ def label_points_by_skeleton(xyz_pcd, xyz_skeleton, ctx=None):
     pts = _points(xyz_pcd, "xyz_pcd")
     nodes = _points(sk[:, :3], "xyz_skeleton[:, :3]")
     ctx = ctx or _native.default_context()
-    _, nn = ctx.nn(pts, nodes)                               # exact 1-NN, lowest index on exact ties
+    with ctx.lock:
+        _, nn = ctx.nn(pts, nodes)                               # exact 1-NN, lowest index on exact ties
     return sk[:, 3][nn], nn
 
 

@@ -25,6 +25,8 @@
 extern "C" {
 #endif
 
+#define LIP_ABI_VERSION 2 /* returned by lip_version(); the Python layer refuses a library of another version */
+
 #define LIP_OK        0
 #define LIP_ENODEV   -1   /* no CUDA device / CUDA runtime error at start-up */
 #define LIP_EINVAL   -2   /* bad argument (empty mesh, K mismatch, K too large, null pointer ...) */
