@@ -42,6 +42,9 @@ SIGNATURES = {
     "lip_batch_plan": (c_int, [c_void_p, c_int64, _I64, _I64, _I64, c_int]),
     "lip_batch_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lip_batch_run_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lip_set_map_dtype": (c_int, [c_void_p, c_int]),
+    "lip_series_run_host": (c_int, [c_void_p, c_void_p, c_int64, _I64, _I64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lip_series_run_device": (c_int, [c_void_p, c_void_p, c_int64, _I64, _I64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lip_batch_get_transforms": (c_int, [c_void_p, c_int, _D, _D, _I32, _I32, _D, _D, _I32, _I32]),
     "lip_batch_get_landmark_nn": (c_int, [c_void_p, c_int, _I32, _D]),
     "lip_batch_get_counters": (c_int, [c_void_p, _I64]),
@@ -200,15 +203,54 @@ class Context:
                                             int(directions)))
         self.S, self.n1, self.n2, self.sumK, self.directions = S, int(off1[-1]), int(off2[-1]), int(lm_off[-1]), int(directions)
 
+    map_dtype = np.int64
+
+    def set_map_dtype(self, dtype):
+        """entry type of the maps returned by run_host / run_series / run_device: np.int64 (default, as the reference) or np.int32"""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+            raise ValueError("map dtype must be int32 or int64")
+        self._check(self.lib.lip_set_map_dtype(self.h, 8 * dtype.itemsize))
+        self.map_dtype = dtype.type
+
+    def _maps_out(self, T21, T12):
+        for T, n in ((T21, self.n2), (T12, self.n1)):
+            if T is not None and (T.dtype != self.map_dtype or len(T) != n or not T.flags.c_contiguous):
+                raise ValueError("output maps must be contiguous arrays of the context's map dtype and the planned size")
+        if T21 is None and self.directions & DIR_T21:
+            T21 = np.empty(self.n2, self.map_dtype)
+        if T12 is None and self.directions & DIR_T12:
+            T12 = np.empty(self.n1, self.map_dtype)
+        return T21, T12
+
+    def run_series(self, frames, row1, row2, lm1, lm2, T21=None, T12=None):
+        """time series: ``frames`` (n_rows,3) holds every mesh once; row1[s] / row2[s] = first row of mesh1 / mesh2 of segment
+        pair s of the planned batch (meshes may be shared between pairs); one upload of every mesh."""
+        frames, lm1, lm2, row1, row2 = _f64(frames), _f64(lm1), _f64(lm2), _i64(row1), _i64(row2)
+        if len(row1) != self.S or len(row2) != self.S or len(lm1) != self.sumK or len(lm2) != self.sumK:
+            raise ValueError("array sizes do not match the planned batch")
+        T21, T12 = self._maps_out(T21, T12)
+        self._check(self.lib.lip_series_run_host(self.h, frames.ctypes.data, len(frames), _ptr(row1, c_int64), _ptr(row2, c_int64),
+                                                 lm1.ctypes.data, lm2.ctypes.data,
+                                                 T21.ctypes.data if T21 is not None else None,
+                                                 T12.ctypes.data if T12 is not None else None))
+        return T21, T12
+
+    def run_series_ptr(self, frames, n_rows, row1, row2, lm1, lm2, T21, T12):
+        """same, raw addresses of (pinned) host buffers; row1 / row2 are int64 numpy arrays"""
+        self._check(self.lib.lip_series_run_host(self.h, frames, int(n_rows), _ptr(row1, c_int64), _ptr(row2, c_int64), lm1, lm2, T21, T12))
+
+    def run_series_device(self, d_frames, n_rows, row1, row2, d_lm1, d_lm2, d_T21, d_T12, stream=0):
+        """device addresses, enqueued on `stream`; no sync.  row1 / row2: int64 numpy arrays (host)"""
+        self._check(self.lib.lip_series_run_device(self.h, d_frames, int(n_rows), _ptr(row1, c_int64), _ptr(row2, c_int64),
+                                                   d_lm1, d_lm2, d_T21, d_T12, stream))
+
     def run_host(self, xyz1, xyz2, lm1, lm2, T21=None, T12=None):
         """host numpy in -> host numpy out (H2D, kernels, D2H, sync inside)."""
         xyz1, xyz2, lm1, lm2 = _f64(xyz1), _f64(xyz2), _f64(lm1), _f64(lm2)
         if len(xyz1) != self.n1 or len(xyz2) != self.n2 or len(lm1) != self.sumK or len(lm2) != self.sumK:
             raise ValueError("array sizes do not match the planned batch")
-        if T21 is None and self.directions & DIR_T21:
-            T21 = np.empty(self.n2, np.int64)
-        if T12 is None and self.directions & DIR_T12:
-            T12 = np.empty(self.n1, np.int64)
+        T21, T12 = self._maps_out(T21, T12)
         self._check(self.lib.lip_batch_run_host(self.h, xyz1.ctypes.data, xyz2.ctypes.data, lm1.ctypes.data, lm2.ctypes.data,
                                                 T21.ctypes.data if T21 is not None else None,
                                                 T12.ctypes.data if T12 is not None else None))

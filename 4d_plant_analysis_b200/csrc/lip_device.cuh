@@ -38,6 +38,8 @@ struct __align__(16) IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; in
 struct LipArgs {
     int S, M, B, sumK, n1_total, n_total, dir_mask, n_tiles;
     const double *xyz1, *xyz2, *lm1, *lm2;
+    const int* mesh_row;     // nullptr, or [M]: first row of each mesh in ONE coordinate array (xyz1); meshes may be shared between
+                             // segment pairs (time series: a frame is mesh2 of one frame pair and mesh1 of the next)
     const int* mesh_ubase;   // [M+1] unified vertex base of each mesh
     const int* mesh_bin;     // [M+1] first bin (= unified landmark index) of each mesh
     const int* mesh_tab;     // [M+1] first entry of each mesh's hash table in grid_start
@@ -82,10 +84,19 @@ struct LipArgs {
     int icp_tasks_per_warp, icp_class_shift;   // group sizes of icp_group_kernel (tuning knobs)
     long long warp_work;     // partitions with n_src * n_tgt <= this go to icp_group_kernel, heavier ones to icp_big_kernel
     int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
+    int map32;               // != 0: T12 / T21 point at int32 arrays (lip_set_map_dtype)
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };
 
+// dense-map entry of unified vertex u (mesh1 vertices fill T12, mesh2 vertices T21), int64 like numpy's intp or int32
+__device__ __forceinline__ void store_map(const LipArgs& a, int u, int idx) {
+    const bool side1 = u < a.n1_total;
+    const int i = side1 ? u : u - a.n1_total;
+    long long* t = side1 ? a.T12 : a.T21;
+    if (a.map32) reinterpret_cast<int*>(t)[i] = idx; else t[i] = idx;
+}
 __device__ __forceinline__ const double* mesh_xyz(const LipArgs& a, int m) {
+    if (a.mesh_row) return a.xyz1 + 3 * (size_t)a.mesh_row[m];
     int ub = a.mesh_ubase[m];
     return (m < a.S) ? a.xyz1 + 3 * (size_t)ub : a.xyz2 + 3 * (size_t)(ub - a.n1_total);
 }

@@ -1304,7 +1304,7 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
     const float g = 0.999f * h.h;
     if (best <= g * g) {                                     // certified: nothing outside ring 1 can be closer
         idx = grid_finish(h, tab, pts, mesh_xyz(a, mt), q0, q1, q2, qx, qy, qz, cx, cy, cz, 1, best, sec, idx, a.counters);
-        if (m < a.S) a.T12[u] = idx; else a.T21[u - a.n1_total] = idx;
+        store_map(a, u, idx);
     } else {
         retry_push(a, u, mt, q0, q1, q2);                    // ring 2 / far: second pass over the compacted list
     }
@@ -1572,7 +1572,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
         }
         if (valid[k]) {
             const int u = ub + vq[k];
-            if (m < a.S) a.T12[u] = res; else a.T21[u - a.n1_total] = res;
+            store_map(a, u, res);
         }
     }
 }
@@ -1601,7 +1601,7 @@ __global__ void __launch_bounds__(128) retry_nn_kernel(LipArgs a) {
         NNResult r = grid_nearest(h, a.grid_start + a.mesh_tab[mt], a.grid_pts + a.mesh_ubase[mt], mesh_xyz(a, mt),
                                   q0, q1, q2, a.counters, nullptr, 0);
         if (r.idx < 0) { far_push(a, u, mt, q0, q1, q2); continue; }
-        if (u < a.n1_total) a.T12[u] = r.idx; else a.T21[u - a.n1_total] = r.idx;
+        store_map(a, u, r.idx);
     }
 }
 
@@ -1619,7 +1619,7 @@ __global__ void __launch_bounds__(LIP_TILE) nn_query_kernel(LipArgs a) {
                               xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2], a.counters, &dist, a.profile);
     const int u = ub + v;
     if (r.idx < 0) { far_push(a, u, mt, xyz[3 * (size_t)v], xyz[3 * (size_t)v + 1], xyz[3 * (size_t)v + 2]); return; }
-    if (m < a.S) a.T12[u] = r.idx; else { a.T21[u - a.n1_total] = r.idx; if (a.q_dist) a.q_dist[u - a.n1_total] = dist; }
+    store_map(a, u, r.idx); if (m >= a.S && a.q_dist) a.q_dist[u - a.n1_total] = dist;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1676,9 +1676,8 @@ __global__ void __launch_bounds__(128) far_nn_kernel(LipArgs a) {
             if (lane == 0) atomicAdd(&a.counters[3], 1ull);
         }
         if (lane == 0) {
-            if (u < a.n1_total) a.T12[u] = idx;
-            else {
-                a.T21[u - a.n1_total] = idx;
+            store_map(a, u, idx);
+            if (u >= a.n1_total) {
                 if (a.q_dist)
                     a.q_dist[u - a.n1_total] = sqrt(rdist64(q0, q1, q2, xyz[3 * (size_t)idx], xyz[3 * (size_t)idx + 1], xyz[3 * (size_t)idx + 2]));
             }
@@ -1767,7 +1766,7 @@ __global__ void __launch_bounds__(256) self_knn_kernel(LipArgs a, int side, int 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mi = blockIdx.x, m = side ? a.S + mi : mi;
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
-    const double* __restrict__ xyz = side ? a.xyz2 + 3 * (size_t)(ub - a.n1_total) : a.xyz1 + 3 * (size_t)ub;
+    const double* __restrict__ xyz = mesh_xyz(a, m);
     const int nq = (n + step - 1) / step;
     int* o_base = out + (size_t)KNN * qbase[mi];
     if (n > smem_pts) {                                      // too large for the tile: float64 brute force, index order

@@ -133,6 +133,10 @@ struct lip_ctx {
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool fill_done = false;
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
+    int map_bytes = 8;       // entry size of the dense maps of lip_batch_run_* / lip_series_run_host: 8 (int64, numpy intp) or 4 (lip_set_map_dtype)
+    DevBuf in_frames, d_rows;   // lip_series_run_host: every frame of the series once; first row of each of this context's meshes in it
+    std::vector<int> h_rows;
+    cudaEvent_t ev_piece = nullptr;
     size_t max_map_tiles = 0;
     // host-path pipeline: the batch split into sub-batches, each on its own child context (own stream and
     // workspace), so that H2D of one, kernels of another and D2H of a third overlap (lip_batch_run_host)
@@ -242,6 +246,7 @@ void set_param_args(lip_ctx* c) {
     a.reject_dist = c->params.reject_dist;
     a.profile = c->profiling ? 1 : 0;
     a.map_mode = c->map_mode;
+    a.map32 = c->map_bytes == 4 ? 1 : 0;
     static const int tpw = getenv("LIP_ICP_TASKS_PER_WARP") ? std::max(1, atoi(getenv("LIP_ICP_TASKS_PER_WARP"))) : LIP_ICP_TASKS_PER_WARP;
     static const int csh = getenv("LIP_ICP_CLASS_SHIFT") ? atoi(getenv("LIP_ICP_CLASS_SHIFT")) : LIP_ICP_CLASS_SHIFT;
     a.icp_tasks_per_warp = tpw; a.icp_class_shift = csh;
@@ -329,10 +334,12 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
 }
 
 int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-               long long* T21, long long* T12, double* q_dist, int stages, cudaStream_t st) {
+               long long* T21, long long* T12, double* q_dist, int stages, cudaStream_t st, const int* mesh_row = nullptr) {
     if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     LipArgs& a = c->args;
     a.xyz1 = xyz1; a.xyz2 = xyz2; a.lm1 = lm1; a.lm2 = lm2; a.T21 = T21; a.T12 = T12; a.q_dist = q_dist;
+    a.mesh_row = mesh_row;                                   // (reset below: later calls copy c->args)
+    struct RowReset { LipArgs& a; ~RowReset() { a.mesh_row = nullptr; } } row_reset{a};
     set_param_args(c);
     int64_t launches = 0;
     int evi = 0;
@@ -481,11 +488,16 @@ int host_upload_async(lip_ctx* c, const double* xyz1, const double* xyz2, const 
     return LIP_OK;
 }
 // the whole pipeline on the uploaded (sub-)batch and D2H of the maps, enqueued on the context's stream
-int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12, const MatchOpts* mo = nullptr) {
+struct DevIn { const double *xyz1, *xyz2, *lm1, *lm2; const int* rows; };     // inputs that are not the context's own upload buffers (series)
+int host_compute_async(lip_ctx* c, void* T21, void* T12, const MatchOpts* mo = nullptr, const DevIn* in = nullptr) {
     cudaStream_t st = c->stream;
     static const bool trace = getenv("LIP_TRACE_PIPELINE") != nullptr;
-    int rc = run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
-                        c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
+    const size_t msz = (size_t)c->map_bytes;
+    if (in) { LIP_CUDA(c, c->out_T21.ensure((size_t)c->n2 * 8)); LIP_CUDA(c, c->out_T12.ensure((size_t)c->n1 * 8)); }
+    int rc = in ? run_stages(c, in->xyz1, in->xyz2, in->lm1, in->lm2, c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr,
+                             kFullPipeline, st, in->rows)
+                : run_stages(c, c->in_xyz1.as<double>(), c->in_xyz2.as<double>(), c->in_lm1.as<double>(), c->in_lm2.as<double>(),
+                             c->out_T21.as<long long>(), c->out_T12.as<long long>(), nullptr, kFullPipeline, st);
     if (rc) return rc;
     if (mo) {                                                // the rest of the per-segment body, maps still on the device
         const int64_t hot = c->last_launches;
@@ -497,8 +509,8 @@ int host_compute_async(lip_ctx* c, int64_t* T21, int64_t* T12, const MatchOpts* 
         c->last_launches = hot + (mo->refine ? 2 : 0) + 2;
     }
     if (trace) cudaEventRecord(c->tr[2], st);
-    if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * 8, cudaMemcpyDeviceToHost, st));
-    if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * 8, cudaMemcpyDeviceToHost, st));
+    if ((c->directions & 1) && T21) LIP_CUDA(c, cudaMemcpyAsync(T21, c->out_T21.p, (size_t)c->n2 * msz, cudaMemcpyDeviceToHost, st));
+    if ((c->directions & 2) && T12) LIP_CUDA(c, cudaMemcpyAsync(T12, c->out_T12.p, (size_t)c->n1 * msz, cudaMemcpyDeviceToHost, st));
     if (trace) cudaEventRecord(c->tr[3], st);
     return LIP_OK;
 }
@@ -542,8 +554,10 @@ int check_finite(lip_ctx* c, const double* xyz1, const double* xyz2, const doubl
 // of sub-batch k (in order), the calling thread enqueues its upload as soon as it is full and the kernels + download of the
 // sub-batches already uploaded in between; finished maps go from the pinned output buffers to the caller's arrays.
 int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                    int64_t* T21, int64_t* T12, const MatchOpts* mo) {
+                    void* T21v, void* T12v, const MatchOpts* mo) {
     const int nk = c->n_kids;
+    const size_t msz = (size_t)c->map_bytes;
+    char *T21 = (char*)T21v, *T12 = (char*)T12v;
     if (!c->pool) c->pool = new StagePool();
     c->pool->start(staging_threads());
     StagePool& pool = *c->pool;
@@ -551,7 +565,7 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
     std::vector<std::atomic<int>> in_left(nk), out_left(nk);
     std::atomic<int> bad(0);
     std::atomic<int>* chk = c->validate_inputs ? &bad : nullptr;
-    struct Part { size_t b1, b2, bl; char* in; int64_t *o21, *o12; };
+    struct Part { size_t b1, b2, bl; char* in; char *o21, *o12; };
     std::vector<Part> part(nk);
     for (int k = 0; k < nk; ++k) {
         lip_ctx* kc = c->kids[k];
@@ -560,7 +574,7 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
         LIP_CUDA(c, kc->st_in.ensure(p.b1 + p.b2 + 2 * p.bl));
         LIP_CUDA(c, kc->st_out.ensure(((size_t)kc->n1 + (size_t)kc->n2) * 8));
         p.in = (char*)kc->st_in.p;
-        p.o21 = (int64_t*)kc->st_out.p; p.o12 = p.o21 + kc->n2;
+        p.o21 = (char*)kc->st_out.p; p.o12 = p.o21 + (size_t)kc->n2 * msz;
         const int64_t s0 = c->kid_seg[k];
         in_left[k].store(StagePool::slices_of(p.b1, slice) + StagePool::slices_of(p.b2, slice) + 2 * StagePool::slices_of(p.bl, slice));
         pool.submit(p.in, xyz1 + 3 * c->h_off1[s0], p.b1, slice, &in_left[k], chk);
@@ -575,7 +589,7 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
             if (bad.load()) { rc = fail(c, LIP_EINVAL, "Input contains NaN or infinity."); break; }   // nothing of it was uploaded
             lip_ctx* kc = c->kids[up];
             const Part& p = part[up];
-            kc->params = c->params;
+            kc->params = c->params; kc->map_bytes = c->map_bytes;
             rc = host_upload_async(kc, (const double*)p.in, (const double*)(p.in + p.b1), (const double*)(p.in + p.b1 + p.b2),
                                    (const double*)(p.in + p.b1 + p.b2 + p.bl), c->side[1]);
             if (rc) c->err = "pipeline upload: " + kc->err;
@@ -593,10 +607,10 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
         out_left[k].store(0);
         if (rc != LIP_OK || k >= cp) continue;
         const int64_t s0 = c->kid_seg[k];
-        const size_t o1 = T12 ? (size_t)c->kids[k]->n1 * 8 : 0, o2 = T21 ? (size_t)c->kids[k]->n2 * 8 : 0;
+        const size_t o1 = T12 ? (size_t)c->kids[k]->n1 * msz : 0, o2 = T21 ? (size_t)c->kids[k]->n2 * msz : 0;
         out_left[k].store(StagePool::slices_of(o1, slice) + StagePool::slices_of(o2, slice));
-        if (o2) pool.submit(T21 + c->h_off2[s0], part[k].o21, o2, slice, &out_left[k]);
-        if (o1) pool.submit(T12 + c->h_off1[s0], part[k].o12, o1, slice, &out_left[k]);
+        if (o2) pool.submit(T21 + (size_t)c->h_off2[s0] * msz, part[k].o21, o2, slice, &out_left[k]);
+        if (o1) pool.submit(T12 + (size_t)c->h_off1[s0] * msz, part[k].o12, o1, slice, &out_left[k]);
     }
     for (int k = 0; k < nk; ++k) { pool.wait(in_left[k]); pool.wait(out_left[k]); }   // nothing of this call left in the queue
     if (rc != LIP_OK) return rc;
@@ -608,7 +622,9 @@ int run_host_staged(lip_ctx* c, const double* xyz1, const double* xyz2, const do
 // and copies out of different sub-batches overlap.  mo != nullptr: the whole per-segment body (lip_batch_match_host), the
 // score counts of sub-batch k are left in kids[k]->h_counts.
 int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                   int64_t* T21, int64_t* T12, const MatchOpts* mo) {
+                   void* T21v, void* T12v, const MatchOpts* mo) {
+    const size_t msz = (size_t)c->map_bytes;
+    char *T21 = (char*)T21v, *T12 = (char*)T12v;
     if (staging_threads() > 0 &&
         (is_pageable(xyz1) || is_pageable(xyz2) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12)))) {
         bool ready = true;                                   // pinned staging buffers for every sub-batch; if the host cannot pin
@@ -632,7 +648,7 @@ int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const dou
     for (int k = 0; k < c->n_kids; ++k) {
         lip_ctx* kc = c->kids[k];
         const int64_t s0 = c->kid_seg[k];
-        kc->params = c->params;
+        kc->params = c->params; kc->map_bytes = c->map_bytes;
         int rc = host_upload_async(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
                                    c->side[1]);             // one upload stream: the sub-batches arrive in order, each as early as possible
         if (rc) { drain(); return fail(c, rc, "pipeline upload: " + kc->err); }
@@ -640,7 +656,7 @@ int run_host_split(lip_ctx* c, const double* xyz1, const double* xyz2, const dou
     for (int k = 0; k < c->n_kids; ++k) {
         lip_ctx* kc = c->kids[k];
         const int64_t s0 = c->kid_seg[k];
-        int rc = host_compute_async(kc, T21 ? T21 + c->h_off2[s0] : nullptr, T12 ? T12 + c->h_off1[s0] : nullptr, mo);
+        int rc = host_compute_async(kc, T21 ? T21 + (size_t)c->h_off2[s0] * msz : nullptr, T12 ? T12 + (size_t)c->h_off1[s0] * msz : nullptr, mo);
         if (rc) { drain(); return fail(c, rc, "pipeline run: " + kc->err); }
     }
     for (int k = 0; k < c->n_kids; ++k) LIP_CUDA(c, cudaStreamSynchronize(c->kids[k]->stream));
@@ -811,6 +827,8 @@ void lip_destroy(lip_ctx* c) {
     for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    c->in_frames.release(); c->d_rows.release();
+    if (c->ev_piece) cudaEventDestroy(c->ev_piece);
     for (DevBuf* b : {&c->d_plan, &c->ws, &c->in_xyz1, &c->in_xyz2, &c->in_lm1, &c->in_lm2, &c->out_T21, &c->out_T12, &c->misc, &c->misc2})
         b->release();
     delete c->pool;
@@ -841,6 +859,13 @@ int lip_set_map_mode(lip_ctx* c, int mode) {
         c->planned = false; c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;
     }
     c->map_mode = mode;
+    return LIP_OK;
+}
+
+int lip_set_map_dtype(lip_ctx* c, int bits) {
+    if (!c) return LIP_EINVAL;
+    if (bits != 32 && bits != 64) return fail(c, LIP_EINVAL, "map dtype must be 32 or 64 bits");
+    c->map_bytes = bits / 8;
     return LIP_OK;
 }
 
@@ -928,7 +953,7 @@ int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* of
 }
 
 int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                         int64_t* T21, int64_t* T12, void* stream) {
+                         void* T21, void* T12, void* stream) {
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
@@ -941,10 +966,12 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
         for (int k = 0; k < c->n_dkids; ++k) {
             lip_ctx* kc = c->dkids[k];
             const int64_t s0 = c->dkid_seg[k];
-            kc->params = c->params;
+            kc->params = c->params; kc->map_bytes = c->map_bytes;
             LIP_CUDA(c, cudaStreamWaitEvent(kc->stream, c->ev_fork, 0));
+            const size_t msz = (size_t)c->map_bytes;
             int rc = run_stages(kc, xyz1 + 3 * c->h_off1[s0], xyz2 + 3 * c->h_off2[s0], lm1 + 3 * c->h_lm_off[s0], lm2 + 3 * c->h_lm_off[s0],
-                                T21 ? (long long*)T21 + c->h_off2[s0] : nullptr, T12 ? (long long*)T12 + c->h_off1[s0] : nullptr,
+                                T21 ? (long long*)((char*)T21 + (size_t)c->h_off2[s0] * msz) : nullptr,
+                                T12 ? (long long*)((char*)T12 + (size_t)c->h_off1[s0] * msz) : nullptr,
                                 nullptr, kFullPipeline, kc->stream);
             if (rc) return fail(c, rc, "device split: " + kc->err);
             LIP_CUDA(c, cudaEventRecord(kc->ev_begin, kc->stream));      // (ev_begin is free again once run_stages has forked)
@@ -958,7 +985,7 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
 }
 
 int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-                       int64_t* T21, int64_t* T12) {
+                       void* T21, void* T12) {
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
@@ -974,6 +1001,176 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
     if (rc == LIP_OK) rc = host_compute_async(c, T21, T12);
     if (rc) return rc;
     LIP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LIP_OK;
+}
+
+// Time series (run_registration_pipeline.py:64,100-104: frame k is day2 of frame pair k-1 and day1 of frame pair k).
+// `frames` holds every mesh ONCE; row1[s] / row2[s] = first row of mesh1 / mesh2 of segment pair s in it, so meshes can be shared
+// between segment pairs.  Rows of this context's meshes as the kernels want them ([mesh1 of every pair | mesh2 of every pair]):
+static int series_rows(lip_ctx* kc, const int64_t* row1, const int64_t* row2, int64_t s0, int64_t n_rows, const int64_t* off1,
+                       const int64_t* off2, cudaStream_t st) {
+    const int64_t S = kc->S;
+    kc->h_rows.resize(2 * (size_t)S);
+    for (int64_t s = 0; s < S; ++s) {
+        const int64_t r1 = row1[s0 + s], r2 = row2[s0 + s];
+        if (r1 < 0 || r2 < 0 || r1 + (off1[s0 + s + 1] - off1[s0 + s]) > n_rows || r2 + (off2[s0 + s + 1] - off2[s0 + s]) > n_rows)
+            return fail(kc, LIP_EINVAL, "series: a mesh of segment pair " + std::to_string(s0 + s) + " does not lie inside `frames`");
+        kc->h_rows[s] = (int)r1; kc->h_rows[S + s] = (int)r2;
+    }
+    LIP_CUDA(kc, kc->d_rows.ensure(2 * (size_t)S * 4));
+    LIP_CUDA(kc, cudaMemcpyAsync(kc->d_rows.p, kc->h_rows.data(), 2 * (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    return LIP_OK;
+}
+
+int lip_series_run_device(lip_ctx* c, const double* d_frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
+                          const double* d_lm1, const double* d_lm2, void* T21, void* T12, void* stream) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "series: no batch planned");
+    if (!d_frames || !row1 || !row2 || !d_lm1 || !d_lm2) return fail(c, LIP_EINVAL, "series: null input pointer");
+    if (((c->directions & 1) && !T21) || ((c->directions & 2) && !T12)) return fail(c, LIP_EINVAL, "series: null output pointer");
+    if (n_rows <= 0 || n_rows >= ((int64_t)1 << 31)) return fail(c, LIP_EINVAL, "series: n_rows out of range");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const size_t msz = (size_t)c->map_bytes;
+    if (c->n_dkids >= 2 && !c->profiling) {
+        LIP_CUDA(c, cudaEventRecord(c->ev_fork, st));
+        for (int k = 0; k < c->n_dkids; ++k) {
+            lip_ctx* kc = c->dkids[k];
+            const int64_t s0 = c->dkid_seg[k];
+            kc->params = c->params; kc->map_bytes = c->map_bytes;
+            LIP_CUDA(c, cudaStreamWaitEvent(kc->stream, c->ev_fork, 0));
+            int rc = series_rows(kc, row1, row2, s0, n_rows, c->h_off1.data(), c->h_off2.data(), kc->stream);
+            if (rc == LIP_OK)
+                rc = run_stages(kc, d_frames, d_frames, d_lm1 + 3 * c->h_lm_off[s0], d_lm2 + 3 * c->h_lm_off[s0],
+                                T21 ? (long long*)((char*)T21 + (size_t)c->h_off2[s0] * msz) : nullptr,
+                                T12 ? (long long*)((char*)T12 + (size_t)c->h_off1[s0] * msz) : nullptr,
+                                nullptr, kFullPipeline, kc->stream, kc->d_rows.as<int>());
+            if (rc) return fail(c, rc, "series device split: " + kc->err);
+            LIP_CUDA(c, cudaEventRecord(kc->ev_begin, kc->stream));
+            LIP_CUDA(c, cudaStreamWaitEvent(st, kc->ev_begin, 0));
+        }
+        c->last_run_split = true; c->last_run_dsplit = true;
+        return LIP_OK;
+    }
+    c->last_run_split = false; c->last_run_dsplit = false;
+    int rc = series_rows(c, row1, row2, 0, n_rows, c->h_off1.data(), c->h_off2.data(), st);
+    if (rc) return rc;
+    return run_stages(c, d_frames, d_frames, d_lm1, d_lm2, (long long*)T21, (long long*)T12, nullptr, kFullPipeline, st, c->d_rows.as<int>());
+}
+
+// One upload of `frames` (in pieces, so that the sub-batches of the pipeline start as soon as their rows have arrived) instead
+// of the two uploads of lip_batch_run_host.
+int lip_series_run_host(lip_ctx* c, const double* frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
+                        const double* lm1, const double* lm2, void* T21v, void* T12v) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "series: no batch planned");
+    if (!frames || !row1 || !row2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "series: null input pointer");
+    if (((c->directions & 1) && !T21v) || ((c->directions & 2) && !T12v)) return fail(c, LIP_EINVAL, "series: null output pointer");
+    if (n_rows <= 0 || n_rows >= ((int64_t)1 << 31)) return fail(c, LIP_EINVAL, "series: n_rows out of range");
+    cudaSetDevice(c->device);
+    const size_t msz = (size_t)c->map_bytes;
+    char *T21 = (char*)T21v, *T12 = (char*)T12v;
+    const int nk = c->n_kids >= 2 ? c->n_kids : 1;
+    auto kid = [&](int k) { return c->n_kids >= 2 ? c->kids[k] : c; };
+    auto seg0 = [&](int k) { return c->n_kids >= 2 ? c->kid_seg[k] : (int64_t)0; };
+    auto seg1 = [&](int k) { return c->n_kids >= 2 ? c->kid_seg[k + 1] : c->S; };
+    if (!c->ev_piece) LIP_CUDA(c, cudaEventCreateWithFlags(&c->ev_piece, cudaEventDisableTiming));
+    const size_t bl = (size_t)c->sumK * 24;
+    LIP_CUDA(c, c->in_frames.ensure((size_t)n_rows * 24));
+    LIP_CUDA(c, c->in_lm1.ensure(bl)); LIP_CUDA(c, c->in_lm2.ensure(bl));
+    // rows sub-batch k needs: up to the end of its last mesh (running maximum: the pieces are uploaded in row order)
+    std::vector<int64_t> need(nk);
+    int64_t run_max = 0;
+    for (int k = 0; k < nk; ++k) {
+        for (int64_t s = seg0(k); s < seg1(k); ++s) {
+            if (row1[s] < 0 || row2[s] < 0) return fail(c, LIP_EINVAL, "series: negative row");
+            run_max = std::max(run_max, std::max(row1[s] + (c->h_off1[s + 1] - c->h_off1[s]), row2[s] + (c->h_off2[s + 1] - c->h_off2[s])));
+        }
+        if (run_max > n_rows) return fail(c, LIP_EINVAL, "series: a mesh does not lie inside `frames`");
+        need[k] = run_max;
+    }
+    const bool stage = staging_threads() > 0 && (size_t)n_rows * 24 >= ((size_t)1 << 21) &&
+                       (is_pageable(frames) || (T21 && is_pageable(T21)) || (T12 && is_pageable(T12)));
+    const size_t slice = (size_t)1 << 20;
+    std::atomic<int> bad(0);
+    std::atomic<int>* chk = c->validate_inputs ? &bad : nullptr;
+    std::vector<std::atomic<int>> in_left(nk), out_left(nk);
+    for (auto& x : in_left) x.store(0);
+    for (auto& x : out_left) x.store(0);
+    const double* src = frames;
+    if (stage) {                                             // pageable caller arrays: the pieces go through one pinned buffer
+        if (c->st_in.ensure((size_t)n_rows * 24 + 256) != cudaSuccess) { cudaGetLastError(); return fail(c, LIP_ECUDA, "series: cannot pin the staging buffer"); }
+        for (int k = 0; k < nk; ++k) {
+            lip_ctx* kc = kid(k);
+            if (kc->st_out.ensure(((size_t)kc->n1 + (size_t)kc->n2) * msz + 256) != cudaSuccess) { cudaGetLastError(); return fail(c, LIP_ECUDA, "series: cannot pin the output buffers"); }
+        }
+        if (!c->pool) c->pool = new StagePool();
+        c->pool->start(staging_threads());
+        int64_t r0 = 0;
+        for (int k = 0; k < nk; ++k) {
+            const size_t bytes = (size_t)(need[k] - r0) * 24;
+            in_left[k].store(StagePool::slices_of(bytes, slice));
+            if (bytes) c->pool->submit((char*)c->st_in.p + (size_t)r0 * 24, (const char*)frames + (size_t)r0 * 24, bytes, slice, &in_left[k], chk);
+            r0 = need[k];
+        }
+        src = (const double*)c->st_in.p;
+    } else if (c->validate_inputs && StagePool::nonfinite(frames, (size_t)need[nk - 1] * 24)) {
+        return fail(c, LIP_EINVAL, "Input contains NaN or infinity.");
+    }
+    if (c->validate_inputs && (StagePool::nonfinite(lm1, bl) || StagePool::nonfinite(lm2, bl))) {
+        if (c->pool) for (int k = 0; k < nk; ++k) c->pool->wait(in_left[k]);
+        return fail(c, LIP_EINVAL, "Input contains NaN or infinity.");
+    }
+    cudaStream_t up = c->side[1];
+    auto wait_all = [&] {
+        cudaStreamSynchronize(up);
+        for (int k = 0; k < nk; ++k) cudaStreamSynchronize(kid(k)->stream);
+        if (c->pool) for (int k = 0; k < nk; ++k) { c->pool->wait(in_left[k]); c->pool->wait(out_left[k]); }
+    };
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm1.p, lm1, bl, cudaMemcpyHostToDevice, up));
+    LIP_CUDA(c, cudaMemcpyAsync(c->in_lm2.p, lm2, bl, cudaMemcpyHostToDevice, up));
+    const double* D = c->in_frames.as<double>();
+    int rc = LIP_OK;
+    int64_t r0 = 0;
+    for (int k = 0; k < nk && rc == LIP_OK; ++k) {
+        lip_ctx* kc = kid(k);
+        if (stage) {
+            c->pool->wait(in_left[k]);
+            if (bad.load()) { rc = fail(c, LIP_EINVAL, "Input contains NaN or infinity."); break; }
+        }
+        if (need[k] > r0) {
+            cudaError_t e = cudaMemcpyAsync((char*)c->in_frames.p + (size_t)r0 * 24, (const char*)src + (size_t)r0 * 24,
+                                            (size_t)(need[k] - r0) * 24, cudaMemcpyHostToDevice, up);
+            if (e != cudaSuccess) { rc = fail(c, LIP_ECUDA, std::string("series upload: ") + cudaGetErrorString(e)); break; }
+            r0 = need[k];
+        }
+        cudaEventRecord(c->ev_piece, up);
+        cudaStreamWaitEvent(kc->stream, c->ev_piece, 0);
+        kc->params = c->params; kc->map_bytes = c->map_bytes;
+        const int64_t s0 = seg0(k);
+        rc = series_rows(kc, row1, row2, s0, n_rows, c->h_off1.data(), c->h_off2.data(), kc->stream);
+        if (rc == LIP_OK) {
+            const DevIn in{D, D, c->in_lm1.as<double>() + 3 * c->h_lm_off[s0], c->in_lm2.as<double>() + 3 * c->h_lm_off[s0], kc->d_rows.as<int>()};
+            char* o21 = T21 ? (stage ? (char*)kc->st_out.p : T21 + (size_t)c->h_off2[s0] * msz) : nullptr;
+            char* o12 = T12 ? (stage ? (char*)kc->st_out.p + (size_t)kc->n2 * msz : T12 + (size_t)c->h_off1[s0] * msz) : nullptr;
+            rc = host_compute_async(kc, o21, o12, nullptr, &in);
+        }
+        if (rc && kc != c) c->err = "series run: " + kc->err;
+    }
+    if (rc != LIP_OK) { wait_all(); return rc; }
+    for (int k = 0; k < nk; ++k) {
+        lip_ctx* kc = kid(k);
+        cudaError_t e = cudaStreamSynchronize(kc->stream);
+        if (e != cudaSuccess) { wait_all(); return fail(c, LIP_ECUDA, std::string("series sync: ") + cudaGetErrorString(e)); }
+        if (!stage) continue;
+        const int64_t s0 = seg0(k);
+        const size_t o2 = T21 ? (size_t)kc->n2 * msz : 0, o1 = T12 ? (size_t)kc->n1 * msz : 0;
+        out_left[k].store(StagePool::slices_of(o1, slice) + StagePool::slices_of(o2, slice));
+        if (o2) c->pool->submit(T21 + (size_t)c->h_off2[s0] * msz, kc->st_out.p, o2, slice, &out_left[k]);
+        if (o1) c->pool->submit(T12 + (size_t)c->h_off1[s0] * msz, (char*)kc->st_out.p + (size_t)kc->n2 * msz, o1, slice, &out_left[k]);
+    }
+    wait_all();
+    c->last_run_split = c->n_kids >= 2; c->last_run_dsplit = false;
     return LIP_OK;
 }
 
@@ -1312,6 +1509,7 @@ int lip_batch_match_host(lip_ctx* c, const double* xyz1, const double* xyz2, con
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "match: no batch planned");
     if (c->directions != LIP_DIR_BOTH) return fail(c, LIP_EINVAL, "match: the batch must be planned for both directions");
+    if (c->map_bytes != 8) return fail(c, LIP_EINVAL, "match: the refinement and the scores work on int64 maps (lip_set_map_dtype(ctx, 64))");
     if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !T12 || !scores) return fail(c, LIP_EINVAL, "match: null pointer");
     if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "match: sample_proportion must be > 0");
     if (refine)

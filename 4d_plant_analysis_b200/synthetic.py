@@ -236,3 +236,125 @@ def make_config(config: int, *, scale: float = 1.0, frame_pairs: int | None = No
         segs += these
         fp += [f0] * len(these)
     return batch_from_segments(segs, np.asarray(fp, np.int32), name=f"C{config}")
+
+
+# ------------------------------------------------------------------------------------------------
+# time series (BASELINE configs[3]: a growth series, all consecutive frame pairs batched)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SeriesBatch:
+    """A growth series of one or several plants: every frame's segments are stored ONCE in ``frames``; segment pair s of
+    the batch (frame k -> frame k + 1 of one plant) reads mesh1 at ``row1[s]`` and mesh2 at ``row2[s]`` — frame k is day2 of
+    frame pair k - 1 and day1 of frame pair k (reference: run_registration_pipeline.py:64,100-104).  off1 / off2 / lm_off /
+    lm1 / lm2 / frame_pair describe the batch exactly as in SegmentPairBatch (sizes and the layout of the outputs)."""
+
+    frames: np.ndarray        # (n_rows, 3) float64
+    row1: np.ndarray          # (S,) int64
+    row2: np.ndarray          # (S,) int64
+    off1: np.ndarray
+    off2: np.ndarray
+    lm1: np.ndarray
+    lm2: np.ndarray
+    lm_off: np.ndarray
+    frame_pair: np.ndarray
+    name: str = ""
+
+    @property
+    def n_segments(self) -> int:
+        return len(self.off1) - 1
+
+    @property
+    def n_frame_pairs(self) -> int:
+        return int(self.frame_pair.max()) + 1 if len(self.frame_pair) else 0
+
+    @property
+    def n_correspondences(self) -> int:
+        return int(self.off1[-1] + self.off2[-1])
+
+    def as_batch(self) -> SegmentPairBatch:
+        """the same segment pairs with every mesh gathered into xyz1 / xyz2 (what a caller without the series entry point
+        would upload: every shared frame twice)"""
+        n1, n2 = np.diff(self.off1), np.diff(self.off2)
+        x1 = np.concatenate([self.frames[r:r + n] for r, n in zip(self.row1, n1)], axis=0)
+        x2 = np.concatenate([self.frames[r:r + n] for r, n in zip(self.row2, n2)], axis=0)
+        return SegmentPairBatch(np.ascontiguousarray(x1), np.ascontiguousarray(x2), self.off1, self.off2, self.lm1, self.lm2,
+                                self.lm_off, self.frame_pair, self.name)
+
+    def take_frame_pairs(self, ids: Sequence[int]) -> "SeriesBatch":
+        """the sub-series holding the given frame pairs (ascending ids): only the meshes they use are kept, each once"""
+        ids = np.asarray(sorted(int(i) for i in ids))
+        keep = np.nonzero(np.isin(self.frame_pair, ids))[0]
+        n1, n2 = np.diff(self.off1)[keep], np.diff(self.off2)[keep]
+        # distinct (row, count) meshes in row order
+        rows = sorted({(int(r), int(n)) for r, n in zip(self.row1[keep], n1)} | {(int(r), int(n)) for r, n in zip(self.row2[keep], n2)})
+        new_row, parts, at = {}, [], 0
+        for r, n in rows:
+            new_row[r] = at
+            parts.append(self.frames[r:r + n])
+            at += n
+        z = lambda n: np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+        lm_keep = np.concatenate([np.arange(self.lm_off[s], self.lm_off[s + 1]) for s in keep]) if len(keep) else np.zeros(0, np.int64)
+        remap = {int(f): i for i, f in enumerate(ids)}
+        return SeriesBatch(np.ascontiguousarray(np.concatenate(parts, axis=0)), np.array([new_row[int(r)] for r in self.row1[keep]], np.int64),
+                           np.array([new_row[int(r)] for r in self.row2[keep]], np.int64), z(n1), z(n2),
+                           np.ascontiguousarray(self.lm1[lm_keep]), np.ascontiguousarray(self.lm2[lm_keep]),
+                           z(np.diff(self.lm_off)[keep]), np.array([remap[int(f)] for f in self.frame_pair[keep]], np.int32), self.name)
+
+
+def make_series(config: int = 4, *, n_frames: int = 16, plants: int = 1, scale: float = 1.0, seed_offset: int = 0,
+                growth=(1.01, 1.05)) -> SeriesBatch:
+    """``plants`` plants of the segment population of ``config`` (1 tomato, 2 maize, 3 arabidopsis, 4 = 1), each observed in
+    ``n_frames`` frames with cumulative growth (length and point count grow by U(growth) per frame, the curvature drifts,
+    every frame is moved rigidly a little further and re-sampled: no identity correspondence) -> plants * (n_frames - 1)
+    frame pairs.  Landmarks are sampled per frame pair, as the reference does (segment_matching_ml.py:210-229)."""
+    kind = {1: "tomato", 2: "maize", 3: "arabidopsis", 4: "tomato", 5: "tomato"}[config]
+    S = max(1, int(round({1: 30, 2: 12, 3: 200, 4: 30, 5: 2000}[config] * scale)))
+    voxel = VOXEL[kind]
+    shape = "ribbon" if kind == "maize" else "tube"
+    frames, row1, row2, n1s, n2s, lm1s, lm2s, fps = [], [], [], [], [], [], [], []
+    at = 0
+    for p in range(plants):
+        rng = np.random.default_rng(1000 * config + 500 + 7919 * (seed_offset + p))
+        seg = []
+        for _ in range(S):
+            if kind == "maize":
+                L, size, n = rng.uniform(60, 150), rng.uniform(4, 8), int(rng.uniform(3200, 4800))
+            elif config == 5:
+                L, size, n = rng.uniform(15, 25), rng.uniform(0.8, 2.0), int(rng.uniform(400, 600))
+            else:
+                L = rng.uniform(15, 60) if kind == "tomato" else rng.uniform(5, 30)
+                size = rng.uniform(0.8, 2.0)
+                n = int(rng.uniform(300, 1100)) if kind == "tomato" else int(rng.uniform(150, 1000))
+            seg.append(dict(L=L, size=size, n=n, kap=rng.uniform(-0.02, 0.02), Rp=_rot(rng.normal(size=3), rng.uniform(0, np.pi)),
+                            tp=rng.uniform(-60, 60, 3), Rm=np.eye(3), tm=np.zeros(3), mirrored=bool(rng.random() < 0.3)))
+        prev = None                                          # rows of the previous frame's segments
+        for f in range(n_frames):
+            rows, arcs = [], []
+            for g in seg:
+                pts = _surface(rng, g["n"], g["L"], g["kap"], shape, g["size"])
+                pts = (pts @ g["Rm"].T + g["tm"]) @ g["Rp"].T + g["tp"]
+                frames.append(pts)
+                rows.append((at, g["n"]))
+                at += g["n"]
+                arcs.append((g["L"], g["kap"], g["Rm"].copy(), g["tm"].copy()))
+            if prev is not None:
+                for (r1, c1), (r2, c2), a1, a2, g in zip(prev[0], rows, prev[1], arcs, seg):
+                    l1, l2 = _landmarks(rng, a1[0], a1[1], a2[0], a2[1], voxel, g["mirrored"])
+                    lm1s.append((l1 @ a1[2].T + a1[3]) @ g["Rp"].T + g["tp"])
+                    lm2s.append((l2 @ a2[2].T + a2[3]) @ g["Rp"].T + g["tp"])
+                    row1.append(r1); row2.append(r2); n1s.append(c1); n2s.append(c2)
+                    fps.append(p * (n_frames - 1) + f - 1)
+            prev = (rows, arcs)
+            for g in seg:                                    # grow and move on to the next frame
+                gr = rng.uniform(*growth)
+                g["L"] *= gr
+                g["n"] = int(round(g["n"] * gr))
+                g["size"] *= rng.uniform(1.0, 1.01)
+                g["kap"] += rng.uniform(-0.002, 0.002)
+                dR = _rot(rng.normal(size=3), np.deg2rad(rng.uniform(0, 4)))
+                g["Rm"], g["tm"] = dR @ g["Rm"], dR @ g["tm"] + rng.uniform(-0.8, 0.8, 3) * (1 / np.sqrt(3))
+    z = lambda n: np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    k = [len(l) for l in lm1s]
+    return SeriesBatch(np.ascontiguousarray(np.concatenate(frames, axis=0)), np.asarray(row1, np.int64), np.asarray(row2, np.int64),
+                       z(n1s), z(n2s), np.ascontiguousarray(np.concatenate(lm1s, axis=0)), np.ascontiguousarray(np.concatenate(lm2s, axis=0)),
+                       z(k), np.asarray(fps, np.int32), name=f"C{config} series {plants}x{n_frames}")

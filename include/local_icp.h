@@ -98,10 +98,24 @@ int  lip_set_input_validation(lip_ctx* ctx, int on);
 int lip_batch_plan(lip_ctx* ctx, int64_t S, const int64_t* off1, const int64_t* off2,
                    const int64_t* lm_off, int directions);
 int lip_batch_run_host(lip_ctx* ctx, const double* xyz1, const double* xyz2,
-                       const double* lm1, const double* lm2, int64_t* T21, int64_t* T12);
+                       const double* lm1, const double* lm2, void* T21, void* T12);
 int lip_batch_run_device(lip_ctx* ctx, const double* d_xyz1, const double* d_xyz2,
                          const double* d_lm1, const double* d_lm2,
-                         int64_t* d_T21, int64_t* d_T12, void* stream);
+                         void* d_T21, void* d_T12, void* stream);
+/* Entry type of the dense maps written by lip_batch_run_* and lip_series_run_host: 64 (default: int64, numpy's intp, what
+ * the reference returns from KDTree.query, p2p_matching_seg_icp.py:488) or 32 (int32: half the device-to-host bytes for
+ * callers of the batched API).  The refinement / score / interpolation entry points always take int64 maps. */
+int lip_set_map_dtype(lip_ctx* ctx, int bits);
+/* A time series — the loop over consecutive day pairs of the reference (run_registration_pipeline.py:64,100-104: frame k is
+ * day2 of frame pair k-1 and day1 of frame pair k).  `frames` (n_rows,3) holds every mesh ONCE; row1[s] / row2[s] (S entries
+ * each, host arrays) give the first row of mesh1 / mesh2 of segment pair s of the planned batch in it, so a mesh can serve any
+ * number of segment pairs.  Sizes, landmarks and the layout of the outputs are those of lip_batch_plan.  Same results as
+ * lip_batch_run_host on the gathered arrays, with one upload of every mesh instead of one per use.
+ * lip_series_run_device: `d_frames`, landmarks and maps on the device, enqueued on `stream`, no synchronisation. */
+int lip_series_run_host(lip_ctx* ctx, const double* frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
+                        const double* lm1, const double* lm2, void* T21, void* T12);
+int lip_series_run_device(lip_ctx* ctx, const double* d_frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
+                          const double* d_lm1, const double* d_lm2, void* d_T21, void* d_T12, void* stream);
 
 /* Per-landmark results of the last run, copied to host (any pointer may be NULL).
  * Row b of the "21" arrays is landmark b of the flattened lm arrays for the mesh2 -> mesh1 ICPs

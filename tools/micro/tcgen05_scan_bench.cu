@@ -186,21 +186,113 @@ __global__ void __launch_bounds__(128) scan_tc_kernel(const float4* __restrict__
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * NCH));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// the same scan, warp-specialised: warps 0..3 epilogue (TMEM -> registers -> minima), warp 4 producer (bulk copies), warp 5
+// MMA issuer; SMEM stages and the two TMEM buffers are handed over through mbarriers only (no CTA barrier per chunk)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int NCH, int STAGES>
+__global__ void __launch_bounds__(192) scan_tc_ws_kernel(const float4* __restrict__ A0g, const float4* __restrict__ A1g,
+                                                          const float4* __restrict__ Bhi, const float4* __restrict__ Blo, int n_chunks,
+                                                          Out* __restrict__ out, long long* __restrict__ cyc) {
+    __shared__ __align__(128) float4 sA[2][128];
+    __shared__ __align__(128) float4 sB[STAGES][2][NCH];
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], t_full[2], t_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t cta_cand = (size_t)blockIdx.x * n_chunks * NCH;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * NCH));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 128) { sA[0][tid] = A0g[(size_t)blockIdx.x * 128 + tid]; sA[1][tid] = A1g[(size_t)blockIdx.x * 128 + tid]; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t idesc = umma_idesc_tf32(128, NCH);
+    constexpr uint32_t plane = NCH * 16;
+    const long long t0 = clock64();
+    if (warp == 4) {
+        if (lane == 0)
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % STAGES;
+                if (c >= STAGES) mbar_wait(&s_empty[s], ((c / STAGES) - 1) & 1);
+                mbar_expect_tx(&s_full[s], 2 * plane);
+                bulk_g2s(&sB[s][0][0], Bhi + cta_cand + (size_t)c * NCH, plane, &s_full[s]);
+                bulk_g2s(&sB[s][1][0], Blo + cta_cand + (size_t)c * NCH, plane, &s_full[s]);
+            }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint64_t ad = umma_desc(&sA[0][0], 128 * 16, 128);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % STAGES, tb = c & 1;
+                mbar_wait(&s_full[s], (c / STAGES) & 1);
+                if (c >= 2) mbar_wait(&t_empty[tb], ((c >> 1) - 1) & 1);
+                tc_fence_after();
+                umma_tf32(tmem + tb * NCH, ad, umma_desc(&sB[s][0][0], 0, 128), idesc, 0);
+                umma_tf32(tmem + tb * NCH, ad, umma_desc(&sB[s][1][0], 0, 128), idesc, 1);
+                umma_commit(&s_empty[s]);                        // SMEM stage free once the MMAs have read it
+                umma_commit(&t_full[tb]);                        // scores of chunk c complete
+            }
+        }
+    } else {
+        float best = INFINITY, sec = INFINITY;
+        int blk = 0;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int tb = c & 1;
+            mbar_wait(&t_full[tb], (c >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + lane_addr + tb * NCH;
+            float r[2][32];
+            tmem_ld32(tbase, r[0]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < NCH / 32; ++g) {
+                if (g + 1 < NCH / 32) tmem_ld32(tbase + (g + 1) * 32, r[(g + 1) & 1]);
+                const float* v = r[g & 1];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) track(min8(v + 8 * k), c * NCH + g * 32 + 8 * k, best, sec, blk);
+                if (g + 1 < NCH / 32) tmem_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[tb]);            // this warp's quarter of the buffer is drained
+        }
+        out[(size_t)blockIdx.x * 128 + tid] = Out{best, sec, blk, 0};
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * NCH));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CUDA-core baseline: the library's scan (tile_scan<2, DOT>): CTA = 128 threads = 256 queries, candidates as float4
 // (y, |y|^2) in SMEM, broadcast LDS.128, 3 FFMA per pair
 // ---------------------------------------------------------------------------------------------------------------
-template <int NCH>
+template <int NCH, int NQ>
 __global__ void __launch_bounds__(128) scan_simt_kernel(const float4* __restrict__ Q, const float4* __restrict__ Y, int n_chunks,
                                                          Out* __restrict__ out, long long* __restrict__ cyc) {
     __shared__ float4 tile[2][NCH];
     const int tid = threadIdx.x;
     const size_t cta_cand = (size_t)blockIdx.x * n_chunks * NCH;
-    float m[2][3], best[2] = {INFINITY, INFINITY}, sec[2] = {INFINITY, INFINITY};
-    int blk[2] = {0, 0};
-    for (int k = 0; k < 2; ++k) {
-        const float4 q = Q[(size_t)blockIdx.x * 256 + k * 128 + tid];
+    float m[NQ][3], best[NQ], sec[NQ];
+    int blk[NQ];
+    for (int k = 0; k < NQ; ++k) {
+        const float4 q = Q[(size_t)blockIdx.x * 128 * NQ + k * 128 + tid];
         m[k][0] = -2.f * q.x; m[k][1] = -2.f * q.y; m[k][2] = -2.f * q.z;
+        best[k] = INFINITY; sec[k] = INFINITY; blk[k] = 0;
     }
     const long long t0 = clock64();
     for (int j = tid; j < NCH; j += 128) tile[0][j] = Y[cta_cand + j];
@@ -214,7 +306,7 @@ __global__ void __launch_bounds__(128) scan_simt_kernel(const float4* __restrict
 #pragma unroll
             for (int k = 0; k < 8; ++k) t[k] = tp[jb + k];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 float cc[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cc[k] = fmaf(m[q][0], t[k].x, fmaf(m[q][1], t[k].y, fmaf(m[q][2], t[k].z, t[k].w)));
@@ -224,13 +316,156 @@ __global__ void __launch_bounds__(128) scan_simt_kernel(const float4* __restrict
         __syncthreads();
     }
     const long long t1 = clock64();
-    for (int k = 0; k < 2; ++k) out[(size_t)blockIdx.x * 256 + k * 128 + tid] = Out{best[k], sec[k], blk[k], 0};
+    for (int k = 0; k < NQ; ++k) out[(size_t)blockIdx.x * 128 * NQ + k * 128 + tid] = Out{best[k], sec[k], blk[k], 0};
     if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// floors: what the two halves of the tensor-core scan cost on their own
+// ---------------------------------------------------------------------------------------------------------------
+// (a) tensor pipe: NMMA dependent MMAs (M = 128, N, K = 32 bytes: 8 tf32 or 16 bf16) per commit, two commits in flight,
+//     operands resident in SMEM (zeros), nothing else in the loop
+template <int N, int NMMA, int BF16>
+__global__ void __launch_bounds__(128) mma_floor_kernel(int iters, long long* __restrict__ cyc) {
+    __shared__ __align__(128) float4 sA[2][128];
+    __shared__ __align__(128) float4 sB[2][N];
+    __shared__ __align__(8) uint64_t done[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * N));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) { mbar_init(&done[0], 1); mbar_init(&done[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < 2 * 128; i += 128) (&sA[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 2 * N; i += 128) (&sB[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    // kind::f16 descriptor: a/b format 1 = bf16
+    const uint32_t idesc = BF16 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : umma_idesc_tf32(128, N);
+    const uint64_t ad = umma_desc(&sA[0][0], 128 * 16, 128), bd = umma_desc(&sB[0][0], N * 16, 128);
+    const long long t0 = clock64();
+    if (tid == 0) {
+        for (int it = 0; it < iters; ++it) {
+            const int b = it & 1;
+            if (it >= 2) mbar_wait(&done[b], ((it - 2) >> 1) & 1);
+            for (int k = 0; k < NMMA; ++k) {
+                if (BF16)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem + b * N), "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(k > 0)) : "memory");
+                else umma_tf32(tmem + b * N, ad, bd, idesc, k > 0);
+            }
+            umma_commit(&done[b]);
+        }
+        for (int it = iters - 2 < 0 ? 0 : iters - 2; it < iters; ++it) mbar_wait(&done[it & 1], (it >> 1) & 1);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * N));
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&r)[64]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                 "%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,"
+                 "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                   "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+                   "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+                   "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]), "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]),
+                   "=r"(u[37]), "=r"(u[38]), "=r"(u[39]), "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]),
+                   "=r"(u[46]), "=r"(u[47]), "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]),
+                   "=r"(u[55]), "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
+                 : "r"(taddr) : "memory");
+}
+// (b) epilogue: WARPS warps (4: one per lane quarter; 8: two per quarter, splitting the columns) read NCOLS TMEM columns per
+//     iteration with tcgen05.ld.x32 (double-buffered) or .x64 and run the block-minima tracking; no MMA, no barrier per chunk
+template <int NCOLS, int WARPS, int LDX>
+__global__ void __launch_bounds__(WARPS * 32) epi_floor_kernel(int iters, Out* __restrict__ out, long long* __restrict__ cyc) {
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(NCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    constexpr int SPLIT = WARPS / 4, MYCOLS = NCOLS / SPLIT;
+    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * MYCOLS;
+    float best = INFINITY, sec = INFINITY;
+    int blk = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (LDX == 32) {
+            float r[2][32];
+            tmem_ld32(tbase, r[0]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < MYCOLS / 32; ++g) {
+                if (g + 1 < MYCOLS / 32) tmem_ld32(tbase + (g + 1) * 32, r[(g + 1) & 1]);
+                const float* v = r[g & 1];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) track(min8(v + 8 * k), it * NCOLS + g * 32 + 8 * k, best, sec, blk);
+                if (g + 1 < MYCOLS / 32) tmem_wait_ld();
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < MYCOLS / 64; ++g) {
+                float r[64];
+                tmem_ld64(tbase + g * 64, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) track(min8(r + 8 * k), it * NCOLS + g * 64 + 8 * k, best, sec, blk);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    out[(size_t)blockIdx.x * WARPS * 32 + tid] = Out{best, sec, blk, 0};
+    if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(NCOLS));
+}
+
+template <int N, int NMMA, int BF16> static void run_mma_floor(int n_cta) {
+    long long* dcyc; CK(cudaMalloc(&dcyc, n_cta * 8));
+    const int iters = 200;
+    mma_floor_kernel<N, NMMA, BF16><<<n_cta, 128>>>(iters, dcyc);
+    CK(cudaDeviceSynchronize());
+    mma_floor_kernel<N, NMMA, BF16><<<n_cta, 128>>>(iters, dcyc);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> cyc(n_cta);
+    CK(cudaMemcpy(cyc.data(), dcyc, n_cta * 8, cudaMemcpyDeviceToHost));
+    double m = 0; for (long long c : cyc) m += (double)c; m /= n_cta;
+    printf("  MMA floor %s M=128 N=%3d, %d MMA per commit, %d CTA/SM: %7.1f clk per commit = %6.1f clk per MMA  (%5.2f clk per 32 scores per scheduler at 2 MMAs per score tile)\n",
+           BF16 ? "bf16" : "tf32", N, NMMA, n_cta / 148, m / iters, m / iters / NMMA, (m / iters / NMMA) * 2.0 * 32 * 4 / (128.0 * N) / (n_cta / 148));
+    cudaFree(dcyc);
+}
+template <int NCOLS, int WARPS, int LDX> static void run_epi_floor(int n_cta) {
+    long long* dcyc; Out* dout; CK(cudaMalloc(&dcyc, n_cta * 8)); CK(cudaMalloc(&dout, (size_t)n_cta * WARPS * 32 * sizeof(Out)));
+    const int iters = 100;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    epi_floor_kernel<NCOLS, WARPS, LDX><<<n_cta, WARPS * 32>>>(iters, dout, dcyc);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    epi_floor_kernel<NCOLS, WARPS, LDX><<<n_cta, WARPS * 32>>>(iters, dout, dcyc);
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> cyc(n_cta);
+    CK(cudaMemcpy(cyc.data(), dcyc, n_cta * 8, cudaMemcpyDeviceToHost));
+    double m = 0; for (long long c : cyc) m += (double)c; m /= n_cta;
+    const double scores = (double)n_cta * 128 * NCOLS * iters;
+    const double per_sm_clk = scores / (m) / 148 * 1.0;          // by the CTA clock (independent of the SM clock)
+    printf("  epilogue floor: %3d columns, %d warps/CTA, tcgen05.ld.x%d, %d CTA/SM: %6.2f scores/clk/SM = %5.2f clk per 32 scores per scheduler  (%.3f ms)\n",
+           NCOLS, WARPS, LDX, n_cta / 148, per_sm_clk * (n_cta >= 148 ? 1.0 : 148.0 / n_cta), 32.0 * 4 / per_sm_clk, ms);
+    cudaFree(dcyc); cudaFree(dout);
 }
 
 static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
-template <int NCH, int STAGES, int MODE>
+template <int NCH, int STAGES, int MODE, bool WS = false>
 static int run_tc(const char* name, int n_cta, int n_chunks, const std::vector<float4>& q, const std::vector<float4>& y, bool check) {
     // operands: A planes per CTA (128 queries each), B planes (hi / lo) per candidate
     const size_t nq = (size_t)n_cta * 128, nc = (size_t)n_cta * n_chunks * NCH;
@@ -256,8 +491,21 @@ static int run_tc(const char* name, int n_cta, int n_chunks, const std::vector<f
     const size_t ndump = (size_t)n_chunks * NCH * 128;
     if (check) { CK(cudaMalloc(&ddump, ndump * 4)); CK(cudaMemset(ddump, 0, ndump * 4)); }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    scan_tc_kernel<NCH, STAGES, MODE><<<n_cta, 128>>>(dA0, dA1, dBh, dBl, n_chunks, dout, ddump, dcyc);
+    if (WS) scan_tc_ws_kernel<NCH, STAGES><<<n_cta, 192>>>(dA0, dA1, dBh, dBl, n_chunks, dout, dcyc);
+    else scan_tc_kernel<NCH, STAGES, MODE><<<n_cta, 128>>>(dA0, dA1, dBh, dBl, n_chunks, dout, ddump, dcyc);
     CK(cudaDeviceSynchronize());
+    std::vector<Out> ref_out;
+    if (WS) {                                                    // the warp-specialised kernel must reproduce the plain one bit for bit
+        ref_out.resize(nq);
+        std::vector<Out> got(nq);
+        CK(cudaMemcpy(got.data(), dout, nq * sizeof(Out), cudaMemcpyDeviceToHost));
+        scan_tc_kernel<NCH, 2, 0><<<n_cta, 128>>>(dA0, dA1, dBh, dBl, n_chunks, dout, nullptr, dcyc);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(ref_out.data(), dout, nq * sizeof(Out), cudaMemcpyDeviceToHost));
+        size_t diff = 0;
+        for (size_t i = 0; i < nq; ++i) diff += got[i].best != ref_out[i].best || got[i].sec != ref_out[i].sec || got[i].blk != ref_out[i].blk;
+        if (diff) printf("  !! warp-specialised kernel differs from the plain one on %zu of %zu queries\n", diff, nq);
+    }
     int bad = 0;
     if (check) {                                                 // CTA 0: every score against float64, and the top-2 tracking
         std::vector<float> dump(ndump);
@@ -294,7 +542,8 @@ static int run_tc(const char* name, int n_cta, int n_chunks, const std::vector<f
     float best_ms = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        scan_tc_kernel<NCH, STAGES, MODE><<<n_cta, 128>>>(dA0, dA1, dBh, dBl, n_chunks, dout, nullptr, dcyc);
+        if (WS) scan_tc_ws_kernel<NCH, STAGES><<<n_cta, 192>>>(dA0, dA1, dBh, dBl, n_chunks, dout, dcyc);
+        else scan_tc_kernel<NCH, STAGES, MODE><<<n_cta, 128>>>(dA0, dA1, dBh, dBl, n_chunks, dout, nullptr, dcyc);
         cudaEventRecord(e1);
         CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -311,9 +560,9 @@ static int run_tc(const char* name, int n_cta, int n_chunks, const std::vector<f
     return bad;
 }
 
-template <int NCH>
+template <int NCH, int NQ>
 static void run_simt(const char* name, int n_cta, int n_chunks, const std::vector<float4>& q, const std::vector<float4>& y) {
-    const size_t nq = (size_t)n_cta * 256, nc = (size_t)n_cta * n_chunks * NCH;
+    const size_t nq = (size_t)n_cta * 128 * NQ, nc = (size_t)n_cta * n_chunks * NCH;
     std::vector<float4> Y(nc);
     for (size_t i = 0; i < nc; ++i) { const float4 p = y[i % y.size()]; Y[i] = make_float4(p.x, p.y, p.z, fmaf(p.x, p.x, fmaf(p.y, p.y, p.z * p.z))); }
     std::vector<float4> Q(nq);
@@ -322,12 +571,12 @@ static void run_simt(const char* name, int n_cta, int n_chunks, const std::vecto
     CK(cudaMalloc(&dQ, nq * 16)); CK(cudaMalloc(&dY, nc * 16)); CK(cudaMalloc(&dout, nq * sizeof(Out))); CK(cudaMalloc(&dcyc, n_cta * 8));
     CK(cudaMemcpy(dQ, Q.data(), nq * 16, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dY, Y.data(), nc * 16, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    scan_simt_kernel<NCH><<<n_cta, 128>>>(dQ, dY, n_chunks, dout, dcyc);
+    scan_simt_kernel<NCH, NQ><<<n_cta, 128>>>(dQ, dY, n_chunks, dout, dcyc);
     CK(cudaDeviceSynchronize());
     float best_ms = 1e30f;
     for (int r = 0; r < 5; ++r) {
         cudaEventRecord(e0);
-        scan_simt_kernel<NCH><<<n_cta, 128>>>(dQ, dY, n_chunks, dout, dcyc);
+        scan_simt_kernel<NCH, NQ><<<n_cta, 128>>>(dQ, dY, n_chunks, dout, dcyc);
         cudaEventRecord(e1);
         CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -335,7 +584,7 @@ static void run_simt(const char* name, int n_cta, int n_chunks, const std::vecto
     }
     const double scores = (double)nq * n_chunks * NCH;
     const double per_sm_clk = scores / (best_ms * 1e-3) / 148 / 1.965e9;
-    printf("%-30s grid %5d  %8.3f ms  %7.2f scores/clk/SM  = %5.2f clk per 32 scores per scheduler\n", name, n_cta, best_ms, per_sm_clk,
+    printf("%-26s Q=%d  grid %5d  %8.3f ms  %7.2f scores/clk/SM  = %5.2f clk per 32 scores per scheduler\n", name, NQ, n_cta, best_ms, per_sm_clk,
            32.0 * 4 / per_sm_clk);
     cudaFree(dQ); cudaFree(dY); cudaFree(dout); cudaFree(dcyc);
 }
@@ -365,10 +614,26 @@ int main(int argc, char** argv) {
         run_tc<128, 8, 1>("  MMAs only (no epilogue)", 148 * ps, n_chunks, q, y, false);
         run_tc<128, 8, 2>("  epilogue only (no MMA)", 148 * ps, n_chunks, q, y, false);
     }
+    run_tc<128, 4, 0, true>("tcgen05 warp-specialised N=128", 148, n_chunks, q, y, false);
+    run_tc<128, 4, 0, true>("tcgen05 warp-specialised N=128", 296, n_chunks, q, y, false);
+    run_tc<256, 4, 0, true>("tcgen05 warp-specialised N=256", 148, n_chunks, q, y, false);
+    run_tc<64, 6, 0, true>("tcgen05 warp-specialised N=64", 148 * 4, n_chunks, q, y, false);
     run_tc<256, 4, 0>("tcgen05 N=256, 4 stages", 148, n_chunks, q, y, false);
     run_tc<256, 4, 1>("  MMAs only (no epilogue)", 148, n_chunks, q, y, false);
     run_tc<256, 4, 2>("  epilogue only (no MMA)", 148, n_chunks, q, y, false);
-    for (int ps : {1, 2, 4, 5}) run_simt<128>("CUDA-core tile_scan<2,DOT>", 148 * ps, n_chunks, q, y);
+    for (int ps : {2, 4, 5}) run_simt<128, 2>("CUDA-core tile_scan (library)", 148 * ps, n_chunks, q, y);
+    for (int ps : {2, 4, 5}) run_simt<128, 1>("CUDA-core tile_scan", 148 * ps, n_chunks, q, y);
+    for (int ps : {2, 3, 4}) run_simt<128, 3>("CUDA-core tile_scan", 148 * ps, n_chunks, q, y);
+    for (int ps : {2, 3, 4}) run_simt<128, 4>("CUDA-core tile_scan", 148 * ps, n_chunks, q, y);
+    for (int ps : {2, 3}) run_simt<128, 6>("CUDA-core tile_scan", 148 * ps, n_chunks, q, y);
+    for (int ps : {1, 2}) run_simt<128, 8>("CUDA-core tile_scan", 148 * ps, n_chunks, q, y);
+    printf("== floors ==\n");
+    run_mma_floor<128, 1, 0>(148); run_mma_floor<128, 2, 0>(148); run_mma_floor<128, 4, 0>(148); run_mma_floor<128, 8, 0>(148);
+    run_mma_floor<256, 1, 0>(148); run_mma_floor<256, 2, 0>(148); run_mma_floor<256, 4, 0>(148); run_mma_floor<256, 8, 0>(148);
+    run_mma_floor<256, 8, 1>(148); run_mma_floor<128, 8, 0>(296); run_mma_floor<64, 8, 0>(148 * 4);
+    run_epi_floor<256, 4, 32>(148); run_epi_floor<256, 4, 64>(148); run_epi_floor<256, 8, 32>(148); run_epi_floor<256, 8, 64>(148);
+    run_epi_floor<256, 4, 32>(296); run_epi_floor<256, 4, 64>(296); run_epi_floor<256, 8, 64>(296);
+    run_epi_floor<128, 4, 64>(148 * 4); run_epi_floor<128, 8, 64>(148 * 4); run_epi_floor<128, 4, 32>(148 * 4);
     printf("library today: icp_group_kernel / blend_tile_kernel scan loop = 5.6 clk per 32 scores per scheduler (profiles/README.md)\n");
     return bad ? 1 : 0;
 }
