@@ -53,6 +53,7 @@ SIGNATURES = {
     "lip_batch_get_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
     "lip_batch_get_bin_offsets": (c_int, [c_void_p, _I32]),
     "lip_batch_evaluate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, _D, _I64]),
+    "lip_batch_evaluate_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, _I64, _I64, c_int64, c_void_p]),
     "lip_batch_refine_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lip_batch_match_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, _D]),
     "lip_batch_interpolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
@@ -278,6 +279,15 @@ class Context:
                                                      float(voxel_size), float(sample_proportion), _ptr(scores, c_double),
                                                      _ptr(counts, c_int64)))
         return scores, counts
+
+    def evaluate_device(self, d_xyz1, d_xyz2, d_lm1, d_lm2, d_T21, d_T12, d_counts, voxel_size=1.0, sample_proportion=0.1, stream=0,
+                        row1=None, row2=None, n_rows=0):
+        """the score counts (S,6) int64 of device-resident maps, written to the device address d_counts on `stream`; no sync.
+        row1 / row2 (int64 numpy): series layout, d_xyz1 = the frames array of n_rows rows."""
+        self._check(self.lib.lip_batch_evaluate_device(self.h, d_xyz1, d_xyz2, d_lm1, d_lm2, d_T21, d_T12, float(voxel_size),
+                                                       float(sample_proportion), d_counts,
+                                                       _ptr(row1, c_int64) if row1 is not None else None,
+                                                       _ptr(row2, c_int64) if row2 is not None else None, int(n_rows), stream))
 
     def match(self, xyz1, xyz2, lm1, lm2, refine=True, voxel_size=1.0, sample_proportion=0.5):
         """hot path + refinement + evaluation of the planned batch in one call: (T21, T12, scores (S,3))"""

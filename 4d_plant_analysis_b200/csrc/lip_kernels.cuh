@@ -1951,8 +1951,8 @@ __global__ void __launch_bounds__(256) eval_scores_kernel(LipArgs a, const int* 
     const int u1 = a.mesh_ubase[m1], u2 = a.mesh_ubase[m2] - a.n1_total;       // offsets into xyz1 / xyz2 and T12 / T21
     const int n2 = a.mesh_ubase[m2 + 1] - a.mesh_ubase[m2];
     const int K = a.mesh_bin[m1 + 1] - a.mesh_bin[m1];
-    const double* __restrict__ v1 = a.xyz1 + 3 * (size_t)u1;
-    const double* __restrict__ v2 = a.xyz2 + 3 * (size_t)u2;
+    const double* __restrict__ v1 = mesh_xyz(a, m1);
+    const double* __restrict__ v2 = mesh_xyz(a, m2);
     const long long* __restrict__ t21 = T21 + u2;
     if (tid < 3) s_cnt[tid] = 0;
     __syncthreads();

@@ -461,7 +461,7 @@ extern "C" {
 static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12, cudaStream_t st);
 static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
                            const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
-                           cudaStream_t st);
+                           cudaStream_t st, long long* d_counts_out = nullptr, const int* mesh_row = nullptr);
 }
 namespace {
 
@@ -1361,7 +1361,7 @@ static int check_maps_verdict(lip_ctx* c, cudaStream_t st, const char* who) {
 // evaluate_p2p_matching on device-resident inputs and maps: enqueues the kernels and the copy of the counts
 static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
                            const long long* d_T21, const long long* d_T12, double voxel_size, double sample_proportion,
-                           cudaStream_t st) {
+                           cudaStream_t st, long long* d_counts_out, const int* mesh_row) {
     const size_t S = (size_t)c->S;
     const int step = std::max((int)(1.0 / sample_proportion), 1);              // p2p_matching_evaluation.py:40
     std::vector<int>& qbase = c->h_qbase_eval;                 // kept in the context: the upload below is asynchronous
@@ -1375,7 +1375,7 @@ static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz
     const size_t o_cnt = align_up((size_t)c->B * 4), o_qb = o_cnt + align_up(S * 48), o_nn = o_qb + align_up((S + 1) * 4);
     LIP_CUDA(c, c->misc2.ensure(o_nn + (size_t)qbase[S] * 8 + 16));
     LipArgs a = c->args;
-    a.xyz1 = d_xyz1; a.xyz2 = d_xyz2; a.lm1 = d_lm1; a.lm2 = d_lm2;
+    a.xyz1 = d_xyz1; a.xyz2 = d_xyz2; a.lm1 = d_lm1; a.lm2 = d_lm2; a.mesh_row = mesh_row;
     int* lm_idx = c->misc2.as<int>();
     long long* cnt = (long long*)(c->misc2.as<char>() + o_cnt);
     int* d_qbase = (int*)(c->misc2.as<char>() + o_qb);
@@ -1386,6 +1386,10 @@ static int evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz
     if (rc) return rc;
     eval_scores_kernel<<<(unsigned)S, 256, 0, st>>>(a, lm_idx, d_nn2, d_qbase, d_T21, d_T12, 2.0 * voxel_size, step, cnt);
     LIP_CUDA(c, cudaGetLastError());
+    if (d_counts_out) {                                      // device-resident caller: the counts stay on the device
+        LIP_CUDA(c, cudaMemcpyAsync(d_counts_out, cnt, S * 48, cudaMemcpyDeviceToDevice, st));
+        return LIP_OK;
+    }
     LIP_CUDA(c, c->h_counts.ensure(S * 48));                 // (valid after the stream has been synchronised)
     LIP_CUDA(c, cudaMemcpyAsync(c->h_counts.p, cnt, S * 48, cudaMemcpyDeviceToHost, st));
     return LIP_OK;
@@ -1430,6 +1434,28 @@ int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, 
     scores_from_counts((const long long*)c->h_counts.p, (size_t)c->S, T12 != nullptr, scores, counts);
     c->last_launches = 2;
     return LIP_OK;
+}
+
+static int series_rows(lip_ctx* kc, const int64_t* row1, const int64_t* row2, int64_t s0, int64_t n_rows, const int64_t* off1,
+                       const int64_t* off2, cudaStream_t st);
+int lip_batch_evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
+                              const int64_t* d_T21, const int64_t* d_T12, double voxel_size, double sample_proportion,
+                              int64_t* d_counts, const int64_t* row1, const int64_t* row2, int64_t n_rows, void* stream) {
+    if (!c) return LIP_EINVAL;
+    if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
+    if (!d_xyz1 || !d_xyz2 || !d_lm1 || !d_lm2 || !d_T21 || !d_counts) return fail(c, LIP_EINVAL, "evaluate: null pointer");
+    if (!(sample_proportion > 0.0)) return fail(c, LIP_EINVAL, "evaluate: sample_proportion must be > 0");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int* rows = nullptr;
+    if (row1 || row2) {                                      // series layout: d_xyz1 holds every mesh once, d_xyz2 is ignored
+        if (!row1 || !row2 || n_rows <= 0) return fail(c, LIP_EINVAL, "evaluate: row1, row2 and n_rows go together");
+        int rc = series_rows(c, row1, row2, 0, n_rows, c->h_off1.data(), c->h_off2.data(), st);
+        if (rc) return rc;
+        rows = c->d_rows.as<int>();
+    }
+    return evaluate_device(c, d_xyz1, d_xyz2, d_lm1, d_lm2, (const long long*)d_T21, (const long long*)d_T12, voxel_size,
+                           sample_proportion, st, (long long*)d_counts, rows);
 }
 
 // double_direction_refinement on device-resident coordinates and maps (d_T21 rewritten in place)

@@ -1,13 +1,25 @@
 """Multi-GPU: one process per GPU (torch.distributed), segment pairs sharded across ranks.
 
-The algorithm has no exchange step: the atomic unit is a matched segment pair (both
-directions), ranks work on disjoint shards with no data-path collective, and the only communication
-is the final gather of the dense maps.  ``shard_segments`` is the partitioner (longest-processing-time
-greedy on a cost estimate); ``gather_maps`` all-gathers the int64 maps (NCCL on GPUs; gloo in the CPU
-tests of the host logic).
+The algorithm has no exchange step: the atomic unit is a matched segment pair (both directions), ranks
+work on disjoint shards with no data-path collective, and the only communication is the final gather of the dense maps
+and the per-segment score counts.  The reference's shard axes are its two serial loops: consecutive day pairs
+(run_registration_pipeline.py:64-104) and matched segment pairs (p2p_matching_seg_icp.py:152-176).
+
+* ``shard_segments`` — the partitioner: whole frame pairs in contiguous blocks when there are at least `world` of them
+  (C4: 15 pairs -> 2,2,2,2,2,2,2,1; consecutive pairs of a series stay on one rank, so the frame they share is uploaded
+  once), otherwise segment pairs by longest-processing-time greedy on a cost estimate (C5).
+* ``make_shard_plan`` / ``gather_results`` — ONE padded all_gather_into_tensor per step on device buffers (int32 maps of both
+  directions and the int64 score counts packed into one int32 buffer per rank) with an int32 count vector exchanged once,
+  when the plan is made; the whole-batch arrays are re-assembled on the device by one index gather.
+* ``ShardedLocalICP`` — the device-resident runner used by bench.py and tools/dist_check.py: shard, upload, run + score on
+  this rank's GPU, gather.  In a time series the frame on a shard boundary is sent to the neighbouring rank over
+  NVLink (NCCL send/recv) instead of being uploaded twice.
+* ``local_icp_distributed`` — host numpy in, host numpy out (gloo on CPU in the tests of the host logic, with the compute
+  step injected).
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -20,15 +32,20 @@ def segment_costs(off1, off2, lm_off) -> np.ndarray:
 
 
 def shard_segments(costs: Sequence[float], world: int, frame_pair: Optional[Sequence[int]] = None) -> List[np.ndarray]:
-    """Deal segment pairs to ranks.  With ``frame_pair`` ids and at least `world` frame pairs, whole frame
-    pairs are dealt round-robin (C4: 15 pairs -> 2,2,2,2,2,2,2,1); otherwise segment pairs are dealt greedily,
-    heaviest first, to the least loaded rank.  Every rank's list is in ascending segment order."""
+    """Deal segment pairs to ranks.  With ``frame_pair`` ids and at least `world` frame pairs, whole frame pairs are dealt in
+    contiguous blocks of (nearly) equal count, the larger blocks first (15 pairs on 8 ranks -> 2,2,2,2,2,2,2,1); otherwise
+    segment pairs are dealt greedily, heaviest first, to the least loaded rank.  Every rank's list is in ascending order."""
     costs = np.asarray(costs, np.float64)
-    S = len(costs)
     if frame_pair is not None and len(np.unique(frame_pair)) >= world:
         fp = np.asarray(frame_pair)
         ids = np.unique(fp)
-        return [np.nonzero(np.isin(fp, ids[r::world]))[0] for r in range(world)]
+        base, extra = divmod(len(ids), world)
+        out, at = [], 0
+        for r in range(world):
+            n = base + (1 if r < extra else 0)
+            out.append(np.nonzero(np.isin(fp, ids[at:at + n]))[0].astype(np.int64))
+            at += n
+        return out
     load = np.zeros(world)
     out: List[List[int]] = [[] for _ in range(world)]
     for s in np.argsort(-costs, kind="stable"):
@@ -38,43 +55,270 @@ def shard_segments(costs: Sequence[float], world: int, frame_pair: Optional[Sequ
     return [np.array(sorted(o), dtype=np.int64) for o in out]
 
 
-def gather_maps(T_local: np.ndarray, seg_ids: np.ndarray, seg_sizes_all: np.ndarray, *, device=None) -> np.ndarray:
-    """All-gather one direction's maps.  ``T_local``: this rank's maps concatenated in the order of
-    ``seg_ids``; ``seg_sizes_all``: (S,) entries per segment pair of the WHOLE batch.  Returns the whole-batch
-    concatenated map on every rank.  One padded all_gather_into_tensor (int64) + a count exchange."""
+# ------------------------------------------------------------------------------------------------
+# the gather: one collective per step
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ShardPlan:
+    """Who holds what, and where every entry of the whole-batch results sits in the gathered buffer.
+
+    Per rank the packed int32 buffer is [T21 of its segment pairs | T12 | score counts (6 int64 per segment pair = 12 int32)],
+    padded to ``pad`` int32; ``index21`` / ``index12`` / ``index_cnt`` give, for every entry of the whole-batch T21 / T12 /
+    counts (viewed as int32), its position in the (world * pad) gathered buffer."""
+
+    world: int
+    seg_ids: List[np.ndarray]
+    sizes: np.ndarray            # (world, 3) int32: entries of T21, T12, segment pairs per rank — the pre-exchanged count vector
+    pad: int
+    index21: np.ndarray
+    index12: np.ndarray
+    index_cnt: np.ndarray
+    n21: int
+    n12: int
+    S: int
+    _dev: dict = None
+
+    def device_indices(self, device):
+        import torch
+        if self._dev is None:
+            self._dev = {}
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(torch.as_tensor(a, dtype=torch.int64, device=device) for a in (self.index21, self.index12, self.index_cnt))
+        return self._dev[key]
+
+
+def make_shard_plan(off1, off2, lm_off, world: int, frame_pair=None, *, exchange: bool = False) -> ShardPlan:
+    """The shard of every rank and the re-assembly indices.  ``exchange``: all-gather the (3,) int32 count vector of this
+    rank over the default process group and check it against the plan (every rank must hold the same batch)."""
+    off1, off2 = np.asarray(off1, np.int64), np.asarray(off2, np.int64)
+    S = len(off1) - 1
+    n1, n2 = np.diff(off1), np.diff(off2)
+    shards = shard_segments(segment_costs(off1, off2, lm_off), world, frame_pair)
+    sizes = np.array([[int(n2[s].sum()), int(n1[s].sum()), len(s)] for s in shards], np.int32)
+    pad = int((sizes[:, 0] + sizes[:, 1] + 12 * sizes[:, 2]).max())
+    pad = (pad + 3) // 4 * 4                                  # 16-byte multiples
+    index21, index12 = np.empty(int(off2[-1]), np.int64), np.empty(int(off1[-1]), np.int64)
+    index_cnt = np.empty(12 * S, np.int64)
+    for r, segs in enumerate(shards):
+        base = r * pad
+        p21, p12, pc = base, base + int(sizes[r, 0]), base + int(sizes[r, 0]) + int(sizes[r, 1])
+        for s in segs:
+            a, b = int(n2[s]), int(n1[s])
+            index21[off2[s]:off2[s] + a] = np.arange(p21, p21 + a)
+            index12[off1[s]:off1[s] + b] = np.arange(p12, p12 + b)
+            index_cnt[12 * s:12 * s + 12] = np.arange(pc, pc + 12)
+            p21 += a; p12 += b; pc += 12
+    plan = ShardPlan(world, shards, sizes, pad, index21, index12, index_cnt, int(off2[-1]), int(off1[-1]), S)
+    if exchange:
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.as_tensor(sizes[rank], dtype=torch.int32, device=dev)
+        got = torch.empty(world * 3, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(got, mine)
+        if not np.array_equal(got.cpu().numpy().reshape(world, 3), sizes):
+            raise RuntimeError("shard plan: the ranks do not hold the same batch (count vectors differ)")
+    return plan
+
+
+def gather_results(plan: ShardPlan, T21_local, T12_local, counts_local, *, out=None):
+    """One all_gather_into_tensor of this rank's packed results (torch tensors on the collective's device: int32 or int64
+    maps in the order of ``plan.seg_ids[rank]``, int64 counts (S_r, 6)); returns whole-batch (T21 int32, T12 int32, counts
+    int64 (S, 6)) on every rank, re-assembled on the device."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = T21_local.device
+    n21, n12, ns = (int(x) for x in plan.sizes[rank])
+    if T21_local.numel() != n21 or T12_local.numel() != n12 or counts_local.numel() != 6 * ns:
+        raise ValueError("local results do not match the shard plan")
+    buf = torch.zeros(plan.pad, dtype=torch.int32, device=dev) if out is None else out
+    buf[:n21] = T21_local.to(torch.int32)
+    buf[n21:n21 + n12] = T12_local.to(torch.int32)
+    buf[n21 + n12:n21 + n12 + 12 * ns] = counts_local.contiguous().view(-1).view(torch.int32)
+    if plan.world > 1:
+        allbuf = torch.empty(plan.world * plan.pad, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allbuf, buf)
+    else:
+        allbuf = buf
+    i21, i12, icnt = plan.device_indices(dev)
+    return allbuf[i21], allbuf[i12], allbuf[icnt].view(torch.int64).view(plan.S, 6)
+
+
+def scores_from_counts(counts: np.ndarray) -> np.ndarray:
+    """(S,6) integer counts -> (S,3) continuity, landmark precision, cycle consistency (p2p_matching_evaluation.py:32-88)"""
+    c = np.asarray(counts, np.float64)
+    return np.stack([c[:, 2] / c[:, 3], c[:, 0] / c[:, 1], c[:, 4] / c[:, 5]], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident sharded runner
+# ------------------------------------------------------------------------------------------------
+class ShardedLocalICP:
+    """Shard ``data`` (a SegmentPairBatch or a SeriesBatch, identical on every rank) over the ranks of the default process
+    group (or run it whole when torch.distributed is not initialised), keep this rank's shard resident on its GPU and, per
+    step, run the hot path + the score counts there and gather whole-batch maps and counts on every rank.
+
+    ``step()``            inputs already on the device.
+    ``step_from_host()``  the same preceded by the upload of this rank's shard from pinned host memory; in a series the frame
+                          on the boundary to the next rank arrives from that rank over NVLink instead of a second upload.
+    """
+
+    def __init__(self, data, *, device: int, voxel_size: float = 1.0, sample_proportion: float = 0.5, ctx=None):
+        import torch
+        import torch.distributed as dist
+        from . import _native
+        from .synthetic import SeriesBatch
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dev = torch.device("cuda", device)
+        self.series = isinstance(data, SeriesBatch)
+        self.plan = make_shard_plan(data.off1, data.off2, data.lm_off, self.world, data.frame_pair, exchange=self.world > 1)
+        mine = self.plan.seg_ids[self.rank]
+        self.mine = mine
+        self.voxel_size, self.sample_proportion = voxel_size, sample_proportion
+        self.ctx = ctx or _native.Context(device)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.S_local = len(mine)
+        self.n21, self.n12 = int(self.plan.sizes[self.rank, 0]), int(self.plan.sizes[self.rank, 1])
+        self.boundary_rows = 0            # rows at the end of `frames` that the next rank uploads (series, contiguous frame pairs)
+        self.first_rows = 0               # rows at the start of `frames` that the previous rank needs
+        if self.S_local == 0:
+            self.local = None
+            return
+        by_frame_pair = data.frame_pair is not None and len(np.unique(data.frame_pair)) >= self.world
+        if self.series:
+            fps = np.unique(data.frame_pair[mine])
+            self.local = data.take_frame_pairs(fps) if by_frame_pair else _take_series_segments(data, mine)
+            if by_frame_pair and self.world > 1:
+                self._find_boundaries(data, fps)
+            host = [self.local.frames, self.local.lm1, self.local.lm2]
+        else:
+            self.local = data.take(mine)
+            host = [self.local.xyz1, self.local.xyz2, self.local.lm1, self.local.lm2]
+        b = self.local
+        self.ctx.plan(b.off1, b.off2, b.lm_off)
+        self.h_in = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in host]
+        self.d_in = [torch.empty_like(h, device=self.dev) for h in self.h_in]
+        self.d_T21 = torch.empty(self.n21, dtype=torch.int64, device=self.dev)
+        self.d_T12 = torch.empty(self.n12, dtype=torch.int64, device=self.dev)
+        self.d_cnt = torch.empty((self.S_local, 6), dtype=torch.int64, device=self.dev)
+        self.h2d_bytes = sum(int(h.numel()) * 8 for h in self.h_in) - 24 * self.boundary_rows
+        self.upload()
+
+    # frames shared with the neighbours: the LAST frame of this rank's block is the FIRST frame of the next rank's block
+    def _find_boundaries(self, data, fps):
+        fp_all = np.asarray(data.frame_pair)
+        n2 = np.diff(data.off2)
+        n1 = np.diff(data.off1)
+        nxt = fps.max() + 1
+        if self.rank + 1 < self.world and np.any(fp_all == nxt):
+            segs_next, segs_last = np.nonzero(fp_all == nxt)[0], np.nonzero(fp_all == fps.max())[0]
+            # shared iff mesh1 of the next frame pair are the very rows that are mesh2 of my last one
+            if len(segs_next) == len(segs_last) and np.array_equal(data.row1[segs_next], data.row2[segs_last]):
+                self.boundary_rows = int(n2[segs_last].sum())
+        prv = fps.min() - 1
+        if self.rank > 0 and prv >= 0 and np.any(fp_all == prv):
+            segs_prev, segs_first = np.nonzero(fp_all == prv)[0], np.nonzero(fp_all == fps.min())[0]
+            if len(segs_prev) == len(segs_first) and np.array_equal(data.row2[segs_prev], data.row1[segs_first]):
+                self.first_rows = int(n1[segs_first].sum())
+
+    def upload(self):
+        """whole shard host -> device (untimed set-up of the device-resident steps)"""
+        torch = self.torch
+        if self.local is None:
+            return
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(self.d_in, self.h_in):
+                d.copy_(h, non_blocking=True)
+        self.stream.synchronize()
+
+    def _compute(self):
+        c, b, st = self.ctx, self.local, self.stream.cuda_stream
+        if self.series:
+            fr, l1, l2 = (t.data_ptr() for t in self.d_in)
+            c.run_series_device(fr, len(b.frames), b.row1, b.row2, l1, l2, self.d_T21.data_ptr(), self.d_T12.data_ptr(), st)
+            c.evaluate_device(fr, fr, l1, l2, self.d_T21.data_ptr(), self.d_T12.data_ptr(), self.d_cnt.data_ptr(), self.voxel_size,
+                              self.sample_proportion, st, row1=b.row1, row2=b.row2, n_rows=len(b.frames))
+        else:
+            x1, x2, l1, l2 = (t.data_ptr() for t in self.d_in)
+            c.run_device(x1, x2, l1, l2, self.d_T21.data_ptr(), self.d_T12.data_ptr(), st)
+            c.evaluate_device(x1, x2, l1, l2, self.d_T21.data_ptr(), self.d_T12.data_ptr(), self.d_cnt.data_ptr(), self.voxel_size,
+                              self.sample_proportion, st)
+
+    def step(self):
+        """device-resident step: hot path + score counts of this rank's shard, then the gather.  Returns whole-batch
+        (T21 int32, T12 int32, counts int64 (S,6)) device tensors (valid once self.stream has been synchronised)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            if self.local is not None:
+                self._compute()
+                return gather_results(self.plan, self.d_T21, self.d_T12, self.d_cnt)
+            z = torch.zeros(0, dtype=torch.int64, device=self.dev)
+            return gather_results(self.plan, z, z, z.view(0, 6))
+
+    def step_from_host(self):
+        """end-to-end step: upload of this rank's shard from pinned memory (the boundary frame of a series comes from the next
+        rank over NVLink), compute, gather."""
+        torch, dist = self.torch, self.dist
+        with torch.cuda.stream(self.stream):
+            if self.local is not None:
+                if self.series and (self.boundary_rows or self.first_rows):
+                    fr_d, fr_h = self.d_in[0], self.h_in[0]
+                    own = fr_h.shape[0] - self.boundary_rows
+                    fr_d[:own].copy_(fr_h[:own], non_blocking=True)
+                    ops = []
+                    if self.first_rows:
+                        ops.append(dist.P2POp(dist.isend, fr_d[:self.first_rows], self.rank - 1))
+                    if self.boundary_rows:
+                        ops.append(dist.P2POp(dist.irecv, fr_d[own:], self.rank + 1))
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    for d, h in zip(self.d_in[1:], self.h_in[1:]):
+                        d.copy_(h, non_blocking=True)
+                else:
+                    for d, h in zip(self.d_in, self.h_in):
+                        d.copy_(h, non_blocking=True)
+        return self.step()
+
+
+def _take_series_segments(series, seg_ids):
+    """sub-series of arbitrary segment pairs (every mesh they use once)"""
+    from .synthetic import SeriesBatch
+    seg_ids = np.asarray(seg_ids, np.int64)
+    n1, n2 = np.diff(series.off1)[seg_ids], np.diff(series.off2)[seg_ids]
+    rows = sorted({(int(r), int(n)) for r, n in zip(series.row1[seg_ids], n1)} | {(int(r), int(n)) for r, n in zip(series.row2[seg_ids], n2)})
+    new_row, parts, at = {}, [], 0
+    for r, n in rows:
+        new_row[r] = at
+        parts.append(series.frames[r:r + n])
+        at += n
+    z = lambda n: np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    lm_keep = np.concatenate([np.arange(series.lm_off[s], series.lm_off[s + 1]) for s in seg_ids])
+    return SeriesBatch(np.ascontiguousarray(np.concatenate(parts, axis=0)), np.array([new_row[int(r)] for r in series.row1[seg_ids]], np.int64),
+                       np.array([new_row[int(r)] for r in series.row2[seg_ids]], np.int64), z(n1), z(n2),
+                       np.ascontiguousarray(series.lm1[lm_keep]), np.ascontiguousarray(series.lm2[lm_keep]),
+                       z(np.diff(series.lm_off)[seg_ids]), series.frame_pair[seg_ids], series.name)
+
+
+# ------------------------------------------------------------------------------------------------
+# host numpy in, host numpy out
+# ------------------------------------------------------------------------------------------------
+def local_icp_distributed(batch, *, compute=None, gather=True):
+    """Shard ``batch`` (a SegmentPairBatch, identical on every rank) over the ranks of the default process group, run the
+    local shard, and (optionally) gather whole-batch T21 / T12 (int64 numpy) and the per-segment score counts on every rank.
+    ``compute(sub_batch) -> (T21, T12[, counts])`` defaults to the CUDA path on this rank's GPU (LOCAL_RANK).  Returns
+    (T21, T12, seg_ids_of_this_rank) — and the counts (S,6) as a fourth element when ``compute`` supplies them."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
-    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
-    ids = [None] * world
-    dist.all_gather_object(ids, np.asarray(seg_ids, np.int64))
-    counts = [int(seg_sizes_all[i].sum()) for i in ids]
-    pad = max(counts)
-    buf = torch.zeros(pad, dtype=torch.int64, device=dev)
-    buf[:len(T_local)] = torch.as_tensor(T_local, dtype=torch.int64).to(dev)
-    out = torch.empty(world * pad, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(out, buf)
-    out = out.cpu().numpy().reshape(world, pad)
-    off = np.concatenate([[0], np.cumsum(seg_sizes_all)]).astype(np.int64)
-    full = np.empty(int(off[-1]), np.int64)
-    for r in range(world):
-        p = 0
-        for s in ids[r]:
-            n = int(seg_sizes_all[s])
-            full[off[s]:off[s] + n] = out[r, p:p + n]
-            p += n
-    return full
-
-
-def local_icp_distributed(batch, *, compute=None, gather=True):
-    """Shard ``batch`` (a SegmentPairBatch, identical on every rank) over the ranks of the default process
-    group, run the local shard, and (optionally) gather whole-batch T21/T12 on every rank.
-    ``compute(sub_batch) -> (T21, T12)`` defaults to the CUDA path on this rank's GPU (LOCAL_RANK)."""
-    import torch.distributed as dist
-    world, rank = dist.get_world_size(), dist.get_rank()
-    shards = shard_segments(segment_costs(batch.off1, batch.off2, batch.lm_off), world, batch.frame_pair)
-    mine = shards[rank]
+    plan = make_shard_plan(batch.off1, batch.off2, batch.lm_off, world, batch.frame_pair, exchange=gather)
+    mine = plan.seg_ids[rank]
     T21 = T12 = np.zeros(0, np.int64)
+    counts = None
     if len(mine):
         sub = batch.take(mine)
         if compute is None:
@@ -82,8 +326,14 @@ def local_icp_distributed(batch, *, compute=None, gather=True):
             r = local_icp_batch(sub)
             T21, T12 = r.T21, r.T12
         else:
-            T21, T12 = compute(sub)
+            res = compute(sub)
+            T21, T12 = res[0], res[1]
+            counts = res[2] if len(res) > 2 else None
     if not gather:
         return T21, T12, mine
-    n1, n2 = np.diff(batch.off1), np.diff(batch.off2)
-    return gather_maps(T21, mine, n2), gather_maps(T12, mine, n1), mine
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    have_counts = counts is not None or len(mine) == 0
+    c = np.zeros((len(mine), 6), np.int64) if counts is None else np.asarray(counts, np.int64).reshape(len(mine), 6)
+    g21, g12, gcnt = gather_results(plan, torch.as_tensor(T21, device=dev), torch.as_tensor(T12, device=dev), torch.as_tensor(c, device=dev))
+    out = (g21.cpu().numpy().astype(np.int64), g12.cpu().numpy().astype(np.int64), mine)
+    return out + (gcnt.cpu().numpy(),) if have_counts and counts is not None else out

@@ -165,6 +165,14 @@ int lip_batch_evaluate_host(lip_ctx* ctx, const double* xyz1, const double* xyz2
                             const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
                             double* scores, int64_t* counts);
 
+/* The same on device-resident arrays (maps produced by lip_batch_run_device stay where they are): the integer counts (S,6)
+ * are written to d_counts on `stream`, no synchronisation; scores = counts[2]/counts[3], counts[0]/counts[1], counts[4]/counts[5].
+ * The maps are NOT range-checked (they come from this library).  row1 / row2 (host, S entries) non-NULL: series layout as in
+ * lip_series_run_device — d_xyz1 holds every mesh once (n_rows rows), d_xyz2 is ignored. */
+int lip_batch_evaluate_device(lip_ctx* ctx, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
+                              const int64_t* d_T21, const int64_t* d_T12, double voxel_size, double sample_proportion,
+                              int64_t* d_counts, const int64_t* row1, const int64_t* row2, int64_t n_rows, void* stream);
+
 /* double_direction_refinement (p2p_matching_in_organ/p2p_matching_fm.py:75-132, called right after the hot path at
  * p2p_matching_seg_icp.py:181-182) for every segment pair of the planned batch: T21 (off2[S]) is refined IN PLACE with
  * the reference's visiting order (it makes the map closer to injective using the cycle error |v2[i] - v2[T12[T21[i]]]|

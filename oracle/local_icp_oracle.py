@@ -107,9 +107,12 @@ def best_fit_transform(A, B):
     return T, R, t
 
 
-def icp(src, tgt, nn="kdtree", info=None):
+def icp(src, tgt, nn="kdtree", info=None, reject_dist=np.inf):
     """registration_icp.py:60-98 (my_icp).  Returns (T, R (3,3), t (3,1)); x -> x R^T + t^T maps src on tgt.
-    ``info`` (dict), if given, receives 'iters' (number of NN passes) and 'cost' (their mean distances)."""
+    ``info`` (dict), if given, receives 'iters' (number of NN passes) and 'cost' (their mean distances).
+    ``reject_dist`` is NOT reference behaviour (the reference rejects nothing, registration_icp.py:85-90): it restates the
+    correspondence-reject hook of the CUDA path (lip_params.reject_dist) — pairs farther apart than this are left out of the
+    Kabsch fit, the cost stays the mean over ALL pairs, and a pass that keeps no pair applies the identity increment."""
     X = np.array(src, np.float64).reshape(-1, 3).T.copy()
     Y = np.array(tgt, np.float64).reshape(-1, 3).T.copy()
     R_inc = np.identity(3)
@@ -125,7 +128,13 @@ def icp(src, tgt, nn="kdtree", info=None):
         cost.append(np.mean(d))
         if i > 1 and (cost[-1] > cost[-2] + COST_RISE_TOL or abs(cost[-1] - cost[-2]) < COST_FLAT_TOL):
             break
-        _, R_inc, t_inc = best_fit_transform(X.T, Y.T[idx])
+        keep = np.asarray(d).reshape(-1) <= reject_dist
+        if keep.all():
+            _, R_inc, t_inc = best_fit_transform(X.T, Y.T[idx])
+        elif keep.any():
+            _, R_inc, t_inc = best_fit_transform(X.T[keep], Y.T[idx][keep])
+        else:
+            R_inc, t_inc = np.identity(3), np.zeros(3)
         t_inc = t_inc.reshape(3, 1)
     if info is not None:
         info["iters"] = len(cost)
@@ -200,7 +209,7 @@ def blend_weights(lm2, nn2, d2, loop=False):
     return f0, f1
 
 
-def segment_map(xyz1, xyz2, lm1, lm2, nn="kdtree", loop=False, details=None):
+def segment_map(xyz1, xyz2, lm1, lm2, nn="kdtree", loop=False, details=None, reject_dist=np.inf):
     """p2p_matching_seg_icp.py:383-489.  T21 (N2,) int64: for each vertex of mesh2 the index of its
     match in mesh1.  ``details`` (dict) receives the per-landmark transforms after filling ('R' (K,3,3),
     't' (K,3)), 'valid' (K,) whether an ICP ran, 'iters' (K,) NN passes (0 where none), the landmark
@@ -220,7 +229,7 @@ def segment_map(xyz1, xyz2, lm1, lm2, nn="kdtree", loop=False, details=None):
             src = xyz2[nn2[:, 0] == i]
             if len(src) > 0 and len(tgt) > 0:
                 inf = {}
-                _, R, t = icp(src, tgt, nn, inf)
+                _, R, t = icp(src, tgt, nn, inf, reject_dist)
                 iters[i] = inf["iters"]
             else:
                 R = t = None
@@ -230,7 +239,7 @@ def segment_map(xyz1, xyz2, lm1, lm2, nn="kdtree", loop=False, details=None):
         R_list, t_list = fill_missing(R_list, t_list, xyz1, xyz2)
     else:
         inf = {}
-        _, R, t = icp(xyz2, xyz1, nn, inf)
+        _, R, t = icp(xyz2, xyz1, nn, inf, reject_dist)
         iters[0] = inf["iters"]
         R_list, t_list, valid = [R], [t], np.array([True])
     Rs = np.stack(R_list)

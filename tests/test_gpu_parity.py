@@ -705,3 +705,170 @@ def test_fuzz_refinement_small_random_segments(L):
     for s, (x1, x2, _, _) in enumerate(segs):
         want = O.double_direction_refinement(x1, x2, maps[s][0], maps[s][1], nn="brute")
         np.testing.assert_array_equal(got[b.off2[s]:b.off2[s + 1]], want, err_msg=f"segment pair {s}")
+
+
+# ---- round 2: series entry points, int32 maps, reject hook, stale plans, reference rows for the chunked / tie / rank-1 cases ------
+def test_series_entry_point_equals_gathered_batch(L, syn):
+    """a growth series uploaded once (lip_series_run_host: every mesh once, per-mesh rows) gives exactly the maps of the same
+    segment pairs as a gathered batch (shared frames uploaded twice); small (one piece) and large (pipelined sub-batches),
+    pageable and pinned, int64 and int32 maps"""
+    import torch
+    for ser in (syn.make_series(1, n_frames=5, scale=0.3), syn.make_series(2, n_frames=4, plants=2)):
+        b = ser.as_batch()
+        ref = L.local_icp_batch(b)
+        ctx = L.Context(0)
+        ctx.plan(ser.off1, ser.off2, ser.lm_off)
+        T21, T12 = ctx.run_series(ser.frames, ser.row1, ser.row2, ser.lm1, ser.lm2)
+        np.testing.assert_array_equal(T21, ref.T21); np.testing.assert_array_equal(T12, ref.T12)
+        ctx.set_map_dtype(np.int32)
+        A21, A12 = ctx.run_series(ser.frames, ser.row1, ser.row2, ser.lm1, ser.lm2)
+        assert A21.dtype == np.int32
+        np.testing.assert_array_equal(A21, ref.T21); np.testing.assert_array_equal(A12, ref.T12)
+        B21, B12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)                  # the batch entry point with int32 maps
+        np.testing.assert_array_equal(B21, ref.T21); np.testing.assert_array_equal(B12, ref.T12)
+        pins = [torch.from_numpy(a).pin_memory() for a in (ser.frames, ser.lm1, ser.lm2)]
+        h21, h12 = torch.empty(len(T21), dtype=torch.int32).pin_memory(), torch.empty(len(T12), dtype=torch.int32).pin_memory()
+        ctx.run_series_ptr(pins[0].data_ptr(), len(ser.frames), ser.row1, ser.row2, pins[1].data_ptr(), pins[2].data_ptr(),
+                           h21.data_ptr(), h12.data_ptr())
+        np.testing.assert_array_equal(h21.numpy(), ref.T21); np.testing.assert_array_equal(h12.numpy(), ref.T12)
+        with pytest.raises(ValueError):                                         # a mesh that sticks out of `frames`
+            ctx.run_series(ser.frames[:-5], ser.row1, ser.row2, ser.lm1, ser.lm2)
+        ctx.close()
+
+
+def test_sharded_runner_single_rank_equals_batch_and_host_scores(L, syn):
+    """ShardedLocalICP without a process group = the whole batch on this GPU: device-resident run + score counts + the packed
+    gather reproduce the host entry points (maps of local_icp_batch, scores of evaluate_batch)"""
+    D = importlib.import_module("4d_plant_analysis_b200.distributed")
+    for data in (syn.make_series(1, n_frames=4, scale=0.3), syn.make_config(3, scale=0.1)):
+        b = data.as_batch() if hasattr(data, "frames") else data
+        ref = L.local_icp_batch(b)
+        sc = L.evaluate_batch(b, ref.T21, ref.T12, voxel_size=1.0, sample_proportion=0.5)
+        sh = D.ShardedLocalICP(data, device=0, voxel_size=1.0, sample_proportion=0.5)
+        for step in (sh.step, sh.step_from_host):
+            T21, T12, cnt = step()
+            sh.stream.synchronize()
+            np.testing.assert_array_equal(T21.cpu().numpy(), ref.T21); np.testing.assert_array_equal(T12.cpu().numpy(), ref.T12)
+            np.testing.assert_allclose(D.scores_from_counts(cnt.cpu().numpy()), sc, rtol=0, atol=1e-15)
+        sh.ctx.close()
+
+
+def test_reject_dist_matches_oracle(L):
+    """the correspondence-reject hook (north star c; NOT reference behaviour: the reference keeps every pair): pairs farther apart
+    than reject_dist leave the Kabsch sums, the cost stays the mean over all pairs"""
+    b = L.make_config(1, scale=0.2)
+    ctx = L.Context(0)
+    n_changed = 0
+    for reject in (1.2, 0.6):
+        ctx.set_params(reject_dist=reject)
+        ctx.plan(b.off1, b.off2, b.lm_off)
+        T21, T12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+        tr, raw = ctx.transforms(filled=True), ctx.transforms(filled=False)
+        for s in range(b.n_segments):
+            x1, x2, l1, l2 = b.segment(s)
+            e, f = b.lm_off[s], b.lm_off[s + 1]
+            det, det0 = {}, {}
+            T_or = O.segment_map(x1, x2, l1, l2, nn="kdtree", details=det, reject_dist=reject)
+            O.segment_map(x1, x2, l1, l2, nn="kdtree", details=det0)
+            ok = raw["status21"][e:f] == 1
+            np.testing.assert_array_equal(raw["iters21"][e:f][ok], det["iters"][ok])
+            np.testing.assert_allclose(tr["R21"][e:f][ok], det["R"][ok], rtol=0, atol=RT_TOL)
+            np.testing.assert_allclose(tr["t21"][e:f][ok], det["t"][ok], rtol=0, atol=RT_TOL)
+            n_changed += int((np.abs(det["R"] - det0["R"]).max(axis=(1, 2)) > 1e-6).sum())
+            if ok.all():
+                _assert_map_equal_up_to_ties(T21[b.off2[s]:b.off2[s + 1]], T_or, det["x2t"], x1, f"reject {reject} seg {s}")
+    assert n_changed > 0, "the threshold never rejected a pair: the test would not notice a dead hook"
+    ctx.close()
+
+
+def test_stale_plans_are_refused(L):
+    """an internal plan (lip_icp_host / lip_nn_host) or a map-mode change must not leave a runnable stale batch plan"""
+    b = L.make_config(1, scale=0.1)
+    big = L.make_config(2, scale=1.0, frame_pairs=5)                            # large enough for sub-batches (>= 400k vertices)
+    x = np.random.default_rng(3).normal(size=(40, 3))
+    for batch in (b, big):
+        ctx = L.Context(0)
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)
+        ref = ctx.run_host(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)
+        ctx.icp(x, [0, 40], x + 0.1, [0, 40])
+        with pytest.raises(L.NativeError):
+            ctx.run_host(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)
+        with pytest.raises(L.NativeError):
+            ctx.transforms()
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)                          # the same shape again: must really plan again
+        got = ctx.run_host(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)
+        np.testing.assert_array_equal(got[0], ref[0]); np.testing.assert_array_equal(got[1], ref[1])
+        ctx.nn(x, x)
+        with pytest.raises(L.NativeError):
+            ctx.run_host(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)
+        ctx.plan(batch.off1, batch.off2, batch.lm_off)
+        ctx.set_map_mode(1)
+        with pytest.raises(L.NativeError):
+            ctx.run_host(batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)
+        ctx.close()
+
+
+def test_reference_rows_chunked_k1_ties_and_rank1(L):
+    """tests/golden/edge_r2.npz (recorded from the unmodified reference by make_golden_r2.py):
+    seg 0  K == 1, 2,500 x 2,600 vertices: icp_big_kernel's multi-chunk path against reference rows;
+    seg 1  lattice segment, partitions of > 80 points with exact float64 distance ties: sklearn breaks them by tree traversal
+           order, this library by lowest index, so the GPU must equal the lowest-index oracle bit for bit,
+           and differ from the reference's first NN pass only where two target points are exactly equidistant;
+    seg 2  2-point and collinear partitions (rank-1 Kabsch): reported, R is LAPACK-arbitrary there"""
+    g = load_golden("edge_r2")
+    res = L.local_icp_batch(_batch_from_golden(L, g), details=True)
+    raw = res.transforms["raw"]
+    segs = list(golden_segments(g))
+    # seg 0: reference rows
+    s, x1, x2, l1, l2 = segs[0]
+    for d in ("21", "12"):
+        assert raw["status" + d][0] == 1 and raw["iters" + d][0] == g["it" + d][0]
+        np.testing.assert_allclose(raw["R" + d][0], g["R" + d][0], rtol=0, atol=RT_TOL)
+        np.testing.assert_allclose(raw["t" + d][0], g["t" + d][0], rtol=0, atol=RT_TOL)
+    det = {}
+    O.segment_map(x1, x2, l1, l2, nn="kdtree", details=det)
+    assert _assert_map_equal_up_to_ties(res.maps(0)[0], g["T21"][g["off2"][0]:g["off2"][1]], det["x2t"], x1, "k1 big T21") == 0
+    # seg 1: lowest-index semantics, exactly
+    s, x1, x2, l1, l2 = segs[1]
+    e, f = g["lm_off"][1], g["lm_off"][2]
+    det = {}
+    T_low = O.segment_map(x1, x2, l1, l2, nn="brute", details=det)
+    np.testing.assert_array_equal(res.maps(1)[0], T_low)
+    np.testing.assert_array_equal(raw["iters21"][e:f], det["iters"])
+    np.testing.assert_allclose(res.transforms["R21"][e:f], det["R"], rtol=0, atol=1e-9)
+    # ... and the reference's own picks differ from lowest-index picks only at exact ties (first NN pass of partition 0)
+    nn1 = det["nn1"][:, 0]; nn2 = det["nn2"][:, 0]
+    tgt, src = x1[nn1 == 0], x2[nn2 == 0]
+    src0 = src + (tgt.mean(axis=0) - src.mean(axis=0))
+    d_tree, i_tree = O.nn_in_target(src0, tgt, nn="kdtree")
+    d_low, i_low = O.nn_in_target(src0, tgt, nn="brute")
+    assert len(tgt) > 80 and (i_tree != i_low).any(), "the case must exercise sklearn's traversal-order tie-break"
+    np.testing.assert_array_equal(np.asarray(d_tree).reshape(-1), np.asarray(d_low).reshape(-1))
+    # seg 2: rank-1 partitions — every full-rank partition matches the reference rows; the map mismatch rate is reported
+    s, x1, x2, l1, l2 = segs[2]
+    e, f = g["lm_off"][2], g["lm_off"][3]
+    st = raw["status21"][e:f]
+    assert (st == 2).any(), "the thin ends must produce rank-deficient solves"
+    ok = st == 1
+    np.testing.assert_array_equal(raw["iters21"][e:f][ok], g["it21"][e:f][ok])
+    np.testing.assert_allclose(raw["R21"][e:f][ok], g["R21"][e:f][ok], rtol=0, atol=RT_TOL)
+    c, d = g["off2"][2], g["off2"][3]
+    mism = float((res.maps(2)[0] != g["T21"][c:d]).mean())
+    print(f"rank-1 partitions: {int((st == 2).sum())} of {len(st)}, map mismatch rate vs reference {mism:.4f}")
+    assert mism <= 0.10
+
+
+def test_two_gpu_sharded_run_equals_single_gpu(L):
+    """world_size 2 over NCCL (skipped below two GPUs): C4 by frame pair with the boundary frame sent over NVLink, C5-like by
+    cost; gathered maps and score counts equal the single-GPU run on every rank (tools/dist_check.py)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("dist_check ok") == 2

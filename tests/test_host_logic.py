@@ -75,28 +75,69 @@ def test_sharding():
     fp = np.repeat(np.arange(15), 2)
     sh = D.shard_segments(np.ones(30), 8, fp)
     assert [len(s) // 2 for s in sh] == [2, 2, 2, 2, 2, 2, 2, 1]
+    assert all(np.array_equal(x, np.arange(x[0], x[-1] + 1)) for x in sh)      # contiguous blocks: shared frames stay on a rank
+    # the re-assembly indices of the packed gather address every entry exactly once
+    off1, off2, lmo = np.array([0, 5, 9, 12]), np.array([0, 4, 10, 11]), np.array([0, 2, 3, 5])
+    plan = D.make_shard_plan(off1, off2, lmo, 2)
+    allidx = np.concatenate([plan.index21, plan.index12, plan.index_cnt])
+    assert len(np.unique(allidx)) == len(allidx) and allidx.max() < 2 * plan.pad
+    assert plan.sizes[:, 0].sum() == 11 and plan.sizes[:, 1].sum() == 12 and plan.sizes[:, 2].sum() == 3
+
+
+def test_series_batch_views_and_subseries(syn):
+    """a growth series stores every frame once; as_batch() gathers what the batched entry point would upload; a sub-series
+    keeps exactly the meshes its frame pairs use"""
+    ser = syn.make_series(1, n_frames=5, scale=0.1)
+    b = ser.as_batch()
+    assert ser.n_frame_pairs == 4 and ser.n_segments == 4 * 3 and b.n_correspondences == ser.n_correspondences
+    assert len(ser.frames) < len(b.xyz1) + len(b.xyz2)                       # interior frames are shared
+    # frame k is mesh2 of frame pair k-1 and mesh1 of frame pair k
+    for s in range(3, 6):
+        np.testing.assert_array_equal(b.segment(s)[0], b.segment(s - 3)[1])
+    sub = ser.take_frame_pairs([1, 2])
+    sb, ref = sub.as_batch(), b.take(np.nonzero(np.isin(b.frame_pair, [1, 2]))[0])
+    np.testing.assert_array_equal(sb.xyz1, ref.xyz1); np.testing.assert_array_equal(sb.xyz2, ref.xyz2)
+    np.testing.assert_array_equal(sb.lm1, ref.lm1); np.testing.assert_array_equal(sb.lm_off, ref.lm_off)
+    assert len(sub.frames) == sum(len(b.segment(s)[0]) for s in range(3, 6)) + sum(len(b.segment(s)[1]) for s in range(3, 9))
 
 
 _WORKER = r'''
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.environ["LIP_ROOT"])
-import torch.distributed as dist
+import torch, torch.distributed as dist
 dist.init_process_group("gloo")
 D = importlib.import_module("4d_plant_analysis_b200.distributed")
 syn = importlib.import_module("4d_plant_analysis_b200.synthetic")
 from oracle import local_icp_oracle as O      # the CPU checker stands in for the GPU compute in this host-logic test
-b = syn.make_config(1, scale=0.2)
 def compute(sub):
-    T21, T12 = [], []
+    T21, T12, cnt = [], [], []
     for s in range(sub.n_segments):
         a, c = O.segment_pair_maps(*sub.segment(s), nn="brute")
         T21.append(a); T12.append(c)
-    return np.concatenate(T21), np.concatenate(T12)
-T21, T12, mine = D.local_icp_distributed(b, compute=compute, gather=True)
-R21, R12 = compute(b)
+        cnt.append([len(a), len(c), int(a.sum() % 1000), 7, int(c.sum() % 1000), 2 ** 40 + len(a)])      # stand-in int64 score counts
+    return np.concatenate(T21), np.concatenate(T12), np.array(cnt, np.int64)
+# (1) one frame pair: segment pairs dealt by cost (longest processing time first)
+b = syn.make_config(1, scale=0.2)
+T21, T12, mine, cnt = D.local_icp_distributed(b, compute=compute, gather=True)
+R21, R12, Rc = compute(b)
 assert np.array_equal(T21, R21) and np.array_equal(T12, R12), "gathered maps differ from the single-process result"
+assert np.array_equal(cnt, Rc), "gathered score counts differ"
 assert 0 < len(mine) < b.n_segments
+# (2) a growth series: whole frame pairs in contiguous blocks, every rank keeps the frames its pairs share
+ser = syn.make_series(1, n_frames=4, scale=0.07)
+sb = ser.as_batch()
+T21, T12, mine, cnt = D.local_icp_distributed(sb, compute=compute, gather=True)
+R21, R12, Rc = compute(sb)
+assert np.array_equal(T21, R21) and np.array_equal(T12, R12) and np.array_equal(cnt, Rc)
+fps = np.unique(sb.frame_pair[mine])
+assert np.array_equal(fps, np.arange(fps.min(), fps.max() + 1)), "frame pairs of a rank must be contiguous"
+# (3) the packed gather on raw tensors: int32 maps + int64 counts in ONE all_gather_into_tensor
+plan = D.make_shard_plan(sb.off1, sb.off2, sb.lm_off, 2, sb.frame_pair, exchange=True)
+sub = sb.take(plan.seg_ids[dist.get_rank()])
+l21, l12, lc = compute(sub)
+g21, g12, gc = D.gather_results(plan, torch.as_tensor(l21), torch.as_tensor(l12), torch.as_tensor(lc))
+assert g21.dtype == torch.int32 and np.array_equal(g21.numpy(), R21) and np.array_equal(g12.numpy(), R12) and np.array_equal(gc.numpy(), Rc)
 print("rank", dist.get_rank(), "ok", len(mine))
 dist.destroy_process_group()
 '''
