@@ -46,13 +46,20 @@ struct LipArgs {
     const int* bin_mesh;     // [B]   mesh of each bin
     const int* tile_mesh;    // [n_tiles] blend/query tiles: mesh and first local vertex
     const int* tile_first;   // [n_tiles]
+    const int* ptile_mesh;   // [n_ptiles] tiles of the partition kernels (LIP_PART_CHUNK vertices of one mesh, every mesh): mesh,
+    const int* ptile_first;  // [n_ptiles] first local vertex,
+    const int* ptile_cnt;    // [n_ptiles + 1] offset of the tile's per-landmark counts in tile_cnt;
+    const int* mesh_ptile;   // [M+1] first tile of each mesh
+    int* tile_cnt;           // per (tile, landmark of its mesh): members in this tile
+    int* tile_base;          // ... and in the earlier tiles of the mesh (partition_scan_kernel)
+    float4* bin_tmp;         // [n_total] fp32 offset from the bin's landmark + local vertex id, bins in member (vertex) order
+    double* tile_sum;        // [n_ptiles * 4] coordinate sums of the tile's vertices
     int *nn0, *nn1;          // [n_total] nearest / second nearest landmark (local index)
     double *d0, *d1;         // [n_total] their distances
     int* bin_off;            // [B+1] unified start of each bin in part_vid
     int* part_vid;           // [n_total] local vertex ids grouped by bin, ascending inside a bin
     int* nn_idx;             // [n_total] ICP scratch: current nearest-neighbour index of every source point (same layout)
     float4* bin_pts;         // [n_total] vertices in part_vid order as fp32 offsets from their OWN landmark, .w = local vertex id
-    float4* bin_tmp;         // [n_total] the same in vertex order inside each bin (scratch of the partition kernel)
     double* bin_xyz;         // [3 * n_total] the same vertices in float64, planes x | y | z in part_vid order
     double* bin_q;           // [3 * n_total] blended positions of the source vertices (blend_kernel), same layout
     int *pos_bin, *pos_nn1;  // [n_total] bin and second-nearest landmark of every slot (bin order)

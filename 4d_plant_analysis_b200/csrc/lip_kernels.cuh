@@ -37,12 +37,15 @@
 #endif
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
 #ifndef LIP_MAP_THREADS
-#define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA, two queries per thread
+#define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA
 #endif
+#ifndef LIP_MAP_Q
+#define LIP_MAP_Q 2          // ... and queries per thread.  Measured (profiles/README.md, round 2): 3 / 4 queries per thread (a ~150-point
+#endif                       // bin as ONE tile, fewer LDS per score) lose to 2 — 1.24 / 1.34 ms against 1.13: the box cull works per tile
 #ifndef LIP_MAP_MINBLOCKS
-#define LIP_MAP_MINBLOCKS 12 // CTAs per SM blend_tile_kernel is compiled for
+#define LIP_MAP_MINBLOCKS (LIP_MAP_Q > 2 ? 8 : 12) // CTAs per SM blend_tile_kernel is compiled for
 #endif
-#define LIP_MAP_TILE (2 * LIP_MAP_THREADS)
+#define LIP_MAP_TILE (LIP_MAP_Q * LIP_MAP_THREADS)
 #ifndef LIP_MAP_CHUNK
 #define LIP_MAP_CHUNK 512    // candidates staged per scan
 #endif
@@ -54,231 +57,373 @@
 // =============================================================================================
 // K0  landmark assignment + stable partition of every mesh by nearest landmark
 //     replaces KDTree(lm).query(xyz, k=2) and the boolean masks NN_skel[:,0]==i
-//     (p2p_matching_in_organ/p2p_matching_seg_icp.py:388-392, 413-414).  One CTA per mesh.
+//     (p2p_matching_in_organ/p2p_matching_seg_icp.py:388-392, 413-414).
+//     Four grid-wide kernels over tiles of LIP_PART_CHUNK vertices of one mesh (no per-mesh CTA, no chain of
+//     barrier-separated phases: the parallelism is the vertex count of the batch, not the mesh count):
+//       landmark_nn_kernel      two nearest landmarks of every vertex (index order, strict '<' = sklearn's single-leaf scan),
+//                               counts per (tile, landmark), coordinate sums per tile
+//       partition_scan_kernel   per mesh: bin offsets (exclusive scan over landmarks) and, per (tile, landmark), the number of
+//                               members in earlier tiles
+//       partition_place_kernel  stable placement (ascending vertex id inside a bin, as the reference's boolean masks give it):
+//                               writes every bin-ordered array the later kernels read coalesced
+//       bin_stats_kernel        per bin: box of the fp32 offsets, float64 mean
 // =============================================================================================
-__global__ void __launch_bounds__(256, 3) landmark_partition_kernel(LipArgs a) {
+#ifndef LIP_PART_CHUNK
+#define LIP_PART_CHUNK 512
+#endif
+#define LIP_PART_THREADS 256
+__global__ void __launch_bounds__(LIP_PART_THREADS) landmark_nn_kernel(LipArgs a) {
     extern __shared__ double smem_d[];
-    __shared__ double msum[8][3];
-    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    __shared__ double tsum[LIP_PART_THREADS / 32][3];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = a.ptile_mesh[t], first = a.ptile_first[t];
     const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
     const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
-    const double* xyz = mesh_xyz(a, m);
-    const double* lm = mesh_lm(a, m);
-    double* lmS = smem_d;
-    int* hist = (int*)(lmS + 3 * K);
-    int* excl = hist + K;                                   // K+1 entries
-    for (int i = tid; i < 3 * K; i += blockDim.x) lmS[i] = lm[i];
-    for (int i = tid; i < K; i += blockDim.x) hist[i] = 0;
+    const double* __restrict__ xyz = mesh_xyz(a, m);
+    const double* __restrict__ lm = mesh_lm(a, m);
+    double* lmS = smem_d;                                    // landmarks, float64
+    float4* lmF = (float4*)(lmS + 3 * K + (K & 1));          // ... and as fp32 offsets from landmark 0 (the prefilter), 16-byte aligned
+    int* hist = (int*)(lmF + K);
+    constexpr int PER = LIP_PART_CHUNK / LIP_PART_THREADS;
+    const int end = min(n, first + LIP_PART_CHUNK);
+    double px[PER], py[PER], pz[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {                          // the vertex loads are in flight while the landmarks are staged
+        const int v = min(first + r * LIP_PART_THREADS + tid, end - 1);
+        px[r] = xyz[3 * (size_t)v]; py[r] = xyz[3 * (size_t)v + 1]; pz[r] = xyz[3 * (size_t)v + 2];
+    }
+    const double o0 = lm[0], o1 = lm[1], o2 = lm[2];
+    for (int i = tid; i < K; i += LIP_PART_THREADS) {
+        const double l0 = lm[3 * i], l1 = lm[3 * i + 1], l2 = lm[3 * i + 2];
+        lmS[3 * i] = l0; lmS[3 * i + 1] = l1; lmS[3 * i + 2] = l2;
+        lmF[i] = make_float4((float)(l0 - o0), (float)(l1 - o1), (float)(l2 - o2), 0.f);
+        hist[i] = 0;
+    }
     __syncthreads();
+    // fp32 prefilter: the three nearest landmarks in fp32 (the tile's vertices of a thread side by side: independent chains,
+    // one broadcast LDS.128 per landmark for all of them); if the third is clearly farther than the second (beyond a bound on
+    // the fp32 evaluation error) the two nearest are among the three, and only those are evaluated in float64 — in index order
+    // with strict '<', which is what the scan over all K gives.  Otherwise (rare) the full float64 scan decides.
+    // The landmark index rides in the low mantissa bits of the fp32 score, so that the three smallest (score, index) keys come
+    // out of a branch-free min / max network (landmarks lie along the skeleton: the running minimum improves at almost every
+    // step up to the nearest one, a compare-and-branch update would diverge all the way).
+    float xf[PER], yf[PER], zf[PER], b0[PER], b1[PER], b2[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        xf[r] = (float)(px[r] - o0); yf[r] = (float)(py[r] - o1); zf[r] = (float)(pz[r] - o2);
+        b0[r] = b1[r] = b2[r] = INFINITY;
+    }
+    int ibits = 1;
+    while ((1 << ibits) < K) ++ibits;                        // <= 11 (LIP_MAX_LANDMARKS = 2048)
+    const unsigned imask = (1u << ibits) - 1u;
+    if (K > 3) {
+#pragma unroll 2
+        for (int i = 0; i < K; ++i) {
+            const float4 l = lmF[i];
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const float dx = xf[r] - l.x, dy = yf[r] - l.y, dz = zf[r] - l.z;
+                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float key = __uint_as_float((__float_as_uint(d) & ~imask) | (unsigned)i);     // d >= 0: keys order like (d rounded down, i)
+                const float m0 = fminf(b0[r], key); key = fmaxf(b0[r], key); b0[r] = m0;
+                const float m1 = fminf(b1[r], key); key = fmaxf(b1[r], key); b1[r] = m1;
+                b2[r] = fminf(b2[r], key);
+            }
+        }
+    }
     double sx = 0, sy = 0, sz = 0;
-    double nx = 0, ny = 0, nz = 0;                           // the next vertex of this thread: its load is in flight during the scan
-    if (tid < n) { nx = xyz[3 * (size_t)tid]; ny = xyz[3 * (size_t)tid + 1]; nz = xyz[3 * (size_t)tid + 2]; }
-    for (int v = tid; v < n; v += blockDim.x) {
-        const double x = nx, y = ny, z = nz;
-        const int vn = v + blockDim.x;
-        if (vn < n) { nx = xyz[3 * (size_t)vn]; ny = xyz[3 * (size_t)vn + 1]; nz = xyz[3 * (size_t)vn + 2]; }
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int v = first + r * LIP_PART_THREADS + tid;
+        if (v >= end) continue;
+        const double x = px[r], y = py[r], z = pz[r];
         sx += x; sy += y; sz += z;
         double best = INFINITY, sec = INFINITY;
         int i0 = 0, i1 = 0;
-        for (int i = 0; i < K; ++i) {                       // index order, strict '<': sklearn single-leaf scan
-            double d = rdist64(x, y, z, lmS[3 * i], lmS[3 * i + 1], lmS[3 * i + 2]);
-            if (d < best) { sec = best; i1 = i0; best = d; i0 = i; }
-            else if (d < sec) { sec = d; i1 = i; }
+        bool decided = false;
+        if (K > 3) {
+            // |fp32 distance - true distance| <= e for every landmark at most sqrt(b2) away: input roundings 2^-24 (|q| + |l|) per
+            // coordinate with |l| <= |q| + d, three roundings in the sum; 1e-6 (...) is > 8x that
+            // the key drops `ibits` mantissa bits of d^2 (relative 2^(ibits-23), i.e. 2^(ibits-24) of the distance)
+            const int ja = (int)(__float_as_uint(b0[r]) & imask), jb = (int)(__float_as_uint(b1[r]) & imask), jc = (int)(__float_as_uint(b2[r]) & imask);
+            const float s1 = sqrtf(b1[r]), s2 = sqrtf(b2[r]);
+            const float e = 1e-6f * (1.f + 2.f * (fabsf(xf[r]) + fabsf(yf[r]) + fabsf(zf[r])) + s2) + s2 * (float)(1u << ibits) * 1.2e-7f;
+            if (s2 - s1 > 2.f * e) {
+                const int lo = min(ja, min(jb, jc)), hi = max(ja, max(jb, jc)), mid = ja + jb + jc - lo - hi;
+                const int cand[3] = {lo, mid, hi};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = cand[k];
+                    const double d = rdist64(x, y, z, lmS[3 * i], lmS[3 * i + 1], lmS[3 * i + 2]);
+                    if (d < best) { sec = best; i1 = i0; best = d; i0 = i; }
+                    else if (d < sec) { sec = d; i1 = i; }
+                }
+                decided = true;
+            }
+        }
+        if (!decided) {
+            best = INFINITY; sec = INFINITY; i0 = 0; i1 = 0;
+            for (int i = 0; i < K; ++i) {                   // index order, strict '<': sklearn single-leaf scan
+                const double d = rdist64(x, y, z, lmS[3 * i], lmS[3 * i + 1], lmS[3 * i + 2]);
+                if (d < best) { sec = best; i1 = i0; best = d; i0 = i; }
+                else if (d < sec) { sec = d; i1 = i; }
+            }
         }
         if (K == 1) { sec = best; i1 = i0; }
         a.nn0[ub + v] = i0; a.nn1[ub + v] = i1;
         a.d0[ub + v] = sqrt(best); a.d1[ub + v] = sqrt(sec);
-        atomicAdd(&hist[i0], 1);
+        atomicAdd(&hist[i0], 1);                             // integer adds commute: deterministic
     }
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    if (lane == 0) { msum[warp][0] = sx; msum[warp][1] = sy; msum[warp][2] = sz; }
+    if (lane == 0) { tsum[warp][0] = sx; tsum[warp][1] = sy; tsum[warp][2] = sz; }
     __syncthreads();
-    if (tid < 3) {                                          // vertex sum of the mesh (mean-shift fallback of the fill step)
+    if (tid < 3) {
         double s = 0;
-        for (int w = 0; w < nwarps; ++w) s += msum[w][tid];
-        a.mesh_sum[4 * (size_t)m + tid] = s;
+        for (int w = 0; w < LIP_PART_THREADS / 32; ++w) s += tsum[w][tid];
+        a.tile_sum[4 * (size_t)t + tid] = s;
     }
-    if (tid == 3) a.mesh_sum[4 * (size_t)m + 3] = (double)n;
-    if (warp == 0) {                                        // exclusive scan of the K bin counts
-        int running = 0;
-        for (int base = 0; base < K; base += 32) {
-            int i = base + lane;
-            int c = (i < K) ? hist[i] : 0, inc = c;
+    int* __restrict__ cnt = a.tile_cnt + a.ptile_cnt[t];
+    for (int i = tid; i < K; i += LIP_PART_THREADS) cnt[i] = hist[i];
+}
+
+// one warp per mesh: bin offsets; per (tile, landmark) the number of members in earlier tiles (tile_base)
+__global__ void __launch_bounds__(128) partition_scan_kernel(LipArgs a) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= a.M) return;
+    const int t0 = a.mesh_ptile[m], t1 = a.mesh_ptile[m + 1];
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const int* __restrict__ cnt = a.tile_cnt + a.ptile_cnt[t0];
+    int* __restrict__ tb = a.tile_base + a.ptile_cnt[t0];
+    int running = 0;
+    for (int base = 0; base < K; base += 32) {
+        const int i = base + lane;
+        int tot = 0;
+        if (i < K)
+            for (int t = t0; t < t1; ++t) {
+                const size_t o = (size_t)(t - t0) * K + i;
+                tb[o] = tot;
+                tot += cnt[o];
+            }
+        int inc = tot;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
-            if (i < K) excl[i] = running + inc - c;
-            running += __shfl_sync(LIP_FULL, inc, 31);
-        }
-        if (lane == 0) excl[K] = running;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += u; }
+        if (i < K) a.bin_off[bb + i] = ub + running + inc - tot;
+        running += __shfl_sync(LIP_FULL, inc, 31);
     }
+    if (m == a.M - 1 && lane == 0) a.bin_off[a.B] = a.n_total;
+    if (lane < 3) {                                          // vertex sum of the mesh (mean-shift fallback of the fill step), fixed order
+        double s = 0;
+        for (int t = t0; t < t1; ++t) s += a.tile_sum[4 * (size_t)t + lane];
+        a.mesh_sum[4 * (size_t)m + lane] = s;
+    }
+    if (lane == 3) a.mesh_sum[4 * (size_t)m + 3] = (double)n;
+}
+
+// Stable placement of a tile's vertices into the member lists of their bins (ascending vertex id inside a bin, as the boolean
+// masks of the reference give it).  Rank of a vertex among the tile's members of its bin = rank inside the warp
+// (__match_any_sync) + members in the earlier warps of the round (per-warp counts) + members in earlier rounds (cursors).  The
+// records (fp32 offset from the bin's own landmark, vertex id) are first sorted by bin inside SMEM, so that the members a tile
+// contributes to one bin leave as one contiguous run: coalesced 16-byte stores instead of one scattered store per vertex.
+__global__ void __launch_bounds__(LIP_PART_THREADS) partition_place_kernel(LipArgs a) {
+    extern __shared__ int smem_i[];
+    __shared__ float4 rec[LIP_PART_CHUNK];
+    __shared__ int dst[LIP_PART_CHUNK];
+    __shared__ int wtot[LIP_PART_THREADS / 32];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = LIP_PART_THREADS / 32;
+    const int m = a.ptile_mesh[t], first = a.ptile_first[t];
+    const int ub = a.mesh_ubase[m], n = a.mesh_ubase[m + 1] - ub;
+    const int bb = a.mesh_bin[m], K = a.mesh_bin[m + 1] - bb;
+    const double* __restrict__ xyz = mesh_xyz(a, m);
+    const double* __restrict__ lm = mesh_lm(a, m);
+    const int* __restrict__ cnt = a.tile_cnt + a.ptile_cnt[t];
+    const int* __restrict__ tb = a.tile_base + a.ptile_cnt[t];
+    int* lstart = smem_i;                                    // K: first SMEM slot of every bin's run, then its cursor
+    int* gbase = lstart + K;                                 // K: global position of the run's first member minus its first slot
+    int* wcnt = gbase + K;                                   // NW x K per-warp counts of the current round
+    // exclusive scan of the tile's K counts (each thread a contiguous piece)
+    const int per = (K + LIP_PART_THREADS - 1) / LIP_PART_THREADS;
+    int mine = 0;
+    for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < K) mine += cnt[i]; }
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) wtot[warp] = inc;
+    for (int i = tid; i < NW * K; i += LIP_PART_THREADS) wcnt[i] = 0;
     __syncthreads();
-    for (int i = tid; i < K; i += blockDim.x) a.bin_off[bb + i] = ub + excl[i];
-    if (m == a.M - 1 && tid == 0) a.bin_off[a.B] = a.n_total;
-    // Stable partition of the vertices by nearest landmark (ascending vertex id inside a bin, as the boolean
-    // masks of the reference give it), one chunk of blockDim vertices at a time: rank inside the warp by
-    // __match_any_sync, offsets of the earlier warps of the chunk from per-warp bin counts, running bin
-    // cursors across chunks.  Besides the member list it writes the bin's points as fp32 offsets from the
-    // bin's own landmark: the search tiles of the ICP and of the final map are assembled from these with
-    // coalesced 16-byte loads.
-    int* running = excl + K + 1;                            // K cursors
-    int* wcnt = running + K;                                // nwarps x K per-warp counts of the current chunk
-    for (int i = tid; i < K; i += blockDim.x) running[i] = excl[i];
-    for (int i = tid; i < nwarps * K; i += blockDim.x) wcnt[i] = 0;
+    int run = inc - mine;
+    for (int w = 0; w < warp; ++w) run += wtot[w];
+    for (int k = 0; k < per; ++k) {
+        const int i = tid * per + k;
+        if (i < K) { lstart[i] = run; gbase[i] = a.bin_off[bb + i] + tb[i] - run; run += cnt[i]; }
+    }
+    const int end = min(n, first + LIP_PART_CHUNK);
     __syncthreads();
-    int bin_n = -1;                                          // this thread's vertex of the NEXT chunk: loads in flight across the barriers
-    double px = 0, py = 0, pz = 0;
-    if (tid < n) { bin_n = a.nn0[ub + tid]; px = xyz[3 * (size_t)tid]; py = xyz[3 * (size_t)tid + 1]; pz = xyz[3 * (size_t)tid + 2]; }
-    for (int base = 0; base < n; base += blockDim.x) {
+    for (int base = first; base < end; base += LIP_PART_THREADS) {
         const int v = base + tid;
-        const int bin = bin_n;
-        const double vx = px, vy = py, vz = pz;
-        {
-            const int vn = v + blockDim.x;
-            bin_n = -1;
-            if (vn < n) { bin_n = a.nn0[ub + vn]; px = xyz[3 * (size_t)vn]; py = xyz[3 * (size_t)vn + 1]; pz = xyz[3 * (size_t)vn + 2]; }
+        int bin = -1;
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < end) {
+            bin = a.nn0[ub + v];
+            r4 = make_float4((float)(xyz[3 * (size_t)v] - lm[3 * bin]), (float)(xyz[3 * (size_t)v + 1] - lm[3 * bin + 1]),
+                             (float)(xyz[3 * (size_t)v + 2] - lm[3 * bin + 2]), __int_as_float(v));
         }
         const unsigned peers = __match_any_sync(LIP_FULL, bin);
         const int rank = __popc(peers & ((1u << lane) - 1));
         if (bin >= 0 && rank == 0) wcnt[warp * K + bin] = __popc(peers);
         __syncthreads();
         if (bin >= 0) {
-            int pos = ub + running[bin] + rank;
-            for (int w = 0; w < warp; ++w) pos += wcnt[w * K + bin];
-            const float fx = (float)(vx - lmS[3 * bin]), fy = (float)(vy - lmS[3 * bin + 1]), fz = (float)(vz - lmS[3 * bin + 2]);
-            a.bin_tmp[pos] = make_float4(fx, fy, fz, __int_as_float(v));
+            int slot = lstart[bin] + rank;
+            for (int w = 0; w < warp; ++w) slot += wcnt[w * K + bin];
+            rec[slot] = r4;
+            dst[slot] = gbase[bin] + slot;
         }
         __syncthreads();
-        if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the chunk
-            atomicAdd(&running[bin], __popc(peers));         // integer adds commute: the cursors stay deterministic
+        if (bin >= 0 && rank == 0) {                         // one lane per (warp, bin) present in the round
+            atomicAdd(&lstart[bin], __popc(peers));          // integer adds commute: the cursors stay deterministic
             wcnt[warp * K + bin] = 0;
         }
         __syncthreads();
     }
-    // per bin (one warp): bounding box of the fp32 offsets, float64 mean of the vertices (in member order: the means
-    // give my_icp's initial translation, registration_icp.py:70, and the centre of the ICP frame), and the FINAL
-    // order of the bin: members sorted along the axis of the box's largest extent (stable counting sort by an
-    // 8-bit key = position along the axis in 1/256 of the extent), so that every search can be restricted to a
-    // window of the list around the query.  Windows are certified from exact per-block bounds, so the order only
-    // has to be approximately monotone; ties are always decided by vertex id.  Bins of up to 256 members (the
-    // usual case) are held in registers across the passes and permuted through SMEM: every global store coalesced.
-    unsigned* skey = (unsigned*)(wcnt + nwarps * K) + warp * 256;                    // 256 bucket counters per warp
-    float4* sdat = (float4*)(((size_t)((unsigned*)(wcnt + nwarps * K) + nwarps * 256) + 15) & ~(size_t)15) + warp * 256;   // the bin in sorted order
+    for (int j = tid; j < end - first; j += LIP_PART_THREADS) a.bin_tmp[dst[j]] = rec[j];
+}
+
+// per bin (one warp): bounding box of the fp32 offsets, float64 mean of the vertices (in member order: the means
+// give my_icp's initial translation, registration_icp.py:70, and the centre of the ICP frame), and the FINAL
+// order of the bin: members sorted along the axis of the box's largest extent (stable counting sort by an
+// 8-bit key = position along the axis in 1/256 of the extent): spatially neighbouring queries share a warp (their
+// winners' float64 gathers hit the same lines) and the boxes of query tiles are tight.  Ties are always decided by vertex id.
+// Bins of up to 256 members (the usual case) are held in registers across the passes and permuted through SMEM: every
+// global store coalesced.
+#define LIP_SORT_WARPS 4
+__global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a) {
+    __shared__ unsigned skey_all[LIP_SORT_WARPS][256];
+    __shared__ float4 sdat_all[LIP_SORT_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * LIP_SORT_WARPS + warp;
+    if (b >= a.B) return;
+    const int m = a.bin_mesh[b];
+    const int ub = a.mesh_ubase[m];
+    const double* __restrict__ xyz = mesh_xyz(a, m);
+    unsigned* skey = skey_all[warp];
+    float4* sdat = sdat_all[warp];
     const size_t N = (size_t)a.n_total;
-    for (int i = warp; i < K; i += nwarps) {
-        const int s0 = ub + excl[i], e0 = ub + excl[i + 1], nb = e0 - s0;
-        const bool fast = nb <= 256;
-        float4 tt[8];
-        float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
-        double bx0 = 0, bx1 = 0, bx2 = 0;
-        if (fast) {
+    {
+    const int s0 = a.bin_off[b], e0 = a.bin_off[b + 1], nb = e0 - s0;
+    const bool fast = nb <= 256;
+    float4 tt[8];
+    float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
+    double bx0 = 0, bx1 = 0, bx2 = 0;
+    if (fast) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const int e = lane + 32 * k; if (e < nb) tt[k] = a.bin_tmp[s0 + e]; }
+        for (int k = 0; k < 8; ++k) { const int e = lane + 32 * k; if (e < nb) tt[k] = a.bin_tmp[s0 + e]; }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (lane + 32 * k >= nb) continue;
-                const float4 t = tt[k];
-                lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
-                hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
-                const size_t v = (size_t)__float_as_int(t.w);
-                bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
-            }
-        } else {
-            for (int p = s0 + lane; p < e0; p += 32) {
-                const float4 t = a.bin_tmp[p];
-                lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
-                hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
-                const size_t v = (size_t)__float_as_int(t.w);
-                bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
-            }
+        for (int k = 0; k < 8; ++k) {
+            if (lane + 32 * k >= nb) continue;
+            const float4 t = tt[k];
+            lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
+            hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
+            const size_t v = (size_t)__float_as_int(t.w);
+            bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
         }
-        lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
-        hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
-        bx0 = warp_sum(bx0); bx1 = warp_sum(bx1); bx2 = warp_sum(bx2);
-        const float ex0 = hi0 - lo0, ex1 = hi1 - lo1, ex2 = hi2 - lo2;
-        const int axis = (ex0 >= ex1 && ex0 >= ex2) ? 0 : (ex1 >= ex2) ? 1 : 2;
-        if (lane == 0) {
-            float* bx = a.bin_box + 8 * (size_t)(bb + i);
-            bx[0] = lo0; bx[1] = lo1; bx[2] = lo2; bx[3] = hi0; bx[4] = hi1; bx[5] = hi2;
-            bx[6] = fmaxf(fmaxf(fmaxf(fabsf(lo0), fabsf(hi0)), fmaxf(fabsf(lo1), fabsf(hi1))), fmaxf(fabsf(lo2), fabsf(hi2)));
-            bx[7] = (float)axis;
-            double* bs = a.bin_sum + 4 * (size_t)(bb + i);
-            const double cnt = (double)nb;
-            bs[0] = bx0 / cnt; bs[1] = bx1 / cnt; bs[2] = bx2 / cnt; bs[3] = cnt;     // (NaN for an empty bin: never read)
+    } else {
+        for (int p = s0 + lane; p < e0; p += 32) {
+            const float4 t = a.bin_tmp[p];
+            lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
+            hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
+            const size_t v = (size_t)__float_as_int(t.w);
+            bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
         }
-        const float alo = axis == 0 ? lo0 : axis == 1 ? lo1 : lo2, aex = axis == 0 ? ex0 : axis == 1 ? ex1 : ex2;
-        const float scale = 255.999f / fmaxf(aex, 1e-30f);
-        auto bucket_of = [&](const float4& t) {
-            const float c = axis == 0 ? t.x : axis == 1 ? t.y : t.z;
-            return (int)fminf(fmaxf((c - alo) * scale, 0.f), 255.f);
-        };
-        __syncwarp();
+    }
+    lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
+    hi0 = warp_maxf(hi0); hi1 = warp_maxf(hi1); hi2 = warp_maxf(hi2);
+    bx0 = warp_sum(bx0); bx1 = warp_sum(bx1); bx2 = warp_sum(bx2);
+    const float ex0 = hi0 - lo0, ex1 = hi1 - lo1, ex2 = hi2 - lo2;
+    const int axis = (ex0 >= ex1 && ex0 >= ex2) ? 0 : (ex1 >= ex2) ? 1 : 2;
+    if (lane == 0) {
+        float* bx = a.bin_box + 8 * (size_t)(b);
+        bx[0] = lo0; bx[1] = lo1; bx[2] = lo2; bx[3] = hi0; bx[4] = hi1; bx[5] = hi2;
+        bx[6] = fmaxf(fmaxf(fmaxf(fabsf(lo0), fabsf(hi0)), fmaxf(fabsf(lo1), fabsf(hi1))), fmaxf(fabsf(lo2), fabsf(hi2)));
+        bx[7] = (float)axis;
+        double* bs = a.bin_sum + 4 * (size_t)(b);
+        const double cnt = (double)nb;
+        bs[0] = bx0 / cnt; bs[1] = bx1 / cnt; bs[2] = bx2 / cnt; bs[3] = cnt;     // (NaN for an empty bin: never read)
+    }
+    const float alo = axis == 0 ? lo0 : axis == 1 ? lo1 : lo2, aex = axis == 0 ? ex0 : axis == 1 ? ex1 : ex2;
+    const float scale = 255.999f / fmaxf(aex, 1e-30f);
+    auto bucket_of = [&](const float4& t) {
+        const float c = axis == 0 ? t.x : axis == 1 ? t.y : t.z;
+        return (int)fminf(fmaxf((c - alo) * scale, 0.f), 255.f);
+    };
+    __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) skey[lane + 32 * k] = 0u;
-        __syncwarp();
-        if (fast) {
+    for (int k = 0; k < 8; ++k) skey[lane + 32 * k] = 0u;
+    __syncwarp();
+    if (fast) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (lane + 32 * k < nb) atomicAdd(&skey[bucket_of(tt[k])], 1u);
-        } else {
-            for (int e = lane; e < nb; e += 32) atomicAdd(&skey[bucket_of(a.bin_tmp[s0 + e])], 1u);
+        for (int k = 0; k < 8; ++k) if (lane + 32 * k < nb) atomicAdd(&skey[bucket_of(tt[k])], 1u);
+    } else {
+        for (int e = lane; e < nb; e += 32) atomicAdd(&skey[bucket_of(a.bin_tmp[s0 + e])], 1u);
+    }
+    __syncwarp();
+    {                                                    // exclusive scan of the 256 counts: lane l owns buckets 8l .. 8l+7
+        unsigned c8[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c8[k] = skey[8 * lane + k]; tot += c8[k]; }
+        unsigned inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
+        unsigned run = inc - tot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { skey[8 * lane + k] = run; run += c8[k]; }
+    }
+    __syncwarp();
+    // placement, chunk by chunk in member order: rank among the chunk's members of the same bucket + bucket cursor
+    if (fast) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (32 * k >= nb) break;                     // uniform
+            const int e = lane + 32 * k;
+            const int bucket = e < nb ? bucket_of(tt[k]) : -1;
+            const unsigned peers = __match_any_sync(LIP_FULL, bucket);
+            const int rk = __popc(peers & ((1u << lane) - 1));
+            if (e < nb) sdat[(int)skey[bucket] + rk] = tt[k];
+            __syncwarp();
+            if (e < nb && rk == 0) skey[bucket] += __popc(peers);
+            __syncwarp();
         }
-        __syncwarp();
-        {                                                    // exclusive scan of the 256 counts: lane l owns buckets 8l .. 8l+7
-            unsigned c8[8], tot = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { c8[k] = skey[8 * lane + k]; tot += c8[k]; }
-            unsigned inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(LIP_FULL, inc, o); if (lane >= o) inc += t; }
-            unsigned run = inc - tot;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { skey[8 * lane + k] = run; run += c8[k]; }
+        for (int pr = lane; pr < nb; pr += 32) {         // coalesced stores of everything that is kept in bin order
+            const float4 t = sdat[pr];
+            const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + pr;
+            a.part_vid[p] = (int)v;
+            a.bin_pts[p] = t;
+            a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
+            a.pos_bin[p] = b; a.pos_nn1[p] = a.nn1[ub + v];
+            a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
         }
-        __syncwarp();
-        // placement, chunk by chunk in member order: rank among the chunk's members of the same bucket + bucket cursor
-        if (fast) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (32 * k >= nb) break;                     // uniform
-                const int e = lane + 32 * k;
-                const int bucket = e < nb ? bucket_of(tt[k]) : -1;
-                const unsigned peers = __match_any_sync(LIP_FULL, bucket);
-                const int rk = __popc(peers & ((1u << lane) - 1));
-                if (e < nb) sdat[(int)skey[bucket] + rk] = tt[k];
-                __syncwarp();
-                if (e < nb && rk == 0) skey[bucket] += __popc(peers);
-                __syncwarp();
-            }
-            for (int pr = lane; pr < nb; pr += 32) {         // coalesced stores of everything that is kept in bin order
-                const float4 t = sdat[pr];
-                const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + pr;
+    } else {
+        for (int base = 0; base < nb; base += 32) {
+            const int e = base + lane;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            int bucket = -1;
+            if (e < nb) { t = a.bin_tmp[s0 + e]; bucket = bucket_of(t); }
+            const unsigned peers = __match_any_sync(LIP_FULL, bucket);
+            const int rk = __popc(peers & ((1u << lane) - 1));
+            if (e < nb) {
+                const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + skey[bucket] + rk;
                 a.part_vid[p] = (int)v;
                 a.bin_pts[p] = t;
                 a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
-                a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
+                a.pos_bin[p] = b; a.pos_nn1[p] = a.nn1[ub + v];
                 a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
             }
-        } else {
-            for (int base = 0; base < nb; base += 32) {
-                const int e = base + lane;
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                int bucket = -1;
-                if (e < nb) { t = a.bin_tmp[s0 + e]; bucket = bucket_of(t); }
-                const unsigned peers = __match_any_sync(LIP_FULL, bucket);
-                const int rk = __popc(peers & ((1u << lane) - 1));
-                if (e < nb) {
-                    const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + skey[bucket] + rk;
-                    a.part_vid[p] = (int)v;
-                    a.bin_pts[p] = t;
-                    a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
-                    a.pos_bin[p] = bb + i; a.pos_nn1[p] = a.nn1[ub + v];
-                    a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
-                }
-                __syncwarp();
-                if (e < nb && rk == 0) skey[bucket] += __popc(peers);
-                __syncwarp();
-            }
+            __syncwarp();
+            if (e < nb && rk == 0) skey[bucket] += __popc(peers);
+            __syncwarp();
         }
-        __syncwarp();
+    }
+
     }
 }
 
@@ -337,9 +482,9 @@ __device__ __forceinline__ float tile_score(const float4 t, const float* m) {
     const float dx = t.x - m[0], dy = t.y - m[1], dz = t.z - m[2];
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
-template <int Q, bool DOT>
-__device__ __forceinline__ void tile_scan(const float4* __restrict__ tp, int npad, const float (&m)[2][3], float (&best)[2],
-                                          float (&sec)[2], int (&blk)[2]) {
+template <int Q, bool DOT, int QMAX>
+__device__ __forceinline__ void tile_scan(const float4* __restrict__ tp, int npad, const float (&m)[QMAX][3], float (&best)[QMAX],
+                                          float (&sec)[QMAX], int (&blk)[QMAX]) {
 #pragma unroll 1
     for (int jb = 0; jb < npad; jb += 8) {
         float4 t[8];
@@ -1344,11 +1489,12 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     const int home = T.b - bb;                               // the queries' nearest landmark (local index)
     const double* __restrict__ lmt = mesh_lm(a, mt);
     const double C0 = T.C[0], C1 = T.C[1], C2 = T.C[2];      // tile origin: the target's landmark
-    float mq[2][3], qq[2], qabs[2], best[2], sec[2], sec_in[2];
-    int idx[2], blk[2], vq[2];
-    bool valid[2];
+    constexpr int Q = LIP_MAP_Q;
+    float mq[Q][3], qq[Q], qabs[Q], best[Q], sec[Q], sec_in[Q];
+    int idx[Q], blk[Q], vq[Q];
+    bool valid[Q];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < Q; ++k) {
         const int slot = first + tid + k * LIP_MAP_THREADS;
         valid[k] = tid + k * LIP_MAP_THREADS < nq;
         vq[k] = valid[k] ? a.part_vid[so + slot] : 0;
@@ -1363,7 +1509,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
         best[k] = INFINITY; sec[k] = INFINITY; sec_in[k] = INFINITY; idx[k] = -1; blk[k] = 0;
     }
     // queries in use by this WARP (units of 32 queries are dealt warp 0, warp 1, warp 0, warp 1)
-    const int qw = (nq > LIP_MAP_THREADS + 32 * warp) ? 2 : (nq > 32 * warp) ? 1 : 0;
+    const int qw = min(Q, max(0, (nq - 32 * warp + LIP_MAP_THREADS - 1) / LIP_MAP_THREADS));
     __syncthreads();                                         // the previous tile of this CTA is done with the shared arrays
     for (int i = tid; i < (K + 31) / 32; i += LIP_MAP_THREADS) need[i] = 0u;
     float mabs = 0.f;                                        // max |coordinate| staged so far (uniform)
@@ -1383,7 +1529,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
 #pragma unroll
             for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < Q; ++k) {
                 if (!valid[k]) continue;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const float f = -0.5f * mq[k][c]; v[c] = fminf(v[c], f); v[3 + c] = fmaxf(v[3 + c], f); }
@@ -1446,7 +1592,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                     cm &= cm - 1;
                     bool nd = false;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < Q; ++k) {
                         if (!valid[k]) continue;
                         float bd2 = 0.f;
 #pragma unroll
@@ -1522,11 +1668,14 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                 const int npad = (fill + 7) & ~7;
                 if (tid < npad - fill) { tp[fill + tid] = make_float4(0.f, 0.f, 0.f, 3.0e38f); tv[fill + tid] = 0x7fffffff; }
                 __syncthreads();
-                const float prev0 = best[0], prev1 = best[1];
-                if (qw == 2) tile_scan<2, true>(tp, npad, mq, best, sec, blk);
-                else if (qw == 1) tile_scan<1, true>(tp, npad, mq, best, sec, blk);
-                if (best[0] < prev0) idx[0] = tv[tile_recover<true>(tp, blk[0], best[0], mq[0], sec_in[0])];
-                if (best[1] < prev1) idx[1] = tv[tile_recover<true>(tp, blk[1], best[1], mq[1], sec_in[1])];
+                float prev[Q];
+#pragma unroll
+                for (int k = 0; k < Q; ++k) prev[k] = best[k];
+                if (qw > (Q + 1) / 2) tile_scan<Q, true>(tp, npad, mq, best, sec, blk);
+                else if (qw > 0) tile_scan<(Q + 1) / 2, true>(tp, npad, mq, best, sec, blk);
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    if (best[k] < prev[k]) idx[k] = tv[tile_recover<true>(tp, blk[k], best[k], mq[k], sec_in[k])];
                 __syncthreads();
                 staged += fill;
                 fill = 0;
@@ -1538,7 +1687,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     // ---- result: near ties are decided in float64 over everything that was staged, a warp per query -------
     const double* __restrict__ xt = mesh_xyz(a, mt);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < Q; ++k) {
         const float d2b = fmaxf(best[k] + qq[k], 0.f), d2s = fmaxf(fminf(sec[k], sec_in[k]) + qq[k], 0.f);
         const float e = 4e-7f * (qabs[k] + mabs);
         const float tol = d2_err(d2b, e) + d2_err(d2s, e) + 2.f * dot_err(qq[k], d2s);

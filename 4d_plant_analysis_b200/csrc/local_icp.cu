@@ -157,6 +157,10 @@ struct lip_ctx {
     int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0;
     int M = 0, B = 0, n_tiles = 0, tab_total = 0, directions = 3;
     std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first, h_plan;
+    std::vector<int> h_ptile_mesh, h_ptile_first, h_ptile_cnt, h_mesh_ptile;   // tiles of the partition kernels
+    int n_ptiles = 0;
+    int64_t tile_cnt_total = 0;
+    int *ptile_mesh = nullptr, *ptile_first = nullptr, *ptile_cnt = nullptr, *mesh_ptile = nullptr;
     DevBuf d_plan;      // all plan arrays in one allocation
     int *mesh_ubase = nullptr, *mesh_bin = nullptr, *mesh_tab = nullptr, *bin_mesh = nullptr, *tile_mesh = nullptr,
         *tile_first = nullptr;
@@ -214,7 +218,9 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
     const size_t o_bxyz = take(n * 24), o_bq = take(n * 24), o_pb = take(n * 4), o_pn = take(n * 4), o_pd = take(n * 16);
-    const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile)), o_btmp = take(n * 16);
+    const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile));
+    const size_t o_tcnt = take((size_t)c->tile_cnt_total * 4), o_tsum = take((size_t)c->n_ptiles * 32);
+    const size_t o_tbase = take((size_t)c->tile_cnt_total * 4), o_btmp = take(n * 16);
     LIP_CUDA(c, c->ws.ensure(off));
     char* base = c->ws.as<char>();
     LipArgs& a = c->args;
@@ -230,7 +236,9 @@ int carve_workspace(lip_ctx* c) {
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
     a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
-    a.map_tiles = (MapTile*)(base + o_mt); a.bin_tmp = (float4*)(base + o_btmp);
+    a.map_tiles = (MapTile*)(base + o_mt);
+    a.tile_cnt = (int*)(base + o_tcnt); a.tile_sum = (double*)(base + o_tsum);
+    a.tile_base = (int*)(base + o_tbase); a.bin_tmp = (float4*)(base + o_btmp);
     a.bin_xyz = (double*)(base + o_bxyz); a.bin_q = (double*)(base + o_bq);
     a.pos_bin = (int*)(base + o_pb); a.pos_nn1 = (int*)(base + o_pn); a.pos_d = (double*)(base + o_pd);
     return LIP_OK;
@@ -307,18 +315,37 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
         for (int f = 0; f < n; f += tile) { c->h_tile_mesh.push_back(m); c->h_tile_first.push_back(f); }
     }
     c->n_tiles = (int)c->h_tile_mesh.size();
+    // tiles of the partition kernels: LIP_PART_CHUNK vertices of one mesh, every mesh; per tile one count per landmark of its mesh
+    c->h_ptile_mesh.clear(); c->h_ptile_first.clear(); c->h_ptile_cnt.clear(); c->h_mesh_ptile.assign(M + 1, 0);
+    int64_t cnt_total = 0;
+    for (int m = 0; m < M; ++m) {
+        c->h_mesh_ptile[m] = (int)c->h_ptile_mesh.size();
+        const int n = c->h_mesh_ubase[m + 1] - c->h_mesh_ubase[m], K = c->h_mesh_bin[m + 1] - c->h_mesh_bin[m];
+        for (int f = 0; f < n; f += LIP_PART_CHUNK) {
+            c->h_ptile_mesh.push_back(m); c->h_ptile_first.push_back(f); c->h_ptile_cnt.push_back((int)cnt_total);
+            cnt_total += K;
+            if (cnt_total >= (int64_t)1 << 30) return fail(c, LIP_EINVAL, "plan: too many (tile, landmark) counters; split the batch");
+        }
+    }
+    c->h_mesh_ptile[M] = (int)c->h_ptile_mesh.size();
+    c->h_ptile_cnt.push_back((int)cnt_total);
+    c->n_ptiles = (int)c->h_ptile_mesh.size();
+    c->tile_cnt_total = cnt_total;
     // upload
     size_t off = 0;
     auto take = [&](size_t cnt) { size_t o = off; off = align_up(off + cnt * 4); return o; };
     const size_t o0 = take(M + 1), o1 = take(M + 1), o2 = take(M + 1), o3 = take(c->B), o4 = take(c->n_tiles), o5 = take(c->n_tiles);
+    const size_t o6 = take(c->n_ptiles), o7 = take(c->n_ptiles), o8 = take(c->n_ptiles + 1), o9 = take(M + 1);
     LIP_CUDA(c, c->d_plan.ensure(off));
     char* base = c->d_plan.as<char>();
     c->mesh_ubase = (int*)(base + o0); c->mesh_bin = (int*)(base + o1); c->mesh_tab = (int*)(base + o2);
     c->bin_mesh = (int*)(base + o3); c->tile_mesh = (int*)(base + o4); c->tile_first = (int*)(base + o5);
+    c->ptile_mesh = (int*)(base + o6); c->ptile_first = (int*)(base + o7); c->ptile_cnt = (int*)(base + o8); c->mesh_ptile = (int*)(base + o9);
     // one upload for all six arrays; complete on return, whatever stream the kernels will run on
     c->h_plan.assign(off / 4, 0);
     auto put = [&](size_t o, const std::vector<int>& h) { if (!h.empty()) memcpy(c->h_plan.data() + o / 4, h.data(), h.size() * 4); };
     put(o0, c->h_mesh_ubase); put(o1, c->h_mesh_bin); put(o2, c->h_mesh_tab); put(o3, c->h_bin_mesh); put(o4, c->h_tile_mesh); put(o5, c->h_tile_first);
+    put(o6, c->h_ptile_mesh); put(o7, c->h_ptile_first); put(o8, c->h_ptile_cnt); put(o9, c->h_mesh_ptile);
     LIP_CUDA(c, cudaMemcpyAsync(base, c->h_plan.data(), off, cudaMemcpyHostToDevice, c->stream));
     LIP_CUDA(c, cudaStreamSynchronize(c->stream));
     int rc = carve_workspace(c);
@@ -328,6 +355,7 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     a.dir_mask = c->directions; a.n_tiles = c->n_tiles;
     a.mesh_ubase = c->mesh_ubase; a.mesh_bin = c->mesh_bin; a.mesh_tab = c->mesh_tab; a.bin_mesh = c->bin_mesh;
     a.tile_mesh = c->tile_mesh; a.tile_first = c->tile_first;
+    a.ptile_mesh = c->ptile_mesh; a.ptile_first = c->ptile_first; a.ptile_cnt = c->ptile_cnt; a.mesh_ptile = c->mesh_ptile;
     a.q_dist = nullptr;
     c->planned = true;
     return LIP_OK;
@@ -364,10 +392,15 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
     if (stages & ST_PARTITION) {
-        size_t smem = (size_t)c->maxK * 24 + ((size_t)c->maxK * 3 + 1) * 4 + (size_t)c->maxK * 8 * 4 + 8 * 256 * 4 + 8 * 256 * 16 + 16;
-        landmark_partition_kernel<<<c->M, 256, smem, st>>>(a);
-        ++launches;
-        LIP_CHECK("landmark_partition_kernel");
+        landmark_nn_kernel<<<c->n_ptiles, LIP_PART_THREADS, (size_t)c->maxK * 44 + 32, st>>>(a);
+        LIP_CHECK("landmark_nn_kernel");
+        partition_scan_kernel<<<(c->M + 3) / 4, 128, 0, st>>>(a);
+        LIP_CHECK("partition_scan_kernel");
+        partition_place_kernel<<<c->n_ptiles, LIP_PART_THREADS, (size_t)c->maxK * 4 * (2 + LIP_PART_THREADS / 32) + 16, st>>>(a);
+        LIP_CHECK("partition_place_kernel");
+        bin_sort_kernel<<<(c->B + LIP_SORT_WARPS - 1) / LIP_SORT_WARPS, LIP_SORT_WARPS * 32, 0, st>>>(a);
+        launches += 4;
+        LIP_CHECK("bin_sort_kernel");
     }
     mark();                                                  // 1: after partition
     bool forked_icp = false, forked_grid = false;
@@ -808,8 +841,9 @@ int lip_create(lip_ctx** out, int device) {
         c->map_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
-    cudaFuncSetAttribute(landmark_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         LIP_MAX_LANDMARKS * 68 + 64 + 8 * 256 * 4 + 8 * 256 * 16 + 16);
+    cudaFuncSetAttribute(landmark_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LIP_MAX_LANDMARKS * 44 + 32);
+    cudaFuncSetAttribute(partition_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         LIP_MAX_LANDMARKS * 4 * (2 + LIP_PART_THREADS / 32) + 16);
     memset(&c->args, 0, sizeof(c->args));
     *out = c;
     return LIP_OK;

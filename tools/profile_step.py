@@ -1,22 +1,20 @@
-"""Short device-resident run of the hot path for ncu captures: `python tools/profile_step.py [config] [frame_pairs] [steps]`."""
+"""one device-resident step of the headline workload (or --config N --frame-pairs F independent pairs), batch in one piece, for ncu:
+   LIP_DEVICE_CHUNKS=1 ncu --metrics gpu__time_duration.sum ... python tools/profile_step.py [steps]"""
 import importlib, os, sys
-import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
 native = importlib.import_module("4d_plant_analysis_b200._native")
 syn = importlib.import_module("4d_plant_analysis_b200.synthetic")
-cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-fp = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-b = syn.make_config(cfg, frame_pairs=fp)
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+data = syn.make_series(2, n_frames=17, plants=4)
 ctx = native.Context(0)
-ctx.plan(b.off1, b.off2, b.lm_off)
+ctx.set_map_dtype(np.int32)
+ctx.plan(data.off1, data.off2, data.lm_off)
 dev = torch.device("cuda", 0)
-d = [torch.from_numpy(a).to(dev) for a in (b.xyz1, b.xyz2, b.lm1, b.lm2)]
-T21 = torch.empty(int(b.off2[-1]), dtype=torch.int64, device=dev)
-T12 = torch.empty(int(b.off1[-1]), dtype=torch.int64, device=dev)
+d = [torch.from_numpy(a).to(dev) for a in (data.frames, data.lm1, data.lm2)]
+T21 = torch.empty(int(data.off2[-1]), dtype=torch.int32, device=dev); T12 = torch.empty(int(data.off1[-1]), dtype=torch.int32, device=dev)
+st = torch.cuda.Stream(dev)
 for _ in range(steps):
-    ctx.run_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), T21.data_ptr(), T12.data_ptr(), 0)
+    ctx.run_series_device(d[0].data_ptr(), len(data.frames), data.row1, data.row2, d[1].data_ptr(), d[2].data_ptr(), T21.data_ptr(), T12.data_ptr(), st.cuda_stream)
 torch.cuda.synchronize()
-print("ok", b.n_correspondences, ctx.counters())
+print("ok", ctx.counters())
