@@ -24,5 +24,6 @@ from .p2p_matching_fm import double_direction_refinement, refine_batch  # noqa: 
 from .p2p_matching_seg_icp import get_p2p_mapping_from_segments_using_icp, get_triangle_angles  # noqa: F401
 from .registration_icp import get_best_fit_transform, get_NN_in_target, my_icp  # noqa: F401
 from .segment_matching_utils import label_points_by_skeleton, skeleton_landmarks, split_by_label  # noqa: F401
-from .synthetic import SegmentPairBatch, SeriesBatch, batch_from_segments, make_config, make_series  # noqa: F401
+from .containers import SegmentPairBatch, SeriesBatch, batch_from_segments, concat_batches  # noqa: F401
+from .synthetic import make_config, make_series  # noqa: F401
 from .distributed import ShardedLocalICP, gather_results, local_icp_distributed, make_shard_plan, shard_segments  # noqa: F401

@@ -336,10 +336,11 @@ class Context:
         out.update(R21=R21, t21=t21, iters21=i21, status21=s21, R12=R12, t12=t12, iters12=i12, status12=s12)
         return out
 
-    def landmark_nn(self, side):
+    def landmark_nn(self, side, distances=True):
+        """two nearest landmarks (local indices) of every vertex of side 1 / 2 and, unless distances=False, their distances"""
         n = self.n1 if side == 1 else self.n2
-        nn, d = np.empty((n, 2), np.int32), np.empty((n, 2))
-        self._check(self.lib.lip_batch_get_landmark_nn(self.h, side, _ptr(nn, c_int32), _ptr(d, c_double)))
+        nn, d = np.empty((n, 2), np.int32), (np.empty((n, 2)) if distances else None)
+        self._check(self.lib.lip_batch_get_landmark_nn(self.h, side, _ptr(nn, c_int32), _ptr(d, c_double) if distances else None))
         return nn, d
 
     def counters(self):

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native
-from .synthetic import SegmentPairBatch, batch_from_segments
+from .containers import SegmentPairBatch, batch_from_segments
 
 
 @dataclass

@@ -1258,15 +1258,22 @@ int lip_batch_get_landmark_nn(lip_ctx* c, int side, int32_t* nn, double* dist) {
         }
         return LIP_OK;
     }
-    LIP_CUDA(c, cudaDeviceSynchronize());
     const LipArgs& a = c->args;
     const size_t first = side == 1 ? 0 : (size_t)c->n1, n = side == 1 ? (size_t)c->n1 : (size_t)c->n2;
-    std::vector<int> i0(n), i1(n);
-    std::vector<double> e0(n), e1(n);
-    LIP_CUDA(c, cudaMemcpy(i0.data(), a.nn0 + first, n * 4, cudaMemcpyDeviceToHost));
-    LIP_CUDA(c, cudaMemcpy(i1.data(), a.nn1 + first, n * 4, cudaMemcpyDeviceToHost));
-    LIP_CUDA(c, cudaMemcpy(e0.data(), a.d0 + first, n * 8, cudaMemcpyDeviceToHost));
-    LIP_CUDA(c, cudaMemcpy(e1.data(), a.d1 + first, n * 8, cudaMemcpyDeviceToHost));
+    // only what the caller asked for travels (the drop-in's vertex colours need the nearest landmark alone); one synchronisation
+    std::vector<int> i0(nn ? n : 0), i1(nn ? n : 0);
+    std::vector<double> e0(dist ? n : 0), e1(dist ? n : 0);
+    cudaStream_t st = c->stream;
+    LIP_CUDA(c, cudaDeviceSynchronize());
+    if (nn) {
+        LIP_CUDA(c, cudaMemcpyAsync(i0.data(), a.nn0 + first, n * 4, cudaMemcpyDeviceToHost, st));
+        LIP_CUDA(c, cudaMemcpyAsync(i1.data(), a.nn1 + first, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (dist) {
+        LIP_CUDA(c, cudaMemcpyAsync(e0.data(), a.d0 + first, n * 8, cudaMemcpyDeviceToHost, st));
+        LIP_CUDA(c, cudaMemcpyAsync(e1.data(), a.d1 + first, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    LIP_CUDA(c, cudaStreamSynchronize(st));
     for (size_t i = 0; i < n; ++i) {
         if (nn) { nn[2 * i] = i0[i]; nn[2 * i + 1] = i1[i]; }
         if (dist) { dist[2 * i] = e0[i]; dist[2 * i + 1] = e1[i]; }

@@ -170,7 +170,7 @@ class ShardedLocalICP:
         import torch
         import torch.distributed as dist
         from . import _native
-        from .synthetic import SeriesBatch
+        from .containers import SeriesBatch
         self.torch, self.dist = torch, dist
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
@@ -287,7 +287,7 @@ class ShardedLocalICP:
 
 def _take_series_segments(series, seg_ids):
     """sub-series of arbitrary segment pairs (every mesh they use once)"""
-    from .synthetic import SeriesBatch
+    from .containers import SeriesBatch
     seg_ids = np.asarray(seg_ids, np.int64)
     n1, n2 = np.diff(series.off1)[seg_ids], np.diff(series.off2)[seg_ids]
     rows = sorted({(int(r), int(n)) for r, n in zip(series.row1[seg_ids], n1)} | {(int(r), int(n)) for r, n in zip(series.row2[seg_ids], n2)})

@@ -9,8 +9,6 @@ one direction) through liblocalicp.so.
 """
 from __future__ import annotations
 
-import copy
-
 import numpy as np
 
 from . import _native
@@ -35,8 +33,10 @@ def _vector3d(colors):
 def get_p2p_mapping_from_segments_using_icp(mesh1, mesh2, lm1, lm2, voxel_size):
     """T21 (N2,) int64: for every vertex of mesh2 the index of its match among the vertices of mesh1.
     ``voxel_size`` is accepted and ignored, as in the reference."""
-    xyz1 = _points(np.asarray(copy.deepcopy(mesh1).vertices), "mesh1.vertices")
-    xyz2 = _points(np.asarray(copy.deepcopy(mesh2).vertices), "mesh2.vertices")
+    # (the reference deep-copies both meshes, :384-385, only to protect its inputs; nothing here writes to the vertices, and
+    # _points returns a contiguous float64 array — a copy whenever the mesh does not already hold one)
+    xyz1 = _points(np.asarray(mesh1.vertices), "mesh1.vertices")
+    xyz2 = _points(np.asarray(mesh2.vertices), "mesh2.vertices")
     lm1 = _points(lm1, "lm1")
     lm2 = _points(lm2, "lm2")
     if lm1.shape[0] != lm2.shape[0]:
@@ -50,8 +50,8 @@ def get_p2p_mapping_from_segments_using_icp(mesh1, mesh2, lm1, lm2, voxel_size):
             # by nearest landmark
             color_setting = np.random.random((lm1.shape[0], 3))
             try:
-                nn1, _ = ctx.landmark_nn(1)
-                nn2, _ = ctx.landmark_nn(2)
+                nn1, _ = ctx.landmark_nn(1, distances=False)
+                nn2, _ = ctx.landmark_nn(2, distances=False)
                 mesh1.vertex_colors = _vector3d(color_setting[nn1[:, 0]])
                 mesh2.vertex_colors = _vector3d(color_setting[nn2[:, 0]])
             except AttributeError:
