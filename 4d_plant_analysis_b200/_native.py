@@ -187,7 +187,7 @@ class Context:
         self._check(self.lib.lip_set_params(self.h, byref(p)))
 
     def set_map_mode(self, mode: int):
-        """0 = landmark-bin tiles (default), 1 = hashed grid; plan again afterwards."""
+        """0 = landmark-bin tiles on the CUDA cores (default), 1 = hashed grid, 2 = the tiles with the scores on the tensor cores (tcgen05 + TMEM); same maps in every mode; plan again afterwards."""
         self._check(self.lib.lip_set_map_mode(self.h, int(mode)))
 
     # ---- batch --------------------------------------------------------------------------------

@@ -164,6 +164,66 @@ __device__ __forceinline__ float d2_err(float d2, float e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 5th-generation tensor cores (tcgen05): PTX wrappers used by blend_tile_tc_kernel.  Operands are K-major,
+// not swizzled: a core matrix is 8 rows x 16 bytes stored as 128 contiguous bytes; the descriptor holds the
+// byte distance between 8-row groups (sbo) and between the two 16-byte K halves of a K = 8 tf32 step (lbo).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a protocol error must end in a trap (reported as a launch failure), never in a hung GPU
+__device__ __noinline__ void mbar_timeout() { __trap(); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#pragma unroll 1
+    for (int i = 0; i < (1 << 26); ++i) if (mbar_try_wait(bar, parity)) return;
+    mbar_timeout();
+}
+__device__ __forceinline__ unsigned long long umma_desc(const void* p, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((tc_smem_u32(p) >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M x N
+__host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&r)[32]) {
+    unsigned* u = reinterpret_cast<unsigned*>(r);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                 "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                   "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+                   "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+                   "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// upper part of an fp32 that a tf32 operand represents exactly (10 explicit mantissa bits): whatever the tensor core does with
+// the low 13 bits (truncate or round) is then a no-op
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---------------------------------------------------------------------------------------------
 // 3x3 helpers (row-major)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mat3_mul(const double* A, const double* Bm, double* C) {  // C = A*B (C may alias B)

@@ -1740,6 +1740,377 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS, LIP_MAP_MINBLOCKS) blend_tile
     }
 }
 
+// =============================================================================================
+// K4 on the 5th-generation tensor cores (map mode 2).  Same tiles, same two rounds (home bin, then every bin the box
+// test cannot rule out), same float64 decision of near ties as blend_tile_kernel — but the scores
+//     c(q, y) = |y|^2 - 2 q.y
+// of 128 queries x 128 candidates come out of two tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) into TMEM:
+//     q = qh + ql, y = yh + yl, |y|^2 = nh + nl   (every part exactly representable in tf32)
+//     A row (query)        [-2qh.x -2qh.y -2qh.z 1 | -2ql.x -2ql.y -2ql.z 0]
+//     B row (candidate)    hi plane [yh.x yh.y yh.z nh], lo plane [yl.x yl.y yl.z nl], each read for BOTH K halves (lbo = 0)
+//     D = A Bhi^T ; D += A Blo^T  =  nh + nl - 2 (qh + ql).(yh + yl)                  (tools/micro/tcgen05_scan_bench.cu)
+// Warp roles (192 threads): warps 0-3 own the 128 queries (TMEM lane = query): tcgen05.ld of 32 scores at a time, block
+// minima of 8 + top-2 tracking exactly as tile_scan, winner recovery from the staged candidates, box cull, final decision;
+// warps 4 and 5 are producers: each owns one SMEM stage + one TMEM buffer, stages 128 candidates (shift into the tile frame,
+// |y|^2, hi / lo split), issues the two MMAs and commits to the stage's mbarrier.  Stages are handed back by the query warps
+// through a second mbarrier once the scores are read and the winner recovered; no CTA-wide barrier inside a tile.
+// The tensor-core score differs from the exact one by at most tc_err (measured 2^-20.4 relative to |y|^2 + 2|q||y|; bound used
+// 2^-18): the tolerance of the final decision is widened by it, so ambiguous queries go to the float64 scan as before and the
+// maps stay exact.
+// =============================================================================================
+#define LIP_TC_THREADS 192
+#define LIP_TC_N 128
+struct __align__(128) MapTcSmem {
+    float4 A[2][128];                                   // query operand: K halves as planes
+    float4 hi[2][LIP_TC_N], lo[2][LIP_TC_N];            // candidates of the two stages
+    int tv[2][LIP_TC_N];                                // ... and their vertex ids
+    unsigned need[LIP_MAX_LANDMARKS / 32];
+    float sbox[LIP_MAP_BOXBATCH][8];
+    float red[4][8];
+    unsigned cand[2];
+    struct { int start, end; float sh[3]; } sdesc[LIP_MAP_BOXBATCH];
+    unsigned long long t_full[2], t_empty[2], a_ready, cull_done, r1_ready;
+    int tot1;
+    float mabs1;
+    unsigned tmem_base;
+    int tile;
+};
+__device__ __forceinline__ float tc_err(float qq, float d2) {
+    const float nq = sqrtf(qq), ny = nq + 1.001f * sqrtf(d2) + 1e-3f;
+    return 4e-6f * fmaf(ny, ny, 2.f * nq * ny);
+}
+
+// ---- producer side: stage `take` candidates of bin_pts[src ..] (shifted by sh) at slot `at` of stage w ----
+__device__ __forceinline__ void tc_stage(const LipArgs& a, MapTcSmem& S, int w, int at, int src, int take, float sh0, float sh1, float sh2, int lane) {
+    for (int i = lane; i < take; i += 32) {
+        const float4 t = a.bin_pts[src + i];
+        const float x = t.x + sh0, y = t.y + sh1, z = t.z + sh2;
+        const float n = fmaf(x, x, fmaf(y, y, z * z));
+        const float hx = tf32_hi(x), hy = tf32_hi(y), hz = tf32_hi(z), hn = tf32_hi(n);
+        S.hi[w][at + i] = make_float4(hx, hy, hz, hn);
+        S.lo[w][at + i] = make_float4(tf32_hi(x - hx), tf32_hi(y - hy), tf32_hi(z - hz), tf32_hi(n - hn));
+        S.tv[w][at + i] = __float_as_int(t.w);
+    }
+}
+// chunk `c` of this CTA's chunk sequence is complete in stage w = c & 1: pad, make it visible to the tensor core, multiply
+__device__ __forceinline__ void tc_fire(MapTcSmem& S, int w, int fill, unsigned tmem, int lane) {
+    const int pad_to = min(LIP_TC_N, (fill + 31) & ~31);
+    for (int i = fill + lane; i < pad_to; i += 32) {
+        S.hi[w][i] = make_float4(0.f, 0.f, 0.f, 1e30f); S.lo[w][i] = make_float4(0.f, 0.f, 0.f, 0.f); S.tv[w][i] = 0x7fffffff;
+    }
+    fence_async_smem();
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        tc_fence_after();
+        constexpr unsigned idesc = umma_idesc_tf32(128, LIP_TC_N);
+        const unsigned long long ad = umma_desc(&S.A[0][0], 128 * 16, 128);
+        umma_tf32(tmem + w * LIP_TC_N, ad, umma_desc(&S.hi[w][0], 0, 128), idesc, 0);
+        umma_tf32(tmem + w * LIP_TC_N, ad, umma_desc(&S.lo[w][0], 0, 128), idesc, 1);
+        umma_commit(&S.t_full[w]);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(LIP_TC_THREADS, 2) blend_tile_tc_kernel(LipArgs a) {
+    __shared__ MapTcSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = a.sched[20];
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&S.tmem_base)), "r"(2 * LIP_TC_N));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        mbar_init(&S.t_full[0], 1); mbar_init(&S.t_full[1], 1); mbar_init(&S.t_empty[0], 4); mbar_init(&S.t_empty[1], 4);
+        mbar_init(&S.a_ready, 1); mbar_init(&S.cull_done, 1); mbar_init(&S.r1_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = S.tmem_base;
+    unsigned chunk = 0, n_tile = 0, n_cull = 0;              // identical in every role: they give the barrier phases
+    for (;;) {                                              // persistent CTAs over the tile list
+        __syncthreads();
+        if (tid == 0) S.tile = atomicAdd(&a.sched[21], 1);
+        __syncthreads();
+        const int tile = S.tile;
+        if (tile >= n_tiles) break;
+        const MapTile T = a.map_tiles[tile];
+        const int first = T.first, m = T.m, ub = T.ub, bb = T.bb, K = T.K, bbt = T.bbt, so = T.so, nq = T.nq;
+        const int mt = pair_mesh(a, m);
+        const int home = T.b - bb;
+        const double* __restrict__ lmt = mesh_lm(a, mt);
+        const double C0 = T.C[0], C1 = T.C[1], C2 = T.C[2];
+        const int tot0 = T.te - T.ts, n0 = (tot0 + LIP_TC_N - 1) / LIP_TC_N;
+        const int nwords = (K + 31) / 32;
+        int tot1 = 0;
+        if (warp >= 4) {
+            // ================================ producers ================================
+            const int w = warp - 4;
+            mbar_wait(&S.a_ready, n_tile & 1);               // the queries of this tile are in S.A
+            int pos = 0;                                     // position in the tile's candidate stream
+            auto feed = [&](int src, int cnt, float sh0, float sh1, float sh2, int total) {
+                while (cnt > 0) {
+                    const int at = pos & (LIP_TC_N - 1), take = min(cnt, LIP_TC_N - at);
+                    const unsigned c = chunk + (unsigned)(pos / LIP_TC_N);
+                    const bool mine = (int)(c & 1u) == w;
+                    if (mine) {
+                        if (at == 0 && (c >> 1) >= 1u) mbar_wait(&S.t_empty[w], ((c >> 1) - 1u) & 1u);     // stage and TMEM buffer drained
+                        tc_stage(a, S, w, at, src, take, sh0, sh1, sh2, lane);
+                    }
+                    pos += take; src += take; cnt -= take;
+                    if (mine && ((pos & (LIP_TC_N - 1)) == 0 || pos == total)) tc_fire(S, w, ((pos - 1) & (LIP_TC_N - 1)) + 1, tmem, lane);
+                }
+            };
+            if (tot0 > 0) feed(T.ts, tot0, 0.f, 0.f, 0.f, tot0);
+            chunk += (unsigned)n0;
+            if (K > 1) {
+                mbar_wait(&S.cull_done, n_cull & 1);         // S.need (and S.sdesc for K <= LIP_MAP_BOXBATCH) are final
+                int cnt1 = 0;
+                float mabs1 = 0.f;
+                for (int j = lane; j < K; j += 32) {
+                    if (!((S.need[j >> 5] >> (j & 31)) & 1u)) continue;
+                    const int js = a.bin_off[bbt + j], je = a.bin_off[bbt + j + 1];
+                    if (je <= js) continue;
+                    cnt1 += je - js;
+                    const float s0 = (float)(lmt[3 * j] - C0), s1 = (float)(lmt[3 * j + 1] - C1), s2 = (float)(lmt[3 * j + 2] - C2);
+                    mabs1 = fmaxf(mabs1, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(s0), fabsf(s1)), fabsf(s2)));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { cnt1 += __shfl_xor_sync(LIP_FULL, cnt1, o); mabs1 = fmaxf(mabs1, __shfl_xor_sync(LIP_FULL, mabs1, o)); }
+                tot1 = cnt1;
+                if (w == 0 && lane == 0) { S.tot1 = tot1; S.mabs1 = mabs1; __threadfence_block(); mbar_arrive(&S.r1_ready); }
+                pos = 0;
+                for (int wi = 0; wi < nwords; ++wi) {
+                    unsigned bits = S.need[wi];
+                    while (bits) {
+                        const int j = 32 * wi + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int js = a.bin_off[bbt + j], je = a.bin_off[bbt + j + 1];
+                        if (je <= js) continue;
+                        feed(js, je - js, (float)(lmt[3 * j] - C0), (float)(lmt[3 * j + 1] - C1), (float)(lmt[3 * j + 2] - C2), tot1);
+                    }
+                }
+                chunk += (unsigned)((tot1 + LIP_TC_N - 1) / LIP_TC_N);
+                ++n_cull;
+            }
+        } else {
+            // ================================ query warps ================================
+            const bool valid = tid < nq;
+            const int slot = first + tid;
+            const int vq = valid ? a.part_vid[so + slot] : 0;
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+            if (valid) {                                     // blended positions in bin order, written by blend_kernel
+                const size_t N = (size_t)a.n_total, p = (size_t)so + slot;
+                fx = (float)(a.bin_q[p] - C0); fy = (float)(a.bin_q[N + p] - C1); fz = (float)(a.bin_q[2 * N + p] - C2);
+            }
+            const float mq[3] = {-2.f * fx, -2.f * fy, -2.f * fz};
+            const float qq = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+            const float qabs = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz));
+            {
+                const float hx = tf32_hi(fx), hy = tf32_hi(fy), hz = tf32_hi(fz);
+                S.A[0][tid] = make_float4(-2.f * hx, -2.f * hy, -2.f * hz, 1.f);
+                S.A[1][tid] = make_float4(-2.f * tf32_hi(fx - hx), -2.f * tf32_hi(fy - hy), -2.f * tf32_hi(fz - hz), 0.f);
+            }
+            for (int i = tid; i < nwords; i += 128) S.need[i] = 0u;
+            fence_async_smem();
+            __threadfence_block();
+            bar_sync_named(1, 128);
+            if (tid == 0) mbar_arrive(&S.a_ready);
+            float best = INFINITY, sec = INFINITY, bestf = INFINITY, sec_in = INFINITY;      // best / sec: tensor-core scores; bestf / sec_in: fp32 FFMA
+            int idx = -1;                                                                   // scores of the winner's block of 8
+            float mabs = tot0 > 0 ? T.home_mabs : 0.f;
+            const unsigned lane_addr = (unsigned)(warp * 32) << 16;
+            auto consume = [&](int total) {
+                const int nch = (total + LIP_TC_N - 1) / LIP_TC_N;
+                for (int i = 0; i < nch; ++i) {
+                    const unsigned c = chunk + (unsigned)i;
+                    const int s = (int)(c & 1u);
+                    const int cnt = min(LIP_TC_N, total - LIP_TC_N * i), ng = (cnt + 31) >> 5;
+                    mbar_wait(&S.t_full[s], (c >> 1) & 1u);
+                    tc_fence_after();
+                    const unsigned tbase = tmem + lane_addr + (unsigned)(s * LIP_TC_N);
+                    const float prev = best;
+                    int blk = 0;
+                    float r[2][32];
+                    tmem_ld32(tbase, r[0]);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int g = 0; g < LIP_TC_N / 32; ++g) {
+                        if (g < ng) {
+                            if (g + 1 < ng) tmem_ld32(tbase + (g + 1) * 32, r[(g + 1) & 1]);
+                            const float* v = r[g & 1];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float bm = fminf(fminf(v[8 * k], v[8 * k + 1]), v[8 * k + 2]);
+                                bm = fminf(fminf(bm, v[8 * k + 3]), v[8 * k + 4]);
+                                bm = fminf(fminf(bm, v[8 * k + 5]), v[8 * k + 6]);
+                                bm = fminf(bm, v[8 * k + 7]);
+                                sec = fminf(sec, fmaxf(bm, best));
+                                blk = (bm < best) ? g * 32 + 8 * k : blk;
+                                best = fminf(best, bm);
+                            }
+                            if (g + 1 < ng) tmem_wait_ld();
+                        }
+                    }
+                    if (best < prev) {                       // the winner so far sits in this chunk: its position, from the staged candidates
+                        float b1 = INFINITY, b2 = INFINITY;
+                        int pos = blk;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 h = S.hi[s][blk + k], l = S.lo[s][blk + k];
+                            const float cs = fmaf(mq[0], h.x + l.x, fmaf(mq[1], h.y + l.y, fmaf(mq[2], h.z + l.z, h.w + l.w)));
+                            if (cs < b1) { b2 = b1; b1 = cs; pos = blk + k; } else b2 = fminf(b2, cs);
+                        }
+                        bestf = b1; sec_in = b2; idx = S.tv[s][pos];
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.t_empty[s]);
+                }
+                chunk += (unsigned)nch;
+            };
+            consume(tot0);
+            if (K > 1) {
+                // ---- box cull of the other target bins: CTA-wide bounds, then per query (as blend_tile) ----
+                float (*sbox)[8] = S.sbox;
+                float v[8];
+                v[6] = 0.f; v[7] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { v[c] = INFINITY; v[3 + c] = -INFINITY; }
+                if (valid) {
+                    v[0] = v[3] = fx; v[1] = v[4] = fy; v[2] = v[5] = fz;
+                    v[6] = fmaxf(bestf + qq, 0.f);           // the distance of a real candidate (or infinity): an upper bound of the answer
+                    v[7] = qabs;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = -warp_maxf(-v[c]);
+#pragma unroll
+                for (int c = 3; c < 8; ++c) v[c] = warp_maxf(v[c]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) S.red[warp][c] = v[c];
+                }
+                bar_sync_named(1, 128);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[c] = fminf(v[c], S.red[w][c]);
+#pragma unroll
+                    for (int c = 3; c < 8; ++c) v[c] = fmaxf(v[c], S.red[w][c]);
+                }
+                const float rmax2 = v[6], qabs_max = v[7];
+                const float qq_max = 3.f * qabs_max * qabs_max;
+                for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXBATCH) {
+                    bar_sync_named(1, 128);
+                    if (tid < LIP_MAP_BOXBATCH) {            // boxes of this batch of bins in the tile frame + CTA-level cull
+                        const int j = j0 + tid;
+                        float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
+                        const int js = j < K ? a.bin_off[bbt + j] : 0, je = j < K ? a.bin_off[bbt + j + 1] : 0;
+                        if (j < K && j != home && je > js) {
+                            const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
+                            float bb2 = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float sh = (float)(lmt[3 * j + c] - (c == 0 ? C0 : c == 1 ? C1 : C2));
+                                lo[c] = bx[c] + sh; hi[c] = bx[3 + c] + sh;
+                                mb = fmaxf(mb, fmaxf(fabsf(lo[c]), fabsf(hi[c])));
+                                const float d = fmaxf(fmaxf(lo[c] - v[3 + c], v[c] - hi[c]), 0.f);
+                                bb2 = fmaf(d, d, bb2);
+                            }
+                            const float e = 8e-7f * (qabs_max + fmaxf(mb, mabs));
+                            const float rhs = rmax2 + d2_err(rmax2, e) + 2.f * dot_err(qq_max, rmax2);
+                            const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
+                            flag = (lhs > rhs) ? 0.f : 1.f;      // (NaN compares false -> kept)
+                        }
+                        sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
+                        sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
+                        sbox[tid][6] = mb; sbox[tid][7] = flag;
+                        const unsigned fm = __ballot_sync(LIP_FULL, flag != 0.f);
+                        if (lane == 0) S.cand[warp] = fm;
+                    }
+                    bar_sync_named(1, 128);
+                    unsigned w0 = 0u, w1 = 0u;
+                    unsigned long long cm = ((unsigned long long)S.cand[1] << 32) | S.cand[0];     // uniform
+                    while (cm) {
+                        const int t = __ffsll((long long)cm) - 1;
+                        cm &= cm - 1;
+                        bool nd = false;
+                        if (valid) {
+                            float bd2 = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float f = c == 0 ? fx : c == 1 ? fy : fz;
+                                const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
+                                bd2 = fmaf(d, d, bd2);
+                            }
+                            const float bd = fmaxf(bestf + qq, 0.f);
+                            const float e = 8e-7f * (qabs + fmaxf(sbox[t][6], mabs));
+                            const float tol = d2_err(bd, e) + d2_err(bd2, e) + 2.f * dot_err(qq, bd);
+                            nd = !(bd2 - bd > tol);
+                        }
+                        if (nd) { if (t < 32) w0 |= 1u << t; else w1 |= 1u << (t - 32); }
+                    }
+                    w0 = __reduce_or_sync(LIP_FULL, w0); w1 = __reduce_or_sync(LIP_FULL, w1);
+                    if (lane == 0) {
+                        if (w0) atomicOr(&S.need[j0 / 32], w0);
+                        if (w1) atomicOr(&S.need[j0 / 32 + 1], w1);
+                    }
+                }
+                __threadfence_block();
+                bar_sync_named(1, 128);
+                if (tid == 0) mbar_arrive(&S.cull_done);
+                mbar_wait(&S.r1_ready, n_cull & 1);
+                tot1 = S.tot1;
+                mabs = fmaxf(mabs, S.mabs1);
+                consume(tot1);
+                ++n_cull;
+            }
+            if (a.profile && tid == 0) atomicAdd(&a.counters[7], (unsigned long long)(tot0 + tot1) * (unsigned long long)nq);
+
+            // ---- result: near ties are decided in float64 over everything that was staged, a warp per query -------
+            const double* __restrict__ xt = mesh_xyz(a, mt);
+            const float d2b = fmaxf(bestf + qq, 0.f), d2s = fmaxf(fminf(sec, sec_in) + qq, 0.f);
+            const float e = 8e-7f * (qabs + mabs);
+            const float tol = d2_err(d2b, e) + d2_err(d2s, e) + 4.f * dot_err(qq, d2s) + 2.f * tc_err(qq, d2s);
+            int res = idx;
+            const bool tie = valid && !(d2s - d2b > tol);
+            unsigned ties = __ballot_sync(LIP_FULL, tie);
+            if (ties && lane == 0) atomicAdd(&a.counters[3], (unsigned long long)__popc(ties));
+            while (ties) {
+                const int src = __ffs(ties) - 1;
+                ties &= ties - 1;
+                const size_t N = (size_t)a.n_total;
+                const size_t pq = (size_t)so + first + (tid - lane + src);       // slot of lane `src`
+                const double q0 = a.bin_q[pq], q1 = a.bin_q[N + pq], q2 = a.bin_q[2 * N + pq];
+                double bd = INFINITY;
+                int bi = 0x7fffffff;
+                for (int j = 0; j < K; ++j) {
+                    if (j != home && !((S.need[j >> 5] >> (j & 31)) & 1u)) continue;
+                    for (int p = a.bin_off[bbt + j] + lane; p < a.bin_off[bbt + j + 1]; p += 32) {
+                        const int vv = a.part_vid[p];
+                        const double d = rdist64(q0, q1, q2, xt[3 * (size_t)vv], xt[3 * (size_t)vv + 1], xt[3 * (size_t)vv + 2]);
+                        if (d < bd || (d == bd && vv < bi)) { bd = d; bi = vv; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(LIP_FULL, bd, o);
+                    const int oi = __shfl_xor_sync(LIP_FULL, bi, o);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                }
+                if (lane == src) res = bi;
+            }
+            if (valid) store_map(a, ub + vq, res);
+        }
+        ++n_tile;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * LIP_TC_N));
+}
+
 // queries ring 1 could not certify: one thread per query, ring 1 + ring 2, else far list
 __global__ void __launch_bounds__(128) retry_nn_kernel(LipArgs a) {
     const int n_retry = a.sched[7];

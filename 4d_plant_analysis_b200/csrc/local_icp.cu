@@ -431,7 +431,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         LIP_CHECK("icp_group_kernel / icp_big_kernel");
     } else { mark(); mark(); }
     mark();                                                  // 4: after the CTA ICP kernel
-    const bool tiles = (stages & ST_BLEND) && c->map_mode == 0;      // final map on landmark-bin tiles: no grid needed
+    const bool tiles = (stages & ST_BLEND) && c->map_mode != 1;      // final map on landmark-bin tiles: no grid needed
     if ((stages & (ST_GRID | ST_GRID_ALL)) && !tiles) {
         if (!serial) { LIP_CUDA(c, cudaStreamWaitEvent(s_grid, c->ev_begin, 0)); forked_grid = true; }
         LIP_CUDA(c, cudaMemsetAsync(a.grid_start, 0, (size_t)c->tab_total * 4, s_grid));
@@ -450,8 +450,13 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
             launches += 2;
             LIP_CHECK("blend_kernel");
             mark();                                          // 6: after the blend kernel
-            const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * c->map_blocks_per_sm);
-            blend_tile_kernel<<<(unsigned)gm, LIP_MAP_THREADS, 0, st>>>(a);
+            if (c->map_mode == 2) {                          // scores on the tensor cores (tcgen05 + TMEM): two CTAs per SM share the 512 TMEM columns
+                const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * 2);
+                blend_tile_tc_kernel<<<(unsigned)gm, LIP_TC_THREADS, 0, st>>>(a);
+            } else {
+                const size_t gm = std::min<size_t>(c->max_map_tiles, (size_t)c->sm_count * c->map_blocks_per_sm);
+                blend_tile_kernel<<<(unsigned)gm, LIP_MAP_THREADS, 0, st>>>(a);
+            }
         }
         else { mark(); blend_nn_kernel<<<c->n_tiles, LIP_TILE, 0, st>>>(a); }
         ++launches;
@@ -888,7 +893,7 @@ int lip_set_input_validation(lip_ctx* c, int on) {
 
 int lip_set_map_mode(lip_ctx* c, int mode) {
     if (!c) return LIP_EINVAL;
-    if (mode != 0 && mode != 1) return fail(c, LIP_EINVAL, "map mode must be 0 (landmark-bin tiles) or 1 (hashed grid)");
+    if (mode < 0 || mode > 2) return fail(c, LIP_EINVAL, "map mode must be 0 (landmark-bin tiles), 1 (hashed grid) or 2 (tiles on the tensor cores)");
     if (mode != c->map_mode) {                               // the tile list depends on the mode: plan again (sub-batches too)
         c->planned = false; c->user_plan = false; c->n_kids = 0; c->n_dkids = 0;
     }

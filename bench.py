@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded C4 / C5 runs")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-pairs", type=int, default=16)
-    ap.add_argument("--map-mode", type=int, default=0, help="final map: 0 = landmark-bin tiles (default), 1 = hashed grid")
+    ap.add_argument("--map-mode", type=int, default=0, help="final map: 0 = landmark-bin tiles (default), 1 = hashed grid, 2 = tiles with tensor-core scores")
     return ap.parse_args()
 
 

@@ -61,9 +61,11 @@ int  lip_create(lip_ctx** ctx, int device);
 void lip_destroy(lip_ctx* ctx);
 const char* lip_last_error(const lip_ctx* ctx);   /* ctx may be NULL: start-up error */
 int  lip_set_params(lip_ctx* ctx, const lip_params* p);
-/* Final dense map (p2p_matching_seg_icp.py:452,488, KDTree(xyz1).query): 0 (default) = exact search on
- * landmark-bin tiles (blend_tile_kernel), 1 = exact search in a hashed uniform grid (grid_build_kernel +
- * blend_nn_kernel + retry/far passes).  Same results; call before lip_batch_plan. */
+/* Final dense map (p2p_matching_seg_icp.py:452,488, KDTree(xyz1).query): 0 = exact search on landmark-bin tiles
+ * on the CUDA cores (blend_tile_kernel), 1 = exact search in a hashed uniform grid (grid_build_kernel +
+ * blend_nn_kernel + retry/far passes), 2 = the tiles of mode 0 with the scores computed by the 5th-generation tensor cores
+ * (blend_tile_tc_kernel: tcgen05.mma kind::tf32 on split operands, accumulators in TMEM).  Same results in every mode; call
+ * before lip_batch_plan. */
 int  lip_set_map_mode(lip_ctx* ctx, int mode);
 /* pinned host memory for the *_host entry points.  Optional: lip_batch_run_host stages ordinary (pageable) arrays through
  * pinned buffers of its own with a few copy threads (environment LIP_STAGING_THREADS, default min(6, cores / 2); 0 = leave

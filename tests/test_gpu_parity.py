@@ -872,3 +872,35 @@ def test_two_gpu_sharded_run_equals_single_gpu(L):
                         "--master-port", "29641", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("dist_check ok") == 2
+
+
+def test_tensor_core_map_mode_gives_identical_maps(L, syn):
+    """map mode 2: the final map's scores on the 5th-generation tensor cores (tcgen05.mma kind::tf32 on split operands,
+    accumulators in TMEM, tcgen05.ld epilogue).  The tensor-core error only widens the tolerance that sends a query to the
+    float64 decision, so the maps must equal mode 0's entry for entry — on the goldens' shapes, K == 1 segments, empty
+    partitions, tiny meshes, a many-landmark segment, a pipelined batch and int32 maps."""
+    rng = np.random.default_rng(5)
+    tiny = []
+    for n1, n2, K in [(5, 7, 2), (40, 3, 2), (12, 12, 3), (1, 9, 1), (30, 31, 1), (64, 90, 4), (300, 1, 1), (1, 300, 1), (129, 257, 2)]:
+        Lx = 3.5 * K
+        mk = lambda n: np.stack([rng.uniform(0, Lx, n), rng.normal(0, .8, n), rng.normal(0, .8, n)], 1) + 20.0
+        lm = np.stack([np.linspace(0.5, Lx - 0.5, K) if K > 1 else np.array([Lx / 2]), np.zeros(K), np.zeros(K)], 1) + 20.0
+        tiny.append((mk(n1), mk(n2) + 0.2, lm, lm + 0.2))
+    K = 300
+    many = [(_tube(rng, 9000, 3.0 * K), _tube(rng, 9300, 3.0 * K) + [0.3, 0.1, -0.1],
+             np.stack([np.linspace(1.0, 3.0 * K - 1.0, K), np.zeros(K), np.zeros(K)], 1),
+             np.stack([np.linspace(1.0, 3.0 * K - 1.0, K), np.zeros(K), np.zeros(K)], 1) + [0.3, 0.1, -0.1])]
+    cases = [L.make_config(1), L.make_config(3, scale=0.3), L.make_config(5, scale=0.05), L.batch_from_segments(tiny),
+             L.batch_from_segments(many), _batch_from_golden(L, load_golden("edge_r2")), L.make_config(2, frame_pairs=6)]
+    for i, b in enumerate(cases):
+        out = {}
+        for mode in (0, 2):
+            ctx = L.Context(0)
+            ctx.set_map_mode(mode)
+            if i == len(cases) - 1:
+                ctx.set_map_dtype(np.int32)
+            ctx.plan(b.off1, b.off2, b.lm_off)
+            out[mode] = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+            ctx.close()
+        np.testing.assert_array_equal(out[0][0], out[2][0], err_msg=f"case {i} T21")
+        np.testing.assert_array_equal(out[0][1], out[2][1], err_msg=f"case {i} T12")
