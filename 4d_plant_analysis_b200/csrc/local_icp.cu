@@ -1177,12 +1177,16 @@ int lip_series_run_host(lip_ctx* c, const double* frames, int64_t n_rows, const 
             c->pool->wait(in_left[k]);
             if (bad.load()) { rc = fail(c, LIP_EINVAL, "Input contains NaN or infinity."); break; }
         }
+        static const bool trace = getenv("LIP_TRACE_PIPELINE") != nullptr;
+        if (trace && !kc->tr[0]) for (auto& e : kc->tr) cudaEventCreate(&e);
+        if (trace) cudaEventRecord(kc->tr[0], up);
         if (need[k] > r0) {
             cudaError_t e = cudaMemcpyAsync((char*)c->in_frames.p + (size_t)r0 * 24, (const char*)src + (size_t)r0 * 24,
                                             (size_t)(need[k] - r0) * 24, cudaMemcpyHostToDevice, up);
             if (e != cudaSuccess) { rc = fail(c, LIP_ECUDA, std::string("series upload: ") + cudaGetErrorString(e)); break; }
             r0 = need[k];
         }
+        if (trace) cudaEventRecord(kc->tr[1], up);
         cudaEventRecord(c->ev_piece, up);
         cudaStreamWaitEvent(kc->stream, c->ev_piece, 0);
         kc->params = c->params; kc->map_bytes = c->map_bytes;
@@ -1209,6 +1213,13 @@ int lip_series_run_host(lip_ctx* c, const double* frames, int64_t n_rows, const 
         if (o1) c->pool->submit(T12 + (size_t)c->h_off1[s0] * msz, (char*)kc->st_out.p + (size_t)kc->n2 * msz, o1, slice, &out_left[k]);
     }
     wait_all();
+    if (getenv("LIP_TRACE_PIPELINE") && kid(0)->tr[0]) {
+        for (int k = 0; k < nk; ++k) {
+            float t[4];
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], kid(0)->tr[0], kid(k)->tr[i]);
+            fprintf(stderr, "[lip series] sub-batch %d: H2D %.3f-%.3f ms, kernels end %.3f, D2H end %.3f\n", k, t[0], t[1], t[2], t[3]);
+        }
+    }
     c->last_run_split = c->n_kids >= 2; c->last_run_dsplit = false;
     return LIP_OK;
 }
