@@ -207,10 +207,11 @@ class Context:
     map_dtype = np.int64
 
     def set_map_dtype(self, dtype):
-        """entry type of the maps returned by run_host / run_series / run_device: np.int64 (default, as the reference) or np.int32"""
+        """entry type of the maps returned by run_host / run_series / run_device: np.int64 (default, as the reference), np.int32,
+        or np.uint16 (every mesh of the batch must then have fewer than 65,536 vertices)"""
         dtype = np.dtype(dtype)
-        if dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
-            raise ValueError("map dtype must be int32 or int64")
+        if dtype not in (np.dtype(np.uint16), np.dtype(np.int32), np.dtype(np.int64)):
+            raise ValueError("map dtype must be uint16, int32 or int64")
         self._check(self.lib.lip_set_map_dtype(self.h, 8 * dtype.itemsize))
         self.map_dtype = dtype.type
 

@@ -91,7 +91,7 @@ struct LipArgs {
     int icp_tasks_per_warp, icp_class_shift;   // group sizes of icp_group_kernel (tuning knobs)
     long long warp_work;     // partitions with n_src * n_tgt <= this go to icp_group_kernel, heavier ones to icp_big_kernel
     int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
-    int map32;               // != 0: T12 / T21 point at int32 arrays (lip_set_map_dtype)
+    int map32;               // entry type of T12 / T21: 0 int64, 1 int32, 2 uint16 (lip_set_map_dtype)
     double rise_tol, flat_tol, obtuse_cos, cos_den_eps, reject_dist;
 };
 
@@ -100,7 +100,9 @@ __device__ __forceinline__ void store_map(const LipArgs& a, int u, int idx) {
     const bool side1 = u < a.n1_total;
     const int i = side1 ? u : u - a.n1_total;
     long long* t = side1 ? a.T12 : a.T21;
-    if (a.map32) reinterpret_cast<int*>(t)[i] = idx; else t[i] = idx;
+    if (a.map32 == 1) reinterpret_cast<int*>(t)[i] = idx;
+    else if (a.map32 == 2) reinterpret_cast<unsigned short*>(t)[i] = (unsigned short)idx;
+    else t[i] = idx;
 }
 __device__ __forceinline__ const double* mesh_xyz(const LipArgs& a, int m) {
     if (a.mesh_row) return a.xyz1 + 3 * (size_t)a.mesh_row[m];

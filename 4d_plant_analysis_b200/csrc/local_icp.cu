@@ -154,7 +154,7 @@ struct lip_ctx {
     // plan.  planned: the plan arrays / workspace describe SOME batch (plan_impl); user_plan: that batch is the caller's
     // (lip_batch_plan) and not an internal one of lip_icp_host / lip_nn_host, which clear it before they do anything else
     bool planned = false, user_plan = false;
-    int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0;
+    int64_t S = 0, n1 = 0, n2 = 0, sumK = 0, maxK = 0, max_mesh = 0;
     int M = 0, B = 0, n_tiles = 0, tab_total = 0, directions = 3;
     std::vector<int> h_mesh_ubase, h_mesh_bin, h_mesh_tab, h_bin_mesh, h_tile_mesh, h_tile_first, h_plan;
     std::vector<int> h_ptile_mesh, h_ptile_first, h_ptile_cnt, h_mesh_ptile;   // tiles of the partition kernels
@@ -254,7 +254,7 @@ void set_param_args(lip_ctx* c) {
     a.reject_dist = c->params.reject_dist;
     a.profile = c->profiling ? 1 : 0;
     a.map_mode = c->map_mode;
-    a.map32 = c->map_bytes == 4 ? 1 : 0;
+    a.map32 = c->map_bytes == 4 ? 1 : c->map_bytes == 2 ? 2 : 0;
     static const int tpw = getenv("LIP_ICP_TASKS_PER_WARP") ? std::max(1, atoi(getenv("LIP_ICP_TASKS_PER_WARP"))) : LIP_ICP_TASKS_PER_WARP;
     static const int csh = getenv("LIP_ICP_CLASS_SHIFT") ? atoi(getenv("LIP_ICP_CLASS_SHIFT")) : LIP_ICP_CLASS_SHIFT;
     a.icp_tasks_per_warp = tpw; a.icp_class_shift = csh;
@@ -271,7 +271,7 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
     if ((directions & LIP_DIR_BOTH) == 0) return fail(c, LIP_EINVAL, "plan: directions must include T21 and/or T12");
     if (off1[0] != 0 || off2[0] != 0 || lm_off[0] != 0) return fail(c, LIP_EINVAL, "plan: offsets must start at 0");
-    int64_t maxK = 0;
+    int64_t maxK = 0, max_mesh = 0;
     for (int64_t s = 0; s < S; ++s) {
         if (off1[s + 1] <= off1[s] || off2[s + 1] <= off2[s])
             return fail(c, LIP_EINVAL, "plan: segment pair " + std::to_string(s) + " has an empty mesh");
@@ -279,7 +279,11 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
         if (K <= 0) return fail(c, LIP_EINVAL, "plan: segment pair " + std::to_string(s) + " has no landmarks");
         if (K > LIP_MAX_LANDMARKS) return fail(c, LIP_EINVAL, "plan: more than LIP_MAX_LANDMARKS landmarks in a segment");
         maxK = std::max(maxK, K);
+        max_mesh = std::max(max_mesh, std::max(off1[s + 1] - off1[s], off2[s + 1] - off2[s]));
     }
+    if (c->map_bytes == 2 && max_mesh > 65535 && !c->is_kid)
+        return fail(c, LIP_EINVAL, "plan: 16-bit maps (lip_set_map_dtype) need every mesh to have fewer than 65,536 vertices");
+    c->max_mesh = max_mesh;
     const int64_t n1 = off1[S], n2 = off2[S], sumK = lm_off[S];
     if (n1 + n2 >= (int64_t)1 << 30 || 2 * S >= (int64_t)1 << 28)
         return fail(c, LIP_EINVAL, "plan: batch too large for 32-bit indexing; split it");
@@ -903,7 +907,9 @@ int lip_set_map_mode(lip_ctx* c, int mode) {
 
 int lip_set_map_dtype(lip_ctx* c, int bits) {
     if (!c) return LIP_EINVAL;
-    if (bits != 32 && bits != 64) return fail(c, LIP_EINVAL, "map dtype must be 32 or 64 bits");
+    if (bits != 16 && bits != 32 && bits != 64) return fail(c, LIP_EINVAL, "map dtype must be 16, 32 or 64 bits");
+    if (bits == 16 && c->planned && c->user_plan && c->max_mesh > 65535)
+        return fail(c, LIP_EINVAL, "16-bit maps need every mesh of the planned batch to have fewer than 65,536 vertices");
     c->map_bytes = bits / 8;
     return LIP_OK;
 }

@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (N = 1)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded C4 / C5 runs")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--int32-maps", action="store_true", help="headline with int32 maps instead of uint16")
     ap.add_argument("--parity-pairs", type=int, default=16)
     ap.add_argument("--map-mode", type=int, default=0, help="final map: 0 = landmark-bin tiles (default), 1 = hashed grid, 2 = tiles with tensor-core scores")
     return ap.parse_args()
@@ -212,7 +213,7 @@ class Runner:
         self.ctx.set_map_mode(map_mode)
         self.ctx.set_map_dtype(map_dtype)
         self.map_dtype = map_dtype
-        self.tdt = torch.int32 if map_dtype == np.int32 else torch.int64
+        self.tdt = {np.uint16: torch.int16, np.int32: torch.int32, np.int64: torch.int64}[map_dtype]   # (uint16 maps live in int16 storage)
         self.ctx.plan(data.off1, data.off2, data.lm_off)
         self.host = [data.frames, data.lm1, data.lm2] if self.series else [data.xyz1, data.xyz2, data.lm1, data.lm2]
         self.d_in = [torch.from_numpy(a).to(self.dev) for a in self.host]
@@ -341,6 +342,8 @@ def parity_check(args, data, run, tr_filled, tr_raw):
         ref = pool.map(_cpu_parity, segs, chunksize=1)
     dt = time.perf_counter() - t
     g21, g12 = run.h_T21.numpy(), run.h_T12.numpy()
+    if run.map_dtype == np.uint16:
+        g21, g12 = g21.view(np.uint16), g12.view(np.uint16)
     mism = tot = parts = same_it = 0
     max_dR = max_dt = 0.0
     for s, (T21, T12, d21, d12) in zip(pick, ref):
@@ -488,7 +491,9 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     data, wname = headline_workload(args, rank)
-    run = Runner(torch, native, local, data, map_mode=args.map_mode)
+    # the maps are indices into one segment's mesh: uint16 holds them whenever every mesh has fewer than 65,536 vertices
+    small = max(int(np.diff(data.off1).max()), int(np.diff(data.off2).max())) < 65536
+    run = Runner(torch, native, local, data, map_mode=args.map_mode, map_dtype=np.uint16 if small and not args.int32_maps else np.int32)
     ncorr = data.n_correspondences
     # ---- device-resident steps, clocks sampled during the timed region ----
     for _ in range(max(args.warmup, 3)):
@@ -554,13 +559,14 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": wname, "segment_pairs_per_gpu": data.n_segments, "points_per_gpu": int(n_pts),
                        "correspondences_per_step": int(ncorr_all), "host_cores": host_cores(),
-                       "maps": "int32 (lip_set_map_dtype; the drop-in functions return int64 like the reference)",
+                       "maps": ("uint16" if run.map_dtype == np.uint16 else "int32") + " (lip_set_map_dtype: entries are indices into one segment's mesh, every mesh here has "
+                               "fewer than 65,536 vertices; the drop-in functions return int64 like the reference)",
                        "l2": "inputs per step (%.0f MB float64 + workspace) exceed the 126 MB L2 only together with the ~1 GB workspace the kernels stream; no flush" % (run.h2d_bytes / 1e6),
                        "arithmetic": "fp32 NN search with float64 re-evaluation of near ties; float64 sums, SVD, transforms"},
             "frame_pairs_per_s": nfp_all / (ms_step_all / 1e3),
             "e2e": {"value": ncorr_all / (e2e_ms_all / 1e3), "unit": UNIT, "h2d_bytes_per_step": run.h2d_bytes,
                     "d2h_bytes_per_step": run.d2h_bytes, "ms_per_step": e2e_ms_all, "frame_pairs_per_s": nfp_all / (e2e_ms_all / 1e3),
-                    "path": "lip_series_run_host, pinned host buffers, int32 maps" if run.series else "lip_batch_run_host, pinned host buffers, int32 maps"},
+                    "path": ("lip_series_run_host" if run.series else "lip_batch_run_host") + ", pinned host buffers, " + ("uint16" if run.map_dtype == np.uint16 else "int32") + " maps"},
             "gpu_launches": int(launches), "kernels_per_step": counters["launches"],
             "stage_ms": stage, "counters": counters, "nn_passes": it_stats, "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm}
     # ---- parity inside the run: the oracle on random segment pairs of the batch just timed ----
@@ -589,7 +595,7 @@ def e2e_variants(torch, native, local, args, data, run, ncorr):
     out = {}
     steps = max(3, min(args.steps, 5))
     batch = data.as_batch() if run.series else data
-    # (a) pageable numpy arrays, as a caller of the reference holds them; int32 maps
+    # (a) pageable numpy arrays, as a caller of the reference holds them; same map type as the headline
     ctx = run.ctx
     fn = (lambda: ctx.run_series(data.frames, data.row1, data.row2, data.lm1, data.lm2)) if run.series else \
          (lambda: ctx.run_host(data.xyz1, data.xyz2, data.lm1, data.lm2))
@@ -614,6 +620,13 @@ def e2e_variants(torch, native, local, args, data, run, ncorr):
     ms = float(np.mean(times))
     out["pageable_new_shape_validated"] = {"ms_per_step": ms, "value": ncorr / (ms / 1e3),
                                            "path": "local_icp_batch(): lip_batch_plan of a shape not seen before + NaN/inf validation + lip_batch_run_host on pageable arrays, int64 maps, shared frames uploaded twice"}
+    # (b2) the headline path with int32 maps
+    if run.map_dtype == np.uint16:
+        r32 = Runner(torch, native, local, data, map_dtype=np.int32)
+        r32.step_device()
+        ms = r32.time_host(steps, 2, lambda: torch.cuda.synchronize())
+        out["pinned_int32_maps"] = {"ms_per_step": ms, "value": ncorr / (ms / 1e3), "d2h_bytes_per_step": r32.d2h_bytes, "path": "the headline path with int32 maps"}
+        r32.close()
     # (c) round-1 style: gathered batch (every shared frame uploaded twice), pinned, int64 maps
     r1 = Runner(torch, native, local, batch, map_dtype=np.int64)
     r1.step_device()

@@ -104,9 +104,11 @@ int lip_batch_run_host(lip_ctx* ctx, const double* xyz1, const double* xyz2,
 int lip_batch_run_device(lip_ctx* ctx, const double* d_xyz1, const double* d_xyz2,
                          const double* d_lm1, const double* d_lm2,
                          void* d_T21, void* d_T12, void* stream);
-/* Entry type of the dense maps written by lip_batch_run_* and lip_series_run_host: 64 (default: int64, numpy's intp, what
- * the reference returns from KDTree.query, p2p_matching_seg_icp.py:488) or 32 (int32: half the device-to-host bytes for
- * callers of the batched API).  The refinement / score / interpolation entry points always take int64 maps. */
+/* Entry type of the dense maps written by lip_batch_run_* and lip_series_run_*: 64 (default: int64, numpy's intp, what the
+ * reference returns from KDTree.query, p2p_matching_seg_icp.py:488), 32 (int32) or 16 (uint16: the entries are indices into ONE
+ * segment's mesh, so 16 bits hold them whenever every mesh of the batch has fewer than 65,536 vertices — checked by
+ * lip_batch_plan; a quarter of the device-to-host bytes for callers of the batched API).  The refinement / score /
+ * interpolation entry points always take int64 maps. */
 int lip_set_map_dtype(lip_ctx* ctx, int bits);
 /* A time series — the loop over consecutive day pairs of the reference (run_registration_pipeline.py:64,100-104: frame k is
  * day2 of frame pair k-1 and day1 of frame pair k).  `frames` (n_rows,3) holds every mesh ONCE; row1[s] / row2[s] (S entries

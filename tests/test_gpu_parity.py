@@ -724,6 +724,11 @@ def test_series_entry_point_equals_gathered_batch(L, syn):
         A21, A12 = ctx.run_series(ser.frames, ser.row1, ser.row2, ser.lm1, ser.lm2)
         assert A21.dtype == np.int32
         np.testing.assert_array_equal(A21, ref.T21); np.testing.assert_array_equal(A12, ref.T12)
+        ctx.set_map_dtype(np.uint16)                                            # every mesh here has fewer than 65,536 vertices
+        U21, U12 = ctx.run_series(ser.frames, ser.row1, ser.row2, ser.lm1, ser.lm2)
+        assert U21.dtype == np.uint16
+        np.testing.assert_array_equal(U21, ref.T21); np.testing.assert_array_equal(U12, ref.T12)
+        ctx.set_map_dtype(np.int32)
         B21, B12 = ctx.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)                  # the batch entry point with int32 maps
         np.testing.assert_array_equal(B21, ref.T21); np.testing.assert_array_equal(B12, ref.T12)
         pins = [torch.from_numpy(a).pin_memory() for a in (ser.frames, ser.lm1, ser.lm2)]
@@ -778,6 +783,21 @@ def test_reject_dist_matches_oracle(L):
             if ok.all():
                 _assert_map_equal_up_to_ties(T21[b.off2[s]:b.off2[s + 1]], T_or, det["x2t"], x1, f"reject {reject} seg {s}")
     assert n_changed > 0, "the threshold never rejected a pair: the test would not notice a dead hook"
+    ctx.close()
+
+
+def test_uint16_maps_need_small_meshes(L):
+    rng = np.random.default_rng(9)
+    x1, x2 = _tube(rng, 70000, 300.0), _tube(rng, 500, 300.0)
+    lm = np.stack([np.linspace(1.0, 299.0, 90), np.zeros(90), np.zeros(90)], 1)
+    ctx = L.Context(0)
+    ctx.set_map_dtype(np.uint16)
+    with pytest.raises(ValueError):
+        ctx.plan([0, len(x1)], [0, len(x2)], [0, len(lm)])
+    ctx.set_map_dtype(np.int32)
+    ctx.plan([0, len(x1)], [0, len(x2)], [0, len(lm)])
+    with pytest.raises(ValueError):
+        ctx.set_map_dtype(np.uint16)
     ctx.close()
 
 
