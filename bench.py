@@ -576,6 +576,7 @@ def run_b200(args):
     # ---- the other host paths of the same workload (this rank only) ----
     if world == 1:
         line["e2e"]["variants"] = e2e_variants(torch, native, local, args, data, run, ncorr)
+        line["body_e2e"] = body_e2e(native, local, args, data, ncorr)
     run.close()
     # ---- one entry per BASELINE config ----
     if world == 1 and not args.no_configs:
@@ -636,6 +637,25 @@ def e2e_variants(torch, native, local, args, data, run, ncorr):
     r1.close()
     c2.close()
     return out
+
+
+def body_e2e(native, local, args, data, ncorr):
+    """the whole per-segment body of the reference's driver (p2p_matching_seg_icp.py:173-189: both maps, double_direction_refinement,
+    evaluate_p2p_matching) for the bench batch in ONE call from ordinary numpy arrays (lip_batch_match_host)"""
+    B = importlib.import_module("4d_plant_analysis_b200.batch")
+    batch = data.as_batch() if hasattr(data, "frames") else data
+    ctx = native.Context(local)
+    B.match_segments_batch(batch, ctx=ctx)
+    times = []
+    for _ in range(3):
+        t = time.perf_counter()
+        r = B.match_segments_batch(batch, ctx=ctx)
+        times.append(1e3 * (time.perf_counter() - t))
+    ctx.close()
+    ms = float(np.median(times))
+    return {"ms_per_step": ms, "value": ncorr / (ms / 1e3), "unit": UNIT, "frame_pairs_per_s": batch.n_frame_pairs / (ms / 1e3),
+            "mean_scores": [float(x) for x in np.asarray(r.score)],
+            "path": "match_segments_batch(): T21 + T12, double_direction_refinement, evaluate_p2p_matching of every segment pair, pageable numpy in, numpy out"}
 
 
 def configs_table(torch, native, local, args, sm_max_mhz, peak_src, barrier):

@@ -16,6 +16,10 @@ from oracle import local_icp_oracle as O
 pytestmark = pytest.mark.gpu
 
 RT_TOL = 1e-5          # north_star: rotations / translations within 1e-5
+# what the kernels actually achieve on these fixed seeds (no unused slack); printed by the tests with -s
+SLACK_GOLDEN = {"c1_small": 1.0, "c2_small": 1.0, "c3_small": 1.0, "c5_small": 1.0}   # every partition that ran is compared
+SLACK_FUZZ_ITER = 0.0          # no stop decision differs from the oracle's
+SLACK_MAXLM_ITER = 1.0         # identical iteration count on all 2,048 partitions
 TIE_RTOL = 1e-6        # north_star: ties within 1e-6 relative distance
 
 
@@ -62,7 +66,9 @@ def test_golden_batch(L, case):
     res = L.local_icp_batch(_batch_from_golden(L, g), details=True)
     assert res.T21.dtype == np.int64 and res.T12.dtype == np.int64
     n_checked = _check_against_reference_rows(res, g)
-    assert n_checked >= 0.9 * (g["v21"].sum() + g["v12"].sum())
+    n_ran = int(g["v21"].sum() + g["v12"].sum())
+    print(f"{case}: {n_checked} of {n_ran} partitions compared with the reference's rows (the rest: rank-deficient solves)")
+    assert n_checked >= SLACK_GOLDEN[case] * n_ran
     n_ties = 0
     for s, x1, x2, l1, l2 in golden_segments(g):
         a, b, c, d = g["off1"][s], g["off1"][s + 1], g["off2"][s], g["off2"][s + 1]
@@ -414,7 +420,8 @@ def test_fuzz_small_random_segments(L):
                 continue
             _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, f"fuzz seg {s} T{d}")
             n_checked += 1
-    assert n_checked > 150 and n_iter_diff <= 0.02 * n_checked, (n_checked, n_iter_diff)
+    print(f"fuzz: {n_checked} segment directions compared, {n_iter_diff} with a stop decision exactly on a threshold")
+    assert n_checked > 150 and n_iter_diff <= SLACK_FUZZ_ITER * n_checked, (n_checked, n_iter_diff)
 
 
 @pytest.mark.parametrize("case", ["c1_small", "c3_small", "c5_small"])
@@ -503,10 +510,11 @@ def test_max_landmarks_segment(L):
     np.testing.assert_array_equal(st != 0, det["valid"])
     ok = st == 1
     same = res.transforms["raw"]["iters21"][ok] == det["iters"][ok]
-    assert same.mean() > 0.995
+    print(f"max landmarks: identical iteration count on {same.mean():.5f} of {int(ok.sum())} partitions, {int((res.T21 != T_or).sum())} of {len(T_or)} map entries differ")
+    assert same.mean() >= SLACK_MAXLM_ITER
     np.testing.assert_allclose(res.transforms["R21"][ok][same], det["R"][ok][same], rtol=0, atol=RT_TOL)
     bad = np.nonzero(res.T21 != T_or)[0]
-    assert len(bad) <= 0.002 * len(T_or)                      # only points fed by the few partitions with another stop decision
+    assert len(bad) == 0
     with pytest.raises(ValueError):
         lm3 = np.vstack([lm1, lm1[-1:] + 1.0])
         L.local_icp_batch([(x1, x2, lm3, lm3)])
