@@ -1543,15 +1543,14 @@ static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2,
     int64_t max_n1 = 0, max_n = 0;
     for (size_t s = 0; s < S; ++s) {
         const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
-        max_entries = std::max(max_entries, (size_t)(3 * a2 + 4 * a1));
+        max_entries = std::max(max_entries, (size_t)(2 * a2 + a1 + 4 + (a1 + 31) / 32 * 2));      // the hot tables of refine_kernel (shared memory)
         max_n1 = std::max(max_n1, a1);
         max_n = std::max(max_n, std::max(a1, a2));
     }
     const bool narrow = max_n < 65535;                       // 16-bit tables: 0xFFFF = none
     const size_t esz = narrow ? 2 : 4;
     const size_t o_qb = align_up(n1 * 20), o_scratch = o_qb + align_up((S + 1) * 4);
-    const bool need_scratch = max_entries * esz + 16 > (size_t)(227 * 1024 - 1024);
-    LIP_CUDA(c, c->misc.ensure(o_scratch + (need_scratch ? (3 * n2 + 4 * n1) * esz : 16)));
+    LIP_CUDA(c, c->misc.ensure(o_scratch + (3 * n2 + 4 * n1 + 16 * S) * esz + 16));   // cold tables always, hot ones when they do not fit SMEM
     LipArgs a = c->args;
     a.xyz1 = d_xyz1; a.xyz2 = d_xyz2;
     int* nn4 = c->misc.as<int>();                            // 5 neighbours per vertex of mesh1, row = [self, 4 nearest]
