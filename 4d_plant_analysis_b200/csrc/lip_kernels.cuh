@@ -296,6 +296,9 @@ __global__ void __launch_bounds__(LIP_PART_THREADS) partition_place_kernel(LipAr
 // winners' float64 gathers hit the same lines) and the boxes of query tiles are tight.  Ties are always decided by vertex id.
 // Bins of up to 256 members (the usual case) are held in registers across the passes and permuted through SMEM: every
 // global store coalesced.
+#ifndef LIP_SORT_BATCH
+#define LIP_SORT_BATCH 2      // members per lane whose gathers are issued together in the final pass of bin_sort_kernel
+#endif
 #define LIP_SORT_WARPS 4
 __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a) {
     __shared__ unsigned skey_all[LIP_SORT_WARPS][256];
@@ -393,6 +396,37 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
             if (e < nb && rk == 0) skey[bucket] += __popc(peers);
             __syncwarp();
         }
+#if LIP_SORT_BATCH > 1
+        // coalesced stores of everything that is kept in bin order; the gathers by vertex id of LIP_SORT_BATCH members are in
+        // flight together (the kernel waits on L2 latency, not on bandwidth)
+        for (int pr0 = lane; pr0 < nb; pr0 += 32 * LIP_SORT_BATCH) {
+            double gx[LIP_SORT_BATCH], gy[LIP_SORT_BATCH], gz[LIP_SORT_BATCH], g0[LIP_SORT_BATCH], g1[LIP_SORT_BATCH];
+            int gn[LIP_SORT_BATCH];
+            float4 t[LIP_SORT_BATCH];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_BATCH; ++k) {
+                const int pr = pr0 + 32 * k;
+                if (pr < nb) {
+                    t[k] = sdat[pr];
+                    const size_t v = (size_t)__float_as_int(t[k].w);
+                    gx[k] = xyz[3 * v]; gy[k] = xyz[3 * v + 1]; gz[k] = xyz[3 * v + 2];
+                    gn[k] = a.nn1[ub + v]; g0[k] = a.d0[ub + v]; g1[k] = a.d1[ub + v];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_BATCH; ++k) {
+                const int pr = pr0 + 32 * k;
+                if (pr < nb) {
+                    const size_t p = (size_t)s0 + pr;
+                    a.part_vid[p] = __float_as_int(t[k].w);
+                    a.bin_pts[p] = t[k];
+                    a.bin_xyz[p] = gx[k]; a.bin_xyz[N + p] = gy[k]; a.bin_xyz[2 * N + p] = gz[k];
+                    a.pos_bin[p] = b; a.pos_nn1[p] = gn[k];
+                    a.pos_d[p] = g0[k]; a.pos_d[N + p] = g1[k];
+                }
+            }
+        }
+#else
         for (int pr = lane; pr < nb; pr += 32) {         // coalesced stores of everything that is kept in bin order
             const float4 t = sdat[pr];
             const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + pr;
@@ -402,6 +436,7 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
             a.pos_bin[p] = b; a.pos_nn1[p] = a.nn1[ub + v];
             a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
         }
+#endif
     } else {
         for (int base = 0; base < nb; base += 32) {
             const int e = base + lane;
