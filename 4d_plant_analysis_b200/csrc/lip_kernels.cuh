@@ -2678,7 +2678,9 @@ __device__ __forceinline__ void refine_pair(const LipArgs& a, IT* __restrict__ h
     for (int i = lane; i < n2; i += 32) t21g[i] = (long long)w.t21[i];
 }
 
-template <typename IT>
+// ALL_SMEM: the cold tables live in shared memory too (fewer segment pairs per SM, but every access is an LDS) — the host picks
+// the layout that needs the fewer waves of CTAs for the batch at hand
+template <typename IT, bool ALL_SMEM>
 __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __restrict__ nn5, long long* __restrict__ T21,
                                                     const long long* __restrict__ T12, IT* __restrict__ scratch, int smem_entries_cap) {
     extern __shared__ double smem_ref[];
@@ -2691,9 +2693,11 @@ __global__ void __launch_bounds__(32) refine_kernel(LipArgs a, const int* __rest
     // tables: 3 n2 + 4 n1 + 16 entries per segment pair in the scratch: [hot: 2 n2 + n1 + snapshot bits | cold: n2 + 2 n1]
     IT* region = scratch + 3 * (size_t)u2 + 4 * (size_t)u1 + 16 * (size_t)s;
     const size_t need = 2 * (size_t)n2 + (size_t)n1 + 4 + ((size_t)n1 + 31) / 32 * (4 / sizeof(IT));
-    IT* cold = region + need;
-    if (need <= (size_t)smem_entries_cap) refine_pair<IT>(a, reinterpret_cast<IT*>(smem_ref), cold, nn, t21g, t12g, u2, n1, n2, lane);
-    else refine_pair<IT>(a, region, cold, nn, t21g, t12g, u2, n1, n2, lane);
+    const size_t need_all = need + (size_t)n2 + 2 * (size_t)n1;
+    IT* sm = reinterpret_cast<IT*>(smem_ref);
+    if (ALL_SMEM && need_all <= (size_t)smem_entries_cap) refine_pair<IT>(a, sm, sm + need, nn, t21g, t12g, u2, n1, n2, lane);
+    else if (need <= (size_t)smem_entries_cap) refine_pair<IT>(a, sm, region + need, nn, t21g, t12g, u2, n1, n2, lane);
+    else refine_pair<IT>(a, region, region + need, nn, t21g, t12g, u2, n1, n2, lane);
 }
 
 

@@ -1525,13 +1525,28 @@ int lip_batch_evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_
 extern "C++" {
 template <typename IT>
 static int launch_refine(lip_ctx* c, const LipArgs& a, const int* nn5, long long* d_T21, const long long* d_T12, IT* scratch,
-                         size_t max_entries, cudaStream_t st) {
+                         size_t max_entries, size_t max_entries_all, cudaStream_t st) {
     int smem_cap = 0;
     LIP_CUDA(c, cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     smem_cap -= 1024;
-    const size_t smem = std::min<size_t>((size_t)smem_cap, max_entries * sizeof(IT) + 16);
-    LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_kernel<IT><<<(unsigned)c->S, 32, smem, st>>>(a, nn5, d_T21, d_T12, scratch, (int)(smem / sizeof(IT)));
+    // Two layouts: every table in shared memory (fast steps, few segment pairs per SM) or only the hot ones (slower steps — the
+    // cold tables are L2 accesses — but more pairs per SM).  One lane walks a pair from start to end, so the time is
+    // waves x time per pair: measured 4.7 ms per maize pair with all tables in SMEM, ~8 ms with the hot ones only.
+    const size_t smem_hot = std::min<size_t>((size_t)smem_cap, max_entries * sizeof(IT) + 16);
+    const size_t smem_all = std::min<size_t>((size_t)smem_cap, max_entries_all * sizeof(IT) + 16);
+    const size_t sm_smem = 227 * 1024;
+    // (a sub-batch of a pipelined call shares the GPU with its siblings' kernels: count their segment pairs as well)
+    const size_t in_flight = (size_t)c->S * (c->is_kid ? LIP_PIPELINE_CHUNKS : 1);
+    auto waves = [&](size_t smem) { const size_t per_sm = std::max<size_t>(1, std::min<size_t>(32, sm_smem / (smem + 1024))); return (in_flight + per_sm * c->sm_count - 1) / (per_sm * c->sm_count); };
+    static const int force = getenv("LIP_REFINE_LAYOUT") ? atoi(getenv("LIP_REFINE_LAYOUT")) : 0;     // 1: all in SMEM, 2: hot only
+    const bool all = force ? force == 1 : (max_entries_all * sizeof(IT) + 16 <= (size_t)smem_cap && 1.0 * waves(smem_all) <= 1.7 * waves(smem_hot));
+    if (all) {
+        LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel<IT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+        refine_kernel<IT, true><<<(unsigned)c->S, 32, smem_all, st>>>(a, nn5, d_T21, d_T12, scratch, (int)(smem_all / sizeof(IT)));
+    } else {
+        LIP_CUDA(c, cudaFuncSetAttribute(refine_kernel<IT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
+        refine_kernel<IT, false><<<(unsigned)c->S, 32, smem_hot, st>>>(a, nn5, d_T21, d_T12, scratch, (int)(smem_hot / sizeof(IT)));
+    }
     LIP_CUDA(c, cudaGetLastError());
     return LIP_OK;
 }
@@ -1539,11 +1554,12 @@ static int launch_refine(lip_ctx* c, const LipArgs& a, const int* nn5, long long
 static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, long long* d_T21, const long long* d_T12,
                          cudaStream_t st) {
     const size_t n1 = (size_t)c->n1, n2 = (size_t)c->n2, S = (size_t)c->S;
-    size_t max_entries = 0;
+    size_t max_entries = 0, max_entries_all = 0;
     int64_t max_n1 = 0, max_n = 0;
     for (size_t s = 0; s < S; ++s) {
         const int64_t a1 = c->h_off1[s + 1] - c->h_off1[s], a2 = c->h_off2[s + 1] - c->h_off2[s];
         max_entries = std::max(max_entries, (size_t)(2 * a2 + a1 + 4 + (a1 + 31) / 32 * 2));      // the hot tables of refine_kernel (shared memory)
+        max_entries_all = std::max(max_entries_all, (size_t)(3 * a2 + 3 * a1 + 4 + (a1 + 31) / 32 * 2));   // ... and all of them
         max_n1 = std::max(max_n1, a1);
         max_n = std::max(max_n, std::max(a1, a2));
     }
@@ -1562,8 +1578,8 @@ static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2,
     LIP_CUDA(c, cudaMemcpyAsync(d_qbase, qbase.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
     int rc5 = launch_self_knn<5>(c, a, 0, 1, d_qbase, nn4, max_n1, st);
     if (rc5) return rc5;
-    return narrow ? launch_refine<unsigned short>(c, a, nn4, d_T21, d_T12, (unsigned short*)scratch, max_entries, st)
-                  : launch_refine<int>(c, a, nn4, d_T21, d_T12, (int*)scratch, max_entries, st);
+    return narrow ? launch_refine<unsigned short>(c, a, nn4, d_T21, d_T12, (unsigned short*)scratch, max_entries, max_entries_all, st)
+                  : launch_refine<int>(c, a, nn4, d_T21, d_T12, (int*)scratch, max_entries, max_entries_all, st);
 }
 
 int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12) {
