@@ -1,6 +1,7 @@
 // Device-side building blocks shared by the local-ICP kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -89,6 +90,8 @@ struct LipArgs {
     unsigned long long* counters;  // [8]
     int max_iter, profile;   // profile != 0: count evaluated candidate pairs (counters[7])
     int icp_tasks_per_warp, icp_class_shift;   // group sizes of icp_group_kernel (tuning knobs)
+    int cluster_coop_parts;                    // ... whose CTAs split one partition between them only in batches of at most this many partitions
+    int big_cluster_cls;                       // CTA work classes >= this one run on thread-block clusters (icp_cluster_kernel); 4: none
     long long warp_work;     // partitions with n_src * n_tgt <= this go to icp_group_kernel, heavier ones to icp_big_kernel
     int map_mode;            // final map: 0 = landmark-bin tiles (blend_tile_kernel), 1 = hashed grid (blend_nn_kernel)
     int map32;               // entry type of T12 / T21: 0 int64, 1 int32, 2 uint16 (lip_set_map_dtype)

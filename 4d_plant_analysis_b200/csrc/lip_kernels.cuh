@@ -35,6 +35,14 @@
 #ifndef LIP_BIG_THREADS
 #define LIP_BIG_THREADS 128
 #endif
+#ifndef LIP_CLUSTER_SIZE
+#define LIP_CLUSTER_SIZE 8        // CTAs per cluster of icp_cluster_kernel (runtime: LIP_CLUSTER_SIZE, 1 = off) ...
+#define LIP_CLUSTER_CLASS 2       // ... which takes the CTA work classes from this one up (2: > 400 k pairs; runtime: LIP_CLUSTER_CLASS)
+#define LIP_CLUSTER_COOP_PARTS 8192   // the cluster kernel runs (and its CTAs co-operate) only in batches of at most this many landmark bins (runtime: LIP_CLUSTER_COOP_PARTS)
+#define LIP_CLUSTER_THREADS 256
+#define LIP_CLUSTER_MINBLOCKS 2    // CTAs per SM the cluster kernel is compiled for (register cap 128)
+#define LIP_CLUSTER_CHUNK 2048    // target points per SMEM tile (also the scratch of the 17-sum reduction: 4 KB per warp)
+#endif
 #define LIP_TILE 128          // vertices per CTA of the blend / query kernels
 #ifndef LIP_MAP_THREADS
 #define LIP_MAP_THREADS 64   // blend_tile_kernel: threads per CTA
@@ -918,14 +926,16 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS, 4) icp_big_kernel(LipArgs a) 
     __shared__ IcpState st_sh;
     IcpState* st = &st_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_big = a.sched[1];
+    const int top = a.big_cluster_cls - 1;                  // classes above `top` belong to icp_cluster_kernel
+    int n_big = 0;
+    for (int k = 0; k <= top; ++k) n_big += a.sched[12 + k];
     for (;;) {                                              // persistent CTAs, heaviest class first
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&a.sched[16], 1);
         __syncthreads();
         const int wi = s_item;
         if (wi >= n_big) break;
-        int cls = 3, ri = wi;
+        int cls = top, ri = wi;
         while (cls > 0 && ri >= a.sched[12 + cls]) { ri -= a.sched[12 + cls]; --cls; }
         const int b = a.big_list[(size_t)cls * a.B + ri];
         const IcpFrame f = a.icp_frames[b];
@@ -964,6 +974,102 @@ __global__ void __launch_bounds__(LIP_BIG_THREADS, 4) icp_big_kernel(LipArgs a) 
         }
         __syncthreads();
         if (tid == 0) icp_store(a, b, st, f.c0, f.c1, f.c2, iters, s_status);
+    }
+}
+
+// ---- thread-block-cluster variant for the heaviest partitions (work classes >= a.big_cluster_cls: whole-organ ICPs of
+// K == 1 segments, p2p_matching_seg_icp.py:440-449).  The serial chain of NN passes of ONE such partition is the critical
+// path of the ICP stage of a small batch (one frame pair, as the reference's driver submits them) when it runs on the 128
+// threads of an icp_big_kernel CTA.  Co-operative mode — as long as every heavy partition of the batch can have a cluster of
+// its own at once: the CTAs of a cluster split the queries of a pass; every CTA stages the whole target, keeps its own copy of
+// the ICP state and runs the identical serial part on the identical totals (each CTA adds the partial sums of all ranks, in
+// rank order, out of their shared memory), so one cluster barrier per pass is the whole exchange.  With more heavy partitions
+// than clusters, or in a batch of more than a.cluster_coop_parts partitions, the stage is throughput-bound, not latency-bound,
+// and every CTA works for itself (one partition per CTA).
+// Measured (profiles/README.md): one 979 x 1,058 ICP 292 -> 107 us, one 5,000 x 5,000 ICP 7.4 -> 1.1 ms.
+template <int NT, int CHUNK>
+__global__ void __launch_bounds__(NT, LIP_CLUSTER_MINBLOCKS) icp_cluster_kernel(LipArgs a) {
+    namespace cg = cooperative_groups;
+    __shared__ float4 tf[CHUNK + 8];
+    __shared__ double red17[NT / 32][17];
+    __shared__ double part[2][17];                          // this CTA's sums of the current pass (two buffers: see the barrier note)
+    __shared__ double tot[17];
+    __shared__ int s_item, s_go, s_status;
+    __shared__ IcpState st_sh;
+    static_assert(!LIP_ICP_SUM17 || (CHUNK + 8) * 16 >= (NT / 32) * 16 * 32 * 8, "search tile doubles as the 17-sum scratch");
+    IcpState* st = &st_sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lo_cls = a.big_cluster_cls;
+    int n_items = 0;
+    for (int k = lo_cls; k < 4; ++k) n_items += a.sched[12 + k];
+    if (n_items == 0) return;
+    // uniform over the grid: co-operate only while no partition would have to wait for a cluster, and only in batches too small
+    // to fill the GPU anyway — a co-operating cluster spends about six times the SM time of a lone CTA on the same partition
+    // (107 us on 8 half-SMs against 292 us on a quarter), which a throughput-bound batch pays in full
+    const bool coop = cluster.num_blocks() > 1 && (long long)n_items * cluster.num_blocks() <= (long long)gridDim.x &&
+                      a.sched[0] + a.sched[1] <= a.cluster_coop_parts;
+    const int rank = coop ? (int)cluster.block_rank() : 0, CL = coop ? (int)cluster.num_blocks() : 1;
+    const int* item0 = coop ? cluster.map_shared_rank(&s_item, 0) : &s_item;
+    for (;;) {                                              // persistent clusters / CTAs, heaviest class first
+        __syncthreads();
+        if (rank == 0 && tid == 0) s_item = atomicAdd(&a.sched[17], 1);
+        if (coop) cluster.sync(); else __syncthreads();
+        const int wi = *item0;
+        if (coop) cluster.sync();                            // everybody has read it: rank 0 may draw again (or leave)
+        if (wi >= n_items) break;
+        int cls = 3, ri = wi;
+        while (cls > lo_cls && ri >= a.sched[12 + cls]) { ri -= a.sched[12 + cls]; --cls; }
+        const int b = a.big_list[(size_t)cls * a.B + ri];
+        const IcpFrame f = a.icp_frames[b];
+        // this CTA's queries: whole warps' worth, the ranks in order
+        const int per = ((f.ns + 32 * CL - 1) / (32 * CL)) * 32;
+        const int q_lo = min(f.ns, rank * per), q_n = min(f.ns, q_lo + per) - q_lo;
+        if (warp == 0) {
+            const double* ss = a.bin_sum + 4 * (size_t)b;
+            const double* ts = a.bin_sum + 4 * (size_t)pair_bin(a, b);
+            icp_state_init(st, ts[0] - ss[0], ts[1] - ss[1], ts[2] - ss[2]);
+            if (lane == 0) { s_go = 1; s_status = 1; }
+        }
+        double prev = 0.0;                                   // warp 0 only
+        int iters = 0;
+        for (int it = 0; it < a.max_iter; ++it) {
+            __syncthreads();
+            if (!s_go) break;                                // identical in every CTA of the cluster
+            if (warp == 0) icp_state_accumulate(st);
+            __syncthreads();
+            if (q_n > 0) {
+                if (f.mabs <= 24.0f) icp_pass<true, NT, CHUNK, false>(a, tf, nullptr, st, tid, f.so + q_lo, q_n, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, red17[warp]);
+                else icp_pass<false, NT, CHUNK, false>(a, tf, nullptr, st, tid, f.so + q_lo, q_n, f.to, f.nt, f.c0, f.c1, f.c2, f.sh0, f.sh1, f.sh2, f.mabs, red17[warp]);
+            } else if (lane < 17) red17[warp][lane] = 0.0;
+            __syncthreads();
+            if (tid < 17) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < NT / 32; ++k) s += red17[k][tid];
+                part[it & 1][tid] = s;
+            }
+            // One barrier per pass.  part[it & 1] is rewritten two passes (or one partition: two barriers) later, by when every
+            // CTA has passed the next barrier and therefore finished reading it.
+            if (coop) cluster.sync(); else __syncthreads();
+            if (warp == 0) {                                 // serial part: all lanes of warp 0 of every CTA identically
+                if (lane < 17) {
+                    double s = 0;
+                    for (int r = 0; r < CL; ++r) s += (coop ? cluster.map_shared_rank(&part[it & 1][0], r) : &part[it & 1][0])[lane];
+                    tot[lane] = s;
+                }
+                __syncwarp();
+                const double cost = tot[0] / f.ns;
+                iters = it + 1;
+                if (it > 1 && (cost > prev + a.rise_tol || fabs(cost - prev) < a.flat_tol)) { if (lane == 0) s_go = 0; }
+                else {
+                    prev = cost;
+                    if (icp_kabsch_step(tot, st) && lane == 0) s_status = 2;
+                }
+            }
+        }
+        __syncthreads();
+        if (rank == 0 && tid == 0) icp_store(a, b, st, f.c0, f.c1, f.c2, iters, s_status);
     }
 }
 

@@ -129,8 +129,12 @@ struct lip_ctx {
     int sm_count = 0;
     int group_blocks_per_sm = 1, big_blocks_per_sm = 1, map_blocks_per_sm = 1;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // concurrent branches: [0] CTA ICP kernel, [1] uploads of the host pipeline, [2] grid build
-    cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent branches: [0] CTA ICP kernel, [1] uploads of the host pipeline, [2] grid build, [3] cluster ICP kernel
+    cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    int cluster_size = LIP_CLUSTER_SIZE, cluster_cls = LIP_CLUSTER_CLASS, cluster_grid = 0;
+    int64_t heavy_bound = 0;                                 // planned batch: upper bound on the partitions the cluster kernel can get
+    bool use_clusters = false;                               // planned batch: small, with whole-organ ICPs (see plan_impl)
+    int64_t cluster_max_bins = LIP_CLUSTER_COOP_PARTS;
     bool fill_done = false;
     int map_mode = 0;        // final map: 0 = landmark-bin tiles, 1 = hashed grid (lip_set_map_mode)
     int map_bytes = 8;       // entry size of the dense maps of lip_batch_run_* / lip_series_run_host: 8 (int64, numpy intp) or 4 (lip_set_map_dtype)
@@ -258,6 +262,8 @@ void set_param_args(lip_ctx* c) {
     static const int tpw = getenv("LIP_ICP_TASKS_PER_WARP") ? std::max(1, atoi(getenv("LIP_ICP_TASKS_PER_WARP"))) : LIP_ICP_TASKS_PER_WARP;
     static const int csh = getenv("LIP_ICP_CLASS_SHIFT") ? atoi(getenv("LIP_ICP_CLASS_SHIFT")) : LIP_ICP_CLASS_SHIFT;
     a.icp_tasks_per_warp = tpw; a.icp_class_shift = csh;
+    a.big_cluster_cls = c->use_clusters ? c->cluster_cls : 4;
+    a.cluster_coop_parts = (int)std::min<int64_t>(c->cluster_max_bins, INT32_MAX);
     // warp / CTA split of the ICP partitions: large batches keep the (more efficient) warp kernel busy with up to 96 k pairs
     // per partition, small ones (the sub-batches of the host pipeline) hand more to the CTA kernel, whose tails are shorter
     static const long long ww = getenv("LIP_WARP_WORK") ? atoll(getenv("LIP_WARP_WORK")) : 0;
@@ -271,7 +277,10 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
     if ((directions & LIP_DIR_BOTH) == 0) return fail(c, LIP_EINVAL, "plan: directions must include T21 and/or T12");
     if (off1[0] != 0 || off2[0] != 0 || lm_off[0] != 0) return fail(c, LIP_EINVAL, "plan: offsets must start at 0");
-    int64_t maxK = 0, max_mesh = 0;
+    int64_t maxK = 0, max_mesh = 0, heavy_bound = 0;
+    bool heavy_hint = false;
+    static const int64_t kClassFloor[5] = {0, 150000, 400000, 1000000, INT64_MAX / 2};   // icp_schedule_kernel's classes
+    const int64_t heavy_thr = kClassFloor[c->cluster_cls];
     for (int64_t s = 0; s < S; ++s) {
         if (off1[s + 1] <= off1[s] || off2[s + 1] <= off2[s])
             return fail(c, LIP_EINVAL, "plan: segment pair " + std::to_string(s) + " has an empty mesh");
@@ -280,7 +289,17 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
         if (K > LIP_MAX_LANDMARKS) return fail(c, LIP_EINVAL, "plan: more than LIP_MAX_LANDMARKS landmarks in a segment");
         maxK = std::max(maxK, K);
         max_mesh = std::max(max_mesh, std::max(off1[s + 1] - off1[s], off2[s + 1] - off2[s]));
+        // partitions of this pair that can exceed the cluster kernel's work threshold: sum of n_src * n_tgt over its bins <= n1 * n2
+        const int64_t pairs = (off1[s + 1] - off1[s]) * (off2[s + 1] - off2[s]);
+        heavy_bound += 2 * std::min<int64_t>(K, pairs / (heavy_thr + 1));
+        heavy_hint = heavy_hint || pairs / (K * K) > heavy_thr / 4;      // the AVERAGE bin pair of this segment pair is near the threshold
     }
+    c->heavy_bound = heavy_bound;
+    // The cluster kernel pays in batches whose ICP stage is the serial chain of a few whole-organ ICPs (one frame pair of small
+    // organs, as the reference's driver submits them).  In large batches the GPU is busy anyway and a co-operating cluster costs
+    // more SM time than a lone CTA; in batches without such partitions its launch is ~10 us of overhead.  Both keep the CTA kernel.
+    c->use_clusters = heavy_hint && heavy_bound > 0 && !c->is_kid && c->cluster_cls < 4 && c->cluster_grid > 0 &&
+                      2 * lm_off[S] <= c->cluster_max_bins;
     if (c->map_bytes == 2 && max_mesh > 65535 && !c->is_kid)
         return fail(c, LIP_EINVAL, "plan: 16-bit maps (lip_set_map_dtype) need every mesh to have fewer than 65,536 vertices");
     c->max_mesh = max_mesh;
@@ -422,16 +441,35 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
         int gb = (int)std::max<int64_t>(1, std::min<int64_t>(bound, (int64_t)c->sm_count * c->big_blocks_per_sm));
         int gs = c->sm_count * c->group_blocks_per_sm;
         gs = std::max(1, std::min(gs, (c->B + LIP_ICP_WARPS - 1) / LIP_ICP_WARPS));
+        // ... and the heaviest of those on thread-block clusters (a partition of > 400 k pairs holds > 632 points on one side)
+        const bool clusters = a.big_cluster_cls < 4;
+        auto launch_clusters = [&](cudaStream_t s) -> cudaError_t {
+            const int64_t ncl = std::max<int64_t>(1, std::min<int64_t>(c->heavy_bound, c->cluster_grid / c->cluster_size));
+            cudaLaunchConfig_t q = {};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)c->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.gridDim = dim3((unsigned)(ncl * c->cluster_size)); q.blockDim = dim3(LIP_CLUSTER_THREADS); q.stream = s;
+            q.attrs = at; q.numAttrs = 1;
+            return cudaLaunchKernelEx(&q, icp_cluster_kernel<LIP_CLUSTER_THREADS, LIP_CLUSTER_CHUNK>, a);
+        };
         if (serial) {
             icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, kGroupSmem, st>>>(a);
             mark();                                          // 3: after the group kernel
+            if (clusters) LIP_CUDA(c, launch_clusters(st));
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, st>>>(a);
         } else {
+            if (clusters) {
+                LIP_CUDA(c, cudaStreamWaitEvent(c->side[3], c->ev_fork, 0));
+                LIP_CUDA(c, launch_clusters(c->side[3]));
+                LIP_CUDA(c, cudaEventRecord(c->ev_join[3], c->side[3]));
+            }
             icp_big_kernel<<<gb, LIP_BIG_THREADS, 0, s_big>>>(a);
             icp_group_kernel<<<gs, LIP_ICP_WARPS * 32, kGroupSmem, st>>>(a);
             mark();
+            if (clusters) LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[3], 0));
         }
-        launches += 3;
+        launches += clusters ? 4 : 3;
         LIP_CHECK("icp_group_kernel / icp_big_kernel");
     } else { mark(); mark(); }
     mark();                                                  // 4: after the CTA ICP kernel
@@ -836,7 +874,7 @@ int lip_create(lip_ctx** out, int device) {
         delete c;
         return fail(nullptr, LIP_ENODEV, cudaGetErrorString(e));
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
@@ -850,6 +888,22 @@ int lip_create(lip_ctx** out, int device) {
         c->map_blocks_per_sm = nb;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_big_kernel, LIP_BIG_THREADS, 0) == cudaSuccess && nb > 0)
         c->big_blocks_per_sm = nb;
+    // thread-block clusters for the heaviest partitions: size and first work class (LIP_CLUSTER_SIZE=1 or LIP_CLUSTER_CLASS=4: off)
+    if (const char* e = getenv("LIP_CLUSTER_SIZE")) c->cluster_size = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("LIP_CLUSTER_CLASS")) c->cluster_cls = std::max(0, std::min(4, atoi(e)));
+    if (c->cluster_size < 2) c->cluster_cls = 4;
+    if (const char* e = getenv("LIP_CLUSTER_COOP_PARTS")) c->cluster_max_bins = std::max<int64_t>(0, atoll(e));
+    if (c->cluster_cls < 4) {
+        cudaLaunchConfig_t q = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)c->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        q.gridDim = dim3((unsigned)c->cluster_size); q.blockDim = dim3(LIP_CLUSTER_THREADS); q.attrs = at; q.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, icp_cluster_kernel<LIP_CLUSTER_THREADS, LIP_CLUSTER_CHUNK>, &q) == cudaSuccess && ncl > 0)
+            c->cluster_grid = ncl * c->cluster_size;
+        else { cudaGetLastError(); c->cluster_cls = 4; }       // no room for such clusters on this device: everything stays with icp_big_kernel
+    }
     cudaFuncSetAttribute(landmark_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LIP_MAX_LANDMARKS * 44 + 32);
     cudaFuncSetAttribute(partition_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          LIP_MAX_LANDMARKS * 4 * (2 + LIP_PART_THREADS / 32) + 16);
@@ -867,7 +921,7 @@ void lip_destroy(lip_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     c->in_frames.release(); c->d_rows.release();

@@ -341,9 +341,11 @@ def _tube(rng, n, L, r=1.2, jitter=0.05):
     return np.stack([s + rng.normal(0, jitter, n), rr * np.cos(th) + 0.02 * s * s / L, rr * np.sin(th)], 1)
 
 
-@pytest.mark.parametrize("n_src,n_tgt", [(100, 600), (600, 100), (3000, 2500), (40, 2300), (1, 300), (300, 1)])
+@pytest.mark.parametrize("n_src,n_tgt", [(100, 600), (600, 100), (3000, 2500), (40, 2300), (1, 300), (300, 1),
+                                         (700, 720), (20, 30000), (5000, 300), (2100, 2049)])
 def test_my_icp_chunked_target_paths(L, n_src, n_tgt):
-    """targets that stream through the SMEM tile in several chunks (warp kernel: > 256 points, CTA kernel: > 1,024)"""
+    """targets that stream through the SMEM tile in several chunks (warp kernel: > 256 points, CTA kernel: > 1,024, cluster
+    kernel — partitions of more than 400 k pairs — > 2,048; 20 queries leave seven of a cluster's eight CTAs without any)"""
     rng = np.random.default_rng(n_src * 7 + n_tgt)
     tgt = _tube(rng, n_tgt, 30.0) + 50.0
     c, s_ = np.cos(0.05), np.sin(0.05)
@@ -932,3 +934,36 @@ def test_tensor_core_map_mode_gives_identical_maps(L, syn):
             ctx.close()
         np.testing.assert_array_equal(out[0][0], out[2][0], err_msg=f"case {i} T21")
         np.testing.assert_array_equal(out[0][1], out[2][1], err_msg=f"case {i} T12")
+
+
+@pytest.mark.gpu
+def test_cluster_icp_equals_cta_icp(L, monkeypatch):
+    """the heaviest partitions run on thread-block clusters (icp_cluster_kernel); with LIP_CLUSTER_SIZE=1 the CTA kernel takes
+    them: same iteration counts, same maps, transforms equal to rounding of the float64 sums (their order differs)"""
+    rng = np.random.default_rng(77)
+    segs = []
+    for n1, n2 in ((900, 880), (2500, 700), (64, 9000), (1300, 1250), (300, 280)):       # K == 1: one whole-organ ICP per direction
+        x1 = _tube(rng, n1, 40.0) + 20.0
+        x2 = _tube(rng, n2, 40.0) * [1.02, 1.0, 1.0] + [20.3, 19.8, 20.1]
+        segs.append((x1, x2, np.array([[40.0, 20.0, 20.0]]), np.array([[40.5, 20.0, 20.0]])))
+    monkeypatch.setenv("LIP_CLUSTER_SIZE", "1")
+    ctx_cta = L.Context(0)
+    monkeypatch.setenv("LIP_CLUSTER_SIZE", "4")
+    ctx_4 = L.Context(0)
+    monkeypatch.delenv("LIP_CLUSTER_SIZE")
+    ctx_8 = L.Context(0)
+    ref = L.local_icp_batch(segs, details=True, ctx=ctx_cta)
+    for ctx in (ctx_4, ctx_8):
+        res = L.local_icp_batch(segs, details=True, ctx=ctx)
+        np.testing.assert_array_equal(res.T21, ref.T21)
+        np.testing.assert_array_equal(res.T12, ref.T12)
+        for d in ("21", "12"):
+            np.testing.assert_array_equal(res.transforms["raw"]["iters" + d], ref.transforms["raw"]["iters" + d])
+            np.testing.assert_array_equal(res.transforms["raw"]["status" + d], ref.transforms["raw"]["status" + d])
+            np.testing.assert_allclose(res.transforms["raw"]["R" + d], ref.transforms["raw"]["R" + d], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(res.transforms["raw"]["t" + d], ref.transforms["raw"]["t" + d], rtol=0, atol=1e-9)
+    assert ctx_8.counters()["launches"] == ctx_cta.counters()["launches"] + 1
+    for i, (x1, x2, l1, l2) in enumerate(segs):              # and against the oracle
+        det = {}
+        T_or = O.segment_map(x1, x2, l1, l2, nn="brute", details=det)
+        _assert_map_equal_up_to_ties(res.maps(i)[0], T_or, det["x2t"], x1, f"cluster segment {i}")
