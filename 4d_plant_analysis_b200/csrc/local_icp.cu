@@ -17,6 +17,7 @@
 #include <limits>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost a pointer test unless a profiler is attached
 
 #ifndef LIP_ARCH
 #define LIP_ARCH 100
@@ -27,6 +28,14 @@
 #define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
 namespace {
+
+// NVTX range on the calling thread (tracing hook): entry points and the stages they enqueue
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 constexpr size_t kGroupSmem = sizeof(IcpGroupSmem) * LIP_ICP_WARPS;     // dynamic SMEM of icp_group_kernel (> 48 KB: opt-in)
 static_assert(LIP_ICP_CHUNK <= 256, "winners of a staged partition are stored as one byte");
@@ -415,6 +424,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     if (!serial) LIP_CUDA(c, cudaEventRecord(c->ev_begin, st));
     mark();                                                  // event 0
     if (stages & ST_PARTITION) {
+        Range r_("lip:partition");
         landmark_nn_kernel<<<c->n_ptiles, LIP_PART_THREADS, (size_t)c->maxK * 44 + 32, st>>>(a);
         LIP_CHECK("landmark_nn_kernel");
         partition_scan_kernel<<<(c->M + 3) / 4, 128, 0, st>>>(a);
@@ -428,6 +438,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     mark();                                                  // 1: after partition
     bool forked_icp = false, forked_grid = false;
     if (stages & ST_ICP) {
+        Range r_("lip:icp");
         icp_schedule_kernel<<<(c->B + 255) / 256, 256, 0, st>>>(a);
         LIP_CHECK("icp_schedule_kernel");
         mark();                                              // 2: after schedule
@@ -486,6 +497,7 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     }
     if (forked_grid) { LIP_CUDA(c, cudaEventRecord(c->ev_join[2], s_grid)); LIP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[2], 0)); }
     if ((stages & ST_BLEND) && c->n_tiles > 0) {
+        Range r_("lip:blend+map");
         if (tiles) {
             bin_desc_kernel<<<(c->B + 127) / 128, 128, 0, st>>>(a);
             blend_kernel<<<(a.n_total + 255) / 256, 256, 0, st>>>(a);
@@ -1023,6 +1035,7 @@ static int plan_kids(lip_ctx* c, KidSet ks, int chunks, int64_t S, const int64_t
 }
 
 int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, const int64_t* lm_off, int directions) {
+    Range nvtx_("lip_batch_plan");
     if (!c) return LIP_EINVAL;
     cudaSetDevice(c->device);
     int chunks = LIP_PIPELINE_CHUNKS;
@@ -1053,6 +1066,7 @@ int lip_batch_plan(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* of
 
 int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                          void* T21, void* T12, void* stream) {
+    Range nvtx_("lip_batch_run_device");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
@@ -1085,6 +1099,7 @@ int lip_batch_run_device(lip_ctx* c, const double* xyz1, const double* xyz2, con
 
 int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                        void* T21, void* T12) {
+    Range nvtx_("lip_batch_run_host");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "run: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "run: null input pointer");
@@ -1123,6 +1138,7 @@ static int series_rows(lip_ctx* kc, const int64_t* row1, const int64_t* row2, in
 
 int lip_series_run_device(lip_ctx* c, const double* d_frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
                           const double* d_lm1, const double* d_lm2, void* T21, void* T12, void* stream) {
+    Range nvtx_("lip_series_run_device");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "series: no batch planned");
     if (!d_frames || !row1 || !row2 || !d_lm1 || !d_lm2) return fail(c, LIP_EINVAL, "series: null input pointer");
@@ -1161,6 +1177,7 @@ int lip_series_run_device(lip_ctx* c, const double* d_frames, int64_t n_rows, co
 // of the two uploads of lip_batch_run_host.
 int lip_series_run_host(lip_ctx* c, const double* frames, int64_t n_rows, const int64_t* row1, const int64_t* row2,
                         const double* lm1, const double* lm2, void* T21v, void* T12v) {
+    Range nvtx_("lip_series_run_host");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan) return fail(c, LIP_ENOPLAN, "series: no batch planned");
     if (!frames || !row1 || !row2 || !lm1 || !lm2) return fail(c, LIP_EINVAL, "series: null input pointer");
@@ -1524,6 +1541,7 @@ static void scores_from_counts(const long long* h, size_t S, bool with_T12, doub
 int lip_batch_evaluate_host(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
                             const int64_t* T21, const int64_t* T12, double voxel_size, double sample_proportion,
                             double* scores, int64_t* counts) {
+    Range nvtx_("lip_batch_evaluate_host");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
     if (!xyz1 || !xyz2 || !lm1 || !lm2 || !T21 || !scores) return fail(c, LIP_EINVAL, "evaluate: null pointer");
@@ -1558,6 +1576,7 @@ static int series_rows(lip_ctx* kc, const int64_t* row1, const int64_t* row2, in
 int lip_batch_evaluate_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2, const double* d_lm1, const double* d_lm2,
                               const int64_t* d_T21, const int64_t* d_T12, double voxel_size, double sample_proportion,
                               int64_t* d_counts, const int64_t* row1, const int64_t* row2, int64_t n_rows, void* stream) {
+    Range nvtx_("lip_batch_evaluate_device");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "evaluate: no batch planned");
     if (!d_xyz1 || !d_xyz2 || !d_lm1 || !d_lm2 || !d_T21 || !d_counts) return fail(c, LIP_EINVAL, "evaluate: null pointer");
@@ -1637,6 +1656,7 @@ static int refine_device(lip_ctx* c, const double* d_xyz1, const double* d_xyz2,
 }
 
 int lip_batch_refine_host(lip_ctx* c, const double* xyz1, const double* xyz2, int64_t* T21, const int64_t* T12) {
+    Range nvtx_("lip_batch_refine_host");
     if (!c) return LIP_EINVAL;
     if (!c->planned || !c->user_plan || c->h_off1.empty()) return fail(c, LIP_ENOPLAN, "refine: no batch planned");
     if (!xyz1 || !xyz2 || !T21 || !T12) return fail(c, LIP_EINVAL, "refine: null pointer");

@@ -967,3 +967,36 @@ def test_cluster_icp_equals_cta_icp(L, monkeypatch):
         det = {}
         T_or = O.segment_map(x1, x2, l1, l2, nn="brute", details=det)
         _assert_map_equal_up_to_ties(res.maps(i)[0], T_or, det["x2t"], x1, f"cluster segment {i}")
+
+
+@pytest.mark.gpu
+def test_device_entry_point_is_graph_capture_safe(L, syn):
+    """a caller that replays one planned batch may capture lip_batch_run_device in a CUDA graph: the library's side streams fork
+    from and join the capturing stream through events, nothing in the step allocates or synchronises (tools/graph_probe.py)"""
+    import torch
+    data = syn.make_config(1, scale=0.5)
+    ctx = L.Context(0)
+    ctx.plan(data.off1, data.off2, data.lm_off)
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(a).to(dev) for a in (data.xyz1, data.xyz2, data.lm1, data.lm2)]
+    T21 = torch.zeros(int(data.off2[-1]), dtype=torch.int64, device=dev)
+    T12 = torch.zeros(int(data.off1[-1]), dtype=torch.int64, device=dev)
+    st = torch.cuda.Stream(dev)
+
+    def step():
+        ctx.run_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), T21.data_ptr(), T12.data_ptr(), st.cuda_stream)
+    step()
+    torch.cuda.synchronize()
+    ref21, ref12 = T21.clone(), T12.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+        step()
+    for _ in range(3):
+        T21.zero_(); T12.zero_()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(T21, ref21) and torch.equal(T12, ref12)
+    ref = L.local_icp_batch(data, ctx=L.Context(0))
+    np.testing.assert_array_equal(ref.T21, ref21.cpu().numpy())
+    np.testing.assert_array_equal(ref.T12, ref12.cpu().numpy())
