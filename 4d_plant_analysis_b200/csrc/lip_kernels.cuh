@@ -308,6 +308,9 @@ __global__ void __launch_bounds__(LIP_PART_THREADS) partition_place_kernel(LipAr
 #define LIP_SORT_BATCH 2      // members per lane whose gathers are issued together in the final pass of bin_sort_kernel
 #endif
 #define LIP_SORT_WARPS 4
+#ifndef LIP_SORT_WIDE
+#define LIP_SORT_WIDE 4       // chunks of 32 members in flight per pass over a bin of more than 256 members
+#endif
 __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a) {
     __shared__ unsigned skey_all[LIP_SORT_WARPS][256];
     __shared__ float4 sdat_all[LIP_SORT_WARPS][256];
@@ -339,12 +342,26 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
             bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
         }
     } else {
-        for (int p = s0 + lane; p < e0; p += 32) {
-            const float4 t = a.bin_tmp[p];
-            lo0 = fminf(lo0, t.x); lo1 = fminf(lo1, t.y); lo2 = fminf(lo2, t.z);
-            hi0 = fmaxf(hi0, t.x); hi1 = fmaxf(hi1, t.y); hi2 = fmaxf(hi2, t.z);
-            const size_t v = (size_t)__float_as_int(t.w);
-            bx0 += xyz[3 * v]; bx1 += xyz[3 * v + 1]; bx2 += xyz[3 * v + 2];
+        // large bins (whole organs of K == 1 segments): the slowest warp of the launch in a small batch, so LIP_SORT_WIDE chunks
+        // of 32 members are in flight together in every pass (same per-lane summation order as one chunk at a time)
+        for (int p0 = s0 + lane; p0 < e0; p0 += 32 * LIP_SORT_WIDE) {
+            float4 t[LIP_SORT_WIDE];
+            double gx[LIP_SORT_WIDE], gy[LIP_SORT_WIDE], gz[LIP_SORT_WIDE];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k) if (p0 + 32 * k < e0) t[k] = a.bin_tmp[p0 + 32 * k];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k)
+                if (p0 + 32 * k < e0) {
+                    const size_t v = (size_t)__float_as_int(t[k].w);
+                    gx[k] = xyz[3 * v]; gy[k] = xyz[3 * v + 1]; gz[k] = xyz[3 * v + 2];
+                }
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k)
+                if (p0 + 32 * k < e0) {
+                    lo0 = fminf(lo0, t[k].x); lo1 = fminf(lo1, t[k].y); lo2 = fminf(lo2, t[k].z);
+                    hi0 = fmaxf(hi0, t[k].x); hi1 = fmaxf(hi1, t[k].y); hi2 = fmaxf(hi2, t[k].z);
+                    bx0 += gx[k]; bx1 += gy[k]; bx2 += gz[k];
+                }
         }
     }
     lo0 = -warp_maxf(-lo0); lo1 = -warp_maxf(-lo1); lo2 = -warp_maxf(-lo2);
@@ -375,7 +392,13 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (lane + 32 * k < nb) atomicAdd(&skey[bucket_of(tt[k])], 1u);
     } else {
-        for (int e = lane; e < nb; e += 32) atomicAdd(&skey[bucket_of(a.bin_tmp[s0 + e])], 1u);
+        for (int e0w = lane; e0w < nb; e0w += 32 * LIP_SORT_WIDE) {
+            float4 t[LIP_SORT_WIDE];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k) if (e0w + 32 * k < nb) t[k] = a.bin_tmp[s0 + e0w + 32 * k];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k) if (e0w + 32 * k < nb) atomicAdd(&skey[bucket_of(t[k])], 1u);
+        }
     }
     __syncwarp();
     {                                                    // exclusive scan of the 256 counts: lane l owns buckets 8l .. 8l+7
@@ -446,24 +469,45 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
         }
 #endif
     } else {
-        for (int base = 0; base < nb; base += 32) {
-            const int e = base + lane;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            int bucket = -1;
-            if (e < nb) { t = a.bin_tmp[s0 + e]; bucket = bucket_of(t); }
-            const unsigned peers = __match_any_sync(LIP_FULL, bucket);
-            const int rk = __popc(peers & ((1u << lane) - 1));
-            if (e < nb) {
-                const size_t v = (size_t)__float_as_int(t.w), p = (size_t)s0 + skey[bucket] + rk;
-                a.part_vid[p] = (int)v;
-                a.bin_pts[p] = t;
-                a.bin_xyz[p] = xyz[3 * v]; a.bin_xyz[N + p] = xyz[3 * v + 1]; a.bin_xyz[2 * N + p] = xyz[3 * v + 2];
-                a.pos_bin[p] = b; a.pos_nn1[p] = a.nn1[ub + v];
-                a.pos_d[p] = a.d0[ub + v]; a.pos_d[N + p] = a.d1[ub + v];
+        for (int base = 0; base < nb; base += 32 * LIP_SORT_WIDE) {
+            float4 t[LIP_SORT_WIDE];
+            size_t dstp[LIP_SORT_WIDE];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k) {
+                t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + 32 * k + lane < nb) t[k] = a.bin_tmp[s0 + base + 32 * k + lane];
             }
-            __syncwarp();
-            if (e < nb && rk == 0) skey[bucket] += __popc(peers);
-            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k) {       // the cursors advance chunk by chunk, in member order
+                if (base + 32 * k >= nb) break;             // uniform
+                const bool in = base + 32 * k + lane < nb;
+                const int bucket = in ? bucket_of(t[k]) : -1;
+                const unsigned peers = __match_any_sync(LIP_FULL, bucket);
+                const int rk = __popc(peers & ((1u << lane) - 1));
+                if (in) dstp[k] = (size_t)s0 + skey[bucket] + rk;
+                __syncwarp();
+                if (in && rk == 0) skey[bucket] += __popc(peers);
+                __syncwarp();
+            }
+            double gx[LIP_SORT_WIDE], gy[LIP_SORT_WIDE], gz[LIP_SORT_WIDE], g0[LIP_SORT_WIDE], g1[LIP_SORT_WIDE];
+            int gn[LIP_SORT_WIDE];
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k)
+                if (base + 32 * k + lane < nb) {
+                    const size_t v = (size_t)__float_as_int(t[k].w);
+                    gx[k] = xyz[3 * v]; gy[k] = xyz[3 * v + 1]; gz[k] = xyz[3 * v + 2];
+                    gn[k] = a.nn1[ub + v]; g0[k] = a.d0[ub + v]; g1[k] = a.d1[ub + v];
+                }
+#pragma unroll
+            for (int k = 0; k < LIP_SORT_WIDE; ++k)
+                if (base + 32 * k + lane < nb) {
+                    const size_t p = dstp[k];
+                    a.part_vid[p] = __float_as_int(t[k].w);
+                    a.bin_pts[p] = t[k];
+                    a.bin_xyz[p] = gx[k]; a.bin_xyz[N + p] = gy[k]; a.bin_xyz[2 * N + p] = gz[k];
+                    a.pos_bin[p] = b; a.pos_nn1[p] = gn[k];
+                    a.pos_d[p] = g0[k]; a.pos_d[N + p] = g1[k];
+                }
         }
     }
 
