@@ -133,6 +133,17 @@ enum Stage { ST_PARTITION = 1, ST_ICP = 2, ST_GRID = 4, ST_BLEND = 16, ST_QUERY 
 
 }  // namespace
 
+// one recorded step (run_stages): the arguments it was captured with and the executable graph
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    LipArgs args;
+    uint64_t plan_gen = 0;
+    int stages = 0, seen = 0;
+    cudaStream_t st = nullptr;
+    int64_t launches = 0;
+    void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; seen = 0; }
+};
+
 struct lip_ctx {
     int device = 0;
     int sm_count = 0;
@@ -142,6 +153,9 @@ struct lip_ctx {
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int cluster_size = LIP_CLUSTER_SIZE, cluster_cls = LIP_CLUSTER_CLASS, cluster_grid = 0;
     int64_t heavy_bound = 0;                                 // planned batch: upper bound on the partitions the cluster kernel can get
+    StepGraph step_graph;                                    // the last step of this context, as a CUDA graph once it has repeated
+    bool graphs_ok = true;                                   // false after a capture / instantiate / launch of a graph failed
+    uint64_t plan_gen = 0;                                   // bumped by every plan_impl
     bool use_clusters = false;                               // planned batch: small, with whole-organ ICPs (see plan_impl)
     int64_t cluster_max_bins = LIP_CLUSTER_COOP_PARTS;
     bool fill_done = false;
@@ -283,6 +297,7 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     const int tile = LIP_TILE;                               // tiles of the grid-mode kernels (blend_nn_kernel, nn_query_kernel)
     if (!c) return LIP_EINVAL;
     c->planned = false;
+    ++c->plan_gen;
     if (S <= 0 || !off1 || !off2 || !lm_off) return fail(c, LIP_EINVAL, "plan: S must be > 0 and offsets non-null");
     if ((directions & LIP_DIR_BOTH) == 0) return fail(c, LIP_EINVAL, "plan: directions must include T21 and/or T12");
     if (off1[0] != 0 || off2[0] != 0 || lm_off[0] != 0) return fail(c, LIP_EINVAL, "plan: offsets must start at 0");
@@ -393,14 +408,9 @@ int plan_impl(lip_ctx* c, int64_t S, const int64_t* off1, const int64_t* off2, c
     return LIP_OK;
 }
 
-int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
-               long long* T21, long long* T12, double* q_dist, int stages, cudaStream_t st, const int* mesh_row = nullptr) {
-    if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
+// the launches of one step (c->args filled in by run_stages)
+int launch_stages(lip_ctx* c, int stages, cudaStream_t st) {
     LipArgs& a = c->args;
-    a.xyz1 = xyz1; a.xyz2 = xyz2; a.lm1 = lm1; a.lm2 = lm2; a.T21 = T21; a.T12 = T12; a.q_dist = q_dist;
-    a.mesh_row = mesh_row;                                   // (reset below: later calls copy c->args)
-    struct RowReset { LipArgs& a; ~RowReset() { a.mesh_row = nullptr; } } row_reset{a};
-    set_param_args(c);
     int64_t launches = 0;
     int evi = 0;
     // While profiling, everything runs back to back on `st` so that the events bracket one kernel each;
@@ -537,6 +547,63 @@ int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double*
     c->last_launches = launches;
     c->ev_valid = c->profiling;
     return LIP_OK;
+}
+
+// One step of the planned batch on `st`.  A caller that repeats the SAME step — the sub-batches of the host pipeline do (their
+// device buffers are their own), and so does a device-resident caller that reuses its buffers — gets it replayed as a CUDA
+// graph from the third identical call on: the second one captures it (memsets, launches, the fork / join of the side streams).
+// What a graph saves is host time, 47-93 -> 5-8 us per (sub-)batch (profiles/README.md): the pipelined host paths of
+// medium-sized batches are bound by exactly that.  LIP_GRAPHS=0 turns it off; profiling, LIP_DEBUG_SYNC and a caller that is
+// capturing `st` itself get plain launches.
+int run_stages(lip_ctx* c, const double* xyz1, const double* xyz2, const double* lm1, const double* lm2,
+               long long* T21, long long* T12, double* q_dist, int stages, cudaStream_t st, const int* mesh_row = nullptr) {
+    if (!c->planned) return fail(c, LIP_ENOPLAN, "run: no batch planned");
+    LipArgs& a = c->args;
+    a.xyz1 = xyz1; a.xyz2 = xyz2; a.lm1 = lm1; a.lm2 = lm2; a.T21 = T21; a.T12 = T12; a.q_dist = q_dist;
+    a.mesh_row = mesh_row;                                   // (reset below: later calls copy c->args)
+    struct RowReset { LipArgs& a; ~RowReset() { a.mesh_row = nullptr; } } row_reset{a};
+    set_param_args(c);
+    static const bool graphs_env = !(getenv("LIP_GRAPHS") && atoi(getenv("LIP_GRAPHS")) == 0);
+    static const bool debug_sync = getenv("LIP_DEBUG_SYNC") != nullptr;
+    StepGraph& g = c->step_graph;
+    bool may = graphs_env && c->graphs_ok && !c->profiling && !debug_sync;
+    if (may) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); may = false; }
+    }
+    if (!may) return launch_stages(c, stages, st);
+    const bool same = g.seen > 0 && g.plan_gen == c->plan_gen && g.stages == stages && g.st == st && !memcmp(&g.args, &a, sizeof(LipArgs));
+    if (same && g.exec) {
+        if (cudaGraphLaunch(g.exec, st) == cudaSuccess) {
+            c->last_launches = g.launches; c->ev_valid = false; c->fill_done = false;
+            return LIP_OK;
+        }
+        cudaGetLastError();
+        c->graphs_ok = false;                                // never again on this context; this step goes out as plain launches
+        return launch_stages(c, stages, st);
+    }
+    if (!same) {
+        g.reset();
+        memcpy(&g.args, &a, sizeof(LipArgs)); g.plan_gen = c->plan_gen; g.stages = stages; g.st = st; g.seen = 1;
+        return launch_stages(c, stages, st);
+    }
+    ++g.seen;                                                // the second identical step: capture it, instantiate, launch
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError(); c->graphs_ok = false;
+        return launch_stages(c, stages, st);
+    }
+    const int rc = launch_stages(c, stages, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+    if (rc == LIP_OK && e_end == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        g.launches = c->last_launches;
+        if (cudaGraphLaunch(g.exec, st) == cudaSuccess) return LIP_OK;
+    } else if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.reset(); c->graphs_ok = false;
+    if (rc != LIP_OK) return rc;
+    return launch_stages(c, stages, st);                     // nothing ran during the capture
 }
 
 const int kFullPipeline = ST_PARTITION | ST_ICP | ST_GRID_ALL | ST_BLEND;   // (the grid is only built in map mode 1; the fill is resolved on the fly)
@@ -932,6 +999,7 @@ void lip_destroy(lip_ctx* c) {
     c->dkids.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->step_graph.reset();
     for (int i = 0; i <= LIP_N_STAGES; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
