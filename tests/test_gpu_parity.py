@@ -1000,3 +1000,63 @@ def test_device_entry_point_is_graph_capture_safe(L, syn):
     ref = L.local_icp_batch(data, ctx=L.Context(0))
     np.testing.assert_array_equal(ref.T21, ref21.cpu().numpy())
     np.testing.assert_array_equal(ref.T12, ref12.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_graph_replay_of_repeated_steps_is_exact_and_never_stale(L, syn, monkeypatch):
+    """a step that repeats is replayed as a CUDA graph from its third call on: same maps every time; a change of parameters,
+    of the data behind the same plan, or of the plan itself must not replay the recorded step"""
+    import torch
+    data = syn.make_series(1, n_frames=4, plants=4)             # large enough for the pipelined host path (sub-batches)
+    batch = data.as_batch()
+    monkeypatch.setenv("LIP_GRAPHS", "0")
+    plain = L.Context(0)
+    monkeypatch.delenv("LIP_GRAPHS")
+    ctx = L.Context(0)
+
+    def host(c, b):
+        c.plan(b.off1, b.off2, b.lm_off)
+        return c.run_host(b.xyz1, b.xyz2, b.lm1, b.lm2)
+    ref21, ref12 = host(plain, batch)
+    for _ in range(5):                                         # plain, capture, replay, replay, replay
+        T21, T12 = host(ctx, batch)
+        np.testing.assert_array_equal(T21, ref21)
+        np.testing.assert_array_equal(T12, ref12)
+    # new parameters behind the recorded step
+    for c in (ctx, plain):
+        c.set_params(reject_dist=0.6)
+    r21, r12 = host(plain, batch)
+    for _ in range(3):
+        T21, T12 = host(ctx, batch)
+        np.testing.assert_array_equal(T21, r21)
+        np.testing.assert_array_equal(T12, r12)
+    assert (r21 != ref21).any() or (r12 != ref12).any()
+    for c in (ctx, plain):
+        c.set_params()
+    # same plan, other coordinates (the recorded step reads the sub-batches' own device buffers: must see the new upload)
+    moved = L.SegmentPairBatch(np.ascontiguousarray(batch.xyz1 * [1.0, 1.01, 1.0]), batch.xyz2, batch.off1, batch.off2, batch.lm1,
+                               batch.lm2, batch.lm_off, batch.frame_pair)
+    m21, m12 = host(plain, moved)
+    for _ in range(3):
+        T21, T12 = host(ctx, moved)
+        np.testing.assert_array_equal(T21, m21)
+        np.testing.assert_array_equal(T12, m12)
+    # another plan of the same size in between, then the first one again
+    other = data.take_frame_pairs(np.arange(0, data.n_frame_pairs - 1)).as_batch()
+    o21, o12 = host(plain, other)
+    T21, T12 = host(ctx, other)
+    np.testing.assert_array_equal(T21, o21)
+    np.testing.assert_array_equal(T12, o12)
+    T21, T12 = host(ctx, batch)
+    np.testing.assert_array_equal(T21, ref21)
+    # the device entry point with the caller's buffers
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (batch.xyz1, batch.xyz2, batch.lm1, batch.lm2)]
+    D21 = torch.zeros(len(ref21), dtype=torch.int64, device=dev); D12 = torch.zeros(len(ref12), dtype=torch.int64, device=dev)
+    ctx.plan(batch.off1, batch.off2, batch.lm_off)
+    for i in range(5):
+        D21.zero_(); D12.zero_()
+        ctx.run_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), D21.data_ptr(), D12.data_ptr())
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(D21.cpu().numpy(), ref21)
+        np.testing.assert_array_equal(D12.cpu().numpy(), ref12)
