@@ -23,7 +23,7 @@
 #define LIP_ARCH 100
 #endif
 #define LIP_PIPELINE_CHUNKS 8             // sub-batches of the pipelined host path
-#define LIP_PIPELINE_RAMP 1.0
+#define LIP_PIPELINE_RAMP 1.6               // sub-batch k ends where the running vertex count passes (k/chunks)^ramp of the total: the first upload is short, the late (GPU-bound) sub-batches large
 #define LIP_DEVICE_CHUNKS 2               // sub-batches of the device-resident entry point
 #define LIP_PIPELINE_MIN_VERTICES 400000   // smaller batches run as one piece
 
@@ -153,6 +153,8 @@ struct lip_ctx {
     cudaEvent_t ev_begin = nullptr, ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int cluster_size = LIP_CLUSTER_SIZE, cluster_cls = LIP_CLUSTER_CLASS, cluster_grid = 0;
     int64_t heavy_bound = 0;                                 // planned batch: upper bound on the partitions the cluster kernel can get
+    bool rows_on_device = false;                             // d_rows holds h_rows (series_rows), uploaded on rows_stream
+    cudaStream_t rows_stream = nullptr;
     StepGraph step_graph;                                    // the last step of this context, as a CUDA graph once it has repeated
     bool graphs_ok = true;                                   // false after a capture / instantiate / launch of a graph failed
     uint64_t plan_gen = 0;                                   // bumped by every plan_impl
@@ -1192,15 +1194,23 @@ int lip_batch_run_host(lip_ctx* c, const double* xyz1, const double* xyz2, const
 static int series_rows(lip_ctx* kc, const int64_t* row1, const int64_t* row2, int64_t s0, int64_t n_rows, const int64_t* off1,
                        const int64_t* off2, cudaStream_t st) {
     const int64_t S = kc->S;
+    bool same = kc->rows_on_device && kc->h_rows.size() == 2 * (size_t)S;      // a series step that repeats: the rows are already there
     kc->h_rows.resize(2 * (size_t)S);
     for (int64_t s = 0; s < S; ++s) {
         const int64_t r1 = row1[s0 + s], r2 = row2[s0 + s];
-        if (r1 < 0 || r2 < 0 || r1 + (off1[s0 + s + 1] - off1[s0 + s]) > n_rows || r2 + (off2[s0 + s + 1] - off2[s0 + s]) > n_rows)
+        if (r1 < 0 || r2 < 0 || r1 + (off1[s0 + s + 1] - off1[s0 + s]) > n_rows || r2 + (off2[s0 + s + 1] - off2[s0 + s]) > n_rows) {
+            kc->rows_on_device = false;
             return fail(kc, LIP_EINVAL, "series: a mesh of segment pair " + std::to_string(s0 + s) + " does not lie inside `frames`");
+        }
+        same = same && kc->h_rows[s] == (int)r1 && kc->h_rows[S + s] == (int)r2;
         kc->h_rows[s] = (int)r1; kc->h_rows[S + s] = (int)r2;
     }
+    const void* before = kc->d_rows.p;
     LIP_CUDA(kc, kc->d_rows.ensure(2 * (size_t)S * 4));
+    if (same && before == kc->d_rows.p && st == kc->rows_stream) return LIP_OK;      // (same stream: ordered after that upload)
+    kc->rows_on_device = false;
     LIP_CUDA(kc, cudaMemcpyAsync(kc->d_rows.p, kc->h_rows.data(), 2 * (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    kc->rows_on_device = true; kc->rows_stream = st;
     return LIP_OK;
 }
 
