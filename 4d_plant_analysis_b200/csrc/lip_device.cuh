@@ -4,6 +4,11 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+
+#ifndef LIP_MAP_SUB
+#define LIP_MAP_SUB 4         // ranges per landmark bin with a bounding box of their own (the unit the final map culls and stages)
+#endif
 
 #define LIP_FULL 0xffffffffu
 
@@ -65,6 +70,7 @@ struct LipArgs {
     double* bin_q;           // [3 * n_total] blended positions of the source vertices (blend_kernel), same layout
     int *pos_bin, *pos_nn1;  // [n_total] bin and second-nearest landmark of every slot (bin order)
     double* pos_d;           // [2 * n_total] distances to the nearest / second-nearest landmark, planes, bin order
+    float4* sub_box;         // [B*2] extents along the bin's sort axis of the LIP_MAP_SUB consecutive ranges of its FINAL order (ceil(n / LIP_MAP_SUB) members each): lo[4], hi[4] in the frame of bin_box; empty range: lo > hi
     float* bin_box;          // [B*8] bounding box of every bin in the same frame: lo xyz, hi xyz, max |coordinate|, sort axis (-1: not sorted)
     MapTile* map_tiles;      // [n_total / LIP_MAP_TILE + B] final-map tiles; count in sched[20]
     double* bin_sum;         // [B*4] float64 mean of the vertices of every bin (x, y, z) and their number

@@ -55,9 +55,12 @@
 #endif
 #define LIP_MAP_TILE (LIP_MAP_Q * LIP_MAP_THREADS)
 #ifndef LIP_MAP_CHUNK
-#define LIP_MAP_CHUNK 512    // candidates staged per scan
+#define LIP_MAP_CHUNK 384    // candidates staged per scan (a tile sees ~340 on average; 512 costs 2.5 KB more SMEM per CTA, which the pipelined host path pays in co-residency)
 #endif
 #define LIP_MAP_BOXBATCH 64
+#ifndef LIP_MAP_BOXB
+#define LIP_MAP_BOXB 64         // bins per box batch of blend_tile_kernel (32: final map 1.07 -> 1.11 ms on the bench batch)
+#endif
 #ifndef LIP_WARP_MINBLOCKS
 #define LIP_WARP_MINBLOCKS 5   // CTAs per SM icp_group_kernel is compiled for (register cap 96)
 #endif
@@ -304,6 +307,27 @@ __global__ void __launch_bounds__(LIP_PART_THREADS) partition_place_kernel(LipAr
 // winners' float64 gathers hit the same lines) and the boxes of query tiles are tight.  Ties are always decided by vertex id.
 // Bins of up to 256 members (the usual case) are held in registers across the passes and permuted through SMEM: every
 // global store coalesced.
+// extent along the sort axis of each of the LIP_MAP_SUB consecutive ranges of a bin's final order (8 lanes per range; `at(pr)` =
+// member pr of that order): with the bin's box in the other two dimensions these are the boxes the final map culls and stages by
+template <typename F>
+__device__ __forceinline__ void sub_boxes(const LipArgs& a, int b, int nb, int axis, int lane, F at) {
+    static_assert(LIP_MAP_SUB == 4, "8 lanes per range");
+    const int per = (nb + LIP_MAP_SUB - 1) / LIP_MAP_SUB, sub = lane >> 3;
+    const int r0 = min(nb, sub * per), r1 = min(nb, r0 + per);
+    float lo = INFINITY, hi = -INFINITY;
+    for (int pr = r0 + (lane & 7); pr < r1; pr += 8) {
+        const float4 t = at(pr);
+        const float c = axis == 0 ? t.x : axis == 1 ? t.y : t.z;
+        lo = fminf(lo, c); hi = fmaxf(hi, c);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(LIP_FULL, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(LIP_FULL, hi, o)); }
+    if ((lane & 7) == 0) {
+        float* sb = reinterpret_cast<float*>(a.sub_box + 2 * (size_t)b);
+        sb[sub] = lo; sb[LIP_MAP_SUB + sub] = hi;            // empty range: lo > hi
+    }
+}
+
 #ifndef LIP_SORT_BATCH
 #define LIP_SORT_BATCH 2      // members per lane whose gathers are issued together in the final pass of bin_sort_kernel
 #endif
@@ -427,6 +451,7 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
             if (e < nb && rk == 0) skey[bucket] += __popc(peers);
             __syncwarp();
         }
+        sub_boxes(a, b, nb, axis, lane, [&](int pr) { return sdat[pr]; });
 #if LIP_SORT_BATCH > 1
         // coalesced stores of everything that is kept in bin order; the gathers by vertex id of LIP_SORT_BATCH members are in
         // flight together (the kernel waits on L2 latency, not on bandwidth)
@@ -509,6 +534,8 @@ __global__ void __launch_bounds__(LIP_SORT_WARPS * 32) bin_sort_kernel(LipArgs a
                     a.pos_d[p] = g0[k]; a.pos_d[N + p] = g1[k];
                 }
         }
+        __syncwarp();                                        // the warp's own stores to bin_pts, read back in final order
+        sub_boxes(a, b, nb, axis, lane, [&](int pr) { return a.bin_pts[(size_t)s0 + pr]; });
     }
 
     }
@@ -1654,11 +1681,12 @@ __global__ void __launch_bounds__(LIP_TILE) blend_nn_kernel(LipArgs a) {
 struct MapSmem {
     float4 tp[LIP_MAP_CHUNK];
     int tv[LIP_MAP_CHUNK];
-    unsigned need[LIP_MAX_LANDMARKS / 32];
-    float sbox[LIP_MAP_BOXBATCH][8];
+    unsigned need[LIP_MAX_LANDMARKS * LIP_MAP_SUB / 32];              // one bit per (bin, range): staged in round 1
+    float sbox[LIP_MAP_BOXB][8];                                  // box of every bin of the batch (tile frame), max |coordinate|, 0 / 1 + sort axis
+    alignas(16) float srange[LIP_MAP_BOXB][2 * LIP_MAP_SUB];                  // ... and the extents of its ranges along that axis (lo[], hi[])
     float red[LIP_MAP_THREADS / 32][8];
     unsigned cand[2];
-    struct { int start, end; float sh[3]; } sdesc[LIP_MAP_BOXBATCH];   // where the bins of the last box batch are, and their shift
+    struct { int start, end; float sh[3]; } sdesc[LIP_MAP_BOXB];   // where the bins of the last box batch are, and their shift
 };
 
 __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int tile) {
@@ -1673,7 +1701,13 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     const int mt = pair_mesh(a, m);
     const int home = T.b - bb;                               // the queries' nearest landmark (local index)
     const double* __restrict__ lmt = mesh_lm(a, mt);
-    const double C0 = T.C[0], C1 = T.C[1], C2 = T.C[2];      // tile origin: the target's landmark
+    // tile origin: the target's landmark (the home bin's stored offsets need no shift) — unless that bin is empty: the queries of
+    // such a tile lie far from everything they will be compared with, and the cancellation error of the dot-form scores (which
+    // grows with |q|^2 about the origin) would send most of them to the float64 rescan.  Their own first query is the origin then.
+    const bool orphan = T.te <= T.ts;
+    const size_t pq0 = (size_t)so + first;
+    const double C0 = orphan ? a.bin_q[pq0] : T.C[0], C1 = orphan ? a.bin_q[(size_t)a.n_total + pq0] : T.C[1],
+                 C2 = orphan ? a.bin_q[2 * (size_t)a.n_total + pq0] : T.C[2];
     constexpr int Q = LIP_MAP_Q;
     float mq[Q][3], qq[Q], qabs[Q], best[Q], sec[Q], sec_in[Q];
     int idx[Q], blk[Q], vq[Q];
@@ -1696,7 +1730,8 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     // queries in use by this WARP (units of 32 queries are dealt warp 0, warp 1, warp 0, warp 1)
     const int qw = min(Q, max(0, (nq - 32 * warp + LIP_MAP_THREADS - 1) / LIP_MAP_THREADS));
     __syncthreads();                                         // the previous tile of this CTA is done with the shared arrays
-    for (int i = tid; i < (K + 31) / 32; i += LIP_MAP_THREADS) need[i] = 0u;
+    const int nwords = (K * LIP_MAP_SUB + 31) / 32;
+    for (int i = tid; i < nwords; i += LIP_MAP_THREADS) need[i] = 0u;
     float mabs = 0.f;                                        // max |coordinate| staged so far (uniform)
     int fill = 0;
     long long staged = 0;
@@ -1704,7 +1739,6 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
     // Two rounds through ONE staging / scanning loop (a single copy of the scan code keeps the kernel small):
     // round 0 stages the target bin of the queries' own landmark, round 1 every other bin that could hold
     // something closer.
-    const int nwords = (K + 31) / 32;
     for (int round = 0; round < 2; ++round) {
         if (round == 1) {
             if (K <= 1) break;
@@ -1739,15 +1773,24 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
             }
             const float rmax2 = v[6], qabs_max = v[7];
             const float qq_max = 3.f * qabs_max * qabs_max;
-            for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXBATCH) {
+            for (int j0 = 0; j0 < K; j0 += LIP_MAP_BOXB) {
                 __syncthreads();
-                if (tid < LIP_MAP_BOXBATCH) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
+                if (tid < LIP_MAP_BOXB) {                    // boxes of this batch of bins in the tile frame + CTA-level cull
                     const int j = j0 + tid;
                     float flag = 0.f, lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f}, mb = 0.f;
                     const int js = j < K ? a.bin_off[bbt + j] : 0, je = j < K ? a.bin_off[bbt + j + 1] : 0;
                     S.sdesc[tid].start = js; S.sdesc[tid].end = je;
                     if (j < K && j != home && je > js) {
-                        const float* bx = a.bin_box + 8 * (size_t)(bbt + j);
+                        const float4* bx4 = reinterpret_cast<const float4*>(a.bin_box + 8 * (size_t)(bbt + j));
+                        const float4 b0 = bx4[0], b1 = bx4[1];               // box, max |coordinate|, axis ...
+                        {
+                            const float4 r0 = a.sub_box[2 * (size_t)(bbt + j)], r1 = a.sub_box[2 * (size_t)(bbt + j) + 1];   // ... and the ranges, one trip
+                            const int ax = (int)b1.w;
+                            const float sha = (float)(lmt[3 * j + ax] - (ax == 0 ? C0 : ax == 1 ? C1 : C2));
+                            *reinterpret_cast<float4*>(&S.srange[tid][0]) = make_float4(r0.x + sha, r0.y + sha, r0.z + sha, r0.w + sha);
+                            *reinterpret_cast<float4*>(&S.srange[tid][4]) = make_float4(r1.x + sha, r1.y + sha, r1.z + sha, r1.w + sha);
+                        }
+                        const float bx[6] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y};
                         float bb2 = 0.f;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
@@ -1761,7 +1804,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                         const float e = 4e-7f * (qabs_max + fmaxf(mb, mabs));
                         const float rhs = rmax2 + d2_err(rmax2, e) + dot_err(qq_max, rmax2);
                         const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
-                        flag = (lhs > rhs) ? 0.f : 1.f;          // (NaN compares false -> kept)
+                        flag = (lhs > rhs) ? 0.f : 1.f + b1.w;                 // (NaN compares false -> kept)
                     }
                     sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
                     sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
@@ -1770,33 +1813,41 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                     if (lane == 0) S.cand[warp] = fm;
                 }
                 __syncthreads();
-                unsigned w0 = 0u, w1 = 0u;
-                unsigned long long cm = ((unsigned long long)S.cand[1] << 32) | S.cand[0];     // uniform
+                unsigned long long cm = LIP_MAP_BOXB > 32 ? ((unsigned long long)S.cand[1] << 32) | S.cand[0] : (unsigned long long)S.cand[0];     // uniform
                 while (cm) {
                     const int t = __ffsll((long long)cm) - 1;
                     cm &= cm - 1;
-                    bool nd = false;
+                    const int axis = (int)sbox[t][7] - 1;
+                    unsigned nd = 0u;                        // ranges of bin j0 + t that some query of this lane still has to see
 #pragma unroll
                     for (int k = 0; k < Q; ++k) {
                         if (!valid[k]) continue;
-                        float bd2 = 0.f;
+                        const float bd = fmaxf(best[k] + qq[k], 0.f);
+                        const float e = 4e-7f * (qabs[k] + fmaxf(sbox[t][6], mabs));
+                        const float tol0 = d2_err(bd, e) + dot_err(qq[k], bd);
+                        float g[3];                          // the whole bin on its own box first
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const float f = -0.5f * mq[k][c];
-                            const float d = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
-                            bd2 = fmaf(d, d, bd2);
+                            g[c] = fmaxf(fmaxf(sbox[t][c] - f, f - sbox[t][3 + c]), 0.f);
                         }
-                        const float bd = fmaxf(best[k] + qq[k], 0.f);
-                        const float e = 4e-7f * (qabs[k] + fmaxf(sbox[t][6], mabs));
-                        const float tol = d2_err(bd, e) + d2_err(bd2, e) + dot_err(qq[k], bd);
-                        nd = nd || !(bd2 - bd > tol);
+                        const float bd2w = fmaf(g[2], g[2], fmaf(g[1], g[1], g[0] * g[0]));
+                        if (bd2w - bd > tol0 + d2_err(bd2w, e)) continue;
+                        // its ranges: the bin's box in the two other dimensions, their own extent along the sort axis
+                        const float fa = -0.5f * (axis == 0 ? mq[k][0] : axis == 1 ? mq[k][1] : mq[k][2]);
+                        const float other = (axis == 0 ? 0.f : g[0] * g[0]) + (axis == 1 ? 0.f : g[1] * g[1]) + (axis == 2 ? 0.f : g[2] * g[2]);
+#pragma unroll
+                        for (int r = 0; r < LIP_MAP_SUB; ++r) {
+                            const float rl = S.srange[t][r], rh = S.srange[t][LIP_MAP_SUB + r];
+                            if (rl > rh) continue;                              // empty range
+                            const float da = fmaxf(fmaxf(rl - fa, fa - rh), 0.f);
+                            const float bd2 = fmaf(da, da, other);
+                            if (!(bd2 - bd > tol0 + d2_err(bd2, e))) nd |= 1u << r;
+                        }
                     }
-                    if (nd) { if (t < 32) w0 |= 1u << t; else w1 |= 1u << (t - 32); }
-                }
-                w0 = __reduce_or_sync(LIP_FULL, w0); w1 = __reduce_or_sync(LIP_FULL, w1);
-                if (lane == 0) {
-                    if (w0) atomicOr(&need[j0 / 32], w0);
-                    if (w1) atomicOr(&need[j0 / 32 + 1], w1);
+                    nd = __reduce_or_sync(LIP_FULL, nd);
+                    const int u = (j0 + t) * LIP_MAP_SUB;
+                    if (lane == 0 && nd) atomicOr(&need[u >> 5], nd << (u & 31));
                 }
             }
             __syncthreads();
@@ -1816,20 +1867,29 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                         mabs = fmaxf(mabs, T.home_mabs);
                         continue;
                     }
+                    int u = -1;                              // next (bin, range) of this round
                     while (bits == 0u && wi < nwords) { bits = need[wi]; base = 32 * wi; ++wi; }
-                    if (bits) { j = base + __ffs(bits) - 1; bits &= bits - 1; }
-                    if (j < 0) { more = false; break; }
-                    if (K <= LIP_MAP_BOXBATCH) {             // descriptors left in SMEM by the box pass
-                        cur_p = S.sdesc[j].start; cur_e = S.sdesc[j].end;
+                    int nr = 1;                              // ... and the ranges of the same bin that follow it directly: one piece
+                    if (bits) {
+                        u = base + __ffs(bits) - 1; bits &= bits - 1;
+                        while ((u + nr) % LIP_MAP_SUB != 0 && ((bits >> ((u + nr) & 31)) & 1u)) { bits &= ~(1u << ((u + nr) & 31)); ++nr; }
+                    }
+                    if (u < 0) { more = false; break; }
+                    j = u / LIP_MAP_SUB;
+                    int bs, be;
+                    if (K <= LIP_MAP_BOXB) {             // descriptors left in SMEM by the box pass
+                        bs = S.sdesc[j].start; be = S.sdesc[j].end;
                         sh0 = S.sdesc[j].sh[0]; sh1 = S.sdesc[j].sh[1]; sh2 = S.sdesc[j].sh[2];
                         mabs = fmaxf(mabs, S.sbox[j][6]);
                     } else {
-                        cur_p = a.bin_off[bbt + j]; cur_e = a.bin_off[bbt + j + 1];
-                        if (cur_e > cur_p) {
+                        bs = a.bin_off[bbt + j]; be = a.bin_off[bbt + j + 1];
+                        if (be > bs) {
                             sh0 = (float)(lmt[3 * j] - C0); sh1 = (float)(lmt[3 * j + 1] - C1); sh2 = (float)(lmt[3 * j + 2] - C2);
                             mabs = fmaxf(mabs, a.bin_box[8 * (size_t)(bbt + j) + 6] + fmaxf(fmaxf(fabsf(sh0), fabsf(sh1)), fabsf(sh2)));
                         }
                     }
+                    const int per = (be - bs + LIP_MAP_SUB - 1) / LIP_MAP_SUB;
+                    cur_p = min(be, bs + (u % LIP_MAP_SUB) * per); cur_e = min(be, cur_p + nr * per);
                     continue;
                 }
                 const int cnt = min(cur_e - cur_p, LIP_MAP_CHUNK - fill);
@@ -1868,6 +1928,10 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
         }
     }
     if (a.profile && tid == 0) atomicAdd(&a.counters[7], (unsigned long long)(staged * nq));
+#ifdef LIP_DEBUG_SLOW_TILES
+    const long long dbg_t1 = clock64();
+    int dbg_ties = 0;
+#endif
 
     // ---- result: near ties are decided in float64 over everything that was staged, a warp per query -------
     const double* __restrict__ xt = mesh_xyz(a, mt);
@@ -1880,18 +1944,40 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
         const bool tie = valid[k] && !(d2s - d2b > tol);
         unsigned ties = __ballot_sync(LIP_FULL, tie);
         if (ties && lane == 0) atomicAdd(&a.counters[3], (unsigned long long)__popc(ties));
+#ifdef LIP_DEBUG_SLOW_TILES
+        dbg_ties += __popc(ties);
+#endif
+        // A rescan reads the staged ranges again as fp32 offsets (coalesced) and takes the float64 coordinates (a gather by vertex id)
+        // only of candidates whose fp32 distance, less its error bound, is not above the best one's upper bound.
+        const float upper = (d2b + d2_err(d2b, e) + dot_err(qq[k], d2b)) * 1.000001f;
         while (ties) {
             const int src = __ffs(ties) - 1;
             ties &= ties - 1;
             const size_t N = (size_t)a.n_total;
             const size_t pq = (size_t)so + first + (tid - lane + src) + k * LIP_MAP_THREADS;     // slot of lane `src`
             const double q0 = a.bin_q[pq], q1 = a.bin_q[N + pq], q2 = a.bin_q[2 * N + pq];
+            const float fx = -0.5f * __shfl_sync(LIP_FULL, mq[k][0], src), fy = -0.5f * __shfl_sync(LIP_FULL, mq[k][1], src),
+                        fz = -0.5f * __shfl_sync(LIP_FULL, mq[k][2], src);
+            const float es = __shfl_sync(LIP_FULL, e, src), us = __shfl_sync(LIP_FULL, upper, src);
             double bd = INFINITY;
             int bi = 0x7fffffff;
             for (int j = 0; j < K; ++j) {
-                if (j != home && !((need[j >> 5] >> (j & 31)) & 1u)) continue;
-                for (int p = a.bin_off[bbt + j] + lane; p < a.bin_off[bbt + j + 1]; p += 32) {
-                    const int vv = a.part_vid[p];
+                const unsigned m4 = j == home ? (1u << LIP_MAP_SUB) - 1 : (need[(j * LIP_MAP_SUB) >> 5] >> ((j * LIP_MAP_SUB) & 31)) & ((1u << LIP_MAP_SUB) - 1);
+                if (!m4) continue;
+                const int bs = a.bin_off[bbt + j], be = a.bin_off[bbt + j + 1], per = (be - bs + LIP_MAP_SUB - 1) / LIP_MAP_SUB;
+                const float s0 = j == home ? 0.f : (float)(lmt[3 * j] - C0), s1 = j == home ? 0.f : (float)(lmt[3 * j + 1] - C1),
+                            s2 = j == home ? 0.f : (float)(lmt[3 * j + 2] - C2);         // as staged
+                const int b1 = bs + per, b2 = bs + 2 * per, b3 = bs + 3 * per;
+                static_assert(LIP_MAP_SUB == 4, "range of a position from three comparisons");
+#pragma unroll 1
+                for (int p = bs + lane; p < be; p += 32) {
+                    const int r = (p >= b1) + (p >= b2) + (p >= b3);
+                    if (!((m4 >> r) & 1u)) continue;         // ranges that were not staged cannot hold anything nearer
+                    const float4 t = a.bin_pts[p];
+                    const float dx = (t.x + s0) - fx, dy = (t.y + s1) - fy, dz = (t.z + s2) - fz;
+                    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d2f - d2_err(d2f, es) > us) continue;
+                    const int vv = __float_as_int(t.w);
                     const double d = rdist64(q0, q1, q2, xt[3 * (size_t)vv], xt[3 * (size_t)vv + 1], xt[3 * (size_t)vv + 2]);
                     if (d < bd || (d == bd && vv < bi)) { bd = d; bi = vv; }
                 }
@@ -1902,13 +1988,17 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                 const int oi = __shfl_xor_sync(LIP_FULL, bi, o);
                 if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
             }
-            if (lane == src) res = bi;
+            if (lane == src && bi != 0x7fffffff) res = bi;
         }
         if (valid[k]) {
             const int u = ub + vq[k];
             store_map(a, u, res);
         }
     }
+#ifdef LIP_DEBUG_SLOW_TILES
+    if (tid == 0 && clock64() - dbg_t1 > LIP_DEBUG_SLOW_TILES / 2)
+        printf("  tile %d: tie phase %lld clk, staged %lld, ties(warp0) %d, K=%d nq=%d mabs=%g\n", tile, clock64() - dbg_t1, staged, dbg_ties, K, nq, mabs);
+#endif
 }
 
 __global__ void __launch_bounds__(LIP_MAP_THREADS, LIP_MAP_MINBLOCKS) blend_tile_kernel(LipArgs a) {
@@ -1921,7 +2011,17 @@ __global__ void __launch_bounds__(LIP_MAP_THREADS, LIP_MAP_MINBLOCKS) blend_tile
         __syncthreads();
         const int tile = s_tile;
         if (tile >= n_tiles) break;
+#ifdef LIP_DEBUG_SLOW_TILES
+        const long long t0 = clock64();
         blend_tile(a, S, tile);
+        const long long dt = clock64() - t0;
+        if (threadIdx.x == 0 && dt > LIP_DEBUG_SLOW_TILES) {
+            const MapTile T = a.map_tiles[tile];
+            printf("slow tile %d of %d: %lld clk K=%d nq=%d home=%d home bin %d..%d\n", tile, n_tiles, dt, T.K, T.nq, T.b - T.bb, T.ts, T.te);
+        }
+#else
+        blend_tile(a, S, tile);
+#endif
     }
 }
 

@@ -244,7 +244,7 @@ int carve_workspace(lip_ctx* c) {
     const size_t o_far = take(n * 8), o_farq = take(n * 24), o_re = take(n * 8), o_req = take(n * 24);
     const size_t o_pts = take(n * 16), o_tab = take((size_t)c->tab_total * 4), o_hdr = take(M * sizeof(GridHdr));
     const size_t o_cnt = take(8 * 8);
-    const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_msum = take(M * 32);
+    const size_t o_bpts = take(n * 16), o_bbox = take(B * 32), o_sbox = take(B * 32), o_msum = take(M * 32);
     c->max_map_tiles = n / LIP_MAP_TILE + B + 1;
     const size_t o_bxyz = take(n * 24), o_bq = take(n * 24), o_pb = take(n * 4), o_pn = take(n * 4), o_pd = take(n * 16);
     const size_t o_mt = take(c->max_map_tiles * sizeof(MapTile));
@@ -264,7 +264,7 @@ int carve_workspace(lip_ctx* c) {
     a.retry_list = (int*)(base + o_re); a.retry_q = (double*)(base + o_req);
     a.grid_pts = (float4*)(base + o_pts); a.grid_start = (int*)(base + o_tab); a.grid_hdr = (GridHdr*)(base + o_hdr);
     a.counters = (unsigned long long*)(base + o_cnt);
-    a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.mesh_sum = (double*)(base + o_msum);
+    a.bin_pts = (float4*)(base + o_bpts); a.bin_box = (float*)(base + o_bbox); a.sub_box = (float4*)(base + o_sbox); a.mesh_sum = (double*)(base + o_msum);
     a.map_tiles = (MapTile*)(base + o_mt);
     a.tile_cnt = (int*)(base + o_tcnt); a.tile_sum = (double*)(base + o_tsum);
     a.tile_base = (int*)(base + o_tbase); a.bin_tmp = (float4*)(base + o_btmp);

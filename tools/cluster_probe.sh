@@ -1,9 +1,7 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for rep in 1 2; do for gr in 0 1; do
-LIP_GRAPHS=$gr python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-sharded --no-parity > gpurun_out/gr.json 2>gpurun_out/gr.err; python - $gr <<PY
+AB_ARGS="--no-sharded --no-parity" bash tools/ab.sh cur=build/cur.so boxb32=build/sub4.so c384b64=build/c384b64.so c384b32=build/c384b32.so
+for v in cur boxb32 c384b64 c384b32; do python - $v <<PY
 import json, sys
-d=json.loads(open("gpurun_out/gr.json").read().strip().splitlines()[-1])
-print("graphs", sys.argv[1], "headline", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],3), {k: round(v["ms_per_step"],2) for k,v in d["e2e"]["variants"].items()}, [(c["config"], round(c["ms_per_step"],3), round(c["e2e_ms_per_step"],3)) for c in d["configs"]])
+d=json.loads(open("gpurun_out/ab_%s_2.json" % sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], [(c["config"], round(c["ms_per_step"],3), round(c["e2e_ms_per_step"],3), c["stage_ms"]["final_map_kernel"]) for c in d["configs"]], {k: round(x["ms_per_step"],2) for k,x in d["e2e"]["variants"].items()})
 PY
-done; done
-for gr in 0 1; do LIP_GRAPHS=$gr python tools/trace_series.py 4 16 1 2>&1 | grep step | tail -2; done
+done

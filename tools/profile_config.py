@@ -28,3 +28,8 @@ with torch.cuda.stream(st):
     e1.record(st)
 torch.cuda.synchronize()
 print("ms/step %.3f" % (e0.elapsed_time(e1) / 5), ctx.counters())
+if os.environ.get("LIP_PROFILE_COUNTERS"):
+    ctx.set_profiling(True)
+    step(); torch.cuda.synchronize()
+    print("stage_ms", {k: round(v, 4) for k, v in ctx.stage_ms().items() if v > 0.002}, ctx.counters())
+    ctx.set_profiling(False)
