@@ -963,6 +963,11 @@ def test_cluster_icp_equals_cta_icp(L, monkeypatch):
             np.testing.assert_allclose(res.transforms["raw"]["R" + d], ref.transforms["raw"]["R" + d], rtol=0, atol=1e-11)
             np.testing.assert_allclose(res.transforms["raw"]["t" + d], ref.transforms["raw"]["t" + d], rtol=0, atol=1e-9)
     assert ctx_8.counters()["launches"] == ctx_cta.counters()["launches"] + 1
+    for _ in range(4):                                       # the step with the cluster launch, captured and replayed as a graph
+        again = L.local_icp_batch(segs, details=True, ctx=ctx_8)
+        np.testing.assert_array_equal(again.T21, ref.T21)
+        np.testing.assert_array_equal(again.T12, ref.T12)
+        np.testing.assert_array_equal(again.transforms["raw"]["iters21"], ref.transforms["raw"]["iters21"])
     for i, (x1, x2, l1, l2) in enumerate(segs):              # and against the oracle
         det = {}
         T_or = O.segment_map(x1, x2, l1, l2, nn="brute", details=det)
