@@ -1785,7 +1785,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                         const float4 b0 = bx4[0], b1 = bx4[1];               // box, max |coordinate|, axis ...
                         {
                             const float4 r0 = a.sub_box[2 * (size_t)(bbt + j)], r1 = a.sub_box[2 * (size_t)(bbt + j) + 1];   // ... and the ranges, one trip
-                            const int ax = (int)b1.w;
+                            const int ax = min(max((int)b1.w, 0), 2);          // bin_sort_kernel's sort axis
                             const float sha = (float)(lmt[3 * j + ax] - (ax == 0 ? C0 : ax == 1 ? C1 : C2));
                             *reinterpret_cast<float4*>(&S.srange[tid][0]) = make_float4(r0.x + sha, r0.y + sha, r0.z + sha, r0.w + sha);
                             *reinterpret_cast<float4*>(&S.srange[tid][4]) = make_float4(r1.x + sha, r1.y + sha, r1.z + sha, r1.w + sha);
@@ -1804,7 +1804,7 @@ __device__ __forceinline__ void blend_tile(const LipArgs& a, MapSmem& S, int til
                         const float e = 4e-7f * (qabs_max + fmaxf(mb, mabs));
                         const float rhs = rmax2 + d2_err(rmax2, e) + dot_err(qq_max, rmax2);
                         const float lhs = bb2 * 0.9999f - d2_err(bb2, e);
-                        flag = (lhs > rhs) ? 0.f : 1.f + b1.w;                 // (NaN compares false -> kept)
+                        flag = (lhs > rhs) ? 0.f : 1.f + fminf(fmaxf(b1.w, 0.f), 2.f);     // (NaN compares false -> kept)
                     }
                     sbox[tid][0] = lo[0]; sbox[tid][1] = lo[1]; sbox[tid][2] = lo[2];
                     sbox[tid][3] = hi[0]; sbox[tid][4] = hi[1]; sbox[tid][5] = hi[2];
