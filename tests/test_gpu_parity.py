@@ -1065,3 +1065,26 @@ def test_graph_replay_of_repeated_steps_is_exact_and_never_stale(L, syn, monkeyp
         torch.cuda.synchronize()
         np.testing.assert_array_equal(D21.cpu().numpy(), ref21)
         np.testing.assert_array_equal(D12.cpu().numpy(), ref12)
+
+
+@pytest.mark.gpu
+def test_large_bins_final_map_against_oracle(L):
+    """segments with few landmarks and many vertices: bins of 400-1,500 members take bin_sort_kernel's path for more than 256
+    members (range extents read back from global memory), and the final map culls and stages their quarters"""
+    rng = np.random.default_rng(123)
+    segs = []
+    for n1, n2, K, Lx in ((1500, 1400, 2, 30.0), (3000, 3100, 3, 60.0), (2400, 2000, 4, 45.0), (900, 2600, 2, 25.0)):
+        x1 = _tube(rng, n1, Lx, r=2.0)
+        x2 = _tube(rng, n2, Lx, r=2.0) * [1.02, 1.0, 1.0] + [0.3, -0.2, 0.1]
+        lm1 = np.stack([np.linspace(0.15 * Lx, 0.85 * Lx, K), 0.02 * np.linspace(0.15 * Lx, 0.85 * Lx, K) ** 2 / Lx, np.zeros(K)], 1)
+        lm2 = lm1 * [1.02, 1.0, 1.0] + [0.3, -0.2, 0.1]
+        segs.append((x1, x2, lm1, lm2))
+    res = L.local_icp_batch(segs, details=True)
+    n_diff = 0
+    for i, (x1, x2, l1, l2) in enumerate(segs):
+        T21, T12 = res.maps(i)
+        for (xt, xs, lt, ls, T) in ((x1, x2, l1, l2, T21), (x2, x1, l2, l1, T12)):
+            det = {}
+            T_or = O.segment_map(xt, xs, lt, ls, nn="brute", details=det)
+            n_diff += _assert_map_equal_up_to_ties(T, T_or, det["x2t"], xt, f"large bins, segment {i}")
+    assert n_diff <= 2
