@@ -39,7 +39,7 @@ struct MapTile {
 
 // frame of one partition ICP: centre = target centroid, tile shift = target landmark - centre, bound on |tile coordinate|,
 // source / target ranges in bin order (written per landmark bin by icp_schedule_kernel, read once per pass)
-struct __align__(16) IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; int pad[2]; };
+struct __align__(16) IcpFrame { double c0, c1, c2; float sh0, sh1, sh2, mabs; int so, ns, to, nt; int axis; float wb; };   // axis, wb: sort axis of the target bin and the width of one bucket of its counting sort
 
 struct LipArgs {
     int S, M, B, sumK, n1_total, n_total, dir_mask, n_tiles;
