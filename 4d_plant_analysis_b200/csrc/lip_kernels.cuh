@@ -2903,6 +2903,32 @@ __device__ __forceinline__ IT refine_keep(const RefineView<IT>& w, int t) {
     }
     return keep;
 }
+// the same decision taken by the whole warp: lane l walks to position l of the list and fetches that source's coordinates, so the
+// loads of all sources (and of the reference point) are in flight together instead of one L2 round trip after the other; the
+// distances are the same float64 expressions, the winner is the first of the smallest (lowest position).  Uniform result.
+// Lists of more than 32 sources take the serial walk.
+template <typename IT>
+__device__ __forceinline__ IT refine_keep_warp(const RefineView<IT>& w, int t, int lane) {
+    constexpr IT NONE = RefineView<IT>::NONE;
+    const IT head = w.head21[t];
+    IT ind = head;
+    for (int s = 0; s < lane && ind != NONE; ++s) ind = w.next21[ind];
+    const bool longer = __shfl_sync(LIP_FULL, (int)(ind != NONE && w.next21[ind] != NONE), 31) != 0;
+    if (longer) return refine_keep(w, t);                    // (every lane computes the same)
+    const double* ref = w.v2 + 3 * (size_t)w.t12[t];
+    double d = INFINITY;
+    if (ind != NONE) d = refine_norm(w.v2 + 3 * (size_t)ind, ref);
+    if (!(d < 10000.0)) d = INFINITY;                        // the reference starts from best = 10 ** 4: such a source never wins
+    int pos = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(LIP_FULL, d, o);
+        const int op = __shfl_xor_sync(LIP_FULL, pos, o);
+        if (od < d || (od == d && op < pos)) { d = od; pos = op; }
+    }
+    const IT winner = (IT)__shfl_sync(LIP_FULL, (int)ind, pos);
+    return d < INFINITY ? winner : head;
+}
 // move source ind from the list of t_from to its place (ascending) in the list of t_to
 template <typename IT>
 __device__ __forceinline__ void refine_move(const RefineView<IT>& w, IT ind, int t_from, int t_to) {
@@ -2946,30 +2972,35 @@ __device__ __forceinline__ void refine_pair(const LipArgs& a, IT* __restrict__ h
         if (lane == 0) snap[t0 >> 5] = bits;
     }
     __syncwarp();
-    if (lane == 0) {
-        for (int t = 0; t < n1; ++t) {
-            if (!((snap[t >> 5] >> (t & 31)) & 1u) || w.head21[t] == NONE || w.next21[w.head21[t]] == NONE) continue;   // a single source: nothing to do
-            const IT keep = refine_keep(w, t);
-            IT ind = w.head21[t];
-            while (ind != NONE) {
-                const IT nxt = w.next21[ind];                // the reference iterates over the list as it was
-                if (ind != keep) {
-                    int t_keep = -1;
-                    if (w.head12[ind] != NONE) {             // targets whose T12 points at this source (:100-101)
-                        t_keep = w.head12[ind];
-                        for (IT c = w.head12[ind]; c != NONE; c = w.next12[c]) if (w.head21[c] == NONE) t_keep = c;
-                    } else {                                 // the four nearest neighbours of the target (:102-103)
-                        const int c0 = nn[5 * (size_t)t], c1 = nn[5 * (size_t)t + 1], c2 = nn[5 * (size_t)t + 2], c3 = nn[5 * (size_t)t + 3];
-                        t_keep = c0;
-                        if (c0 >= 0 && w.head21[c0] == NONE) t_keep = c0;
-                        if (c1 >= 0 && w.head21[c1] == NONE) t_keep = c1;
-                        if (c2 >= 0 && w.head21[c2] == NONE) t_keep = c2;
-                        if (c3 >= 0 && w.head21[c3] == NONE) t_keep = c3;
-                    }
-                    if (t_keep >= 0 && t_keep != t) refine_move(w, ind, t, t_keep);
+    // Every lane walks the targets (all of them read the same table entries: broadcasts, uniform control flow); the loads a
+    // decision waits for are spread over the lanes (refine_keep_warp), lane 0 alone rewrites the lists, in the reference's order.
+    for (int t = 0; t < n1; ++t) {
+        if (!((snap[t >> 5] >> (t & 31)) & 1u) || w.head21[t] == NONE || w.next21[w.head21[t]] == NONE) continue;   // a single source: nothing to do
+        const IT keep = refine_keep_warp(w, t, lane);
+        const int nrow = (lane < 4) ? nn[5 * (size_t)t + lane] : -1;     // the target's four neighbours, one load for the row
+        IT ind = w.head21[t];
+        while (ind != NONE) {
+            const IT nxt = w.next21[ind];                    // the reference iterates over the list as it was
+            if (ind != keep) {
+                int t_keep = -1;
+                if (w.head12[ind] != NONE) {                 // targets whose T12 points at this source (:100-101)
+                    t_keep = w.head12[ind];
+                    for (IT c = w.head12[ind]; c != NONE; c = w.next12[c]) if (w.head21[c] == NONE) t_keep = c;
+                } else {                                     // the four nearest neighbours of the target (:102-103)
+                    const int c0 = __shfl_sync(LIP_FULL, nrow, 0), c1 = __shfl_sync(LIP_FULL, nrow, 1), c2 = __shfl_sync(LIP_FULL, nrow, 2),
+                              c3 = __shfl_sync(LIP_FULL, nrow, 3);
+                    t_keep = c0;
+                    if (c0 >= 0 && w.head21[c0] == NONE) t_keep = c0;
+                    if (c1 >= 0 && w.head21[c1] == NONE) t_keep = c1;
+                    if (c2 >= 0 && w.head21[c2] == NONE) t_keep = c2;
+                    if (c3 >= 0 && w.head21[c3] == NONE) t_keep = c3;
                 }
-                ind = nxt;
+                if (t_keep >= 0 && t_keep != t) {
+                    if (lane == 0) refine_move(w, ind, t, t_keep);
+                    __syncwarp();                            // the lists as lane 0 left them, for every lane
+                }
             }
+            ind = nxt;
         }
     }
     __syncwarp();
@@ -2986,7 +3017,8 @@ __device__ __forceinline__ void refine_pair(const LipArgs& a, IT* __restrict__ h
             if (w.head21[t] != NONE) continue;               // uniform
             int nb = __shfl_sync(LIP_FULL, row, 4 * j + (lane & 3));
             IT keep = NONE;
-            if (lane < 4 && nb >= 0 && nb != t && w.head21[nb] != NONE) keep = refine_keep(w, nb); else nb = -1;
+            // (a neighbour with a single source keeps it whatever the distances are: nothing to compare, nothing to move)
+            if (lane < 4 && nb >= 0 && nb != t && w.head21[nb] != NONE && w.next21[w.head21[nb]] != NONE) keep = refine_keep(w, nb); else nb = -1;
             __syncwarp();
             for (int k = 0; k < 4; ++k) {
                 const int nbk = __shfl_sync(LIP_FULL, nb, k);
